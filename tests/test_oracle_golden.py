@@ -69,7 +69,13 @@ def test_reference_sampler_obeys_sampling_rule(name):
                 if f == -1 or nb.size <= f:
                     assert np.array_equal(got, nb)
                 else:
-                    assert got.size == f and np.unique(got).size == f and np.isin(got, nb).all()
+                    # distinct POSITIONS of the column (cora's edge file holds a few duplicate
+                    # edges, so an id may repeat up to its multiplicity in the column)
+                    assert got.size == f
+                    ids, cnt = np.unique(got, return_counts=True)
+                    nid, ncnt = np.unique(nb, return_counts=True)
+                    assert np.isin(ids, nid).all()
+                    assert (cnt <= ncnt[np.searchsorted(nid, ids)]).all()
 
 
 def test_stored_weights_equal_recomputed_weights():
