@@ -1,0 +1,271 @@
+/* include/nts_b200.h -- C ABI of libnts_b200.so, the B200 (sm_100a) implementation of
+ * NeutronOrch's sample-based training hot path.
+ *
+ * This is the drop-in boundary. The reference's boundary is the C++ header cuda/ntsCUDA.hpp
+ * (free functions :30-71, class Cuda_Stream :177-595) implemented by cuda/ntsCUDAGraphOP.cu;
+ * every entry point below names the reference interface it replaces (paths relative to the
+ * reference repository). A header-only C++ adaptor with the reference's exact class and
+ * method names (sample-based-gnn_b200/host/ntsCUDA.hpp) forwards to these functions, so
+ * core/ and toolkits/ of the reference compile against it unchanged; INTEGRATION.md shows how.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - every function returns 0 on success, a negative nb_status otherwise, and never exits
+ *     the process (the reference's wrappers print and exit(1), cuda/ntsCUDAGraphOP.cu:21-60;
+ *     the adaptor keeps that convention on top of the status codes);
+ *   - all work is ordered on the ctx's CUDA stream; nothing synchronises unless documented;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with NB_ERR_CUDA.
+ *   - VertexId = uint32_t, ValueType = float (dep/gemini/type.hpp:29-31), labels int64_t.
+ */
+#ifndef NTS_B200_H
+#define NTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_ABI_VERSION 1
+
+typedef enum nb_status {
+  NB_OK = 0,
+  NB_ERR_CUDA = -1,      /* a CUDA runtime call failed; nb_last_error() has the string      */
+  NB_ERR_ARG = -2,       /* invalid argument                                                 */
+  NB_ERR_CAPACITY = -3,  /* a sampler arena would overflow (reference: assert, FullyRepGraph.hpp:264) */
+  NB_ERR_ALIGN = -4,     /* pointer / width not usable by any vector path                    */
+  NB_ERR_NCCL = -5,
+  NB_ERR_UNSUPPORTED = -6
+} nb_status;
+
+/* weight applied to a sampled edge (src,dst). core/ntsFastSampler.hpp:27 (enum WeightType)
+ * and :1111-1119; NB_WEIGHT_MEAN_SAMPLED is the GPU kernel's variant
+ * (cuda/ntsCUDATransferKernel.cuh:319-342: divide by the sampled column length). */
+typedef enum nb_weight_type {
+  NB_WEIGHT_SUM = 0,           /* 1/(sqrt(out_deg[src])*sqrt(in_deg[dst]))                  */
+  NB_WEIGHT_MEAN = 1,          /* the above / in_deg[dst]                                   */
+  NB_WEIGHT_NONE = 2,          /* no weights computed                                       */
+  NB_WEIGHT_MEAN_SAMPLED = 3   /* the above / (number of sampled in-edges of dst)           */
+} nb_weight_type;
+
+/* sampler flags */
+#define NB_SAMPLER_MERGE_SRC_DST 1u /* every dst is also a src; dst_local_id is produced
+                                       (sampCSC::set_merge_src_dst, core/coocsc.hpp:407-412)      */
+#define NB_SAMPLER_UP_DEGREE     2u /* weights use per-batch sampled degrees (cfg UP_DEGREE:1;
+                                       core/FullyRepGraph.hpp:189-226)                            */
+#define NB_SAMPLER_BUILD_CSR     4u /* also build row_offset / column_indices / e_w_b
+                                       (sampCSC::csc_to_csr, core/coocsc.hpp:82-111)             */
+
+typedef struct nb_ctx nb_ctx;         /* replaces class Cuda_Stream, cuda/ntsCUDA.hpp:177-199     */
+typedef struct nb_graph nb_graph;     /* replaces the device side of FullyRepGraph +
+                                         FastSampler's GPU ctor, core/ntsFastSampler.hpp:125-176  */
+typedef struct nb_sampler nb_sampler; /* replaces SampledSubgraph's GPU arenas and per-layer
+                                         state, core/FullyRepGraph.hpp:91-131, 258-524            */
+typedef struct nb_table nb_table;     /* HBM-resident (optionally GPU-sharded) feature table:
+                                         replaces GNNDatum's pinned table + per-GPU cache,
+                                         core/ntsDataloador.hpp:187,483; GS_SAMPLE_PC_MULTI.hpp:916-1015 */
+
+/* One sampled layer, all pointers in device memory and owned by the sampler; valid until the
+ * next nb_sampler_sample()/replay() on the same sampler. Mirrors class sampCSC's dev_* members
+ * (core/coocsc.hpp:427-461). */
+typedef struct nb_layer_view {
+  uint32_t n_dst, n_edges, n_src, reserved;
+  const uint32_t *destination;    /* [n_dst]   global ids            (dev_destination)          */
+  const uint32_t *column_offset;  /* [n_dst+1]                       (dev_column_offset)        */
+  const uint32_t *sample_ans;     /* [n_edges] global src per edge   (host-only in reference)   */
+  const uint32_t *row_indices;    /* [n_edges] local src ids         (dev_row_indices)          */
+  const uint32_t *source;         /* [n_src]   global ids ASCENDING  (dev_source)               */
+  const uint32_t *row_offset;     /* [n_src+1] CSR                   (dev_row_offset)           */
+  const uint32_t *column_indices; /* [n_edges] local dst ids, CSR    (dev_column_indices)       */
+  const uint32_t *csr_to_csc;     /* [n_edges] CSC position of each CSR entry (new)             */
+  const float *edge_weight_forward;  /* [n_edges] CSC order (dev_edge_weight_forward / edge_weight) */
+  const float *edge_weight_backward; /* [n_edges] CSR order (dev_edge_weight_backward)          */
+  const uint32_t *dst_local_id;   /* [n_dst] row of each dst inside source (dev_dst_local_id)   */
+  const uint32_t *src_to_dst;     /* [n_src] index of the dst equal to this src, or 0xffffffff (new) */
+} nb_layer_view;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int nb_abi_version(void);
+const char *nb_last_error(void); /* thread-local, valid until the next failing call */
+int nb_device_count(int *count);
+
+/* ---- context: class Cuda_Stream (cuda/ntsCUDA.hpp:177-199; cuda/ntsCUDAGraphOP.cu:203-262) ----
+ * nb_ctx_create      <- Cuda_Stream::Cuda_Stream()     (creates a non-blocking stream)
+ * nb_ctx_set_stream  <- Cuda_Stream::setNewStream()    (adopts a caller stream; unlike the
+ *                       reference the previous own stream is destroyed only if we made it)
+ * nb_ctx_stream      <- Cuda_Stream::getStream()
+ * nb_ctx_synchronize <- Cuda_Stream::CUDA_DEVICE_SYNCHRONIZE() (stream synchronise)
+ * nb_ctx_destroy     <- Cuda_Stream::destory_Stream() */
+int nb_ctx_create(int device, void *cuda_stream_or_null, nb_ctx **out);
+int nb_ctx_destroy(nb_ctx *ctx);
+int nb_ctx_set_stream(nb_ctx *ctx, void *cuda_stream);
+void *nb_ctx_stream(nb_ctx *ctx);
+int nb_ctx_device(nb_ctx *ctx);
+int nb_ctx_synchronize(nb_ctx *ctx);
+uint64_t nb_ctx_launch_count(nb_ctx *ctx); /* kernels this ctx has launched (bench "gpu_launches") */
+
+/* ---- memory helpers: free functions cuda/ntsCUDA.hpp:30-71 -------------------------------
+ * nb_malloc_pinned <- cudaMallocPinned (mapped, portable)   nb_free_host    <- ntsFreeHost
+ * nb_device_pointer<- getDevicePointer                       nb_malloc_device<- cudaMallocGPU / allocate_gpu_buffer/edge
+ * nb_free_device   <- FreeBuffer / FreeEdge                  nb_memcpy_*     <- move_bytes_in/out(_async)
+ * byte counts are size_t (the reference's `int size` helpers overflow beyond 2 GiB). */
+int nb_malloc_pinned(size_t bytes, void **out);
+int nb_free_host(void *p);
+int nb_device_pointer(void *host_mapped, void **out);
+int nb_malloc_device(size_t bytes, void **out);
+int nb_free_device(void *p);
+int nb_memcpy_h2d(nb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, int sync);
+int nb_memcpy_d2h(nb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, int sync);
+int nb_memset_async(nb_ctx *ctx, void *dst_dev, int value, size_t bytes); /* cudaSetMemAsync */
+
+/* ---- global graph ------------------------------------------------------------------------
+ * Replaces: FullyRepGraph::column_offset / row_indices (core/FullyRepGraph.hpp:700-701,724-798)
+ * as FastSampler's GPU ctor ships them (core/ntsFastSampler.hpp:156-166: offsets to device,
+ * adjacency left in mapped host memory and read over PCIe) and move_degree_to_gpu
+ * (cuda/ntsCUDA.hpp:492-493). Here the whole in-edge CSC lives in HBM.
+ * in_degree/out_degree are Graph::in/out_degree_for_backward (clamped >= 1, core/graph.hpp:4525-4530);
+ * either may be NULL, then they are derived on the device from the CSC with the same clamp. */
+int nb_graph_create(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *column_offset_host,
+                    const uint32_t *row_indices_host, const uint32_t *in_degree_host, const uint32_t *out_degree_host,
+                    nb_graph **out);
+int nb_graph_destroy(nb_graph *g);
+int nb_graph_info(nb_graph *g, uint32_t *n_vertices, uint64_t *n_edges, const uint32_t **column_offset_dev,
+                  const uint32_t **row_indices_dev, const uint32_t **in_degree_dev, const uint32_t **out_degree_dev);
+
+/* ---- sampler -----------------------------------------------------------------------------
+ * nb_sampler_create <- SampledSubgraph(layers, batch, fanout, |V|, Cuda_Stream*) (FullyRepGraph.hpp:91-131).
+ *   Arenas are sized from max_batch * prod(fanout) (bounded by |V| and |E|) and checked, never
+ *   asserted. fanout[i] == -1 means take every in-neighbour (CPU semantics, ntsFastSampler.hpp:1003-1006);
+ *   max_edges_hint bounds such a layer (0 = derive from the maximum in-degree).
+ * nb_sampler_sample <- FastSampler::sample_gpu_fast / sample_gpu_fast_omit (ntsFastSampler.hpp:648-915)
+ *   and, stage by stage, Cuda_Stream::sample_processing_get_co_gpu[_omit],
+ *   sample_processing_traverse_gpu, set_dst_local_index, sample_processing_update_ri_gpu,
+ *   ReFreshDegree/UpdateDegree[Cache], GetWeight/GetMeanWeight (cuda/ntsCUDA.hpp:331-368,420-437,506-519,562).
+ *   One call samples every layer of a mini-batch with no host round trip; the only device->host
+ *   traffic is the final copy of the per-layer sizes. Sampling is uniform without replacement
+ *   per dst (all in-neighbours, in stored order, when deg <= fanout), driven by Philox4x32-10
+ *   keyed by (rng_seed, rng_offset, layer, dst slot): reproducible, unlike the reference's
+ *   random_device-seeded LCG (cuda/ntsCUDAGraphOP.cu:1607-1608).
+ *   Local ids follow the CPU sampler's order -- `source` ascending by global id
+ *   (ntsFastSampler.hpp:1062-1083) -- not the reference GPU path's atomic arrival order.
+ *   omit_flag (device, [|V|], may be NULL): bottom-layer dst v gets 0 edges when
+ *     omit_value != 0xffffffff ? omit_flag[v] == omit_value : omit_flag[v] != 0xffffffff
+ *   (cuda/ntsCUDATransferKernel.cuh:771-822).
+ *   views_out (host, [n_layers], may be NULL) receives each layer's view when `sync` is non-zero
+ *   (one stream synchronise at the end of the batch). With sync == 0 nothing waits: call
+ *   nb_ctx_synchronize() and then nb_sampler_layer() before reading sizes on the host; the
+ *   device pointers are fixed per sampler, so dependent kernels can be enqueued without waiting.
+ * nb_sampler_replay: same pipeline but the neighbour draws are supplied: sample_ans_host[i] is
+ *   layer i's global src id per edge in column order (what sampCSC::sample_ans holds). This is
+ *   the bit-exact replay path. n_edges_host[i] must equal the column-offset total.
+ * nb_sampler_layer  <- SampledSubgraph::sampled_sgs[i] (device members). */
+int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout, uint32_t max_batch, uint32_t flags,
+                      uint64_t max_edges_hint, nb_sampler **out);
+int nb_sampler_destroy(nb_sampler *s);
+int nb_sampler_sample(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int seeds_on_device, uint64_t rng_seed,
+                      uint64_t rng_offset, int weight_type, const uint32_t *omit_flag_dev, uint32_t omit_value,
+                      nb_layer_view *views_out, int sync);
+int nb_sampler_replay(nb_sampler *s, const uint32_t *seeds_host, uint32_t n_seeds, const uint32_t *const *sample_ans_host,
+                      const uint32_t *n_edges_host, int weight_type, nb_layer_view *views_out);
+int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out);
+
+/* ---- feature / label gather ----------------------------------------------------------------
+ * nb_gather_rows        <- Cuda_Stream::zero_copy_feature_move_gpu (cuda/ntsCUDA.hpp:370-374): out[i,:] = table[ids[i],:].
+ *                          `table` may be device memory or mapped pinned host memory; table_pitch
+ *                          is the row pitch in floats (>= feature_size; the reference is always dense).
+ * nb_gather_rows_cached <- FastSampler::load_feature_gpu_cache (core/ntsFastSampler.hpp:263-317) =
+ *                          zero_copy_feature_move_gpu_cache + gather_feature_from_gpu_cache (:378-383) with
+ *                          the hot/cold split done on the device in the same kernel:
+ *                          slot = cache_node_hashmap[ids[i]]; slot != -1 ? cache_table[slot,:] : cold_table[ids[i],:].
+ * nb_gather_labels      <- Cuda_Stream::global_copy_label_move_gpu (:384-387).
+ * nb_row_override       <- Cuda_Stream::dev_load_share_embedding (:534-537), dev_load_share_aggregate (:495-497):
+ *                          rows i with cache_map[destination[i]] == super_batch_id (or != -1 when
+ *                          super_batch_id == 0xffffffff) become share[cache_location[destination[i]],:].
+ * nb_row_override2      <- Cuda_Stream::dev_load_share_embedding_and_feature (:521-525): two tensors at once. */
+int nb_gather_rows(nb_ctx *ctx, float *out, const float *table, const uint32_t *ids_dev, uint32_t n_rows,
+                   uint32_t feature_size, uint32_t table_pitch, uint32_t out_pitch);
+int nb_gather_rows_cached(nb_ctx *ctx, float *out, const float *cold_table, uint32_t cold_pitch, const float *cache_table,
+                          uint32_t cache_pitch, const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev,
+                          uint32_t n_rows, uint32_t feature_size, uint32_t out_pitch, uint32_t *hit_count_dev_or_null);
+int nb_gather_labels(nb_ctx *ctx, int64_t *out, const int64_t *labels_dev, const uint32_t *ids_dev, uint32_t n);
+int nb_row_override(nb_ctx *ctx, float *out, const float *share, const uint32_t *cache_map_dev,
+                    const uint32_t *cache_location_dev, const uint32_t *destination_dev, uint32_t n_dst,
+                    uint32_t feature_size, uint32_t super_batch_id);
+int nb_row_override2(nb_ctx *ctx, float *out_feature, float *out_embedding, const float *share_feature,
+                     const float *share_embedding, const uint32_t *cache_map_dev, const uint32_t *cache_location_dev,
+                     const uint32_t *destination_dev, uint32_t n_dst, uint32_t feature_size, uint32_t embedding_size,
+                     uint32_t super_batch_id);
+
+/* Sharded HBM feature table (multi-GPU): row v lives on shard v % n_shards at local row
+ * v / n_shards. shard_ptrs[k] is a device pointer valid on THIS device (local allocation or a
+ * peer mapping obtained through CUDA IPC); the gather kernel reads peers directly over NVLink.
+ * Replaces the per-GPU replicated cache of GS_SAMPLE_PC_MULTI.hpp:916-1015. */
+int nb_table_create(nb_ctx *ctx, uint32_t n_shards, const float *const *shard_ptrs, uint32_t feature_size,
+                    uint32_t pitch, uint64_t n_rows_total, nb_table **out);
+int nb_table_destroy(nb_table *t);
+int nb_table_gather(nb_ctx *ctx, nb_table *t, float *out, const uint32_t *ids_dev, uint32_t n_rows, uint32_t out_pitch);
+/* CUDA IPC plumbing for the above (64-byte opaque handles) */
+int nb_ipc_get_handle(void *dev_ptr, void *handle64_out);
+int nb_ipc_open_handle(const void *handle64, void **dev_ptr_out);
+int nb_ipc_close_handle(void *dev_ptr);
+
+/* ---- sparse aggregation ----------------------------------------------------------------------
+ * nb_aggregate_csc_fwd <- Cuda_Stream::Gather_By_Dst_From_Src_Spmm (cuSPARSE, cuda/ntsCUDAGraphOP.cu:425-587) and
+ *                         Gather_By_Dst_From_Src / _Optim (cuda/ntsCUDA.hpp:223-267):
+ *                         output[d,:] = sum_{e in column d} w[e] * input[row_indices[e],:], column order,
+ *                         multiply then add. weight == NULL means w = 1 (with_weight=false).
+ *                         Writes every output row (an empty column gives zeros).
+ * nb_aggregate_csr_bwd <- Cuda_Stream::Gather_By_Src_From_Dst_Spmm (:901-1042) / Gather_By_Src_From_Dst[_Optim]:
+ *                         output[s,:] = sum_{j in row s} w_b[j] * input[column_indices[j],:].
+ * nb_aggregate_push_bwd<- Cuda_Stream::Push_From_Dst_To_Src_Spmm (:621-770) / Push_From_Dst_To_Src:
+ *                         output[row_indices[e],:] += w[e] * input[d,:] from the CSC alone
+ *                         (vectorised red.global.add; output is zeroed here first; summation order unspecified). */
+int nb_aggregate_csc_fwd(nb_ctx *ctx, const float *input, float *output, const float *weight_forward,
+                         const uint32_t *row_indices, const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src,
+                         uint32_t feature_size);
+int nb_aggregate_csr_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
+                         const uint32_t *row_offset, const uint32_t *column_indices, uint32_t n_src, uint32_t n_dst,
+                         uint32_t feature_size);
+int nb_aggregate_push_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight, const uint32_t *row_indices,
+                          const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src, uint32_t feature_size);
+
+/* ---- GAT edge ops ------------------------------------------------------------------------------
+ * Legacy-shaped (one per reference kernel, so unmodified BatchGPU* ops keep working):
+ * nb_scatter_src_dst_to_msg <- Cuda_Stream::Scatter_Src_Dst_to_Msg (cuda/ntsCUDA.hpp:567-569)
+ * nb_gather_msg_to_src_dst  <- Cuda_Stream::Gather_Msg_To_Src_Dst (:570-573) (output zeroed here)
+ * nb_edge_softmax_fwd       <- Cuda_Stream::Edge_Softmax_Forward_Norm_Block (:321-324) (feature_size 1)
+ * nb_edge_softmax_bwd       <- Cuda_Stream::Edge_Softmax_Backward_Block (:326-329)
+ * nb_gather_msg_to_dst      <- Cuda_Stream::Gather_Msg_to_Dst (:312-314)
+ * nb_scatter_dst_to_msg     <- Cuda_Stream::Scatter_Dst_to_Msg (:308-310)
+ * Fused layer (replaces the five-op chain of toolkits/GAT_SAMPLE_ALL_MULTI.hpp:383-464 between X*W and relu):
+ * nb_gat_fwd: score_pre[e] = h[src(e)].att[0:F] + h[dst_local_id[d]].att[F:2F];
+ *             alpha = edge_softmax(leaky_relu(score_pre, slope)); out[d,:] = sum_e alpha[e]*h[src(e),:].
+ * nb_gat_bwd: gradients of the above w.r.t. h and att, deterministic (CSR gather, no float atomics on dh). */
+int nb_scatter_src_dst_to_msg(nb_ctx *ctx, float *message, const float *src_feature, const uint32_t *row_indices,
+                              const uint32_t *column_offset, uint32_t n_dst, uint32_t feature_size,
+                              const uint32_t *dst_local_id);
+int nb_gather_msg_to_src_dst(nb_ctx *ctx, float *src_grad, const float *message_grad, const uint32_t *row_indices,
+                             const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src, uint32_t feature_size,
+                             const uint32_t *dst_local_id);
+int nb_edge_softmax_fwd(nb_ctx *ctx, float *msg_output, const float *msg_input, float *msg_cached,
+                        const uint32_t *column_offset, uint32_t n_dst);
+int nb_edge_softmax_bwd(nb_ctx *ctx, float *msg_input_grad, const float *msg_output_grad, const float *msg_cached,
+                        const uint32_t *column_offset, uint32_t n_dst);
+int nb_gather_msg_to_dst(nb_ctx *ctx, float *dst_feature, const float *message, const uint32_t *column_offset,
+                         uint32_t n_dst, uint32_t feature_size);
+int nb_scatter_dst_to_msg(nb_ctx *ctx, float *message, const float *dst_feature, const uint32_t *column_offset,
+                          uint32_t n_dst, uint32_t feature_size);
+int nb_gat_fwd(nb_ctx *ctx, const float *h, const float *att, float negative_slope, const uint32_t *column_offset,
+               const uint32_t *row_indices, const uint32_t *dst_local_id, uint32_t n_dst, uint32_t n_src,
+               uint32_t feature_size, float *score_pre, float *alpha, float *out);
+int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slope, const float *dout,
+               const float *score_pre, const float *alpha, const uint32_t *column_offset, const uint32_t *row_indices,
+               const uint32_t *dst_local_id, const uint32_t *row_offset, const uint32_t *column_indices,
+               const uint32_t *csr_to_csc, const uint32_t *src_to_dst, uint32_t n_dst, uint32_t n_src,
+               uint32_t feature_size, float *dh, float *datt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTS_B200_H */

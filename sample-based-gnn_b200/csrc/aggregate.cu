@@ -1,0 +1,189 @@
+// aggregate.cu -- sparse aggregation forward / backward as segment reductions.
+//
+// Replaces (reference file:line)
+//   Gather_By_Dst_From_Src_Spmm  (cuSPARSE SpMM, CSC^T * X)   cuda/ntsCUDAGraphOP.cu:425-587
+//   Gather_By_Src_From_Dst_Spmm  (cuSPARSE SpMM, CSR * dY)     cuda/ntsCUDAGraphOP.cu:901-1042
+//   Push_From_Dst_To_Src_Spmm    (cuSPARSE SpMM, CSC * dY)     cuda/ntsCUDAGraphOP.cu:621-770
+//   and the legacy atomics kernels aggregate_kernel_from_src_with_weight / push_kernel_from_dst_with_weight /
+//   aggregate_kernel_from_dst_with_weight  cuda/ntsCUDAFuseKernel.cuh:272-353, 494-531
+// Semantic definition = the CPU op MiniBatchFuseOp (core/ntsMiniBatchGraphOp.hpp:153-182, 214-268):
+//   out[r,:] = sum over the segment of r, in stored order, of w[j] * in[idx[j],:], multiply then add.
+//
+// HBM bound (<= 0.5 flop/byte); tensor cores are not used. Algorithmic bytes per launch:
+//   E*(4 idx + 4 w + 4F row) + (R+1)*4 offsets + R*4F output.
+// Mapping: one warp per output row; the row's accumulators live in registers (CHUNK vectors per
+// lane, so a 602-float row is 10 float2 per lane); the segment's (idx,w) pairs are fetched 32 at
+// a time, one per lane, and broadcast by shuffle; input rows are read with 64-/128-bit read-only
+// streaming loads, two segment entries in flight per lane. No atomics, every output row is
+// written exactly once (empty segment -> zeros), summation order == the CPU op's.
+#include "common.cuh"
+
+constexpr int AGG_THREADS = 256;
+
+template <int VEC, int CHUNK>
+__global__ void __launch_bounds__(AGG_THREADS)
+k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
+                 const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows, uint32_t nvec,
+                 uint64_t pitch) {
+  const unsigned lane = lane_id();
+  const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
+  for (unsigned r = warp; r < n_rows; r += warps) {
+    const uint32_t beg = offsets[r], end = offsets[r + 1];
+    for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {  // one pass unless the row is wider than 32*CHUNK vectors
+      Vec<VEC> acc[CHUNK];
+#pragma unroll
+      for (int c = 0; c < CHUNK; c++) acc[c].zero();
+      for (uint32_t j0 = beg; j0 < end; j0 += 32) {
+        const uint32_t cnt = min(32u, end - j0);
+        uint32_t my_idx = 0;
+        float my_w = 1.0f;
+        if (lane < cnt) {
+          my_idx = idx[j0 + lane];
+          if (weight) my_w = weight[j0 + lane];
+        }
+        uint32_t t = 0;
+        for (; t + 1 < cnt; t += 2) {
+          const uint32_t s0 = __shfl_sync(FULL_MASK, my_idx, t), s1 = __shfl_sync(FULL_MASK, my_idx, t + 1);
+          const float w0 = __shfl_sync(FULL_MASK, my_w, t), w1 = __shfl_sync(FULL_MASK, my_w, t + 1);
+          const float *p0 = in + (uint64_t)s0 * pitch, *p1 = in + (uint64_t)s1 * pitch;
+          Vec<VEC> x0[CHUNK], x1[CHUNK];
+#pragma unroll
+          for (int c = 0; c < CHUNK; c++) {
+            const unsigned k = c0 + c * 32 + lane;
+            if (k < nvec) { x0[c].load(p0 + (uint64_t)k * VEC); x1[c].load(p1 + (uint64_t)k * VEC); }
+          }
+#pragma unroll
+          for (int c = 0; c < CHUNK; c++) {
+            const unsigned k = c0 + c * 32 + lane;
+            if (k < nvec) { acc[c].axpy(x0[c], w0); acc[c].axpy(x1[c], w1); }
+          }
+        }
+        if (t < cnt) {
+          const uint32_t s0 = __shfl_sync(FULL_MASK, my_idx, t);
+          const float w0 = __shfl_sync(FULL_MASK, my_w, t);
+          const float *p0 = in + (uint64_t)s0 * pitch;
+#pragma unroll
+          for (int c = 0; c < CHUNK; c++) {
+            const unsigned k = c0 + c * 32 + lane;
+            if (k < nvec) { Vec<VEC> x; x.load(p0 + (uint64_t)k * VEC); acc[c].axpy(x, w0); }
+          }
+        }
+      }
+      float *o = out + (uint64_t)r * pitch;
+#pragma unroll
+      for (int c = 0; c < CHUNK; c++) {
+        const unsigned k = c0 + c * 32 + lane;
+        if (k < nvec) acc[c].store(o + (uint64_t)k * VEC);
+      }
+    }
+  }
+}
+
+// out[idx[e],:] += w[e] * in[d,:] for e in column d. One warp per dst row; the dY row is read once
+// into registers and pushed with vector reductions (red.global.add.v2/v4.f32, sm_90+).
+__device__ __forceinline__ void red_add(float *p, const Vec<4> &x, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x.v.x * w), "f"(x.v.y * w), "f"(x.v.z * w), "f"(x.v.w * w) : "memory");
+}
+__device__ __forceinline__ void red_add(float *p, const Vec<2> &x, float w) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(x.v.x * w), "f"(x.v.y * w) : "memory");
+}
+__device__ __forceinline__ void red_add(float *p, const Vec<1> &x, float w) { atomicAdd(p, x.v * w); }
+
+template <int VEC, int CHUNK>
+__global__ void __launch_bounds__(AGG_THREADS)
+k_push(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight, const uint32_t *__restrict__ idx,
+       const uint32_t *__restrict__ offsets, uint32_t n_rows, uint32_t nvec, uint64_t pitch) {
+  const unsigned lane = lane_id();
+  const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
+  for (unsigned r = warp; r < n_rows; r += warps) {
+    const uint32_t beg = offsets[r], end = offsets[r + 1];
+    if (beg == end) continue;
+    const float *p = in + (uint64_t)r * pitch;
+    for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {
+      Vec<VEC> x[CHUNK];
+#pragma unroll
+      for (int c = 0; c < CHUNK; c++) {
+        const unsigned k = c0 + c * 32 + lane;
+        if (k < nvec) x[c].load(p + (uint64_t)k * VEC);
+      }
+      for (uint32_t j = beg; j < end; j++) {
+        const uint32_t s = idx[j];
+        const float w = weight ? weight[j] : 1.0f;
+        float *o = out + (uint64_t)s * pitch;
+#pragma unroll
+        for (int c = 0; c < CHUNK; c++) {
+          const unsigned k = c0 + c * 32 + lane;
+          if (k < nvec) red_add(o + (uint64_t)k * VEC, x[c], w);
+        }
+      }
+    }
+  }
+}
+
+template <int VEC>
+static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
+                          const uint32_t *offsets, uint32_t n_rows, uint32_t F) {
+  const uint32_t nvec = F / VEC;
+  const unsigned grid = nb_grid(n_rows, AGG_THREADS / 32, 8);
+  const uint32_t per_lane = (nvec + 31) / 32;
+#define NB_SEG(C)                                                                                              \
+  do {                                                                                                         \
+    if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
+    else k_segment_reduce<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
+  } while (0)
+  if (per_lane <= 1) NB_SEG(1);
+  else if (per_lane <= 2) NB_SEG(2);
+  else if (per_lane <= 4) NB_SEG(4);
+  else if (per_lane <= 6) NB_SEG(6);
+  else if (per_lane <= 8) NB_SEG(8);
+  else if (per_lane <= 10) NB_SEG(10);
+  else NB_SEG(12);
+#undef NB_SEG
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
+                       const uint32_t *offsets, uint32_t n_rows, uint32_t F) {
+  if (n_rows == 0) return NB_OK;
+  int vec = nb_pick_vec(F, in, F, out, F);
+  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, F);
+  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, F);
+  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, F);
+}
+
+extern "C" {
+
+int nb_aggregate_csc_fwd(nb_ctx *ctx, const float *input, float *output, const float *weight_forward,
+                         const uint32_t *row_indices, const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src,
+                         uint32_t feature_size) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (input && output && row_indices && column_offset)), NB_ERR_ARG, "nb_aggregate_csc_fwd: NULL argument");
+  NB_REQUIRE(feature_size > 0, NB_ERR_ARG, "feature_size must be > 0");
+  (void)n_src;
+  NB_GUARD(ctx);
+  return run_segment(ctx, false, input, output, weight_forward, row_indices, column_offset, n_dst, feature_size);
+}
+
+int nb_aggregate_csr_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
+                         const uint32_t *row_offset, const uint32_t *column_indices, uint32_t n_src, uint32_t n_dst,
+                         uint32_t feature_size) {
+  NB_REQUIRE(ctx && (n_src == 0 || (input && output && row_offset && column_indices)), NB_ERR_ARG, "nb_aggregate_csr_bwd: NULL argument");
+  NB_REQUIRE(feature_size > 0, NB_ERR_ARG, "feature_size must be > 0");
+  (void)n_dst;
+  NB_GUARD(ctx);
+  return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, n_src, feature_size);
+}
+
+int nb_aggregate_push_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight, const uint32_t *row_indices,
+                          const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src, uint32_t feature_size) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (input && row_indices && column_offset)) && (n_src == 0 || output), NB_ERR_ARG,
+             "nb_aggregate_push_bwd: NULL argument");
+  NB_REQUIRE(feature_size > 0, NB_ERR_ARG, "feature_size must be > 0");
+  NB_GUARD(ctx);
+  if (n_src) NB_CUDA(cudaMemsetAsync(output, 0, (size_t)n_src * feature_size * sizeof(float), ctx->stream));
+  return run_segment(ctx, true, input, output, weight, row_indices, column_offset, n_dst, feature_size);
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// common.cuh -- shared device/host helpers for libnts_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nts_b200.h"
+
+#define NB_SM_COUNT 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void nb_set_error(const char *fmt, ...);
+#define NB_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      nb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));          \
+      return NB_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+#define NB_REQUIRE(cond, code, ...)                                                                \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      nb_set_error(__VA_ARGS__);                                                                   \
+      return (code);                                                                               \
+    }                                                                                              \
+  } while (0)
+#define NB_LAUNCH_CHECK(ctx)                                                                       \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    cudaError_t e__ = cudaPeekAtLastError();                                                       \
+    if (e__ != cudaSuccess) {                                                                      \
+      nb_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__));      \
+      return NB_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+struct nb_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  uint64_t launches;
+  int sm_count;
+  void *scratch;         // grow-only device scratch (replaces Cuda_Stream::cuda_buffer, cuda/ntsCUDA.hpp:195-196)
+  size_t scratch_bytes;
+};
+int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);  // stream-ordered reuse; grows with cudaMalloc
+
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(true) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define NB_GUARD(ctx)                                                                              \
+  DeviceGuard guard__((ctx)->device);                                                              \
+  NB_REQUIRE(guard__.ok, NB_ERR_CUDA, "cudaSetDevice(%d) failed (no CUDA device?)", (ctx)->device)
+
+static inline unsigned nb_grid(uint64_t work_items, unsigned items_per_block, unsigned max_blocks_per_sm = 8) {
+  uint64_t need = (work_items + items_per_block - 1) / items_per_block;
+  uint64_t cap = (uint64_t)NB_SM_COUNT * max_blocks_per_sm;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// 128-/64-/32-bit read-only loads that do not pollute L1 (rows are touched once per kernel)
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_stream2(const float *p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+// streaming stores (written once, read by a later kernel through L2)
+__device__ __forceinline__ void stg_stream4(float *p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream2(float *p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream1(float *p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> {
+  float4 v;
+  __device__ __forceinline__ void load(const float *p) { v = ldg_stream4(p); }
+  __device__ __forceinline__ void store(float *p) const { stg_stream4(p, v); }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  // out = out + in*w : multiply, then add, each rounded (core/ntsBaseOp.hpp:546-562 spells it mul+add)
+  __device__ __forceinline__ void axpy(const Vec<4> &in, float w) {
+    v.x = __fadd_rn(v.x, __fmul_rn(in.v.x, w)); v.y = __fadd_rn(v.y, __fmul_rn(in.v.y, w));
+    v.z = __fadd_rn(v.z, __fmul_rn(in.v.z, w)); v.w = __fadd_rn(v.w, __fmul_rn(in.v.w, w));
+  }
+  __device__ __forceinline__ float dot(const Vec<4> &o) const { return v.x * o.v.x + v.y * o.v.y + v.z * o.v.z + v.w * o.v.w; }
+};
+template <> struct Vec<2> {
+  float2 v;
+  __device__ __forceinline__ void load(const float *p) { v = ldg_stream2(p); }
+  __device__ __forceinline__ void store(float *p) const { stg_stream2(p, v); }
+  __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void axpy(const Vec<2> &in, float w) {
+    v.x = __fadd_rn(v.x, __fmul_rn(in.v.x, w)); v.y = __fadd_rn(v.y, __fmul_rn(in.v.y, w));
+  }
+  __device__ __forceinline__ float dot(const Vec<2> &o) const { return v.x * o.v.x + v.y * o.v.y; }
+};
+template <> struct Vec<1> {
+  float v;
+  __device__ __forceinline__ void load(const float *p) { v = ldg_stream1(p); }
+  __device__ __forceinline__ void store(float *p) const { stg_stream1(p, v); }
+  __device__ __forceinline__ void zero() { v = 0.f; }
+  __device__ __forceinline__ void axpy(const Vec<1> &in, float w) { v = __fadd_rn(v, __fmul_rn(in.v, w)); }
+  __device__ __forceinline__ float dot(const Vec<1> &o) const { return v * o.v; }
+};
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL_MASK, x, o);
+  return x;
+}
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(FULL_MASK, x, o));
+  return x;
+}
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL_MASK, x, o);
+  return x;
+}
+
+// ---- Philox4x32-10 (counter based; Salmon et al., SC'11) ---------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(uint64_t key) : k0((uint32_t)key), k1((uint32_t)(key >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+#endif  // __CUDACC__
+
+// vector width usable for rows of `feature_size` floats at pitches/pointers given (4, 2 or 1)
+static inline int nb_pick_vec(uint32_t feature_size, const void *a, uint64_t pitch_a, const void *b, uint64_t pitch_b) {
+  uintptr_t pa = (uintptr_t)a, pb = (uintptr_t)b;
+  if (feature_size % 4 == 0 && pitch_a % 4 == 0 && pitch_b % 4 == 0 && pa % 16 == 0 && pb % 16 == 0) return 4;
+  if (feature_size % 2 == 0 && pitch_a % 2 == 0 && pitch_b % 2 == 0 && pa % 8 == 0 && pb % 8 == 0) return 2;
+  return 1;
+}

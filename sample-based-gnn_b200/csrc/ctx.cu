@@ -1,0 +1,159 @@
+// ctx.cu -- context, error reporting and memory helpers of the C ABI (include/nts_b200.h).
+// Replaces class Cuda_Stream's stream ownership (cuda/ntsCUDAGraphOP.cu:203-262 of the reference)
+// and the free allocation/copy helpers (cuda/ntsCUDA.hpp:30-71).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void nb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out) {
+  if (bytes > ctx->scratch_bytes) {
+    // kernels still using the old buffer are ordered before this point on the stream
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->scratch) NB_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    NB_CUDA(cudaMalloc(&ctx->scratch, want));
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->scratch;
+  return NB_OK;
+}
+
+extern "C" {
+
+int nb_abi_version(void) { return NB_ABI_VERSION; }
+const char *nb_last_error(void) { return g_err; }
+
+int nb_device_count(int *count) {
+  NB_REQUIRE(count, NB_ERR_ARG, "count is NULL");
+  *count = 0;
+  NB_CUDA(cudaGetDeviceCount(count));
+  return NB_OK;
+}
+
+int nb_ctx_create(int device, void *cuda_stream_or_null, nb_ctx **out) {
+  NB_REQUIRE(out, NB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  NB_CUDA(cudaGetDeviceCount(&n));
+  NB_REQUIRE(device >= 0 && device < n, NB_ERR_ARG, "device %d out of range (%d devices)", device, n);
+  nb_ctx *c = new nb_ctx();
+  c->device = device;
+  c->launches = 0;
+  c->scratch = nullptr;
+  c->scratch_bytes = 0;
+  DeviceGuard g(device);
+  if (!g.ok) { delete c; nb_set_error("cudaSetDevice(%d) failed", device); return NB_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; nb_set_error("cudaGetDeviceProperties failed"); return NB_ERR_CUDA; }
+  if (prop.major != 10) {
+    delete c;
+    nb_set_error("device %d is sm_%d%d; libnts_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return NB_ERR_UNSUPPORTED;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  if (cuda_stream_or_null) {
+    c->stream = (cudaStream_t)cuda_stream_or_null;
+    c->own_stream = false;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c; nb_set_error("cudaStreamCreate failed"); return NB_ERR_CUDA;
+    }
+    c->own_stream = true;
+  }
+  *out = c;
+  return NB_OK;
+}
+
+int nb_ctx_destroy(nb_ctx *ctx) {
+  if (!ctx) return NB_OK;
+  DeviceGuard g(ctx->device);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NB_OK;
+}
+
+int nb_ctx_set_stream(nb_ctx *ctx, void *cuda_stream) {
+  NB_REQUIRE(ctx, NB_ERR_ARG, "ctx is NULL");
+  NB_GUARD(ctx);
+  if (ctx->own_stream) { NB_CUDA(cudaStreamSynchronize(ctx->stream)); NB_CUDA(cudaStreamDestroy(ctx->stream)); }
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return NB_OK;
+}
+
+void *nb_ctx_stream(nb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int nb_ctx_device(nb_ctx *ctx) { return ctx ? ctx->device : -1; }
+uint64_t nb_ctx_launch_count(nb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int nb_ctx_synchronize(nb_ctx *ctx) {
+  NB_REQUIRE(ctx, NB_ERR_ARG, "ctx is NULL");
+  NB_GUARD(ctx);
+  NB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NB_OK;
+}
+
+int nb_malloc_pinned(size_t bytes, void **out) {
+  NB_REQUIRE(out, NB_ERR_ARG, "out is NULL");
+  NB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable));
+  return NB_OK;
+}
+int nb_free_host(void *p) { if (p) NB_CUDA(cudaFreeHost(p)); return NB_OK; }
+int nb_device_pointer(void *host_mapped, void **out) {
+  NB_REQUIRE(out, NB_ERR_ARG, "out is NULL");
+  NB_CUDA(cudaHostGetDevicePointer(out, host_mapped, 0));
+  return NB_OK;
+}
+int nb_malloc_device(size_t bytes, void **out) {
+  NB_REQUIRE(out, NB_ERR_ARG, "out is NULL");
+  NB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return NB_OK;
+}
+int nb_free_device(void *p) { if (p) NB_CUDA(cudaFree(p)); return NB_OK; }
+
+int nb_memcpy_h2d(nb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, int sync) {
+  NB_REQUIRE(ctx, NB_ERR_ARG, "ctx is NULL");
+  NB_GUARD(ctx);
+  NB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (sync) NB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NB_OK;
+}
+int nb_memcpy_d2h(nb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, int sync) {
+  NB_REQUIRE(ctx, NB_ERR_ARG, "ctx is NULL");
+  NB_GUARD(ctx);
+  NB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sync) NB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NB_OK;
+}
+int nb_memset_async(nb_ctx *ctx, void *dst_dev, int value, size_t bytes) {
+  NB_REQUIRE(ctx, NB_ERR_ARG, "ctx is NULL");
+  NB_GUARD(ctx);
+  NB_CUDA(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+  return NB_OK;
+}
+
+int nb_ipc_get_handle(void *dev_ptr, void *handle64_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  NB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64_out, dev_ptr));
+  return NB_OK;
+}
+int nb_ipc_open_handle(const void *handle64, void **dev_ptr_out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  NB_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return NB_OK;
+}
+int nb_ipc_close_handle(void *dev_ptr) { NB_CUDA(cudaIpcCloseMemHandle(dev_ptr)); return NB_OK; }
+
+}  // extern "C"

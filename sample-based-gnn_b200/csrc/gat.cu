@@ -1,0 +1,376 @@
+// gat.cu -- GAT edge operators over the sampled CSC.
+//
+// Legacy-shaped kernels (one per reference kernel, cuda/ntsCUDADistKernel.cuh):
+//   scatter_src_dst_to_msg_map :174-196   gather_msg_to_src_dst_map :81-99
+//   get_node_max + edge_softmax_forward_norm_block :371-388, :318-368
+//   edge_softmax_backward_block :440-484  gather_msg_to_dst :218-232  scatter_dst_to_msg :119-133
+// Fused layer: replaces the 5-kernel chain + [E,2F] and [E,F] intermediates of
+// toolkits/GAT_SAMPLE_ALL_MULTI.hpp:383-464 (BatchGPUSrcDstScatterOp -> Linear(2F->1) -> leaky_relu ->
+// BatchGPUEdgeSoftMax -> mul -> BatchGPUAggregateDst, core/ntsPushdownGraphOp.hpp:490-747):
+//   forward : k_gat_node_scores (S*4F read)  +  k_gat_fwd (E*(4 + 4F) + V*4F + 8E, softmax in-warp)
+//   backward: k_gat_bwd_edge (E*4F + V*4F)   +  k_gat_bwd_src (CSR gather, E*4F + S*4F, no atomics on dh)
+//             + k_gat_bwd_att (S*4F + V*4F, block partial sums -> 2F atomics)
+// HBM bound; exp via expf (same as the reference's exp() on float).
+#include "common.cuh"
+
+constexpr int GAT_THREADS = 256;
+
+// ---- legacy-shaped ops ---------------------------------------------------------------------
+__global__ void __launch_bounds__(GAT_THREADS)
+k_scatter_src_dst(float *__restrict__ msg, const float *__restrict__ x, const uint32_t *__restrict__ row_indices,
+                  const uint32_t *__restrict__ col_off, const uint32_t *__restrict__ dl, uint32_t n_dst, uint32_t F) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    const float *xd = x + (uint64_t)dl[d] * F;
+    for (uint32_t e = col_off[d]; e < col_off[d + 1]; e++) {
+      const float *xs = x + (uint64_t)row_indices[e] * F;
+      float *m = msg + (uint64_t)e * 2 * F;
+      for (unsigned k = lane; k < F; k += 32) { m[k] = xs[k]; m[F + k] = xd[k]; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gather_src_dst(float *__restrict__ dx, const float *__restrict__ dmsg, const uint32_t *__restrict__ row_indices,
+                 const uint32_t *__restrict__ col_off, const uint32_t *__restrict__ dl, uint32_t n_dst, uint32_t F) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    float *gd = dx + (uint64_t)dl[d] * F;
+    const uint32_t beg = col_off[d], end = col_off[d + 1];
+    for (unsigned k = lane; k < F; k += 32) {
+      float acc = 0.f;
+      for (uint32_t e = beg; e < end; e++) {
+        const float *m = dmsg + (uint64_t)e * 2 * F;
+        atomicAdd(dx + (uint64_t)row_indices[e] * F + k, m[k]);
+        acc += m[F + k];
+      }
+      if (end > beg) atomicAdd(gd + k, acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GAT_THREADS)
+k_edge_softmax_fwd(float *__restrict__ out, const float *__restrict__ in, float *__restrict__ cached,
+                   const uint32_t *__restrict__ col_off, uint32_t n_dst) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    const uint32_t beg = col_off[d], end = col_off[d + 1];
+    if (beg == end) continue;
+    float mx = -INFINITY;
+    for (uint32_t e = beg + lane; e < end; e += 32) mx = fmaxf(mx, in[e]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (uint32_t e = beg + lane; e < end; e += 32) sum += expf(in[e] - mx);
+    sum = warp_sum(sum);
+    for (uint32_t e = beg + lane; e < end; e += 32) {
+      float a = expf(in[e] - mx) / sum;
+      out[e] = a;
+      if (cached) cached[e] = a;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GAT_THREADS)
+k_edge_softmax_bwd(float *__restrict__ din, const float *__restrict__ dout, const float *__restrict__ cached,
+                   const uint32_t *__restrict__ col_off, uint32_t n_dst) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    const uint32_t beg = col_off[d], end = col_off[d + 1];
+    float agg = 0.f;
+    for (uint32_t e = beg + lane; e < end; e += 32) agg += dout[e] * cached[e];
+    agg = warp_sum(agg);
+    for (uint32_t e = beg + lane; e < end; e += 32) din[e] = dout[e] * cached[e] - agg * cached[e];
+  }
+}
+
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gather_msg_to_dst(float *__restrict__ y, const float *__restrict__ msg, const uint32_t *__restrict__ col_off, uint32_t n_dst, uint32_t F) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    const uint32_t beg = col_off[d], end = col_off[d + 1];
+    for (unsigned k = lane; k < F; k += 32) {
+      float acc = 0.f;
+      for (uint32_t e = beg; e < end; e++) acc += msg[(uint64_t)e * F + k];
+      y[(uint64_t)d * F + k] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GAT_THREADS)
+k_scatter_dst_to_msg(float *__restrict__ msg, const float *__restrict__ y, const uint32_t *__restrict__ col_off, uint32_t n_dst, uint32_t F) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    const uint32_t beg = col_off[d], end = col_off[d + 1];
+    for (unsigned k = lane; k < F; k += 32) {
+      float v = y[(uint64_t)d * F + k];
+      for (uint32_t e = beg; e < end; e++) msg[(uint64_t)e * F + k] = v;
+    }
+  }
+}
+
+// ---- fused layer ---------------------------------------------------------------------------
+// al[s] = h[s,:].att[0:F], ar[s] = h[s,:].att[F:2F]
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_node_scores(const float *__restrict__ h, const float *__restrict__ att, float *__restrict__ al, float *__restrict__ ar,
+                  uint32_t n_src, uint32_t F) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned s = warp; s < n_src; s += warps) {
+    const float *p = h + (uint64_t)s * F;
+    float a = 0.f, b = 0.f;
+    for (unsigned k = lane; k < F; k += 32) { float x = p[k]; a += x * att[k]; b += x * att[F + k]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { al[s] = a; ar[s] = b; }
+  }
+}
+
+__device__ __forceinline__ float lrelu(float s, float slope) { return s > 0.f ? s : slope * s; }
+
+template <int VEC, int CHUNK>
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_fwd(const float *__restrict__ h, const float *__restrict__ al, const float *__restrict__ ar, float slope,
+          const uint32_t *__restrict__ col_off, const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ dl,
+          uint32_t n_dst, uint32_t nvec, uint64_t pitch, float *__restrict__ score_pre, float *__restrict__ alpha, float *__restrict__ out) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    const uint32_t beg = col_off[d], end = col_off[d + 1];
+    const float ard = (beg < end) ? ar[dl[d]] : 0.f;
+    float mx = -INFINITY;
+    for (uint32_t e = beg + lane; e < end; e += 32) mx = fmaxf(mx, lrelu(al[row_indices[e]] + ard, slope));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (uint32_t e = beg + lane; e < end; e += 32) sum += expf(lrelu(al[row_indices[e]] + ard, slope) - mx);
+    sum = warp_sum(sum);
+    for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {
+      Vec<VEC> acc[CHUNK];
+#pragma unroll
+      for (int c = 0; c < CHUNK; c++) acc[c].zero();
+      for (uint32_t j0 = beg; j0 < end; j0 += 32) {
+        const uint32_t cnt = min(32u, end - j0);
+        uint32_t my_idx = 0;
+        float my_w = 0.f;
+        if (lane < cnt) {
+          my_idx = row_indices[j0 + lane];
+          const float s = al[my_idx] + ard;
+          my_w = expf(lrelu(s, slope) - mx) / sum;
+          if (c0 == 0) { score_pre[j0 + lane] = s; alpha[j0 + lane] = my_w; }
+        }
+        for (uint32_t t = 0; t < cnt; t++) {
+          const uint32_t s0 = __shfl_sync(FULL_MASK, my_idx, t);
+          const float w0 = __shfl_sync(FULL_MASK, my_w, t);
+          const float *p0 = h + (uint64_t)s0 * pitch;
+#pragma unroll
+          for (int c = 0; c < CHUNK; c++) {
+            const unsigned k = c0 + c * 32 + lane;
+            if (k < nvec) { Vec<VEC> x; x.load(p0 + (uint64_t)k * VEC); acc[c].axpy(x, w0); }
+          }
+        }
+      }
+      float *o = out + (uint64_t)d * pitch;
+#pragma unroll
+      for (int c = 0; c < CHUNK; c++) {
+        const unsigned k = c0 + c * 32 + lane;
+        if (k < nvec) acc[c].store(o + (uint64_t)k * VEC);
+      }
+    }
+  }
+}
+
+// per dst column: da_e = dout[d].h[src_e]; dm_e = alpha_e (da_e - sum_e' alpha_e' da_e'); ds_e = lrelu'(pre_e) dm_e
+// writes ds[E] and dsum[V] = sum_e ds_e
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_bwd_edge(const float *__restrict__ h, const float *__restrict__ dout, const float *__restrict__ score_pre,
+               const float *__restrict__ alpha, float slope, const uint32_t *__restrict__ col_off,
+               const uint32_t *__restrict__ row_indices, uint32_t n_dst, uint32_t F, float *__restrict__ ds, float *__restrict__ dsum) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned d = warp; d < n_dst; d += warps) {
+    const uint32_t beg = col_off[d], end = col_off[d + 1];
+    const float *g = dout + (uint64_t)d * F;
+    float agg = 0.f;
+    for (uint32_t e = beg; e < end; e++) {
+      const float *p = h + (uint64_t)row_indices[e] * F;
+      float da = 0.f;
+      for (unsigned k = lane; k < F; k += 32) da += g[k] * p[k];
+      da = warp_sum(da);
+      if (lane == 0) ds[e] = da;  // stash da
+      agg += da * alpha[e];
+    }
+    __syncwarp();
+    float tot = 0.f;
+    for (uint32_t e = beg + lane; e < end; e += 32) {
+      const float dm = alpha[e] * (ds[e] - agg);
+      const float v = score_pre[e] > 0.f ? dm : slope * dm;
+      ds[e] = v;
+      tot += v;
+    }
+    tot = warp_sum(tot);
+    if (lane == 0) dsum[d] = tot;
+  }
+}
+
+// per src row (CSR): dh[s,:] = sum_j alpha[e_j] dout[dst_j,:] + (sum_j ds[e_j]) att[0:F] + [s is dst d] dsum[d] att[F:2F]
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_bwd_src(const float *__restrict__ dout, const float *__restrict__ att, const float *__restrict__ alpha,
+              const float *__restrict__ ds, const float *__restrict__ dsum, const uint32_t *__restrict__ row_offset,
+              const uint32_t *__restrict__ column_indices, const uint32_t *__restrict__ csr_to_csc,
+              const uint32_t *__restrict__ src_to_dst, uint32_t n_src, uint32_t F, float *__restrict__ dh, float *__restrict__ rs) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  for (unsigned s = warp; s < n_src; s += warps) {
+    const uint32_t beg = row_offset[s], end = row_offset[s + 1];
+    float rsum = 0.f;
+    for (uint32_t j = beg + lane; j < end; j += 32) rsum += ds[csr_to_csc[j]];
+    rsum = warp_sum(rsum);
+    const uint32_t d = src_to_dst[s];
+    const float dd = d != 0xffffffffu ? dsum[d] : 0.f;
+    if (lane == 0) rs[s] = rsum;
+    for (unsigned k = lane; k < F; k += 32) {
+      float acc = 0.f;
+      for (uint32_t j = beg; j < end; j++) acc += alpha[csr_to_csc[j]] * dout[(uint64_t)column_indices[j] * F + k];
+      dh[(uint64_t)s * F + k] = acc + rsum * att[k] + dd * att[F + k];
+    }
+  }
+}
+
+// datt[0:F] += sum_s rs[s] h[s,:];  datt[F:2F] += sum_d dsum[d] h[dl[d],:]
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_bwd_att(const float *__restrict__ h, const float *__restrict__ rs, const float *__restrict__ dsum,
+              const uint32_t *__restrict__ dl, uint32_t n_src, uint32_t n_dst, uint32_t F, float *__restrict__ datt) {
+  // each block owns a contiguous slice of rows; thread k sums feature column k (coalesced row reads)
+  const unsigned rows_per_block = (n_src + gridDim.x - 1) / gridDim.x;
+  const unsigned r0 = blockIdx.x * rows_per_block, r1 = min(n_src, r0 + rows_per_block);
+  for (unsigned k = threadIdx.x; k < F; k += blockDim.x) {
+    float acc = 0.f;
+    for (unsigned s = r0; s < r1; s++) acc += rs[s] * h[(uint64_t)s * F + k];
+    if (r1 > r0) atomicAdd(&datt[k], acc);
+  }
+  const unsigned dpb = (n_dst + gridDim.x - 1) / gridDim.x;
+  const unsigned d0 = blockIdx.x * dpb, d1 = min(n_dst, d0 + dpb);
+  for (unsigned k = threadIdx.x; k < F; k += blockDim.x) {
+    float acc = 0.f;
+    for (unsigned d = d0; d < d1; d++) acc += dsum[d] * h[(uint64_t)dl[d] * F + k];
+    if (d1 > d0) atomicAdd(&datt[F + k], acc);
+  }
+}
+
+template <int VEC>
+static int launch_gat_fwd(nb_ctx *ctx, const float *h, const float *al, const float *ar, float slope, const uint32_t *co,
+                          const uint32_t *ri, const uint32_t *dl, uint32_t n_dst, uint32_t F, float *pre, float *alpha, float *out) {
+  const uint32_t nvec = F / VEC, per_lane = (nvec + 31) / 32;
+  const unsigned grid = nb_grid(n_dst, GAT_THREADS / 32, 8);
+#define NB_GAT(C) k_gat_fwd<VEC, C><<<grid, GAT_THREADS, 0, ctx->stream>>>(h, al, ar, slope, co, ri, dl, n_dst, nvec, F, pre, alpha, out)
+  if (per_lane <= 1) NB_GAT(1); else if (per_lane <= 2) NB_GAT(2); else if (per_lane <= 4) NB_GAT(4);
+  else if (per_lane <= 8) NB_GAT(8); else NB_GAT(12);
+#undef NB_GAT
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+extern "C" {
+
+int nb_scatter_src_dst_to_msg(nb_ctx *ctx, float *message, const float *src_feature, const uint32_t *row_indices,
+                              const uint32_t *column_offset, uint32_t n_dst, uint32_t feature_size, const uint32_t *dst_local_id) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (message && src_feature && row_indices && column_offset && dst_local_id)), NB_ERR_ARG, "nb_scatter_src_dst_to_msg: NULL argument");
+  NB_GUARD(ctx);
+  if (n_dst == 0) return NB_OK;
+  k_scatter_src_dst<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(message, src_feature, row_indices, column_offset, dst_local_id, n_dst, feature_size);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_gather_msg_to_src_dst(nb_ctx *ctx, float *src_grad, const float *message_grad, const uint32_t *row_indices,
+                             const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src, uint32_t feature_size,
+                             const uint32_t *dst_local_id) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (src_grad && message_grad && row_indices && column_offset && dst_local_id)), NB_ERR_ARG, "nb_gather_msg_to_src_dst: NULL argument");
+  NB_GUARD(ctx);
+  if (n_src) NB_CUDA(cudaMemsetAsync(src_grad, 0, (size_t)n_src * feature_size * 4, ctx->stream));
+  if (n_dst == 0) return NB_OK;
+  k_gather_src_dst<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(src_grad, message_grad, row_indices, column_offset, dst_local_id, n_dst, feature_size);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_edge_softmax_fwd(nb_ctx *ctx, float *msg_output, const float *msg_input, float *msg_cached, const uint32_t *column_offset, uint32_t n_dst) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (msg_output && msg_input && column_offset)), NB_ERR_ARG, "nb_edge_softmax_fwd: NULL argument");
+  NB_GUARD(ctx);
+  if (n_dst == 0) return NB_OK;
+  k_edge_softmax_fwd<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(msg_output, msg_input, msg_cached, column_offset, n_dst);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_edge_softmax_bwd(nb_ctx *ctx, float *msg_input_grad, const float *msg_output_grad, const float *msg_cached, const uint32_t *column_offset, uint32_t n_dst) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (msg_input_grad && msg_output_grad && msg_cached && column_offset)), NB_ERR_ARG, "nb_edge_softmax_bwd: NULL argument");
+  NB_GUARD(ctx);
+  if (n_dst == 0) return NB_OK;
+  k_edge_softmax_bwd<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(msg_input_grad, msg_output_grad, msg_cached, column_offset, n_dst);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_gather_msg_to_dst(nb_ctx *ctx, float *dst_feature, const float *message, const uint32_t *column_offset, uint32_t n_dst, uint32_t feature_size) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (dst_feature && message && column_offset)), NB_ERR_ARG, "nb_gather_msg_to_dst: NULL argument");
+  NB_GUARD(ctx);
+  if (n_dst == 0) return NB_OK;
+  k_gather_msg_to_dst<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(dst_feature, message, column_offset, n_dst, feature_size);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_scatter_dst_to_msg(nb_ctx *ctx, float *message, const float *dst_feature, const uint32_t *column_offset, uint32_t n_dst, uint32_t feature_size) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (message && dst_feature && column_offset)), NB_ERR_ARG, "nb_scatter_dst_to_msg: NULL argument");
+  NB_GUARD(ctx);
+  if (n_dst == 0) return NB_OK;
+  k_scatter_dst_to_msg<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(message, dst_feature, column_offset, n_dst, feature_size);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_gat_fwd(nb_ctx *ctx, const float *h, const float *att, float negative_slope, const uint32_t *column_offset,
+               const uint32_t *row_indices, const uint32_t *dst_local_id, uint32_t n_dst, uint32_t n_src,
+               uint32_t feature_size, float *score_pre, float *alpha, float *out) {
+  NB_REQUIRE(ctx && h && att && column_offset && row_indices && dst_local_id && score_pre && alpha && out, NB_ERR_ARG, "nb_gat_fwd: NULL argument");
+  NB_REQUIRE(feature_size > 0, NB_ERR_ARG, "feature_size must be > 0");
+  NB_GUARD(ctx);
+  if (n_dst == 0) return NB_OK;
+  float *scratch;
+  int rc = nb_ctx_scratch(ctx, (size_t)n_src * 2 * sizeof(float), (void **)&scratch);
+  if (rc) return rc;
+  float *al = scratch, *ar = scratch + n_src;
+  k_gat_node_scores<<<nb_grid(n_src, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(h, att, al, ar, n_src, feature_size);
+  NB_LAUNCH_CHECK(ctx);
+  int vec = nb_pick_vec(feature_size, h, feature_size, out, feature_size);
+  if (vec == 4) return launch_gat_fwd<4>(ctx, h, al, ar, negative_slope, column_offset, row_indices, dst_local_id, n_dst, feature_size, score_pre, alpha, out);
+  if (vec == 2) return launch_gat_fwd<2>(ctx, h, al, ar, negative_slope, column_offset, row_indices, dst_local_id, n_dst, feature_size, score_pre, alpha, out);
+  return launch_gat_fwd<1>(ctx, h, al, ar, negative_slope, column_offset, row_indices, dst_local_id, n_dst, feature_size, score_pre, alpha, out);
+}
+
+int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slope, const float *dout,
+               const float *score_pre, const float *alpha, const uint32_t *column_offset, const uint32_t *row_indices,
+               const uint32_t *dst_local_id, const uint32_t *row_offset, const uint32_t *column_indices,
+               const uint32_t *csr_to_csc, const uint32_t *src_to_dst, uint32_t n_dst, uint32_t n_src,
+               uint32_t feature_size, float *dh, float *datt) {
+  NB_REQUIRE(ctx && h && att && dout && score_pre && alpha && column_offset && row_indices && dst_local_id && row_offset &&
+                 column_indices && csr_to_csc && src_to_dst && dh && datt, NB_ERR_ARG, "nb_gat_bwd: NULL argument (needs a sampler built with MERGE_SRC_DST|BUILD_CSR)");
+  NB_GUARD(ctx);
+  NB_CUDA(cudaMemsetAsync(datt, 0, (size_t)2 * feature_size * 4, ctx->stream));
+  if (n_src == 0) return NB_OK;
+  // n_edges is only on the device side of the caller's view; bound the scratch by the CSR: E <= what row_offset[n_src] says,
+  // so size ds[] from a host copy of that single word.
+  uint32_t E = 0;
+  NB_CUDA(cudaMemcpyAsync(&E, row_offset + n_src, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(cudaStreamSynchronize(ctx->stream));
+  float *scratch;
+  int rc = nb_ctx_scratch(ctx, ((size_t)E + n_dst + n_src + 8) * sizeof(float), (void **)&scratch);
+  if (rc) return rc;
+  float *ds = scratch, *dsum = scratch + E, *rs = dsum + n_dst;
+  if (n_dst) {
+    k_gat_bwd_edge<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(h, dout, score_pre, alpha, negative_slope, column_offset, row_indices, n_dst, feature_size, ds, dsum);
+    NB_LAUNCH_CHECK(ctx);
+  }
+  k_gat_bwd_src<<<nb_grid(n_src, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(dout, att, alpha, ds, dsum, row_offset, column_indices, csr_to_csc, src_to_dst, n_src, feature_size, dh, rs);
+  NB_LAUNCH_CHECK(ctx);
+  k_gat_bwd_att<<<NB_SM_COUNT * 2, GAT_THREADS, 0, ctx->stream>>>(h, rs, dsum, dst_local_id, n_src, n_dst, feature_size, datt);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+}  // extern "C"

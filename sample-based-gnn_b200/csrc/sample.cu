@@ -1,0 +1,750 @@
+// sample.cu -- per-layer neighbour sampling, dedup/reindex into the mini-batch CSC, CSR build,
+// edge weights. One nb_sampler_sample() call runs every layer of a mini-batch on the stream with
+// no host round trip: all sizes (E_i, S_i) live in device memory (LayerMeta) and every kernel is
+// a grid-stride kernel over a capacity-sized grid that reads its extent from there.
+//
+// Replaces (reference file:line)
+//   FastSampler::sample_gpu_fast[_omit]            core/ntsFastSampler.hpp:648-915
+//   SampledSubgraph::gpu_* arenas / per-layer glue core/FullyRepGraph.hpp:91-131, 258-524
+//   sample_processing_get_co_gpu[_omit]  (+ its CPU prefix sum round trip)  cuda/ntsCUDAGraphOP.cu:1246-1559
+//   sample_processing_traverse_gpu (stage2 sort-based sampler, stage3 |V| scan) :1584-1659
+//   sample_processing_update_ri_gpu :1661-1674, set_dst_local_index :1696-1702
+//   ReFreshDegree/UpdateDegree, GetWeight/GetMeanWeight :2015-2113
+//   sampCSC::csc_to_csr (CPU only in the reference) core/coocsc.hpp:82-111
+// Semantics follow the CPU sampler (ntsFastSampler.hpp:962-1140): `source` ascending by global
+// id (bitmap scan order), stable CSR, fp32 weights computed as 1/(sqrtf(out)*sqrtf(in)).
+//
+// Pipeline per layer (kernel : algorithmic bytes; V/E/S = #dst/#edges/#src of the layer)
+//   k_scan<CountOp>   : 12V            min(deg,fanout) + single-pass decoupled look-back scan
+//   k_sample          : 12V + 8E       warp per dst, Philox4x32-10 rejection sampling, bitmap marks
+//   k_scan<BitmapOp>  : 8|V|/32 + 4S   popcount scan over the bitmap words, emits `source` ascending
+//   k_relabel         : 8E + 4E        global -> local ids by popcount rank, CSR histogram
+//   k_scan<RowOp>     : 8S             row_offset
+//   k_csr_fill/k_csr_rows(+long) : 12E + 12E   atomic fill then per-row rank-sort -> stable CSR
+//   k_weights         : 12E + 4E
+#include "common.cuh"
+
+struct LayerMeta {  // device resident, one per layer (+1 sentinel)
+  uint32_t n_dst, n_edges, n_src, err;
+  uint32_t long_rows, pad0, pad1, pad2;
+};
+
+struct LayerBuf {
+  uint32_t cap_dst, cap_edges, cap_src;
+  uint32_t *destination, *column_offset, *sample_ans, *row_indices, *edge_dst, *source;
+  uint32_t *row_offset, *row_count, *row_cursor, *column_indices, *csr_tmp, *csr_to_csc, *long_rows;
+  uint32_t *dst_local_id, *src_to_dst;
+  float *ewf, *ewb;
+};
+
+struct ScanWs {
+  unsigned long long *tile_state;
+  unsigned *ticket;
+  unsigned *done;
+};
+
+struct nb_graph {
+  nb_ctx *ctx;
+  uint32_t V;
+  uint64_t E;
+  uint32_t *col_off, *row_idx, *in_deg, *out_deg;
+  uint32_t max_in_degree;
+};
+
+#define NB_MAX_LAYERS 8
+struct nb_sampler {
+  nb_ctx *ctx;
+  nb_graph *g;
+  int L;
+  int fanout[NB_MAX_LAYERS];
+  uint32_t flags, max_batch;
+  LayerBuf lay[NB_MAX_LAYERS];
+  LayerMeta *meta_dev;   // [L+1]
+  LayerMeta *meta_host;  // pinned [L+1]
+  uint32_t *bitmap, *word_rank;
+  uint32_t n_words;
+  ScanWs ws;
+  void *arena;
+  uint32_t max_tiles;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass exclusive scan (decoupled look-back, Merrill & Garland) over n items, n read from
+// device memory through Op. Tiles are handed out by an atomic ticket so a tile's predecessors are
+// always resident or finished; the last block to leave resets the workspace for the next launch.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
+  __shared__ unsigned s_tile, s_prefix, s_warp[SCAN_THREADS / 32];
+  const unsigned n = op.n();
+  const unsigned ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) op.total(0);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(ws.ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= ntiles) break;
+    unsigned v[SCAN_ITEMS], sum = 0;
+    const unsigned first = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+      v[k] = (first + k < n) ? op.load(first + k) : 0u;
+      sum += v[k];
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned warp_base = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+      unsigned t = s_warp[w];
+      if (w < warp) warp_base += t;
+      block_total += t;
+    }
+    if (threadIdx.x == 0) {
+      unsigned prefix = 0;
+      if (tile == 0) {
+        atomicExch(&ws.tile_state[0], (2ull << 32) | block_total);
+      } else {
+        atomicExch(&ws.tile_state[tile], (1ull << 32) | block_total);
+        int p = (int)tile - 1;
+        while (true) {
+          unsigned long long st = *((volatile unsigned long long *)&ws.tile_state[p]);
+          unsigned flag = (unsigned)(st >> 32);
+          if (flag == 0) continue;
+          prefix += (unsigned)st;
+          if (flag == 2) break;
+          p--;
+        }
+        atomicExch(&ws.tile_state[tile], (2ull << 32) | (unsigned long long)(prefix + block_total));
+      }
+      s_prefix = prefix;
+    }
+    __syncthreads();
+    unsigned base = s_prefix + warp_base + (incl - sum);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+      if (first + k < n) op.store(first + k, base, v[k]);
+      base += v[k];
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) op.total(s_prefix + block_total);
+    __syncthreads();
+  }
+  // self-reset by the last block out
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(ws.done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (unsigned t = threadIdx.x; t < ntiles; t += SCAN_THREADS) ws.tile_state[t] = 0ull;
+    if (threadIdx.x == 0) { *ws.ticket = 0u; *ws.done = 0u; }
+  }
+}
+
+// counts = min(deg, fanout) (fanout -1: deg), 0 for omitted dst; scan -> column_offset; total -> E.
+// Reference: sample_processing_get_co_gpu_kernel[_omit] cuda/ntsCUDATransferKernel.cuh:754-822 and the
+// CPU count lambda core/ntsFastSampler.hpp:1001-1009.
+struct CountOp {
+  const uint32_t *g_col_off, *dst, *omit;
+  uint32_t *col_off;
+  LayerMeta *meta;
+  uint32_t omit_value, cap_edges;
+  int fanout;
+  __device__ unsigned n() const { return meta->n_dst; }
+  __device__ unsigned load(unsigned i) const {
+    uint32_t d = dst[i];
+    uint32_t deg = g_col_off[d + 1] - g_col_off[d];
+    uint32_t c = (fanout < 0 || deg < (uint32_t)fanout) ? deg : (uint32_t)fanout;
+    if (omit) {
+      uint32_t f = omit[d];
+      if (omit_value == 0xffffffffu ? (f != 0xffffffffu) : (f == omit_value)) c = 0;
+    }
+    return c;
+  }
+  __device__ void store(unsigned i, unsigned excl, unsigned) const { col_off[i] = excl; }
+  __device__ void total(unsigned t) const {
+    col_off[meta->n_dst] = t;
+    meta->n_edges = t;
+    meta->long_rows = 0;
+    if (t > cap_edges) meta->err = 1;
+  }
+};
+
+// popcount scan over the dedup bitmap; emits `source` in ascending global id (the CPU sampler's
+// order, core/ntsFastSampler.hpp:1062-1083) and initialises the per-src scratch.
+struct BitmapOp {
+  const uint32_t *bitmap;
+  uint32_t *word_rank, *source, *row_count, *row_cursor, *src_to_dst;
+  LayerMeta *meta, *next_meta;
+  uint32_t n_words, cap_src;
+  __device__ unsigned n() const { return n_words; }
+  __device__ unsigned load(unsigned w) const { return __popc(bitmap[w]); }
+  __device__ void store(unsigned w, unsigned excl, unsigned cnt) const {
+    word_rank[w] = excl;
+    if (cnt == 0 || meta->err) return;
+    uint32_t bits = bitmap[w];
+    unsigned k = excl;
+    while (bits) {
+      unsigned b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (k < cap_src) {
+        source[k] = w * 32u + b;
+        row_count[k] = 0;
+        row_cursor[k] = 0;
+        if (src_to_dst) src_to_dst[k] = 0xffffffffu;
+      }
+      k++;
+    }
+  }
+  __device__ void total(unsigned t) const {
+    meta->n_src = t;
+    if (t > cap_src) meta->err = 2;
+    next_meta->n_dst = t;
+  }
+};
+
+struct RowOp {
+  const uint32_t *row_count;
+  uint32_t *row_offset;
+  const LayerMeta *meta;
+  __device__ unsigned n() const { return meta->err ? 0u : meta->n_src; }
+  __device__ unsigned load(unsigned i) const { return row_count[i]; }
+  __device__ void store(unsigned i, unsigned excl, unsigned) const { row_offset[i] = excl; }
+  __device__ void total(unsigned t) const { row_offset[meta->err ? 0u : meta->n_src] = t; }
+};
+
+__global__ void k_init_meta(LayerMeta *meta, int L, uint32_t n_seeds) {
+  int i = threadIdx.x;
+  if (i <= L) {
+    meta[i].n_dst = i == 0 ? n_seeds : 0;
+    meta[i].n_edges = 0; meta[i].n_src = 0; meta[i].err = 0; meta[i].long_rows = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Neighbour selection: one warp per dst.
+//   deg <= fanout (or fanout < 0): every in-neighbour in stored order (ntsFastSampler.hpp:1040-1048)
+//   otherwise: `fanout` distinct positions, uniform. Lanes draw positions in parallel; a draw that
+//   collides with a held value (or with a lower lane's draw of the same round) is redrawn next
+//   round. This is sequential rejection sampling with the iid draw sequence ordered (round, lane),
+//   i.e. exactly the CPU sampler's law (ntsFastSampler.hpp:1028-1039): a uniform `fanout`-subset.
+//   fanout <= 32 keeps the set in registers (__match_any_sync); larger fanouts use a per-warp
+//   open-addressing set in shared memory.
+// Philox4x32-10 counter = (dst slot, lane + 32*draw block, layer, rng_offset), key = rng_seed.
+// mode 1 (replay): sample_ans was supplied; only edge_dst and the bitmap marks are produced.
+constexpr int SAMPLE_WARPS = 8;
+
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32)
+k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_row_idx, const uint32_t *__restrict__ dst,
+         const uint32_t *__restrict__ col_off, uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst,
+         uint32_t *__restrict__ bitmap, const LayerMeta *meta, int fanout, uint64_t key, uint32_t layer, uint32_t rng_offset,
+         int merge, int replay, int hash_slots) {
+  extern __shared__ uint32_t s_hash[];
+  if (meta->err) return;
+  const unsigned n_dst = meta->n_dst;
+  const unsigned lane = lane_id();
+  const unsigned warps = gridDim.x * SAMPLE_WARPS;
+  uint32_t *my_hash = s_hash + (threadIdx.x >> 5) * hash_slots;
+  const Philox rng(key);
+  for (unsigned j = blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5); j < n_dst; j += warps) {
+    const uint32_t d = dst[j];
+    const uint32_t base = g_col_off[d];
+    const uint32_t deg = g_col_off[d + 1] - base;
+    const uint32_t off = col_off[j];
+    const uint32_t num = col_off[j + 1] - off;
+    if (merge && lane == 0) atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+    if (num == 0) continue;
+    if (replay) {
+      for (uint32_t t = lane; t < num; t += 32) {
+        uint32_t v = sample_ans[off + t];
+        edge_dst[off + t] = j;
+        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+      }
+    } else if (num == deg) {  // take all, stored order
+      for (uint32_t t = lane; t < num; t += 32) {
+        uint32_t v = g_row_idx[base + t];
+        sample_ans[off + t] = v;
+        edge_dst[off + t] = j;
+        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+      }
+    } else if (num <= 32) {
+      const bool holder = lane < num;
+      const unsigned holders = __ballot_sync(FULL_MASK, holder);
+      bool need = holder;
+      uint32_t pos = 0xffffffffu;
+      uint4 r = make_uint4(0, 0, 0, 0);
+      for (unsigned round = 0;; round++) {
+        if (need) {
+          if ((round & 3) == 0) r = rng(j, lane + 32u * (round >> 2), layer, rng_offset);
+          uint32_t x = (round & 3) == 0 ? r.x : (round & 3) == 1 ? r.y : (round & 3) == 2 ? r.z : r.w;
+          pos = __umulhi(x, deg);
+        }
+        bool keep = true;
+        if (holder) {
+          unsigned grp = __match_any_sync(holders, pos);
+          unsigned settled = __ballot_sync(holders, !need);
+          keep = !need || ((grp & settled) == 0 && lane == (unsigned)(__ffs(grp) - 1));
+        }
+        need = !keep;
+        if (!__any_sync(FULL_MASK, need)) break;
+      }
+      if (holder) {
+        uint32_t v = g_row_idx[base + pos];
+        sample_ans[off + lane] = v;
+        edge_dst[off + lane] = j;
+        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+      }
+    } else {  // fanout > 32: shared-memory set, 32 draws per round
+      for (int t = lane; t < hash_slots; t += 32) my_hash[t] = 0xffffffffu;
+      __syncwarp();
+      uint32_t have = 0;
+      for (unsigned round = 0; have < num; round++) {
+        const uint32_t want = num - have;
+        const bool active = lane < want;
+        bool won = false;
+        uint32_t pos = 0;
+        if (active) {
+          uint4 r = rng(j, lane + 32u * round, layer, rng_offset);
+          pos = __umulhi(r.x, deg);
+          uint32_t h = (pos * 2654435761u) & (hash_slots - 1);
+          while (true) {
+            uint32_t old = atomicCAS(&my_hash[h], 0xffffffffu, pos);
+            if (old == 0xffffffffu) { won = true; break; }
+            if (old == pos) break;
+            h = (h + 1) & (hash_slots - 1);
+          }
+        }
+        unsigned wins = __ballot_sync(FULL_MASK, won);
+        if (won) {
+          uint32_t slot = have + __popc(wins & ((1u << lane) - 1));
+          uint32_t v = g_row_idx[base + pos];
+          sample_ans[off + slot] = v;
+          edge_dst[off + slot] = j;
+          atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        }
+        have += __popc(wins);
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
+// Reference: sample_processing_update_ri_gpu_kernel cuda/ntsCUDATransferKernel.cuh:1136-1150,
+// sample_set_dst_local :1189-1196; CPU :1085-1099.
+__global__ void __launch_bounds__(256)
+k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ bitmap,
+          const uint32_t *__restrict__ word_rank, uint32_t *__restrict__ row_count, const uint32_t *__restrict__ dst,
+          uint32_t *__restrict__ dst_local_id, uint32_t *__restrict__ src_to_dst, const LayerMeta *meta, int histogram) {
+  if (meta->err) return;
+  const unsigned E = meta->n_edges, nd = meta->n_dst;
+  const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (unsigned e = tid; e < E; e += stride) {
+    uint32_t v = sample_ans[e];
+    uint32_t local = word_rank[v >> 5] + __popc(bitmap[v >> 5] & ((1u << (v & 31)) - 1u));
+    row_indices[e] = local;
+    if (histogram) atomicAdd(&row_count[local], 1u);
+  }
+  if (dst_local_id)
+    for (unsigned j = tid; j < nd; j += stride) {
+      uint32_t v = dst[j];
+      uint32_t local = word_rank[v >> 5] + __popc(bitmap[v >> 5] & ((1u << (v & 31)) - 1u));
+      dst_local_id[j] = local;
+      src_to_dst[local] = j;
+    }
+}
+
+// Edge weights in CSC order. Reference: get_weight / get_mean_weight cuda/ntsCUDATransferKernel.cuh:294-342,
+// CPU nts_norm_degree core/ntsBaseOp.hpp:652-657. (float)sqrt((double)u32) == sqrtf((float)u32) for
+// u32 < 2^24 (sqrt double rounding is innocuous at 53 >= 2*24+2 bits), so this is bit-identical to the CPU.
+__global__ void __launch_bounds__(256)
+k_weights(float *__restrict__ ewf, const uint32_t *__restrict__ sample_ans, const uint32_t *__restrict__ row_indices,
+          const uint32_t *__restrict__ edge_dst, const uint32_t *__restrict__ dst, const uint32_t *__restrict__ col_off,
+          const uint32_t *__restrict__ row_count, const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg,
+          const LayerMeta *meta, int weight_type, int up_degree) {
+  if (meta->err) return;
+  const unsigned E = meta->n_edges;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    uint32_t j = edge_dst[e];
+    uint32_t col_len = col_off[j + 1] - col_off[j];
+    uint32_t od, id;
+    if (up_degree) { od = row_count[row_indices[e]]; id = col_len; }
+    else { od = out_deg[sample_ans[e]]; id = in_deg[dst[j]]; }
+    float w = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn((float)od), __fsqrt_rn((float)id)));
+    if (weight_type == NB_WEIGHT_MEAN) w = __fdiv_rn(w, (float)id);
+    else if (weight_type == NB_WEIGHT_MEAN_SAMPLED) w = __fdiv_rn(w, (float)col_len);
+    ewf[e] = w;
+  }
+}
+
+// CSR build, step 1: drop every edge into its row in arrival order.
+__global__ void __launch_bounds__(256)
+k_csr_fill(const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ row_offset, uint32_t *__restrict__ row_cursor,
+           uint32_t *__restrict__ csr_tmp, const LayerMeta *meta) {
+  if (meta->err) return;
+  const unsigned E = meta->n_edges;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    uint32_t s = row_indices[e];
+    csr_tmp[row_offset[s] + atomicAdd(&row_cursor[s], 1u)] = e;
+  }
+}
+
+// step 2: order each row by CSC position (== ascending local dst, then position inside the column:
+// exactly sampCSC::csc_to_csr's stable fill, core/coocsc.hpp:98-105) by rank counting, and emit
+// column_indices / csr_to_csc / e_w_b. Short rows: one thread each; long rows are queued for a warp.
+constexpr uint32_t CSR_SHORT = 16;
+__device__ __forceinline__ void csr_emit(uint32_t pos, uint32_t e, uint32_t *column_indices, uint32_t *csr_to_csc,
+                                         const uint32_t *edge_dst, float *ewb, const float *ewf) {
+  csr_to_csc[pos] = e;
+  column_indices[pos] = edge_dst[e];
+  if (ewb) ewb[pos] = ewf[e];
+}
+__global__ void __launch_bounds__(256)
+k_csr_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
+           uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
+           const float *__restrict__ ewf, uint32_t *__restrict__ long_rows, LayerMeta *meta) {
+  if (meta->err) return;
+  const unsigned S = meta->n_src;
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
+    if (n > CSR_SHORT) { long_rows[atomicAdd(&meta->long_rows, 1u)] = s; continue; }
+    uint32_t ev[CSR_SHORT];
+#pragma unroll
+    for (uint32_t i = 0; i < CSR_SHORT; i++) ev[i] = i < n ? csr_tmp[a + i] : 0xffffffffu;
+#pragma unroll
+    for (uint32_t i = 0; i < CSR_SHORT; i++) {
+      if (i < n) {
+        uint32_t rank = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < CSR_SHORT; k++) rank += (ev[k] < ev[i]);
+        csr_emit(a + rank, ev[i], column_indices, csr_to_csc, edge_dst, ewb, ewf);
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
+                uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
+                const float *__restrict__ ewf, const uint32_t *__restrict__ long_rows, const LayerMeta *meta) {
+  if (meta->err) return;
+  const unsigned n_long = meta->long_rows;
+  const unsigned lane = lane_id();
+  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_long; w += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t s = long_rows[w];
+    const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t e = csr_tmp[a + i];
+      uint32_t rank = 0;
+      for (uint32_t k = 0; k < n; k++) rank += (__ldg(&csr_tmp[a + k]) < e);
+      csr_emit(a + rank, e, column_indices, csr_to_csc, edge_dst, ewb, ewf);
+    }
+  }
+}
+
+// degrees from the CSC when the caller has none (clamped >= 1, core/graph.hpp:4525-4530)
+__global__ void k_degrees_from_csc(const uint32_t *col_off, const uint32_t *row_idx, uint32_t *in_deg, uint32_t *out_deg,
+                                   uint32_t V, uint64_t E, int phase) {
+  uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+  if (phase == 0) {
+    for (uint64_t v = tid; v < V; v += stride) { in_deg[v] = col_off[v + 1] - col_off[v]; out_deg[v] = 0; }
+  } else if (phase == 1) {
+    for (uint64_t e = tid; e < E; e += stride) atomicAdd(&out_deg[row_idx[e]], 1u);
+  } else {
+    for (uint64_t v = tid; v < V; v += stride) { if (in_deg[v] < 1) in_deg[v] = 1; if (out_deg[v] < 1) out_deg[v] = 1; }
+  }
+}
+
+// =============================================================================================
+static uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
+
+extern "C" {
+
+int nb_graph_create(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *column_offset_host,
+                    const uint32_t *row_indices_host, const uint32_t *in_degree_host, const uint32_t *out_degree_host,
+                    nb_graph **out) {
+  NB_REQUIRE(ctx && out && column_offset_host && (row_indices_host || n_edges == 0), NB_ERR_ARG, "nb_graph_create: NULL argument");
+  NB_REQUIRE(n_vertices > 0 && n_edges < 0xffffffffull, NB_ERR_ARG, "nb_graph_create: |V| must be > 0 and |E| < 2^32 (u32 offsets)");
+  NB_REQUIRE(column_offset_host[n_vertices] == (uint32_t)n_edges, NB_ERR_ARG, "column_offset[|V|] != |E|");
+  NB_GUARD(ctx);
+  nb_graph *g = new nb_graph();
+  g->ctx = ctx; g->V = n_vertices; g->E = n_edges;
+  g->col_off = g->row_idx = g->in_deg = g->out_deg = nullptr;
+  NB_CUDA(cudaMalloc(&g->col_off, ((size_t)n_vertices + 1) * 4));
+  NB_CUDA(cudaMalloc(&g->row_idx, (size_t)(n_edges ? n_edges : 1) * 4));
+  NB_CUDA(cudaMalloc(&g->in_deg, (size_t)n_vertices * 4));
+  NB_CUDA(cudaMalloc(&g->out_deg, (size_t)n_vertices * 4));
+  NB_CUDA(cudaMemcpyAsync(g->col_off, column_offset_host, ((size_t)n_vertices + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_edges) NB_CUDA(cudaMemcpyAsync(g->row_idx, row_indices_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t mx = 0;
+  for (uint32_t v = 0; v < n_vertices; v++) {
+    uint32_t d = column_offset_host[v + 1] - column_offset_host[v];
+    if (d > mx) mx = d;
+  }
+  g->max_in_degree = mx;
+  if (in_degree_host && out_degree_host) {
+    NB_CUDA(cudaMemcpyAsync(g->in_deg, in_degree_host, (size_t)n_vertices * 4, cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(cudaMemcpyAsync(g->out_deg, out_degree_host, (size_t)n_vertices * 4, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int phase = 0; phase < 3; phase++) {
+      k_degrees_from_csc<<<nb_grid(phase == 1 ? n_edges : n_vertices, 256), 256, 0, ctx->stream>>>(
+          g->col_off, g->row_idx, g->in_deg, g->out_deg, n_vertices, n_edges, phase);
+      NB_LAUNCH_CHECK(ctx);
+    }
+  }
+  NB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = g;
+  return NB_OK;
+}
+
+int nb_graph_destroy(nb_graph *g) {
+  if (!g) return NB_OK;
+  DeviceGuard guard(g->ctx->device);
+  cudaFree(g->col_off); cudaFree(g->row_idx); cudaFree(g->in_deg); cudaFree(g->out_deg);
+  delete g;
+  return NB_OK;
+}
+
+int nb_graph_info(nb_graph *g, uint32_t *n_vertices, uint64_t *n_edges, const uint32_t **column_offset_dev,
+                  const uint32_t **row_indices_dev, const uint32_t **in_degree_dev, const uint32_t **out_degree_dev) {
+  NB_REQUIRE(g, NB_ERR_ARG, "graph is NULL");
+  if (n_vertices) *n_vertices = g->V;
+  if (n_edges) *n_edges = g->E;
+  if (column_offset_dev) *column_offset_dev = g->col_off;
+  if (row_indices_dev) *row_indices_dev = g->row_idx;
+  if (in_degree_dev) *in_degree_dev = g->in_deg;
+  if (out_degree_dev) *out_degree_dev = g->out_deg;
+  return NB_OK;
+}
+
+int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout, uint32_t max_batch, uint32_t flags,
+                      uint64_t max_edges_hint, nb_sampler **out) {
+  NB_REQUIRE(ctx && g && fanout && out, NB_ERR_ARG, "nb_sampler_create: NULL argument");
+  NB_REQUIRE(n_layers >= 1 && n_layers <= NB_MAX_LAYERS, NB_ERR_ARG, "layers must be in [1,%d]", NB_MAX_LAYERS);
+  NB_REQUIRE(max_batch >= 1, NB_ERR_ARG, "max_batch must be >= 1");
+  for (int i = 0; i < n_layers; i++)
+    NB_REQUIRE(fanout[i] == -1 || (fanout[i] >= 1 && fanout[i] <= 512), NB_ERR_UNSUPPORTED,
+               "fanout[%d]=%d: supported values are -1 (all) and 1..512", i, fanout[i]);
+  NB_GUARD(ctx);
+  nb_sampler *s = new nb_sampler();
+  memset(s, 0, sizeof(*s));
+  s->ctx = ctx; s->g = g; s->L = n_layers; s->flags = flags; s->max_batch = max_batch;
+  const bool merge = flags & NB_SAMPLER_MERGE_SRC_DST;
+  // capacities: V_0 = batch, E_i <= V_i * f_i, S_i <= E_i (+V_i when merged), all bounded by the graph
+  uint64_t cap_dst = max_batch < g->V ? max_batch : g->V;
+  size_t words = 0;  // arena size in 4-byte words
+  auto take = [&](size_t n) { size_t at = words; words += (n + 31) & ~(size_t)31; return at; };
+  struct Off { size_t destination, column_offset, sample_ans, row_indices, edge_dst, source, row_offset, row_count, row_cursor,
+               column_indices, csr_tmp, csr_to_csc, long_rows, dst_local_id, src_to_dst, ewf, ewb; } off[NB_MAX_LAYERS];
+  uint64_t max_items = 0;
+  for (int i = 0; i < n_layers; i++) {
+    s->fanout[i] = fanout[i];
+    uint64_t per = fanout[i] < 0 ? g->max_in_degree : (uint64_t)fanout[i];
+    uint64_t cap_e = cap_dst * per;
+    if (fanout[i] < 0 && max_edges_hint && max_edges_hint < cap_e) cap_e = max_edges_hint;
+    if (cap_e > g->E) cap_e = g->E;
+    uint64_t cap_s = cap_e + (merge ? cap_dst : 0);
+    if (cap_s > g->V) cap_s = g->V;
+    NB_REQUIRE(cap_e < 0x7fffffffull, NB_ERR_CAPACITY, "layer %d edge capacity %llu exceeds 2^31", i, (unsigned long long)cap_e);
+    LayerBuf &b = s->lay[i];
+    b.cap_dst = (uint32_t)cap_dst; b.cap_edges = (uint32_t)cap_e; b.cap_src = (uint32_t)cap_s;
+    Off &o = off[i];
+    o.destination = i == 0 ? take(cap_dst) : 0;
+    o.column_offset = take(cap_dst + 1);
+    o.sample_ans = take(cap_e); o.row_indices = take(cap_e); o.edge_dst = take(cap_e);
+    o.source = take(cap_s);
+    o.row_offset = take(cap_s + 1); o.row_count = take(cap_s); o.row_cursor = take(cap_s);
+    o.column_indices = take(cap_e); o.csr_tmp = take(cap_e); o.csr_to_csc = take(cap_e); o.long_rows = take(cap_s);
+    o.dst_local_id = take(cap_dst); o.src_to_dst = take(cap_s);
+    o.ewf = take(cap_e); o.ewb = take(cap_e);
+    if (cap_dst > max_items) max_items = cap_dst;
+    if (cap_s > max_items) max_items = cap_s;
+    cap_dst = cap_s;
+  }
+  s->n_words = (g->V + 31) / 32;
+  if (s->n_words > max_items) max_items = s->n_words;
+  s->max_tiles = (uint32_t)((max_items + SCAN_TILE - 1) / SCAN_TILE) + 1;
+  size_t o_bitmap = take(s->n_words + 1), o_rank = take(s->n_words + 1);
+  size_t o_state = take((size_t)s->max_tiles * 2), o_ctr = take(32);
+  size_t o_meta = take((sizeof(LayerMeta) / 4) * (NB_MAX_LAYERS + 1));
+  size_t bytes = words * 4;
+  size_t free_b = 0, total_b = 0;
+  NB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  if (bytes > free_b) {
+    delete s;
+    nb_set_error("sampler arena needs %zu MiB, %zu MiB free", bytes >> 20, free_b >> 20);
+    return NB_ERR_CAPACITY;
+  }
+  NB_CUDA(cudaMalloc(&s->arena, bytes));
+  NB_CUDA(cudaMemsetAsync(s->arena, 0, bytes, ctx->stream));
+  uint32_t *base = (uint32_t *)s->arena;
+  for (int i = 0; i < n_layers; i++) {
+    LayerBuf &b = s->lay[i];
+    Off &o = off[i];
+    b.destination = i == 0 ? base + o.destination : nullptr;
+    b.column_offset = base + o.column_offset; b.sample_ans = base + o.sample_ans; b.row_indices = base + o.row_indices;
+    b.edge_dst = base + o.edge_dst; b.source = base + o.source; b.row_offset = base + o.row_offset;
+    b.row_count = base + o.row_count; b.row_cursor = base + o.row_cursor; b.column_indices = base + o.column_indices;
+    b.csr_tmp = base + o.csr_tmp; b.csr_to_csc = base + o.csr_to_csc; b.long_rows = base + o.long_rows;
+    b.dst_local_id = base + o.dst_local_id; b.src_to_dst = base + o.src_to_dst;
+    b.ewf = (float *)(base + o.ewf); b.ewb = (float *)(base + o.ewb);
+  }
+  for (int i = 1; i < n_layers; i++) s->lay[i].destination = s->lay[i - 1].source;  // layer chaining (FullyRepGraph.hpp:309)
+  s->bitmap = base + o_bitmap; s->word_rank = base + o_rank;
+  s->ws.tile_state = (unsigned long long *)(base + o_state);
+  s->ws.ticket = base + o_ctr; s->ws.done = base + o_ctr + 1;
+  s->meta_dev = (LayerMeta *)(base + o_meta);
+  NB_CUDA(cudaHostAlloc(&s->meta_host, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1), cudaHostAllocDefault));
+  memset(s->meta_host, 0, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1));
+  NB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = s;
+  return NB_OK;
+}
+
+int nb_sampler_destroy(nb_sampler *s) {
+  if (!s) return NB_OK;
+  DeviceGuard guard(s->ctx->device);
+  cudaFree(s->arena);
+  cudaFreeHost(s->meta_host);
+  delete s;
+  return NB_OK;
+}
+
+static void fill_view(nb_sampler *s, int i, nb_layer_view *v) {
+  const LayerBuf &b = s->lay[i];
+  const LayerMeta &m = s->meta_host[i];
+  const bool csr = s->flags & NB_SAMPLER_BUILD_CSR, merge = s->flags & NB_SAMPLER_MERGE_SRC_DST;
+  v->n_dst = m.n_dst; v->n_edges = m.n_edges; v->n_src = m.n_src; v->reserved = 0;
+  v->destination = b.destination; v->column_offset = b.column_offset; v->sample_ans = b.sample_ans;
+  v->row_indices = b.row_indices; v->source = b.source;
+  v->row_offset = csr ? b.row_offset : nullptr; v->column_indices = csr ? b.column_indices : nullptr;
+  v->csr_to_csc = csr ? b.csr_to_csc : nullptr;
+  v->edge_weight_forward = b.ewf; v->edge_weight_backward = csr ? b.ewb : nullptr;
+  v->dst_local_id = merge ? b.dst_local_id : nullptr; v->src_to_dst = merge ? b.src_to_dst : nullptr;
+}
+
+// enqueue every kernel of one mini-batch; `replay` != 0 when sample_ans was uploaded by the caller
+static int enqueue_batch(nb_sampler *s, uint32_t n_seeds, uint64_t rng_seed, uint64_t rng_offset, int weight_type,
+                         const uint32_t *omit, uint32_t omit_value, int replay) {
+  nb_ctx *ctx = s->ctx;
+  nb_graph *g = s->g;
+  cudaStream_t st = ctx->stream;
+  const bool merge = s->flags & NB_SAMPLER_MERGE_SRC_DST, up = s->flags & NB_SAMPLER_UP_DEGREE,
+             csr = s->flags & NB_SAMPLER_BUILD_CSR;
+  k_init_meta<<<1, 32, 0, st>>>(s->meta_dev, s->L, n_seeds);
+  NB_LAUNCH_CHECK(ctx);
+  for (int i = 0; i < s->L; i++) {
+    LayerBuf &b = s->lay[i];
+    LayerMeta *m = s->meta_dev + i;
+    NB_CUDA(cudaMemsetAsync(s->bitmap, 0, (size_t)(s->n_words + 1) * 4, st));
+    CountOp cop{g->col_off, b.destination, (i == s->L - 1) ? omit : nullptr, b.column_offset, m, omit_value, b.cap_edges, s->fanout[i]};
+    k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, s->ws);
+    NB_LAUNCH_CHECK(ctx);
+    int hash_slots = s->fanout[i] > 32 ? (int)pow2_ceil(2u * (uint32_t)s->fanout[i]) : 0;
+    k_sample<<<nb_grid(b.cap_dst, SAMPLE_WARPS, 8), SAMPLE_WARPS * 32, (size_t)hash_slots * SAMPLE_WARPS * 4, st>>>(
+        g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, s->bitmap, m, s->fanout[i],
+        rng_seed ^ (rng_offset >> 32 << 32), (uint32_t)i, (uint32_t)rng_offset, merge ? 1 : 0, replay, hash_slots);
+    NB_LAUNCH_CHECK(ctx);
+    BitmapOp bop{s->bitmap, s->word_rank, b.source, b.row_count, b.row_cursor, merge ? b.src_to_dst : nullptr, m, m + 1, s->n_words, b.cap_src};
+    k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, s->ws);
+    NB_LAUNCH_CHECK(ctx);
+    const int histogram = (csr || up) ? 1 : 0;
+    k_relabel<<<nb_grid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
+        b.sample_ans, b.row_indices, s->bitmap, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
+        merge ? b.src_to_dst : nullptr, m, histogram);
+    NB_LAUNCH_CHECK(ctx);
+    if (weight_type != NB_WEIGHT_NONE) {
+      k_weights<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.sample_ans, b.row_indices, b.edge_dst, b.destination,
+                                                                b.column_offset, b.row_count, g->in_deg, g->out_deg, m,
+                                                                weight_type, up ? 1 : 0);
+      NB_LAUNCH_CHECK(ctx);
+    }
+    if (csr) {
+      RowOp rop{b.row_count, b.row_offset, m};
+      k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, s->ws);
+      NB_LAUNCH_CHECK(ctx);
+      k_csr_fill<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
+      NB_LAUNCH_CHECK(ctx);
+      float *ewb = weight_type != NB_WEIGHT_NONE ? b.ewb : nullptr;
+      k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
+                                                               ewb, b.ewf, b.long_rows, m);
+      NB_LAUNCH_CHECK(ctx);
+      k_csr_long_rows<<<nb_grid(b.cap_src, 8, 2), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc,
+                                                                  b.edge_dst, ewb, b.ewf, b.long_rows, m);
+      NB_LAUNCH_CHECK(ctx);
+    }
+  }
+  NB_CUDA(cudaMemcpyAsync(s->meta_host, s->meta_dev, sizeof(LayerMeta) * (s->L + 1), cudaMemcpyDeviceToHost, st));
+  return NB_OK;
+}
+
+static int finish_batch(nb_sampler *s, nb_layer_view *views_out) {
+  NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  for (int i = 0; i < s->L; i++) {
+    if (s->meta_host[i].err) {
+      nb_set_error("sampler layer %d: %s capacity exceeded (E=%u cap %u, S=%u cap %u)", i,
+                   s->meta_host[i].err == 1 ? "edge" : "source", s->meta_host[i].n_edges, s->lay[i].cap_edges,
+                   s->meta_host[i].n_src, s->lay[i].cap_src);
+      return NB_ERR_CAPACITY;
+    }
+    if (views_out) fill_view(s, i, views_out + i);
+  }
+  return NB_OK;
+}
+
+int nb_sampler_sample(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int seeds_on_device, uint64_t rng_seed,
+                      uint64_t rng_offset, int weight_type, const uint32_t *omit_flag_dev, uint32_t omit_value,
+                      nb_layer_view *views_out, int sync) {
+  NB_REQUIRE(s && (seeds || n_seeds == 0), NB_ERR_ARG, "nb_sampler_sample: NULL argument");
+  NB_REQUIRE(n_seeds <= s->lay[0].cap_dst, NB_ERR_CAPACITY, "batch of %u seeds exceeds the sampler's max_batch %u", n_seeds, s->lay[0].cap_dst);
+  NB_REQUIRE(weight_type >= 0 && weight_type <= 3, NB_ERR_ARG, "bad weight_type %d", weight_type);
+  NB_GUARD(s->ctx);
+  if (n_seeds)
+    NB_CUDA(cudaMemcpyAsync(s->lay[0].destination, seeds, (size_t)n_seeds * 4,
+                            seeds_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->ctx->stream));
+  int rc = enqueue_batch(s, n_seeds, rng_seed, rng_offset, weight_type, omit_flag_dev, omit_value, 0);
+  if (rc != NB_OK) return rc;
+  if (sync) return finish_batch(s, views_out);
+  return NB_OK;
+}
+
+// Replay: layer i's destination is known only after layer i-1 ran, but the uploads do not depend on it.
+int nb_sampler_replay(nb_sampler *s, const uint32_t *seeds_host, uint32_t n_seeds, const uint32_t *const *sample_ans_host,
+                      const uint32_t *n_edges_host, int weight_type, nb_layer_view *views_out) {
+  NB_REQUIRE(s && seeds_host && sample_ans_host && n_edges_host, NB_ERR_ARG, "nb_sampler_replay: NULL argument");
+  NB_REQUIRE(n_seeds <= s->lay[0].cap_dst, NB_ERR_CAPACITY, "batch of %u seeds exceeds max_batch", n_seeds);
+  NB_GUARD(s->ctx);
+  NB_CUDA(cudaMemcpyAsync(s->lay[0].destination, seeds_host, (size_t)n_seeds * 4, cudaMemcpyHostToDevice, s->ctx->stream));
+  for (int i = 0; i < s->L; i++) {
+    NB_REQUIRE(n_edges_host[i] <= s->lay[i].cap_edges, NB_ERR_CAPACITY, "replay layer %d: %u edges exceed capacity %u", i, n_edges_host[i], s->lay[i].cap_edges);
+    if (n_edges_host[i])
+      NB_CUDA(cudaMemcpyAsync(s->lay[i].sample_ans, sample_ans_host[i], (size_t)n_edges_host[i] * 4, cudaMemcpyHostToDevice, s->ctx->stream));
+  }
+  int rc = enqueue_batch(s, n_seeds, 0, 0, weight_type, nullptr, 0, 1);
+  if (rc != NB_OK) return rc;
+  rc = finish_batch(s, views_out);
+  if (rc != NB_OK) return rc;
+  for (int i = 0; i < s->L; i++)
+    NB_REQUIRE(s->meta_host[i].n_edges == n_edges_host[i], NB_ERR_ARG, "replay layer %d: supplied %u edges, column offsets total %u", i,
+               n_edges_host[i], s->meta_host[i].n_edges);
+  return NB_OK;
+}
+
+int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out) {
+  NB_REQUIRE(s && out && layer >= 0 && layer < s->L, NB_ERR_ARG, "nb_sampler_layer: bad argument");
+  NB_REQUIRE(s->meta_host[layer].err == 0, NB_ERR_CAPACITY, "layer %d overflowed its arena", layer);
+  fill_view(s, layer, out);
+  return NB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libnts_b200.so), against
+ (1) the golden records of the reference's own CPU code (tests/golden, bit-exact on replay),
+ (2) the oracle on seeded inputs, (3) size-independent properties at BASELINE.json's sizes.
+Tolerance for fp32 aggregation / gradients: 1e-5 relative (north star); integers: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from golden_util import load, names
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def u32(t):
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+def f32(t):
+    return t.detach().cpu().numpy()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def cs(nts):
+    return nts.Cuda_Stream(0)
+
+
+def make_graph(nts, cs, V, avg_deg, seed, unique=True, max_deg=None):
+    rng = np.random.default_rng(seed)
+    deg = np.minimum((rng.pareto(1.5, V) * avg_deg * 0.5).astype(np.int64), max_deg or V - 1)
+    deg[rng.random(V) < 0.05] = 0
+    cols = []
+    for v in range(V):
+        if deg[v]:
+            src = rng.choice(V, deg[v], replace=False) if unique else rng.integers(0, V, deg[v])
+            cols.append(np.stack([src, np.full(deg[v], v)], 1))
+    pairs = np.concatenate(cols).astype(np.uint32)
+    pairs = pairs[rng.permutation(len(pairs))]
+    return pairs, nts.FullyRepGraph(cs, V, edge_pairs=pairs)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", names())
+def test_replay_reference_records_bit_exact(nts, cs, name):
+    """north star check 1: replaying the reference's recorded neighbour sets gives bit-exact
+    subgraph indices, CSC, CSR and weights; gather / aggregate / gradients follow."""
+    g = load(name)
+    graph = nts.FullyRepGraph(cs, g["V"], column_offset=g["col_off"], row_indices=g["row_idx"], in_degree=g["in_deg"],
+                              out_degree=g["out_deg"])
+    wt = {0: nts.WeightType.Sum, 1: nts.WeightType.Mean, 2: nts.WeightType.None_}[g["weight_type"]]
+    table_np = oracle.feat(np.arange(g["V"]), np.arange(g["F"]))
+    table = torch.from_numpy(table_np).cuda()
+    for b in g["batches"]:
+        seeds = b["layers"][0]["destination"]
+        sampler = nts.FastSampler(graph, seeds, g["L"], max(len(seeds), 1), g["fanout"], cuda_stream=cs,
+                                  up_degree=g["up_degree"], build_csr=True)
+        sg = sampler.replay(seeds, [l["sample_ans"] for l in b["layers"]], wt)
+        for mine, ref in zip(sg.sampled_sgs, b["layers"]):
+            assert mine.v_size == ref["destination"].size and mine.e_size == ref["sample_ans"].size
+            assert mine.src_size == ref["source"].size
+            assert np.array_equal(u32(mine.dev_destination), ref["destination"])
+            assert np.array_equal(u32(mine.dev_column_offset), ref["column_offset"])
+            assert np.array_equal(u32(mine.dev_source), ref["source"])
+            assert np.array_equal(u32(mine.dev_row_indices), ref["row_indices"])
+            assert np.array_equal(u32(mine.dev_row_offset), ref["row_offset"])
+            assert np.array_equal(u32(mine.dev_column_indices), ref["column_indices"])
+            if g["weight_type"] != 2:
+                assert np.array_equal(u32(mine.dev_edge_weight_forward), bits(ref["e_w_f"]))
+                assert np.array_equal(u32(mine.dev_edge_weight_backward), bits(ref["e_w_b"]))
+        # gather: bit-exact
+        bottom = sg.sampled_sgs[-1]
+        x0 = torch.empty((bottom.src_size, g["F"]), device="cuda")
+        sampler.load_feature_gpu(cs, sg, x0, table)
+        assert np.array_equal(bits(f32(x0).ravel()), bits(b["X0"]))
+        if g["up_degree"] or g["weight_type"] != 0:
+            continue  # the CPU op recomputes Sum weights from whatever degrees are current; covered by the Sum fixtures
+        X = x0
+        for l in range(g["L"]):
+            hop = g["L"] - 1 - l
+            op = nts.SingleGPUAllSampleGraphOp(sg, hop, cs)
+            Y = op.forward(X)
+            ref_y = b[f"Y{hop}"].reshape(Y.shape)
+            np.testing.assert_allclose(f32(Y), ref_y, rtol=RTOL, atol=1e-7)
+            assert np.array_equal(bits(f32(Y)), bits(ref_y)), "forward is expected to be bit-exact (same order, mul+add)"
+            dY = torch.from_numpy(ref_y * np.float32(0.5) + np.float32(0.25)).cuda()
+            dX = op.backward(dY)
+            ref_dx = b[f"dX{hop}"].reshape(dX.shape)
+            np.testing.assert_allclose(f32(dX), ref_dx, rtol=RTOL, atol=1e-7)
+            # the CSC push (reference GPU backward) agrees too, within tolerance (atomic order)
+            dX2 = torch.empty_like(dX)
+            lay = sg.sampled_sgs[hop]
+            cs.Push_From_Dst_To_Src_Spmm(dY, dX2, lay.dev_e_w(), lay.dev_r_i(), lay.dev_c_o(), lay.src_size, 0, 0, 0, 0,
+                                         lay.e_size, lay.v_size, dY.shape[1], True, False)
+            np.testing.assert_allclose(f32(dX2), ref_dx, rtol=1e-4, atol=1e-6)
+            X = Y
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fanout,build_csr,merge,up", [([25, 10], True, False, False), ([5, 5, 5], True, True, False),
+                                                        ([40, 3], True, False, True), ([-1, 4], False, False, False)])
+def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, build_csr, merge, up):
+    V = 20000
+    pairs, graph = make_graph(nts, cs, V, 30, seed=7)
+    co, ri = oracle.build_csc(pairs, V)
+    ind, outd = oracle.degrees(pairs, V)
+    rng = np.random.default_rng(1)
+    seeds = rng.permutation(V)[:777].astype(np.uint32)
+    sampler = nts.FastSampler(graph, seeds, len(fanout), 1024, fanout, cuda_stream=cs, merge_src_dst=merge, up_degree=up,
+                              build_csr=build_csr)
+    sg = sampler.sample_gpu_fast(1024)
+    ans = [u32(l.dev_sample_ans) for l in sg.sampled_sgs]
+    ref = oracle.sample_batch(seeds, co, ri, fanout, V, ind, outd, up_degree=up, merge_src_dst=merge, replay=ans)
+    for i, (l, r) in enumerate(zip(sg.sampled_sgs, ref)):
+        assert np.array_equal(u32(l.dev_column_offset), r["column_offset"]), i
+        assert np.array_equal(u32(l.dev_source), r["source"]), i
+        assert np.array_equal(u32(l.dev_row_indices), r["row_indices"]), i
+        assert np.array_equal(u32(l.dev_edge_weight_forward), bits(r["e_w_f"])), i
+        if build_csr:
+            assert np.array_equal(u32(l.dev_row_offset), r["row_offset"]), i
+            assert np.array_equal(u32(l.dev_column_indices), r["column_indices"]), i
+            assert np.array_equal(u32(l.dev_edge_weight_backward), bits(r["e_w_b"])), i
+            c2c = u32(l.dev_csr_to_csc)
+            assert np.array_equal(np.sort(c2c), np.arange(l.e_size, dtype=np.uint32))
+        if merge:
+            assert np.array_equal(u32(l.dev_dst_local_id), r["dst_local_id"]), i
+            s2d = u32(l.dev_src_to_dst)
+            dl = r["dst_local_id"]
+            assert np.array_equal(s2d[dl], np.arange(l.v_size, dtype=np.uint32))
+            assert (s2d != 0xFFFFFFFF).sum() == l.v_size
+        # sampling rule (core/ntsFastSampler.hpp:1028-1048)
+        lco = r["column_offset"]
+        for j, d in enumerate(r["destination"]):
+            nb = ri[co[d]:co[d + 1]]
+            got = ans[i][lco[j]:lco[j + 1]]
+            f = fanout[i]
+            if f == -1 or nb.size <= f:
+                assert np.array_equal(got, nb)
+            else:
+                assert got.size == f and np.unique(got).size == f and np.isin(got, nb).all()
+
+
+def test_gpu_sampler_is_reproducible_and_counter_based(nts, cs):
+    V = 5000
+    pairs, graph = make_graph(nts, cs, V, 40, seed=3)
+    seeds = np.arange(512, dtype=np.uint32)
+    a = nts.FastSampler(graph, seeds, 2, 512, [10, 5], cuda_stream=cs, rng_seed=123)
+    b = nts.FastSampler(graph, seeds, 2, 512, [10, 5], cuda_stream=cs, rng_seed=123)
+    sa, sb = a.sample_gpu_fast(512), b.sample_gpu_fast(512)
+    assert all(np.array_equal(u32(x.dev_sample_ans), u32(y.dev_sample_ans)) for x, y in zip(sa.sampled_sgs, sb.sampled_sgs))
+    a.restart()
+    sa2 = a.sample_gpu_fast(512)  # batch counter advanced -> different draws
+    assert not np.array_equal(u32(sa2.sampled_sgs[0].dev_sample_ans), u32(sb.sampled_sgs[0].dev_sample_ans))
+    c = nts.FastSampler(graph, seeds, 2, 512, [10, 5], cuda_stream=cs, rng_seed=124)
+    sc = c.sample_gpu_fast(512)
+    assert not np.array_equal(u32(sc.sampled_sgs[0].dev_sample_ans), u32(sb.sampled_sgs[0].dev_sample_ans))
+
+
+@pytest.mark.parametrize("deg,f", [(40, 7), (26, 25), (100, 40), (700, 10), (33, 32)])
+def test_gpu_sampler_chi_square_uniform_inclusion(nts, cs, deg, f):
+    """north star check 2: distribution equivalence. Every in-neighbour of a vertex with deg > f is
+    included with probability f/deg (uniform f-subsets); chi-square over the inclusion counts."""
+    V, trials = 1024, 4096
+    rng = np.random.default_rng(deg * 131 + f)
+    nbrs = rng.permutation(V)[:deg].astype(np.uint32)
+    # vertex 0 has the column under test; every other vertex has one self loop
+    pairs = np.concatenate([np.stack([nbrs, np.zeros(deg, np.uint32)], 1),
+                            np.stack([np.arange(1, V), np.arange(1, V)], 1).astype(np.uint32)])
+    graph = nts.FullyRepGraph(cs, V, edge_pairs=pairs)
+    seeds = np.zeros(1, np.uint32)
+    sampler = nts.FastSampler(graph, np.zeros(trials, np.uint32), 1, 1, [f], cuda_stream=cs, build_csr=False, rng_seed=99)
+    counts = np.zeros(V, np.int64)
+    pair_first = np.zeros(V, np.int64)
+    for t in range(trials):
+        sg = sampler.sample_gpu_fast(1)
+        got = u32(sg.sampled_sgs[0].dev_sample_ans)
+        assert got.size == f and np.unique(got).size == f
+        counts[got] += 1
+        pair_first[got[0]] += 1
+    assert counts[np.setdiff1d(np.arange(V), nbrs)].sum() == 0
+    exp = trials * f / deg
+    chi2 = ((counts[nbrs] - exp) ** 2 / exp).sum() / (1 - f / deg)  # hypergeometric variance correction
+    dof = deg - 1
+    assert chi2 < dof + 5.0 * np.sqrt(2 * dof), (chi2, dof)
+    # the slot-0 element is itself uniform over the neighbours
+    exp0 = trials / deg
+    chi0 = ((pair_first[nbrs] - exp0) ** 2 / exp0).sum()
+    assert chi0 < dof + 5.0 * np.sqrt(2 * dof), (chi0, dof)
+
+
+def test_gpu_sampler_matches_oracle_sampler_distribution(nts, cs):
+    """Same statistic from the oracle's sampler and the GPU sampler: two-sample chi-square."""
+    V, deg, f, trials = 256, 60, 9, 3000
+    rng = np.random.default_rng(5)
+    nbrs = rng.permutation(V)[:deg].astype(np.uint32)
+    pairs = np.stack([nbrs, np.zeros(deg, np.uint32)], 1)
+    graph = nts.FullyRepGraph(cs, V, edge_pairs=pairs)
+    co, ri = oracle.build_csc(pairs, V)
+    sampler = nts.FastSampler(graph, np.zeros(trials, np.uint32), 1, trials, [f], cuda_stream=cs, build_csr=False)
+    sg = sampler.sample_gpu_fast(trials)  # the same dst repeated: independent draws per slot
+    got = u32(sg.sampled_sgs[0].dev_sample_ans).reshape(trials, f)
+    lco, _ = oracle.count_offsets(np.zeros(trials, np.uint32), co, f)
+    ora = oracle.sample_layer(np.zeros(trials, np.uint32), lco, co, ri, f, seed=17).reshape(trials, f)
+    a = np.array([(got == v).sum() for v in nbrs], np.float64)
+    b = np.array([(ora == v).sum() for v in nbrs], np.float64)
+    chi2 = ((a - b) ** 2 / (a + b)).sum()
+    assert chi2 < (deg - 1) + 5.0 * np.sqrt(2 * (deg - 1)), chi2
+
+
+def test_omit_hot_vertices_bottom_layer(nts, cs):
+    V = 4000
+    pairs, graph = make_graph(nts, cs, V, 20, seed=11)
+    co, ri = oracle.build_csc(pairs, V)
+    rng = np.random.default_rng(2)
+    seeds = rng.permutation(V)[:300].astype(np.uint32)
+    flag = np.full(V, 0xFFFFFFFF, np.uint32)
+    hot = rng.permutation(V)[:800]
+    flag[hot] = 3
+    dflag = torch.from_numpy(flag.view(np.int32)).cuda()
+    for value in (3, 0xFFFFFFFF):
+        sampler = nts.FastSampler(graph, seeds, 2, 300, [6, 4], cuda_stream=cs)
+        sg = sampler.sample_gpu_fast_omit(300, dflag, value)
+        top, bottom = sg.sampled_sgs
+        ref0, _ = oracle.count_offsets(seeds, co, 6)
+        assert np.array_equal(u32(top.dev_column_offset), ref0)  # upper layers are not omitted
+        ref1, _ = oracle.count_offsets(u32(bottom.dev_destination), co, 4, skip=flag, skip_value=value)
+        assert np.array_equal(u32(bottom.dev_column_offset), ref1)
+        lens = np.diff(ref1)
+        assert (lens[np.isin(u32(bottom.dev_destination), hot)] == 0).all()
+
+
+def test_capacity_is_checked_not_asserted(nts, cs):
+    V = 3000
+    pairs, graph = make_graph(nts, cs, V, 20, seed=13)
+    sampler = nts.FastSampler(graph, np.arange(100, dtype=np.uint32), 1, 10, [3], cuda_stream=cs)
+    with pytest.raises(nts.NtsError):
+        sampler.sample_gpu_fast(100)  # more seeds than max_batch
+    with pytest.raises(nts.NtsError):
+        nts.FastSampler(graph, np.arange(10, dtype=np.uint32), 1, 10, [600], cuda_stream=cs)  # unsupported fanout
+
+
+def test_empty_and_degenerate_batches(nts, cs):
+    V = 64
+    pairs = np.array([[1, 0], [2, 0], [3, 1]], np.uint32)  # most vertices have no in-edges
+    graph = nts.FullyRepGraph(cs, V, edge_pairs=pairs)
+    sampler = nts.FastSampler(graph, np.array([5, 6, 7, 0], np.uint32), 2, 8, [2, 2], cuda_stream=cs)
+    sg = sampler.sample_gpu_fast(3)  # three isolated seeds: zero edges everywhere
+    assert [l.e_size for l in sg.sampled_sgs] == [0, 0] and [l.src_size for l in sg.sampled_sgs] == [0, 0]
+    assert np.array_equal(u32(sg.sampled_sgs[0].dev_column_offset), np.zeros(4, np.uint32))
+    x = torch.zeros((0, 8), device="cuda")
+    y = nts.SingleGPUAllSampleGraphOp(sg, 0, cs).forward(x)
+    assert y.shape == (3, 8) and float(y.abs().sum()) == 0.0  # every output row is written (zeros)
+    sg = sampler.sample_gpu_fast(1)  # seed 0: two in-neighbours, one of which has one
+    assert sg.sampled_sgs[0].e_size == 2 and np.array_equal(u32(sg.sampled_sgs[0].dev_source), [1, 2])
+    assert sg.sampled_sgs[1].e_size == 1 and np.array_equal(u32(sg.sampled_sgs[1].dev_source), [3])
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F", [1, 7, 16, 41, 100, 128, 256, 602, 1433])
+def test_gather_and_aggregate_match_oracle(nts, cs, F):
+    V = 3000
+    pairs, graph = make_graph(nts, cs, V, 25, seed=F)
+    co, ri = oracle.build_csc(pairs, V)
+    ind, outd = oracle.degrees(pairs, V)
+    rng = np.random.default_rng(F)
+    seeds = rng.permutation(V)[:400].astype(np.uint32)
+    sampler = nts.FastSampler(graph, seeds, 2, 400, [8, 6], cuda_stream=cs)
+    sg = sampler.sample_gpu_fast(400)
+    lay = sg.sampled_sgs[1]
+    r = dict(co=u32(lay.dev_column_offset), ri=u32(lay.dev_row_indices), ro=u32(lay.dev_row_offset), ci=u32(lay.dev_column_indices),
+             wf=f32(lay.dev_edge_weight_forward), wb=f32(lay.dev_edge_weight_backward), src=u32(lay.dev_source))
+    table_np = rng.standard_normal((V, F)).astype(np.float32)
+    table = torch.from_numpy(table_np).cuda()
+    x0 = torch.empty((lay.src_size, F), device="cuda")
+    sampler.load_feature_gpu(cs, sg, x0, table)
+    X0 = oracle.gather_rows(table_np, r["src"])
+    assert np.array_equal(bits(f32(x0)), bits(X0))
+    op = nts.SingleGPUAllSampleGraphOp(sg, 1, cs)
+    y = op.forward(x0)
+    Y = oracle.aggregate_fwd(X0, r["co"], r["ri"], r["wf"])
+    np.testing.assert_allclose(f32(y), Y, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(bits(f32(y)), bits(Y))
+    dY = rng.standard_normal(Y.shape).astype(np.float32)
+    dy = torch.from_numpy(dY).cuda()
+    dx = op.backward(dy)
+    DX = oracle.aggregate_bwd_csr(dY, r["ro"], r["ci"], r["wb"])
+    np.testing.assert_allclose(f32(dx), DX, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(bits(f32(dx)), bits(DX))
+    dx2 = torch.full_like(dx, 7.0)  # push zeroes its output itself
+    cs.Push_From_Dst_To_Src_Spmm(dy, dx2, lay.dev_e_w(), lay.dev_r_i(), lay.dev_c_o(), lay.src_size, 0, 0, 0, 0,
+                                 lay.e_size, lay.v_size, F, True, False)
+    np.testing.assert_allclose(f32(dx2), DX, rtol=1e-4, atol=1e-5)
+    # unweighted (with_weight=false)
+    y1 = torch.empty_like(y)
+    cs.Gather_By_Dst_From_Src_Spmm(x0, y1, None, lay.dev_r_i(), lay.dev_c_o(), lay.src_size, 0, 0, 0, 0, lay.e_size,
+                                   lay.v_size, F, False, False)
+    np.testing.assert_allclose(f32(y1), oracle.aggregate_fwd(X0, r["co"], r["ri"], np.ones_like(r["wf"])), rtol=RTOL, atol=1e-6)
+    # autograd glue
+    xg = x0.clone().requires_grad_(True)
+    (op(xg) * dy).sum().backward()
+    np.testing.assert_allclose(f32(xg.grad), DX, rtol=RTOL, atol=1e-6)
+
+
+def test_unaligned_views_fall_back_to_narrower_vectors(nts, cs):
+    V, F = 500, 64
+    pairs, graph = make_graph(nts, cs, V, 10, seed=1)
+    rng = np.random.default_rng(0)
+    big = torch.from_numpy(rng.standard_normal(V * F + 3).astype(np.float32)).cuda()
+    ids = torch.from_numpy(rng.integers(0, V, 300).astype(np.int32)).cuda()
+    for shift in (0, 1, 2):
+        table = big[shift:shift + V * F].view(V, F)
+        out = torch.empty((300, F), device="cuda")
+        cs.zero_copy_feature_move_gpu(out, table, ids, F, 300)
+        assert torch.equal(out, table[ids.long()])
+
+
+def test_cached_gather_labels_and_row_override(nts, cs):
+    V, F, E2 = 6000, 100, 48
+    rng = np.random.default_rng(4)
+    table_np = rng.standard_normal((V, F)).astype(np.float32)
+    hot = np.sort(rng.permutation(V)[:1500]).astype(np.uint32)
+    cache_np = table_np[hot] + np.float32(1000.0)  # deliberately different so the source of each row is visible
+    hashmap = np.full(V, 0xFFFFFFFF, np.uint32)
+    hashmap[hot] = np.arange(hot.size, dtype=np.uint32)
+    ids_np = rng.integers(0, V, 5000).astype(np.uint32)
+    ref = oracle.gather_rows_cached(table_np, cache_np, hashmap, ids_np)
+    # cold table in mapped pinned host memory, as the reference keeps it (core/ntsDataloador.hpp:187)
+    cold = torch.from_numpy(table_np).pin_memory()
+    out = torch.empty((5000, F), device="cuda")
+    hits = torch.zeros(1, dtype=torch.int32, device="cuda")
+    cs.gather_feature_cached(out, cold, torch.from_numpy(cache_np).cuda(), torch.from_numpy(hashmap.view(np.int32)).cuda(),
+                             torch.from_numpy(ids_np.view(np.int32)).cuda(), F, 5000, hits)
+    cs.CUDA_DEVICE_SYNCHRONIZE()
+    assert np.array_equal(bits(f32(out)), bits(ref))
+    assert int(hits.item()) == int((hashmap[ids_np] != 0xFFFFFFFF).sum())
+    labels = rng.integers(0, 41, V).astype(np.int64)
+    lab = torch.empty(5000, dtype=torch.int64, device="cuda")
+    cs.global_copy_label_move_gpu(lab, torch.from_numpy(labels).cuda(), torch.from_numpy(ids_np.view(np.int32)).cuda(), 5000)
+    assert np.array_equal(lab.cpu().numpy(), oracle.gather_labels(labels, ids_np))
+    # hot-row override for super batch 2
+    cache_map = np.full(V, 0xFFFFFFFF, np.uint32)
+    cache_loc = np.zeros(V, np.uint32)
+    oracle.set_cache_index(cache_map, cache_loc, 2, hot)
+    other = rng.permutation(V)[:300].astype(np.uint32)
+    cache_map[other] = 1
+    dst = rng.permutation(V)[:2000].astype(np.uint32)
+    emb = rng.standard_normal((2000, E2)).astype(np.float32)
+    feat = rng.standard_normal((2000, F)).astype(np.float32)
+    share_e = rng.standard_normal((hot.size, E2)).astype(np.float32)
+    share_f = rng.standard_normal((hot.size, F)).astype(np.float32)
+    d = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
+    te, tf_ = d(emb.copy()), d(feat.copy())
+    cs.dev_load_share_embedding(te, d(share_e), d(cache_map), d(cache_loc), E2, d(dst), 2000, 2)
+    assert np.array_equal(f32(te), oracle.row_override(emb, share_e, cache_map, cache_loc, dst, 2))
+    te = d(emb.copy())
+    cs.dev_load_share_embedding_and_feature(tf_, te, d(share_f), d(share_e), d(cache_map), d(cache_loc), F, E2, d(dst), 2000, 2)
+    assert np.array_equal(f32(te), oracle.row_override(emb, share_e, cache_map, cache_loc, dst, 2))
+    assert np.array_equal(f32(tf_), oracle.row_override(feat, share_f, cache_map, cache_loc, dst, 2))
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F", [8, 41, 128])
+def test_gat_legacy_ops_and_fused_layer(nts, cs, F):
+    V = 5000
+    pairs, graph = make_graph(nts, cs, V, 30, seed=F + 1)
+    rng = np.random.default_rng(F)
+    seeds = rng.permutation(V)[:500].astype(np.uint32)
+    sampler = nts.FastSampler(graph, seeds, 2, 500, [12, 40], cuda_stream=cs, merge_src_dst=True, build_csr=True)
+    sg = sampler.sample_gpu_fast(500, weightType=nts.WeightType.None_)
+    for hop in (0, 1):
+        lay = sg.sampled_sgs[hop]
+        co, ri, dl = u32(lay.dev_column_offset), u32(lay.dev_row_indices), u32(lay.dev_dst_local_id)
+        H = rng.standard_normal((lay.src_size, F)).astype(np.float32)
+        att = (rng.standard_normal(2 * F) * 0.3).astype(np.float32)
+        h, a = torch.from_numpy(H).cuda(), torch.from_numpy(att).cuda()
+        # legacy chain
+        msg = nts.BatchGPUSrcDstScatterOp(sg, hop, cs).forward(h)
+        MSG = oracle.scatter_src_dst(H, co, ri, dl)
+        assert np.array_equal(f32(msg), MSG)
+        m_np = MSG @ att
+        m_np = np.where(m_np > 0, m_np, np.float32(0.2) * m_np).astype(np.float32)
+        sm = nts.BatchGPUEdgeSoftMax(sg, hop, cs)
+        alpha_t = sm.forward(torch.from_numpy(m_np).cuda().view(-1, 1))
+        A = oracle.edge_softmax_fwd(m_np, co)
+        np.testing.assert_allclose(f32(alpha_t).ravel(), A, rtol=RTOL, atol=1e-7)
+        da = rng.standard_normal(A.shape).astype(np.float32)
+        dm = sm.backward(torch.from_numpy(da).cuda().view(-1, 1))
+        np.testing.assert_allclose(f32(dm).ravel(), oracle.edge_softmax_bwd(da, f32(alpha_t).ravel(), co), rtol=1e-4, atol=1e-6)
+        agg = nts.BatchGPUAggregateDst(sg, hop, cs)
+        emo = MSG[:, :F] * A[:, None]
+        nbr = agg.forward(torch.from_numpy(emo).cuda())
+        np.testing.assert_allclose(f32(nbr), oracle.gather_msg_to_dst(emo, co), rtol=RTOL, atol=1e-5)
+        dn = rng.standard_normal((lay.v_size, F)).astype(np.float32)
+        assert np.array_equal(f32(agg.backward(torch.from_numpy(dn).cuda())), oracle.scatter_dst_to_msg(dn, co))
+        dmsg = rng.standard_normal(MSG.shape).astype(np.float32)
+        gx = nts.BatchGPUSrcDstScatterOp(sg, hop, cs).backward(torch.from_numpy(dmsg).cuda())
+        np.testing.assert_allclose(f32(gx), oracle.gather_src_dst(dmsg, co, ri, dl, lay.src_size), rtol=1e-4, atol=1e-4)
+        # fused layer vs the oracle's restatement of the toolkit's chain
+        op = nts.GATFusedOp(sg, hop, cs)
+        out = op.forward(h, a)
+        OUT, ALPHA, PRE = oracle.gat_layer_fwd(H, att, co, ri, dl)
+        np.testing.assert_allclose(f32(out), OUT, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(f32(op.alpha), ALPHA, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(f32(op.score_pre), PRE, rtol=1e-4, atol=1e-5)
+        dout = rng.standard_normal(OUT.shape).astype(np.float32)
+        dh, datt = op.backward(h, a, torch.from_numpy(dout).cuda())
+        DH, DATT = oracle.gat_layer_bwd(H, att, dout, f32(op.score_pre), f32(op.alpha), co, ri, dl)
+        np.testing.assert_allclose(f32(dh), DH, rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(f32(datt), DATT, rtol=1e-3, atol=1e-3)
+        # autograd glue
+        hg, ag = h.clone().requires_grad_(True), a.clone().requires_grad_(True)
+        (op(hg, ag) * torch.from_numpy(dout).cuda()).sum().backward()
+        np.testing.assert_allclose(f32(hg.grad), DH, rtol=1e-3, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+def reddit_shaped(V=232965, E=114615892, seed=0x5EED0001):
+    """BASELINE.json configs[1] shape, generated on the GPU: power-law in-degree (mean ~492), skewed sources."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    w = torch.rand(V, generator=g, device="cuda").clamp_min(1e-6).pow(-0.65)
+    deg = (w / w.sum() * E).floor().clamp_(1, V - 1).to(torch.int64)
+    deg[0] += E - int(deg.sum()) if int(deg.sum()) < E else 0
+    co = torch.zeros(V + 1, dtype=torch.int64, device="cuda")
+    co[1:] = deg.cumsum(0)
+    total = int(co[-1])
+    src = (torch.rand(total, generator=g, device="cuda").pow(1.6) * V).to(torch.int64).clamp_(0, V - 1)
+    return co.to(torch.int32).cpu().numpy().view(np.uint32), src.to(torch.int32).cpu().numpy().view(np.uint32)
+
+
+def test_full_size_reddit_shaped_properties(nts, cs):
+    """At BASELINE.json's size (233K vertices, ~114M edges, F=602, batch 1024, fanout 25-10): properties
+    that do not need the oracle to finish -- structural invariants and linearity / checksum identities."""
+    V, F = 232965, 602
+    co, ri = reddit_shaped()
+    graph = nts.FullyRepGraph(cs, V, column_offset=co, row_indices=ri)
+    rng = np.random.default_rng(3)
+    seeds = rng.permutation(V)[:1024].astype(np.uint32)
+    sampler = nts.FastSampler(graph, seeds, 2, 1024, [25, 10], cuda_stream=cs)
+    sg = sampler.sample_gpu_fast(1024)
+    top, bottom = sg.sampled_sgs
+    assert top.v_size == 1024 and bottom.v_size == top.src_size
+    assert torch.equal(bottom.dev_destination, top.dev_source)  # layer chaining invariant
+    deg = np.diff(co.astype(np.int64))
+    for lay, f in ((top, 25), (bottom, 10)):
+        lens = np.diff(u32(lay.dev_column_offset).astype(np.int64))
+        assert np.array_equal(lens, np.minimum(deg[u32(lay.dev_destination)], f))
+        src = u32(lay.dev_source).astype(np.int64)
+        assert (np.diff(src) > 0).all()  # ascending, unique
+        assert np.array_equal(np.unique(u32(lay.dev_sample_ans)), src)  # exactly the sampled set
+        assert np.array_equal(src[u32(lay.dev_row_indices)], u32(lay.dev_sample_ans))
+        ro, ci, c2c = u32(lay.dev_row_offset), u32(lay.dev_column_indices), u32(lay.dev_csr_to_csc)
+        assert ro[-1] == lay.e_size and np.array_equal(np.sort(c2c), np.arange(lay.e_size, dtype=np.uint32))
+        assert np.array_equal(u32(lay.dev_row_indices)[c2c], np.repeat(np.arange(lay.src_size), np.diff(ro.astype(np.int64))))
+        e_dst = np.repeat(np.arange(lay.v_size), lens)
+        assert np.array_equal(ci, e_dst[c2c])
+        for s in np.nonzero(np.diff(ro.astype(np.int64)) > 1)[0][:2000]:
+            assert (np.diff(c2c[ro[s]:ro[s + 1]].astype(np.int64)) > 0).all()  # stable order inside a row
+        assert np.array_equal(f32(lay.dev_edge_weight_backward), f32(lay.dev_edge_weight_forward)[c2c])
+    # gather + aggregate identities on the bottom layer at F=602
+    table = torch.randn((V, F), device="cuda")
+    x0 = torch.empty((bottom.src_size, F), device="cuda")
+    sampler.load_feature_gpu(cs, sg, x0, table)
+    assert torch.equal(x0, table[bottom.dev_source.long()])
+    op = nts.SingleGPUAllSampleGraphOp(sg, 1, cs)
+    y = op.forward(x0)
+    # checksum of checksums against an independent fp64 formulation
+    w = bottom.dev_edge_weight_forward.double()
+    e_dst = torch.repeat_interleave(torch.arange(bottom.v_size, device="cuda"), torch.from_numpy(np.diff(u32(bottom.dev_column_offset).astype(np.int64))).cuda())
+    ref = torch.zeros((bottom.v_size, F), dtype=torch.float64, device="cuda")
+    ref.index_add_(0, e_dst, x0.double()[bottom.dev_row_indices.long()] * w[:, None])
+    torch.testing.assert_close(y.double(), ref, rtol=1e-5, atol=1e-5)
+    # linearity: A(2x + z) = 2A(x) + A(z)
+    z = torch.randn_like(x0)
+    torch.testing.assert_close(op.forward(2 * x0 + z), 2 * y + op.forward(z), rtol=1e-4, atol=1e-4)
+    # adjointness: <A x, g> = <x, A^T g>
+    gy = torch.randn_like(y)
+    gx = op.backward(gy)
+    lhs, rhs = (y.double() * gy.double()).sum(), (x0.double() * gx.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-6 * max(1.0, abs(float(lhs)))
+    refb = torch.zeros((bottom.src_size, F), dtype=torch.float64, device="cuda")
+    refb.index_add_(0, bottom.dev_row_indices.long(), gy.double()[e_dst] * w[:, None])
+    torch.testing.assert_close(gx.double(), refb, rtol=1e-5, atol=1e-5)
