@@ -91,13 +91,16 @@ const char *nb_last_error(void); /* thread-local, valid until the next failing c
 int nb_device_count(int *count);
 
 /* ---- context: class Cuda_Stream (cuda/ntsCUDA.hpp:177-199; cuda/ntsCUDAGraphOP.cu:203-262) ----
- * nb_ctx_create      <- Cuda_Stream::Cuda_Stream()     (creates a non-blocking stream)
+ * nb_ctx_create      <- Cuda_Stream::Cuda_Stream()     (adopt_stream == 0: creates a non-blocking stream;
+ *                       otherwise runs on `cuda_stream` as given -- NULL is then the legacy default
+ *                       stream -- which is how the toolkits wrap torch's pool streams,
+ *                       toolkits/GCN_SAMPLE_GPU.hpp:444-466)
  * nb_ctx_set_stream  <- Cuda_Stream::setNewStream()    (adopts a caller stream; unlike the
  *                       reference the previous own stream is destroyed only if we made it)
  * nb_ctx_stream      <- Cuda_Stream::getStream()
  * nb_ctx_synchronize <- Cuda_Stream::CUDA_DEVICE_SYNCHRONIZE() (stream synchronise)
  * nb_ctx_destroy     <- Cuda_Stream::destory_Stream() */
-int nb_ctx_create(int device, void *cuda_stream_or_null, nb_ctx **out);
+int nb_ctx_create(int device, void *cuda_stream, int adopt_stream, nb_ctx **out);
 int nb_ctx_destroy(nb_ctx *ctx);
 int nb_ctx_set_stream(nb_ctx *ctx, void *cuda_stream);
 void *nb_ctx_stream(nb_ctx *ctx);
@@ -169,6 +172,12 @@ int nb_sampler_sample(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, in
 int nb_sampler_replay(nb_sampler *s, const uint32_t *seeds_host, uint32_t n_seeds, const uint32_t *const *sample_ans_host,
                       const uint32_t *n_edges_host, int weight_type, nb_layer_view *views_out);
 int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out);
+/* Device addresses of layer sizes (and the arena capacities that bound them), for the *_dyn entry points below:
+ * kernels that consume a sampled layer read their extents from device memory, so sampling, gather and
+ * aggregation of a mini-batch can be enqueued back to back with no host synchronisation in between
+ * (the reference synchronises after get_co, after traverse and after every gather). */
+int nb_sampler_sizes_dev(nb_sampler *s, int layer, const uint32_t **n_dst_dev, const uint32_t **n_edges_dev,
+                         const uint32_t **n_src_dev, uint32_t *cap_dst, uint32_t *cap_edges, uint32_t *cap_src);
 
 /* ---- feature / label gather ----------------------------------------------------------------
  * nb_gather_rows        <- Cuda_Stream::zero_copy_feature_move_gpu (cuda/ntsCUDA.hpp:370-374): out[i,:] = table[ids[i],:].
@@ -185,6 +194,8 @@ int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out);
  * nb_row_override2      <- Cuda_Stream::dev_load_share_embedding_and_feature (:521-525): two tensors at once. */
 int nb_gather_rows(nb_ctx *ctx, float *out, const float *table, const uint32_t *ids_dev, uint32_t n_rows,
                    uint32_t feature_size, uint32_t table_pitch, uint32_t out_pitch);
+int nb_gather_rows_dyn(nb_ctx *ctx, float *out, const float *table, const uint32_t *ids_dev, const uint32_t *n_rows_dev,
+                       uint32_t max_rows, uint32_t feature_size, uint32_t table_pitch, uint32_t out_pitch);
 int nb_gather_rows_cached(nb_ctx *ctx, float *out, const float *cold_table, uint32_t cold_pitch, const float *cache_table,
                           uint32_t cache_pitch, const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev,
                           uint32_t n_rows, uint32_t feature_size, uint32_t out_pitch, uint32_t *hit_count_dev_or_null);
@@ -227,6 +238,13 @@ int nb_aggregate_csc_fwd(nb_ctx *ctx, const float *input, float *output, const f
 int nb_aggregate_csr_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
                          const uint32_t *row_offset, const uint32_t *column_indices, uint32_t n_src, uint32_t n_dst,
                          uint32_t feature_size);
+/* same operators with the row count read from device memory and explicit row pitches (in floats) */
+int nb_aggregate_csc_fwd_dyn(nb_ctx *ctx, const float *input, float *output, const float *weight_forward,
+                             const uint32_t *row_indices, const uint32_t *column_offset, const uint32_t *n_dst_dev,
+                             uint32_t max_dst, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch);
+int nb_aggregate_csr_bwd_dyn(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
+                             const uint32_t *row_offset, const uint32_t *column_indices, const uint32_t *n_src_dev,
+                             uint32_t max_src, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch);
 int nb_aggregate_push_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight, const uint32_t *row_indices,
                           const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src, uint32_t feature_size);
 

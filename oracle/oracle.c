@@ -100,7 +100,11 @@ void orc_sample_layer(const vid_t *destination, vid_t n_dst, const vid_t *column
     vid_t num = column_offset[i + 1] - column_offset[i];
     vid_t *out = sample_ans + column_offset[i];
     if (fanout >= 0 && nbr > (vid_t)fanout && num > 0) {
-      uint64_t s = seed ^ ((uint64_t)i * 0x9e3779b97f4a7c15ull);
+      /* independent stream per dst slot: hash (seed, i) first -- consecutive splitmix64 states differ by
+       * the golden-ratio increment, so seeding with seed + i*increment would make the streams shifted copies */
+      uint64_t t = seed ^ ((uint64_t)i * 0xd6e8feb86659fd93ull);
+      uint64_t s = splitmix64(&t);
+      s ^= splitmix64(&t) << 1;
       vid_t have = 0;
       vid_t *pos = (vid_t *)malloc(sizeof(vid_t) * num);
       while (have < num) {

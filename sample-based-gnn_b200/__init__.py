@@ -50,15 +50,22 @@ def _view(address, n, kind, device, owner):
 class Cuda_Stream:
     """cuda/ntsCUDA.hpp:177-595. One per (device, pipeline slot); all work is ordered on `stream`."""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, adopt=None):
+        """stream=None: own non-blocking stream (the reference's default ctor). A torch.cuda.Stream or a raw
+        cudaStream_t handle is adopted (handle 0 = the legacy default stream needs adopt=True)."""
         h = C.c_void_p()
-        check(lib().nb_ctx_create(int(device), ptr(stream), C.byref(h)))
+        if hasattr(stream, "cuda_stream"):
+            stream, adopt = stream.cuda_stream, True
+        if adopt is None:
+            adopt = stream is not None
+        check(lib().nb_ctx_create(int(device), ptr(stream) or None, 1 if adopt else 0, C.byref(h)))
         self._h = h
         self.device = torch.device("cuda", int(device))
 
     @classmethod
     def on_torch_stream(cls, device=0):
-        return cls(device, torch.cuda.current_stream(device).cuda_stream)
+        """ordered with torch's current stream, as the toolkits do (setCurrentCUDAStream + setNewStream)"""
+        return cls(device, torch.cuda.current_stream(device))
 
     def __del__(self):
         try:

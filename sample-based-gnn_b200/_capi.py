@@ -38,7 +38,7 @@ _SIGS = {
     "nb_abi_version": (I32, []),
     "nb_last_error": (C.c_char_p, []),
     "nb_device_count": (I32, [C.POINTER(I32)]),
-    "nb_ctx_create": (I32, [I32, P, C.POINTER(P)]),
+    "nb_ctx_create": (I32, [I32, P, I32, C.POINTER(P)]),
     "nb_ctx_destroy": (I32, [P]),
     "nb_ctx_set_stream": (I32, [P, P]),
     "nb_ctx_stream": (P, [P]),
@@ -61,7 +61,11 @@ _SIGS = {
     "nb_sampler_sample": (I32, [P, P, U32, I32, U64, U64, I32, P, U32, C.POINTER(LayerView), I32]),
     "nb_sampler_replay": (I32, [P, P, U32, C.POINTER(P), C.POINTER(U32), I32, C.POINTER(LayerView)]),
     "nb_sampler_layer": (I32, [P, I32, C.POINTER(LayerView)]),
+    "nb_sampler_sizes_dev": (I32, [P, I32, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(U32), C.POINTER(U32), C.POINTER(U32)]),
     "nb_gather_rows": (I32, [P, P, P, P, U32, U32, U32, U32]),
+    "nb_gather_rows_dyn": (I32, [P, P, P, P, P, U32, U32, U32, U32]),
+    "nb_aggregate_csc_fwd_dyn": (I32, [P, P, P, P, P, P, P, U32, U32, U32, U32]),
+    "nb_aggregate_csr_bwd_dyn": (I32, [P, P, P, P, P, P, P, U32, U32, U32, U32]),
     "nb_gather_rows_cached": (I32, [P, P, P, U32, P, U32, P, P, U32, U32, U32, P]),
     "nb_gather_labels": (I32, [P, P, P, P, U32]),
     "nb_row_override": (I32, [P, P, P, P, P, P, U32, U32, U32]),

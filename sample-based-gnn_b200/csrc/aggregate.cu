@@ -23,11 +23,12 @@ constexpr int AGG_THREADS = 256;
 template <int VEC, int CHUNK>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
-                 const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows, uint32_t nvec,
-                 uint64_t pitch) {
+                 const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
+                 const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch) {
   const unsigned lane = lane_id();
   const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
   const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
+  if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
   for (unsigned r = warp; r < n_rows; r += warps) {
     const uint32_t beg = offsets[r], end = offsets[r + 1];
     for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {  // one pass unless the row is wider than 32*CHUNK vectors
@@ -70,7 +71,7 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
           }
         }
       }
-      float *o = out + (uint64_t)r * pitch;
+      float *o = out + (uint64_t)r * out_pitch;
 #pragma unroll
       for (int c = 0; c < CHUNK; c++) {
         const unsigned k = c0 + c * 32 + lane;
@@ -124,14 +125,15 @@ k_push(const float *__restrict__ in, float *__restrict__ out, const float *__res
 
 template <int VEC>
 static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
-                          const uint32_t *offsets, uint32_t n_rows, uint32_t F) {
+                          const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
+                          uint64_t out_pitch) {
   const uint32_t nvec = F / VEC;
   const unsigned grid = nb_grid(n_rows, AGG_THREADS / 32, 8);
   const uint32_t per_lane = (nvec + 31) / 32;
 #define NB_SEG(C)                                                                                              \
   do {                                                                                                         \
     if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
-    else k_segment_reduce<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
+    else k_segment_reduce<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch); \
   } while (0)
   if (per_lane <= 1) NB_SEG(1);
   else if (per_lane <= 2) NB_SEG(2);
@@ -146,12 +148,15 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
 }
 
 static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
-                       const uint32_t *offsets, uint32_t n_rows, uint32_t F) {
+                       const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev = nullptr,
+                       uint64_t in_pitch = 0, uint64_t out_pitch = 0) {
   if (n_rows == 0) return NB_OK;
-  int vec = nb_pick_vec(F, in, F, out, F);
-  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, F);
-  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, F);
-  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, F);
+  if (!in_pitch) in_pitch = F;
+  if (!out_pitch) out_pitch = F;
+  int vec = nb_pick_vec(F, in, in_pitch, out, out_pitch);
+  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch);
+  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch);
+  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch);
 }
 
 extern "C" {
@@ -159,7 +164,7 @@ extern "C" {
 int nb_aggregate_csc_fwd(nb_ctx *ctx, const float *input, float *output, const float *weight_forward,
                          const uint32_t *row_indices, const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src,
                          uint32_t feature_size) {
-  NB_REQUIRE(ctx && (n_dst == 0 || (input && output && row_indices && column_offset)), NB_ERR_ARG, "nb_aggregate_csc_fwd: NULL argument");
+  NB_REQUIRE(ctx && (n_dst == 0 || ((input || n_src == 0) && output && column_offset)), NB_ERR_ARG, "nb_aggregate_csc_fwd: NULL argument");
   NB_REQUIRE(feature_size > 0, NB_ERR_ARG, "feature_size must be > 0");
   (void)n_src;
   NB_GUARD(ctx);
@@ -169,11 +174,30 @@ int nb_aggregate_csc_fwd(nb_ctx *ctx, const float *input, float *output, const f
 int nb_aggregate_csr_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
                          const uint32_t *row_offset, const uint32_t *column_indices, uint32_t n_src, uint32_t n_dst,
                          uint32_t feature_size) {
-  NB_REQUIRE(ctx && (n_src == 0 || (input && output && row_offset && column_indices)), NB_ERR_ARG, "nb_aggregate_csr_bwd: NULL argument");
+  NB_REQUIRE(ctx && (n_src == 0 || ((input || n_dst == 0) && output && row_offset)), NB_ERR_ARG, "nb_aggregate_csr_bwd: NULL argument");
   NB_REQUIRE(feature_size > 0, NB_ERR_ARG, "feature_size must be > 0");
   (void)n_dst;
   NB_GUARD(ctx);
   return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, n_src, feature_size);
+}
+
+// Extents from device memory (nb_sampler_sizes_dev): no host round trip between sampling and aggregation.
+int nb_aggregate_csc_fwd_dyn(nb_ctx *ctx, const float *input, float *output, const float *weight_forward,
+                             const uint32_t *row_indices, const uint32_t *column_offset, const uint32_t *n_dst_dev,
+                             uint32_t max_dst, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch) {
+  NB_REQUIRE(ctx && input && output && row_indices && column_offset && n_dst_dev, NB_ERR_ARG, "nb_aggregate_csc_fwd_dyn: NULL argument");
+  NB_REQUIRE(feature_size > 0 && input_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
+  NB_GUARD(ctx);
+  return run_segment(ctx, false, input, output, weight_forward, row_indices, column_offset, max_dst, feature_size, n_dst_dev, input_pitch, output_pitch);
+}
+
+int nb_aggregate_csr_bwd_dyn(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
+                             const uint32_t *row_offset, const uint32_t *column_indices, const uint32_t *n_src_dev,
+                             uint32_t max_src, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch) {
+  NB_REQUIRE(ctx && input && output && row_offset && column_indices && n_src_dev, NB_ERR_ARG, "nb_aggregate_csr_bwd_dyn: NULL argument");
+  NB_REQUIRE(feature_size > 0 && input_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
+  NB_GUARD(ctx);
+  return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, max_src, feature_size, n_src_dev, input_pitch, output_pitch);
 }
 
 int nb_aggregate_push_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight, const uint32_t *row_indices,

@@ -41,7 +41,7 @@ int nb_device_count(int *count) {
   return NB_OK;
 }
 
-int nb_ctx_create(int device, void *cuda_stream_or_null, nb_ctx **out) {
+int nb_ctx_create(int device, void *cuda_stream, int adopt_stream, nb_ctx **out) {
   NB_REQUIRE(out, NB_ERR_ARG, "out is NULL");
   *out = nullptr;
   int n = 0;
@@ -62,8 +62,8 @@ int nb_ctx_create(int device, void *cuda_stream_or_null, nb_ctx **out) {
     return NB_ERR_UNSUPPORTED;
   }
   c->sm_count = prop.multiProcessorCount;
-  if (cuda_stream_or_null) {
-    c->stream = (cudaStream_t)cuda_stream_or_null;
+  if (adopt_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
     c->own_stream = false;
   } else {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {

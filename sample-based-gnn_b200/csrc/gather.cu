@@ -22,18 +22,24 @@ struct nb_table {
 constexpr int GATHER_THREADS = 256;
 
 // MODE 0: plain table. MODE 1: hot/cold (cache_map slot != -1 -> cache table). MODE 2: sharded table (v % n, v / n).
-template <int VEC, int MODE>
+// CHUNK = vectors per lane held in registers: a row of up to 32*CHUNK vectors is fetched with CHUNK independent
+// requests per lane before the first store (602 floats = 301 float2 -> CHUNK 10, 2.4 KB in flight per warp);
+// the next row's id is fetched one iteration ahead so the id -> row dependency is off the critical path.
+template <int VEC, int CHUNK, int MODE>
 __global__ void __launch_bounds__(GATHER_THREADS)
 k_gather_rows(float *__restrict__ out, const float *__restrict__ table, uint64_t table_pitch, const float *__restrict__ cache,
               uint64_t cache_pitch, const uint32_t *__restrict__ cache_map, const float *const *__restrict__ shards,
-              uint32_t n_shards, const uint32_t *__restrict__ ids, uint32_t n_rows, uint32_t nvec, uint64_t out_pitch,
-              uint32_t *hit_count) {
+              uint32_t n_shards, const uint32_t *__restrict__ ids, uint32_t n_rows, const uint32_t *__restrict__ n_rows_dev,
+              uint32_t nvec, uint64_t out_pitch, uint32_t *hit_count) {
   const unsigned lane = lane_id();
   const unsigned warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
   const unsigned warps = (gridDim.x * GATHER_THREADS) >> 5;
+  if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
   unsigned hits = 0;
+  uint32_t v_next = warp < n_rows ? ids[warp] : 0;
   for (unsigned i = warp; i < n_rows; i += warps) {
-    const uint32_t v = ids[i];
+    const uint32_t v = v_next;
+    if (i + warps < n_rows) v_next = ids[i + warps];
     const float *src;
     if (MODE == 0) src = table + (uint64_t)v * table_pitch;
     else if (MODE == 1) {
@@ -42,19 +48,18 @@ k_gather_rows(float *__restrict__ out, const float *__restrict__ table, uint64_t
       else src = table + (uint64_t)v * table_pitch;
     } else src = shards[v % n_shards] + (uint64_t)(v / n_shards) * table_pitch;
     float *dst = out + (uint64_t)i * out_pitch;
-    // 4 independent vector requests per lane per step
-    unsigned k = lane;
-    for (; k + 96 < nvec; k += 128) {
-      Vec<VEC> a, b, c, d;
-      a.load(src + (uint64_t)k * VEC); b.load(src + (uint64_t)(k + 32) * VEC);
-      c.load(src + (uint64_t)(k + 64) * VEC); d.load(src + (uint64_t)(k + 96) * VEC);
-      a.store(dst + (uint64_t)k * VEC); b.store(dst + (uint64_t)(k + 32) * VEC);
-      c.store(dst + (uint64_t)(k + 64) * VEC); d.store(dst + (uint64_t)(k + 96) * VEC);
-    }
-    for (; k < nvec; k += 32) {
-      Vec<VEC> a;
-      a.load(src + (uint64_t)k * VEC);
-      a.store(dst + (uint64_t)k * VEC);
+    for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {
+      Vec<VEC> x[CHUNK];
+#pragma unroll
+      for (int c = 0; c < CHUNK; c++) {
+        const unsigned k = c0 + c * 32 + lane;
+        if (k < nvec) x[c].load(src + (uint64_t)k * VEC);
+      }
+#pragma unroll
+      for (int c = 0; c < CHUNK; c++) {
+        const unsigned k = c0 + c * 32 + lane;
+        if (k < nvec) x[c].store(dst + (uint64_t)k * VEC);
+      }
     }
   }
   if (MODE == 1 && hit_count && lane == 0 && hits) atomicAdd(hit_count, hits);
@@ -94,20 +99,30 @@ k_row_override(float *__restrict__ out_a, const float *__restrict__ share_a, uin
   }
 }
 
+template <int VEC, int MODE>
+static int launch_gather_v(nb_ctx *ctx, float *out, const float *table, uint64_t table_pitch, const float *cache, uint64_t cache_pitch,
+                           const uint32_t *cache_map, const float *const *shards, uint32_t n_shards, const uint32_t *ids,
+                           uint32_t n_rows, const uint32_t *n_rows_dev, uint32_t F, uint64_t out_pitch, uint32_t *hit_count) {
+  const uint32_t nvec = F / VEC, per_lane = (nvec + 31) / 32;
+  const unsigned grid = nb_grid(n_rows, GATHER_THREADS / 32, 8);
+#define NB_G(C) k_gather_rows<VEC, C, MODE><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, table, table_pitch, cache, cache_pitch, \
+      cache_map, shards, n_shards, ids, n_rows, n_rows_dev, nvec, out_pitch, hit_count)
+  if (per_lane <= 1) NB_G(1); else if (per_lane <= 2) NB_G(2); else if (per_lane <= 4) NB_G(4);
+  else if (per_lane <= 5) NB_G(5); else if (per_lane <= 8) NB_G(8); else NB_G(10);
+#undef NB_G
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
 template <int MODE>
 static int launch_gather(nb_ctx *ctx, float *out, const float *table, uint64_t table_pitch, const float *cache, uint64_t cache_pitch,
                          const uint32_t *cache_map, const float *const *shards, uint32_t n_shards, const uint32_t *ids,
-                         uint32_t n_rows, uint32_t F, uint64_t out_pitch, uint32_t *hit_count, int vec) {
+                         uint32_t n_rows, uint32_t F, uint64_t out_pitch, uint32_t *hit_count, int vec,
+                         const uint32_t *n_rows_dev = nullptr) {
   if (n_rows == 0) return NB_OK;
-  unsigned grid = nb_grid(n_rows, GATHER_THREADS / 32, 8);
-  if (vec == 4)
-    k_gather_rows<4, MODE><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, F / 4, out_pitch, hit_count);
-  else if (vec == 2)
-    k_gather_rows<2, MODE><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, F / 2, out_pitch, hit_count);
-  else
-    k_gather_rows<1, MODE><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, F, out_pitch, hit_count);
-  NB_LAUNCH_CHECK(ctx);
-  return NB_OK;
+  if (vec == 4) return launch_gather_v<4, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count);
+  if (vec == 2) return launch_gather_v<2, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count);
+  return launch_gather_v<1, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count);
 }
 
 extern "C" {
@@ -119,6 +134,15 @@ int nb_gather_rows(nb_ctx *ctx, float *out, const float *table, const uint32_t *
   NB_GUARD(ctx);
   int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch);
   return launch_gather<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, n_rows, feature_size, out_pitch, nullptr, vec);
+}
+
+int nb_gather_rows_dyn(nb_ctx *ctx, float *out, const float *table, const uint32_t *ids_dev, const uint32_t *n_rows_dev,
+                       uint32_t max_rows, uint32_t feature_size, uint32_t table_pitch, uint32_t out_pitch) {
+  NB_REQUIRE(ctx && out && table && ids_dev && n_rows_dev, NB_ERR_ARG, "nb_gather_rows_dyn: NULL argument");
+  NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && out_pitch >= feature_size, NB_ERR_ARG, "nb_gather_rows_dyn: bad pitch");
+  NB_GUARD(ctx);
+  int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch);
+  return launch_gather<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, max_rows, feature_size, out_pitch, nullptr, vec, n_rows_dev);
 }
 
 int nb_gather_rows_cached(nb_ctx *ctx, float *out, const float *cold_table, uint32_t cold_pitch, const float *cache_table,

@@ -22,6 +22,8 @@
 //   k_scan<RowOp>     : 8S             row_offset
 //   k_csr_fill/k_csr_rows(+long) : 12E + 12E   atomic fill then per-row rank-sort -> stable CSR
 //   k_weights         : 12E + 4E
+#include <stdlib.h>
+
 #include "common.cuh"
 
 struct LayerMeta {  // device resident, one per layer (+1 sentinel)
@@ -37,10 +39,18 @@ struct LayerBuf {
   float *ewf, *ewb;
 };
 
+// Everything that changes from batch to batch lives in device memory so that the kernel
+// arguments are constant and the whole batch can be replayed as one CUDA graph.
+struct BatchParams {
+  uint64_t rng_seed, rng_offset;
+  const uint32_t *omit;  // device, [|V|] or NULL
+  uint32_t n_seeds, weight_type, omit_value, replay;
+  uint32_t epoch, pad[3];
+};
+
 struct ScanWs {
-  unsigned long long *tile_state;
-  unsigned *ticket;
-  unsigned *done;
+  unsigned long long *tile_state;  // one array per scan launch of a batch; entries are tagged with the batch epoch
+  const BatchParams *params;
 };
 
 struct nb_graph {
@@ -63,9 +73,18 @@ struct nb_sampler {
   LayerMeta *meta_host;  // pinned [L+1]
   uint32_t *bitmap, *word_rank;
   uint32_t n_words;
-  ScanWs ws;
+  unsigned long long *tile_states;  // [3 * L][max_tiles]
+  BatchParams *params_dev;
   void *arena;
   uint32_t max_tiles;
+  // host staging ring for (params, seeds): pinned, guarded by events
+  static const int RING = 8;
+  uint8_t *stage[RING];
+  cudaEvent_t stage_done[RING];
+  int stage_next;
+  uint32_t epoch;
+  cudaGraphExec_t graph_exec;
+  bool use_graph;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -78,16 +97,15 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 template <class Op>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
-  __shared__ unsigned s_tile, s_prefix, s_warp[SCAN_THREADS / 32];
+  __shared__ unsigned s_prefix, s_warp[SCAN_THREADS / 32];
   const unsigned n = op.n();
   const unsigned ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) op.total(0);
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  while (true) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(ws.ticket, 1u);
-    __syncthreads();
-    const unsigned tile = s_tile;
-    if (tile >= ntiles) break;
+  // tile state word: [63:34] batch epoch, [33:32] 1 = aggregate, 2 = inclusive prefix, [31:0] value.
+  // The grid never exceeds the number of co-resident blocks, so waiting on a lower tile cannot deadlock.
+  const unsigned long long tag = ((unsigned long long)(ws.params->epoch & 0x3fffffffu)) << 34;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     unsigned v[SCAN_ITEMS], sum = 0;
     const unsigned first = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
@@ -113,19 +131,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
     if (threadIdx.x == 0) {
       unsigned prefix = 0;
       if (tile == 0) {
-        atomicExch(&ws.tile_state[0], (2ull << 32) | block_total);
+        atomicExch(&ws.tile_state[0], tag | (2ull << 32) | block_total);
       } else {
-        atomicExch(&ws.tile_state[tile], (1ull << 32) | block_total);
+        atomicExch(&ws.tile_state[tile], tag | (1ull << 32) | block_total);
         int p = (int)tile - 1;
         while (true) {
           unsigned long long st = *((volatile unsigned long long *)&ws.tile_state[p]);
-          unsigned flag = (unsigned)(st >> 32);
-          if (flag == 0) continue;
+          if ((st >> 34 << 34) != tag) continue;  // not written in this batch yet
+          unsigned flag = (unsigned)(st >> 32) & 3u;
           prefix += (unsigned)st;
           if (flag == 2) break;
           p--;
         }
-        atomicExch(&ws.tile_state[tile], (2ull << 32) | (unsigned long long)(prefix + block_total));
+        atomicExch(&ws.tile_state[tile], tag | (2ull << 32) | (unsigned long long)(prefix + block_total));
       }
       s_prefix = prefix;
     }
@@ -139,35 +157,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
     if (tile == ntiles - 1 && threadIdx.x == 0) op.total(s_prefix + block_total);
     __syncthreads();
   }
-  // self-reset by the last block out
-  __shared__ bool s_last;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(ws.done, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (s_last) {
-    for (unsigned t = threadIdx.x; t < ntiles; t += SCAN_THREADS) ws.tile_state[t] = 0ull;
-    if (threadIdx.x == 0) { *ws.ticket = 0u; *ws.done = 0u; }
-  }
 }
 
 // counts = min(deg, fanout) (fanout -1: deg), 0 for omitted dst; scan -> column_offset; total -> E.
 // Reference: sample_processing_get_co_gpu_kernel[_omit] cuda/ntsCUDATransferKernel.cuh:754-822 and the
 // CPU count lambda core/ntsFastSampler.hpp:1001-1009.
 struct CountOp {
-  const uint32_t *g_col_off, *dst, *omit;
+  const uint32_t *g_col_off, *dst;
+  const BatchParams *params;
   uint32_t *col_off;
   LayerMeta *meta;
-  uint32_t omit_value, cap_edges;
-  int fanout;
+  uint32_t cap_edges;
+  int fanout, bottom;  // omit applies to the bottom layer only (ntsFastSampler.hpp:747-763)
   __device__ unsigned n() const { return meta->n_dst; }
   __device__ unsigned load(unsigned i) const {
     uint32_t d = dst[i];
     uint32_t deg = g_col_off[d + 1] - g_col_off[d];
     uint32_t c = (fanout < 0 || deg < (uint32_t)fanout) ? deg : (uint32_t)fanout;
+    const uint32_t *omit = bottom ? params->omit : nullptr;
     if (omit) {
       uint32_t f = omit[d];
+      const uint32_t omit_value = params->omit_value;
       if (omit_value == 0xffffffffu ? (f != 0xffffffffu) : (f == omit_value)) c = 0;
     }
     return c;
@@ -185,34 +195,39 @@ struct CountOp {
 // order, core/ntsFastSampler.hpp:1062-1083) and initialises the per-src scratch.
 struct BitmapOp {
   const uint32_t *bitmap;
-  uint32_t *word_rank, *source, *row_count, *row_cursor, *src_to_dst;
+  uint32_t *word_rank;
   LayerMeta *meta, *next_meta;
   uint32_t n_words, cap_src;
   __device__ unsigned n() const { return n_words; }
   __device__ unsigned load(unsigned w) const { return __popc(bitmap[w]); }
-  __device__ void store(unsigned w, unsigned excl, unsigned cnt) const {
-    word_rank[w] = excl;
-    if (cnt == 0 || meta->err) return;
-    uint32_t bits = bitmap[w];
-    unsigned k = excl;
-    while (bits) {
-      unsigned b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      if (k < cap_src) {
-        source[k] = w * 32u + b;
-        row_count[k] = 0;
-        row_cursor[k] = 0;
-        if (src_to_dst) src_to_dst[k] = 0xffffffffu;
-      }
-      k++;
-    }
-  }
+  __device__ void store(unsigned w, unsigned excl, unsigned) const { word_rank[w] = excl; }
   __device__ void total(unsigned t) const {
     meta->n_src = t;
     if (t > cap_src) meta->err = 2;
     next_meta->n_dst = t;
   }
 };
+
+// one thread per vertex bit: source[rank] = v for every marked v, rank = word prefix + popcount below.
+// A warp covers one bitmap word, so the writes of a warp are consecutive.
+__global__ void __launch_bounds__(256)
+k_emit_sources(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ word_rank, uint32_t *__restrict__ source,
+               uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor, uint32_t *__restrict__ src_to_dst,
+               const LayerMeta *meta, uint32_t n_words) {
+  if (meta->err) return;
+  const unsigned lane = lane_id();
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+    const uint32_t bits = bitmap[w];
+    if (bits & (1u << lane)) {
+      const uint32_t k = word_rank[w] + __popc(bits & ((1u << lane) - 1u));
+      source[k] = w * 32u + lane;
+      row_count[k] = 0;
+      row_cursor[k] = 0;
+      if (src_to_dst) src_to_dst[k] = 0xffffffffu;
+    }
+  }
+}
 
 struct RowOp {
   const uint32_t *row_count;
@@ -224,10 +239,10 @@ struct RowOp {
   __device__ void total(unsigned t) const { row_offset[meta->err ? 0u : meta->n_src] = t; }
 };
 
-__global__ void k_init_meta(LayerMeta *meta, int L, uint32_t n_seeds) {
+__global__ void k_init_meta(LayerMeta *meta, int L, const BatchParams *params) {
   int i = threadIdx.x;
   if (i <= L) {
-    meta[i].n_dst = i == 0 ? n_seeds : 0;
+    meta[i].n_dst = i == 0 ? params->n_seeds : 0;
     meta[i].n_edges = 0; meta[i].n_src = 0; meta[i].err = 0; meta[i].long_rows = 0;
   }
 }
@@ -248,10 +263,13 @@ constexpr int SAMPLE_WARPS = 8;
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32)
 k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_row_idx, const uint32_t *__restrict__ dst,
          const uint32_t *__restrict__ col_off, uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst,
-         uint32_t *__restrict__ bitmap, const LayerMeta *meta, int fanout, uint64_t key, uint32_t layer, uint32_t rng_offset,
-         int merge, int replay, int hash_slots) {
+         uint32_t *__restrict__ bitmap, const LayerMeta *meta, int fanout, const BatchParams *params, uint32_t layer,
+         int merge, int hash_slots) {
   extern __shared__ uint32_t s_hash[];
   if (meta->err) return;
+  const uint64_t key = params->rng_seed ^ (params->rng_offset >> 32 << 32);
+  const uint32_t rng_offset = (uint32_t)params->rng_offset;
+  const int replay = params->replay;
   const unsigned n_dst = meta->n_dst;
   const unsigned lane = lane_id();
   const unsigned warps = gridDim.x * SAMPLE_WARPS;
@@ -343,18 +361,36 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
 // global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
 // Reference: sample_processing_update_ri_gpu_kernel cuda/ntsCUDATransferKernel.cuh:1136-1150,
 // sample_set_dst_local :1189-1196; CPU :1085-1099.
+__device__ __forceinline__ float edge_weight(uint32_t od, uint32_t id, uint32_t col_len, int weight_type) {
+  float w = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn((float)od), __fsqrt_rn((float)id)));
+  if (weight_type == NB_WEIGHT_MEAN) w = __fdiv_rn(w, (float)id);
+  else if (weight_type == NB_WEIGHT_MEAN_SAMPLED) w = __fdiv_rn(w, (float)col_len);
+  return w;
+}
+
+// fuse_weights: edge weights from the graph's degree arrays are computed in the same pass (UP_DEGREE needs the
+// finished histogram and runs k_weights afterwards). Weights: get_weight / get_mean_weight
+// cuda/ntsCUDATransferKernel.cuh:294-342, CPU nts_norm_degree core/ntsBaseOp.hpp:652-657. (float)sqrt((double)u32) ==
+// sqrtf((float)u32) for u32 < 2^24 (sqrt double rounding is innocuous at 53 >= 2*24+2 bits): bit-identical to the CPU.
 __global__ void __launch_bounds__(256)
 k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ bitmap,
           const uint32_t *__restrict__ word_rank, uint32_t *__restrict__ row_count, const uint32_t *__restrict__ dst,
-          uint32_t *__restrict__ dst_local_id, uint32_t *__restrict__ src_to_dst, const LayerMeta *meta, int histogram) {
+          uint32_t *__restrict__ dst_local_id, uint32_t *__restrict__ src_to_dst, const LayerMeta *meta, int histogram,
+          int fuse_weights, float *__restrict__ ewf, const uint32_t *__restrict__ edge_dst, const uint32_t *__restrict__ col_off,
+          const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg, const BatchParams *params) {
   if (meta->err) return;
   const unsigned E = meta->n_edges, nd = meta->n_dst;
+  const int weight_type = params->weight_type;
   const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
   for (unsigned e = tid; e < E; e += stride) {
     uint32_t v = sample_ans[e];
     uint32_t local = word_rank[v >> 5] + __popc(bitmap[v >> 5] & ((1u << (v & 31)) - 1u));
     row_indices[e] = local;
     if (histogram) atomicAdd(&row_count[local], 1u);
+    if (fuse_weights && weight_type != NB_WEIGHT_NONE) {
+      const uint32_t j = edge_dst[e];
+      ewf[e] = edge_weight(out_deg[v], in_deg[dst[j]], col_off[j + 1] - col_off[j], weight_type);
+    }
   }
   if (dst_local_id)
     for (unsigned j = tid; j < nd; j += stride) {
@@ -365,26 +401,19 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
     }
 }
 
-// Edge weights in CSC order. Reference: get_weight / get_mean_weight cuda/ntsCUDATransferKernel.cuh:294-342,
-// CPU nts_norm_degree core/ntsBaseOp.hpp:652-657. (float)sqrt((double)u32) == sqrtf((float)u32) for
-// u32 < 2^24 (sqrt double rounding is innocuous at 53 >= 2*24+2 bits), so this is bit-identical to the CPU.
+// UP_DEGREE weights: sampled degrees (out = CSR row length, in = CSC column length), core/FullyRepGraph.hpp:189-207.
 __global__ void __launch_bounds__(256)
-k_weights(float *__restrict__ ewf, const uint32_t *__restrict__ sample_ans, const uint32_t *__restrict__ row_indices,
-          const uint32_t *__restrict__ edge_dst, const uint32_t *__restrict__ dst, const uint32_t *__restrict__ col_off,
-          const uint32_t *__restrict__ row_count, const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg,
-          const LayerMeta *meta, int weight_type, int up_degree) {
+k_weights_sampled(float *__restrict__ ewf, const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ edge_dst,
+                  const uint32_t *__restrict__ col_off, const uint32_t *__restrict__ row_count, const LayerMeta *meta,
+                  const BatchParams *params) {
   if (meta->err) return;
+  const int weight_type = params->weight_type;
+  if (weight_type == NB_WEIGHT_NONE) return;
   const unsigned E = meta->n_edges;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-    uint32_t j = edge_dst[e];
-    uint32_t col_len = col_off[j + 1] - col_off[j];
-    uint32_t od, id;
-    if (up_degree) { od = row_count[row_indices[e]]; id = col_len; }
-    else { od = out_deg[sample_ans[e]]; id = in_deg[dst[j]]; }
-    float w = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn((float)od), __fsqrt_rn((float)id)));
-    if (weight_type == NB_WEIGHT_MEAN) w = __fdiv_rn(w, (float)id);
-    else if (weight_type == NB_WEIGHT_MEAN_SAMPLED) w = __fdiv_rn(w, (float)col_len);
-    ewf[e] = w;
+    const uint32_t j = edge_dst[e];
+    const uint32_t col_len = col_off[j + 1] - col_off[j];
+    ewf[e] = edge_weight(row_count[row_indices[e]], col_len, col_len, weight_type);
   }
 }
 
@@ -413,8 +442,9 @@ __device__ __forceinline__ void csr_emit(uint32_t pos, uint32_t e, uint32_t *col
 __global__ void __launch_bounds__(256)
 k_csr_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
            uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
-           const float *__restrict__ ewf, uint32_t *__restrict__ long_rows, LayerMeta *meta) {
+           const float *__restrict__ ewf, uint32_t *__restrict__ long_rows, LayerMeta *meta, const BatchParams *params) {
   if (meta->err) return;
+  if (params->weight_type == NB_WEIGHT_NONE) ewb = nullptr;
   const unsigned S = meta->n_src;
   for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
     const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
@@ -436,8 +466,10 @@ k_csr_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__
 __global__ void __launch_bounds__(256)
 k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
                 uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
-                const float *__restrict__ ewf, const uint32_t *__restrict__ long_rows, const LayerMeta *meta) {
+                const float *__restrict__ ewf, const uint32_t *__restrict__ long_rows, const LayerMeta *meta,
+                const BatchParams *params) {
   if (meta->err) return;
+  if (params->weight_type == NB_WEIGHT_NONE) ewb = nullptr;
   const unsigned n_long = meta->long_rows;
   const unsigned lane = lane_id();
   for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_long; w += (gridDim.x * blockDim.x) >> 5) {
@@ -540,9 +572,9 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   memset(s, 0, sizeof(*s));
   s->ctx = ctx; s->g = g; s->L = n_layers; s->flags = flags; s->max_batch = max_batch;
   const bool merge = flags & NB_SAMPLER_MERGE_SRC_DST;
-  // capacities: V_0 = batch, E_i <= V_i * f_i, S_i <= E_i (+V_i when merged), all bounded by the graph
-  uint64_t cap_dst = max_batch < g->V ? max_batch : g->V;
-  size_t words = 0;  // arena size in 4-byte words
+  // capacities: V_0 = batch, E_i <= V_i * f_i, S_i <= E_i (+V_i when merged), bounded by the graph
+  uint64_t cap_dst = max_batch;  // seeds may repeat, so |V| does not bound layer 0
+  size_t words = 0;              // arena size in 4-byte words
   auto take = [&](size_t n) { size_t at = words; words += (n + 31) & ~(size_t)31; return at; };
   struct Off { size_t destination, column_offset, sample_ans, row_indices, edge_dst, source, row_offset, row_count, row_cursor,
                column_indices, csr_tmp, csr_to_csc, long_rows, dst_local_id, src_to_dst, ewf, ewb; } off[NB_MAX_LAYERS];
@@ -552,10 +584,14 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     uint64_t per = fanout[i] < 0 ? g->max_in_degree : (uint64_t)fanout[i];
     uint64_t cap_e = cap_dst * per;
     if (fanout[i] < 0 && max_edges_hint && max_edges_hint < cap_e) cap_e = max_edges_hint;
-    if (cap_e > g->E) cap_e = g->E;
+    if (i > 0 && cap_e > g->E) cap_e = g->E;  // dst of layers > 0 are unique vertices
     uint64_t cap_s = cap_e + (merge ? cap_dst : 0);
     if (cap_s > g->V) cap_s = g->V;
-    NB_REQUIRE(cap_e < 0x7fffffffull, NB_ERR_CAPACITY, "layer %d edge capacity %llu exceeds 2^31", i, (unsigned long long)cap_e);
+    if (cap_e >= 0x7fffffffull) {
+      delete s;
+      nb_set_error("layer %d edge capacity %llu exceeds 2^31", i, (unsigned long long)cap_e);
+      return NB_ERR_CAPACITY;
+    }
     LayerBuf &b = s->lay[i];
     b.cap_dst = (uint32_t)cap_dst; b.cap_edges = (uint32_t)cap_e; b.cap_src = (uint32_t)cap_s;
     Off &o = off[i];
@@ -575,8 +611,9 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   if (s->n_words > max_items) max_items = s->n_words;
   s->max_tiles = (uint32_t)((max_items + SCAN_TILE - 1) / SCAN_TILE) + 1;
   size_t o_bitmap = take(s->n_words + 1), o_rank = take(s->n_words + 1);
-  size_t o_state = take((size_t)s->max_tiles * 2), o_ctr = take(32);
+  size_t o_state = take((size_t)s->max_tiles * 2 * 3 * n_layers);
   size_t o_meta = take((sizeof(LayerMeta) / 4) * (NB_MAX_LAYERS + 1));
+  size_t o_params = take(sizeof(BatchParams) / 4 + 8);
   size_t bytes = words * 4;
   size_t free_b = 0, total_b = 0;
   NB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -601,11 +638,17 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   }
   for (int i = 1; i < n_layers; i++) s->lay[i].destination = s->lay[i - 1].source;  // layer chaining (FullyRepGraph.hpp:309)
   s->bitmap = base + o_bitmap; s->word_rank = base + o_rank;
-  s->ws.tile_state = (unsigned long long *)(base + o_state);
-  s->ws.ticket = base + o_ctr; s->ws.done = base + o_ctr + 1;
+  s->tile_states = (unsigned long long *)(base + o_state);
   s->meta_dev = (LayerMeta *)(base + o_meta);
+  s->params_dev = (BatchParams *)(base + o_params);
   NB_CUDA(cudaHostAlloc(&s->meta_host, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1), cudaHostAllocDefault));
   memset(s->meta_host, 0, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1));
+  for (int r = 0; r < nb_sampler::RING; r++) {
+    NB_CUDA(cudaHostAlloc(&s->stage[r], sizeof(BatchParams) + (size_t)max_batch * 4, cudaHostAllocDefault));
+    NB_CUDA(cudaEventCreateWithFlags(&s->stage_done[r], cudaEventDisableTiming));
+  }
+  const char *ng = getenv("NB_NO_GRAPH");
+  s->use_graph = !(ng && ng[0] == '1');
   NB_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = s;
   return NB_OK;
@@ -614,6 +657,9 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
 int nb_sampler_destroy(nb_sampler *s) {
   if (!s) return NB_OK;
   DeviceGuard guard(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  for (int r = 0; r < nb_sampler::RING; r++) { cudaFreeHost(s->stage[r]); cudaEventDestroy(s->stage_done[r]); }
   cudaFree(s->arena);
   cudaFreeHost(s->meta_host);
   delete s;
@@ -633,56 +679,109 @@ static void fill_view(nb_sampler *s, int i, nb_layer_view *v) {
   v->dst_local_id = merge ? b.dst_local_id : nullptr; v->src_to_dst = merge ? b.src_to_dst : nullptr;
 }
 
-// enqueue every kernel of one mini-batch; `replay` != 0 when sample_ans was uploaded by the caller
-static int enqueue_batch(nb_sampler *s, uint32_t n_seeds, uint64_t rng_seed, uint64_t rng_offset, int weight_type,
-                         const uint32_t *omit, uint32_t omit_value, int replay) {
+// Every kernel of one mini-batch. All arguments are constants of the sampler (per-batch values come from
+// params_dev), so the sequence is captured once into a CUDA graph and replayed.
+static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
   nb_ctx *ctx = s->ctx;
   nb_graph *g = s->g;
-  cudaStream_t st = ctx->stream;
   const bool merge = s->flags & NB_SAMPLER_MERGE_SRC_DST, up = s->flags & NB_SAMPLER_UP_DEGREE,
              csr = s->flags & NB_SAMPLER_BUILD_CSR;
-  k_init_meta<<<1, 32, 0, st>>>(s->meta_dev, s->L, n_seeds);
+  const BatchParams *pp = s->params_dev;
+  k_init_meta<<<1, 32, 0, st>>>(s->meta_dev, s->L, pp);
   NB_LAUNCH_CHECK(ctx);
   for (int i = 0; i < s->L; i++) {
     LayerBuf &b = s->lay[i];
     LayerMeta *m = s->meta_dev + i;
+    ScanWs ws0{s->tile_states + (size_t)(3 * i + 0) * s->max_tiles, pp}, ws1{s->tile_states + (size_t)(3 * i + 1) * s->max_tiles, pp},
+        ws2{s->tile_states + (size_t)(3 * i + 2) * s->max_tiles, pp};
     NB_CUDA(cudaMemsetAsync(s->bitmap, 0, (size_t)(s->n_words + 1) * 4, st));
-    CountOp cop{g->col_off, b.destination, (i == s->L - 1) ? omit : nullptr, b.column_offset, m, omit_value, b.cap_edges, s->fanout[i]};
-    k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, s->ws);
+    CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, b.cap_edges, s->fanout[i], i == s->L - 1 ? 1 : 0};
+    k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
     NB_LAUNCH_CHECK(ctx);
     int hash_slots = s->fanout[i] > 32 ? (int)pow2_ceil(2u * (uint32_t)s->fanout[i]) : 0;
     k_sample<<<nb_grid(b.cap_dst, SAMPLE_WARPS, 8), SAMPLE_WARPS * 32, (size_t)hash_slots * SAMPLE_WARPS * 4, st>>>(
-        g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, s->bitmap, m, s->fanout[i],
-        rng_seed ^ (rng_offset >> 32 << 32), (uint32_t)i, (uint32_t)rng_offset, merge ? 1 : 0, replay, hash_slots);
+        g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, s->bitmap, m, s->fanout[i], pp,
+        (uint32_t)i, merge ? 1 : 0, hash_slots);
     NB_LAUNCH_CHECK(ctx);
-    BitmapOp bop{s->bitmap, s->word_rank, b.source, b.row_count, b.row_cursor, merge ? b.src_to_dst : nullptr, m, m + 1, s->n_words, b.cap_src};
-    k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, s->ws);
+    BitmapOp bop{s->bitmap, s->word_rank, m, m + 1, s->n_words, b.cap_src};
+    k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+    NB_LAUNCH_CHECK(ctx);
+    k_emit_sources<<<nb_grid(s->n_words, 8, 8), 256, 0, st>>>(s->bitmap, s->word_rank, b.source, b.row_count, b.row_cursor,
+                                                               merge ? b.src_to_dst : nullptr, m, s->n_words);
     NB_LAUNCH_CHECK(ctx);
     const int histogram = (csr || up) ? 1 : 0;
     k_relabel<<<nb_grid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
         b.sample_ans, b.row_indices, s->bitmap, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
-        merge ? b.src_to_dst : nullptr, m, histogram);
+        merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp);
     NB_LAUNCH_CHECK(ctx);
-    if (weight_type != NB_WEIGHT_NONE) {
-      k_weights<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.sample_ans, b.row_indices, b.edge_dst, b.destination,
-                                                                b.column_offset, b.row_count, g->in_deg, g->out_deg, m,
-                                                                weight_type, up ? 1 : 0);
+    if (up) {
+      k_weights_sampled<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
     if (csr) {
       RowOp rop{b.row_count, b.row_offset, m};
-      k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, s->ws);
+      k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, ws2);
       NB_LAUNCH_CHECK(ctx);
       k_csr_fill<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
       NB_LAUNCH_CHECK(ctx);
-      float *ewb = weight_type != NB_WEIGHT_NONE ? b.ewb : nullptr;
       k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
-                                                               ewb, b.ewf, b.long_rows, m);
+                                                               b.ewb, b.ewf, b.long_rows, m, pp);
       NB_LAUNCH_CHECK(ctx);
       k_csr_long_rows<<<nb_grid(b.cap_src, 8, 2), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc,
-                                                                  b.edge_dst, ewb, b.ewf, b.long_rows, m);
+                                                                  b.edge_dst, b.ewb, b.ewf, b.long_rows, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
+  }
+  return NB_OK;
+}
+
+// stage (params, seeds) in pinned memory, upload, run the batch (graph replay), fetch the sizes
+static int run_batch(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int seeds_on_device, uint64_t rng_seed,
+                     uint64_t rng_offset, int weight_type, const uint32_t *omit, uint32_t omit_value, int replay) {
+  nb_ctx *ctx = s->ctx;
+  cudaStream_t st = ctx->stream;
+  const int slot = s->stage_next;
+  s->stage_next = (slot + 1) % nb_sampler::RING;
+  NB_CUDA(cudaEventSynchronize(s->stage_done[slot]));  // the upload that last used this slot has completed
+  BatchParams *hp = (BatchParams *)s->stage[slot];
+  memset(hp, 0, sizeof(*hp));
+  hp->rng_seed = rng_seed; hp->rng_offset = rng_offset; hp->omit = omit; hp->n_seeds = n_seeds;
+  hp->weight_type = (uint32_t)weight_type; hp->omit_value = omit_value; hp->replay = (uint32_t)replay;
+  hp->epoch = ++s->epoch;
+  NB_CUDA(cudaMemcpyAsync(s->params_dev, hp, sizeof(BatchParams), cudaMemcpyHostToDevice, st));
+  if (n_seeds) {
+    if (seeds_on_device) {
+      NB_CUDA(cudaMemcpyAsync(s->lay[0].destination, seeds, (size_t)n_seeds * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      uint32_t *hs = (uint32_t *)(s->stage[slot] + sizeof(BatchParams));
+      memcpy(hs, seeds, (size_t)n_seeds * 4);
+      NB_CUDA(cudaMemcpyAsync(s->lay[0].destination, hs, (size_t)n_seeds * 4, cudaMemcpyHostToDevice, st));
+    }
+  }
+  NB_CUDA(cudaEventRecord(s->stage_done[slot], st));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  NB_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (s->use_graph && cap == cudaStreamCaptureStatusNone) {
+    if (!s->graph_exec) {
+      cudaStream_t cst;
+      NB_CUDA(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      NB_CUDA(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
+      const uint64_t launches0 = ctx->launches;
+      int rc = enqueue_kernels(s, cst);
+      cudaError_t ce = cudaStreamEndCapture(cst, &graph);
+      cudaStreamDestroy(cst);
+      s->ctx->launches = launches0;
+      if (rc != NB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      NB_CUDA(ce);
+      NB_CUDA(cudaGraphInstantiate(&s->graph_exec, graph, 0));
+      NB_CUDA(cudaGraphDestroy(graph));
+    }
+    NB_CUDA(cudaGraphLaunch(s->graph_exec, st));
+    ctx->launches += (uint64_t)1 + (uint64_t)s->L * (5 + ((s->flags & NB_SAMPLER_UP_DEGREE) ? 1 : 0) + ((s->flags & NB_SAMPLER_BUILD_CSR) ? 4 : 0));
+  } else {
+    int rc = enqueue_kernels(s, st);
+    if (rc != NB_OK) return rc;
   }
   NB_CUDA(cudaMemcpyAsync(s->meta_host, s->meta_dev, sizeof(LayerMeta) * (s->L + 1), cudaMemcpyDeviceToHost, st));
   return NB_OK;
@@ -709,28 +808,24 @@ int nb_sampler_sample(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, in
   NB_REQUIRE(n_seeds <= s->lay[0].cap_dst, NB_ERR_CAPACITY, "batch of %u seeds exceeds the sampler's max_batch %u", n_seeds, s->lay[0].cap_dst);
   NB_REQUIRE(weight_type >= 0 && weight_type <= 3, NB_ERR_ARG, "bad weight_type %d", weight_type);
   NB_GUARD(s->ctx);
-  if (n_seeds)
-    NB_CUDA(cudaMemcpyAsync(s->lay[0].destination, seeds, (size_t)n_seeds * 4,
-                            seeds_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->ctx->stream));
-  int rc = enqueue_batch(s, n_seeds, rng_seed, rng_offset, weight_type, omit_flag_dev, omit_value, 0);
+  int rc = run_batch(s, seeds, n_seeds, seeds_on_device, rng_seed, rng_offset, weight_type, omit_flag_dev, omit_value, 0);
   if (rc != NB_OK) return rc;
   if (sync) return finish_batch(s, views_out);
   return NB_OK;
 }
 
-// Replay: layer i's destination is known only after layer i-1 ran, but the uploads do not depend on it.
+// Replay: the recorded draws of every layer are uploaded first; the kernels then only mark and relabel them.
 int nb_sampler_replay(nb_sampler *s, const uint32_t *seeds_host, uint32_t n_seeds, const uint32_t *const *sample_ans_host,
                       const uint32_t *n_edges_host, int weight_type, nb_layer_view *views_out) {
   NB_REQUIRE(s && seeds_host && sample_ans_host && n_edges_host, NB_ERR_ARG, "nb_sampler_replay: NULL argument");
   NB_REQUIRE(n_seeds <= s->lay[0].cap_dst, NB_ERR_CAPACITY, "batch of %u seeds exceeds max_batch", n_seeds);
   NB_GUARD(s->ctx);
-  NB_CUDA(cudaMemcpyAsync(s->lay[0].destination, seeds_host, (size_t)n_seeds * 4, cudaMemcpyHostToDevice, s->ctx->stream));
   for (int i = 0; i < s->L; i++) {
     NB_REQUIRE(n_edges_host[i] <= s->lay[i].cap_edges, NB_ERR_CAPACITY, "replay layer %d: %u edges exceed capacity %u", i, n_edges_host[i], s->lay[i].cap_edges);
     if (n_edges_host[i])
       NB_CUDA(cudaMemcpyAsync(s->lay[i].sample_ans, sample_ans_host[i], (size_t)n_edges_host[i] * 4, cudaMemcpyHostToDevice, s->ctx->stream));
   }
-  int rc = enqueue_batch(s, n_seeds, 0, 0, weight_type, nullptr, 0, 1);
+  int rc = run_batch(s, seeds_host, n_seeds, 0, 0, 0, weight_type, nullptr, 0, 1);
   if (rc != NB_OK) return rc;
   rc = finish_batch(s, views_out);
   if (rc != NB_OK) return rc;
@@ -744,6 +839,21 @@ int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out) {
   NB_REQUIRE(s && out && layer >= 0 && layer < s->L, NB_ERR_ARG, "nb_sampler_layer: bad argument");
   NB_REQUIRE(s->meta_host[layer].err == 0, NB_ERR_CAPACITY, "layer %d overflowed its arena", layer);
   fill_view(s, layer, out);
+  return NB_OK;
+}
+
+// Device addresses of a layer's sizes, for the *_dyn entry points that take their extents from device memory
+// (no host round trip between sampling and the kernels that consume the sampled layer).
+int nb_sampler_sizes_dev(nb_sampler *s, int layer, const uint32_t **n_dst_dev, const uint32_t **n_edges_dev,
+                         const uint32_t **n_src_dev, uint32_t *cap_dst, uint32_t *cap_edges, uint32_t *cap_src) {
+  NB_REQUIRE(s && layer >= 0 && layer < s->L, NB_ERR_ARG, "nb_sampler_sizes_dev: bad argument");
+  LayerMeta *m = s->meta_dev + layer;
+  if (n_dst_dev) *n_dst_dev = &m->n_dst;
+  if (n_edges_dev) *n_edges_dev = &m->n_edges;
+  if (n_src_dev) *n_src_dev = &m->n_src;
+  if (cap_dst) *cap_dst = s->lay[layer].cap_dst;
+  if (cap_edges) *cap_edges = s->lay[layer].cap_edges;
+  if (cap_src) *cap_src = s->lay[layer].cap_src;
   return NB_OK;
 }
 

@@ -27,7 +27,7 @@ def bits(a):
 
 @pytest.fixture(scope="module")
 def cs(nts):
-    return nts.Cuda_Stream(0)
+    return nts.Cuda_Stream.on_torch_stream(0)  # same stream as torch's ops, like the toolkits
 
 
 def make_graph(nts, cs, V, avg_deg, seed, unique=True, max_deg=None):
