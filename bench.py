@@ -169,6 +169,8 @@ def main_b200(args):
     import torch.distributed as dist
     import __graft_entry__ as ge
     nts = ge.load_package()
+    C = nts._capi.C
+    lib, check, ptr = nts._capi.lib(), nts._capi.check, nts._capi.ptr
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -184,147 +186,160 @@ def main_b200(args):
     n_steps = args.warmup + args.steps
     reps = -(-n_steps * BATCH // my_seeds.size)
     my_seeds = np.tile(my_seeds, reps)[: n_steps * BATCH]
+    P = max(1, args.pipeline)
+    PITCH = args.pitch if args.pitch else F0          # row pitch of the 602-wide tensors, in floats
 
-    stream = torch.cuda.Stream(dev)
-    with torch.cuda.stream(stream):
-        cs = nts.Cuda_Stream(local, stream)
-        graph = nts.FullyRepGraph(cs, v, column_offset=col_off, row_indices=src)
-        sampler = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, cuda_stream=cs, build_csr=True, rng_seed=SEED_SAMPLER + rank)
-        lib, check, ptr = nts._capi.lib(), nts._capi.check, nts._capi.ptr
+    st_sample, st_train = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    cs_sample, cs_train = nts.Cuda_Stream(local, st_sample), nts.Cuda_Stream(local, st_train)
+    with torch.cuda.stream(st_train):
+        graph = nts.FullyRepGraph(cs_sample, v, column_offset=col_off, row_indices=src)
+        # one sampler (arena) per pipeline slot, all on the sampling stream (the reference's PIPELINE_NUM SampledSubgraphs)
+        sampler = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=P, cuda_stream=[cs_sample] * P, build_csr=True,
+                                  rng_seed=SEED_SAMPLER + rank)
+        fast = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, cuda_stream=cs_train, build_csr=True, rng_seed=SEED_SAMPLER + rank)
         gen = torch.Generator(device=dev).manual_seed(0x5EED0002)
-        table = torch.rand((v, F0), generator=gen, device=dev) * 2 - 1          # HBM-resident feature table
-        cap_s1 = min(BATCH * 25 * 10, v)
-        cap_s0 = min(BATCH * 25, v)
-        x0 = torch.empty((cap_s1, F0), device=dev)
-        y1 = torch.empty((cap_s0, F0), device=dev)
-        h1 = torch.rand((cap_s0, F1), generator=gen, device=dev)               # stands in for relu(Y1 W1)
+        table = torch.zeros((v, PITCH), device=dev)                               # HBM-resident feature table
+        table[:, :F0] = torch.rand((v, F0), generator=gen, device=dev) * 2 - 1
+        cap_s1, cap_s0 = min(BATCH * 25 * 10, v), min(BATCH * 25, v)
+        x0 = torch.zeros((cap_s1, PITCH), device=dev)
+        y1 = torch.zeros((cap_s0, PITCH), device=dev)
+        h1 = torch.rand((cap_s0, F1), generator=gen, device=dev)                 # stands in for relu(Y1 W1)
         y0 = torch.empty((BATCH, F1), device=dev)
         dy0 = torch.rand((BATCH, F1), generator=gen, device=dev)
         dh1 = torch.empty((cap_s0, F1), device=dev)
-        grads = torch.zeros(F0 * F1 + F1 * NCLS, device=dev)                    # dense W gradients, one bucket
+        grads = torch.zeros(F0 * F1 + F1 * NCLS, device=dev)                      # dense W gradients, one bucket
         seeds_dev = torch.from_numpy(my_seeds.view(np.int32)).to(dev)
-        seeds_pin = torch.from_numpy(my_seeds.view(np.int32)).pin_memory()
         y0_host = torch.empty((BATCH, F1)).pin_memory()
-        C = nts._capi.C
-        views = (nts._capi.LayerView * 2)()
-        # one synchronous batch: fixes the arena pointers of both layers (they never change afterwards)
-        check(lib.nb_sampler_sample(sampler._samplers[0], ptr(seeds_pin[:BATCH]), BATCH, 0, SEED_SAMPLER + rank, 0,
-                                    nts.WeightType.Sum, None, 0xFFFFFFFF, views, 1))
-        top, bot = views[0], views[1]
-        nd, ne, ns = [[C.c_void_p() for _ in range(2)] for _ in range(3)]
-        caps = [[C.c_uint32() for _ in range(3)] for _ in range(2)]
-        for l in range(2):
-            check(lib.nb_sampler_sizes_dev(sampler._samplers[0], l, C.byref(nd[l]), C.byref(ne[l]), C.byref(ns[l]),
-                                           C.byref(caps[l][0]), C.byref(caps[l][1]), C.byref(caps[l][2])))
-        assert caps[1][2].value <= cap_s1 and caps[0][2].value <= cap_s0
-        sizes_pin = torch.zeros((n_steps, 8), dtype=torch.int32).pin_memory()   # LayerMeta of the bottom layer per step
+        sizes_pin = torch.zeros((n_steps, 8), dtype=torch.int32).pin_memory()     # LayerMeta of the bottom layer per step
         sizes_top = torch.zeros((n_steps, 8), dtype=torch.int32).pin_memory()
-        fast = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, cuda_stream=cs, build_csr=True, rng_seed=SEED_SAMPLER + rank)
-        op_bot_cls = nts.SingleGPUAllSampleGraphOp
+    torch.cuda.synchronize()
 
-        ev = lambda: torch.cuda.Event(enable_timing=True)
-        kern_ev = {"gather": [], "agg_fwd_602": []}
+    # fixed arena pointers and device-side size addresses of every pipeline slot
+    slots = []
+    with torch.cuda.stream(st_sample):
+        for k in range(P):
+            views = (nts._capi.LayerView * 2)()
+            check(lib.nb_sampler_sample(sampler._samplers[k], ptr(my_seeds[:BATCH]), BATCH, 0, SEED_SAMPLER + rank, 0,
+                                        nts.WeightType.Sum, None, 0xFFFFFFFF, views, 1))
+            nd, ns, caps = [C.c_void_p(), C.c_void_p()], [C.c_void_p(), C.c_void_p()], [[C.c_uint32() for _ in range(3)] for _ in range(2)]
+            for l in range(2):
+                check(lib.nb_sampler_sizes_dev(sampler._samplers[k], l, C.byref(nd[l]), None, C.byref(ns[l]), C.byref(caps[l][0]),
+                                               C.byref(caps[l][1]), C.byref(caps[l][2])))
+            assert caps[1][2].value <= cap_s1 and caps[0][2].value <= cap_s0
+            slots.append(dict(top=views[0], bot=views[1], nd=nd, ns=ns, caps=caps, sampled=torch.cuda.Event(), consumed=torch.cuda.Event()))
+    torch.cuda.synchronize()
 
-        def step_async(i, timed):
-            """value: inputs resident in HBM, no host synchronisation anywhere in the step (sizes stay on the device)."""
-            check(lib.nb_sampler_sample(sampler._samplers[0], ptr(seeds_dev[i * BATCH:(i + 1) * BATCH]), BATCH, 1,
-                                        SEED_SAMPLER + rank, i, nts.WeightType.Sum, None, 0xFFFFFFFF, None, 0))
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    kern_ev = {"gather": [], "agg_fwd_602": []}
+
+    def step_async(i, timed, fused=False):
+        """value: inputs resident in HBM, no host synchronisation anywhere (sizes stay on the device). Batch i is sampled on
+        the sampling stream into arena i % P while the training stream gathers / aggregates batch i-1."""
+        sl = slots[i % P]
+        top, bot, nd, ns, caps = sl["top"], sl["bot"], sl["nd"], sl["ns"], sl["caps"]
+        st_sample.wait_event(sl["consumed"])
+        check(lib.nb_sampler_sample(sampler._samplers[i % P], ptr(seeds_dev[i * BATCH:(i + 1) * BATCH]), BATCH, 1,
+                                    SEED_SAMPLER + rank, i, nts.WeightType.Sum, None, 0xFFFFFFFF, None, 0))
+        sl["sampled"].record(st_sample)
+        st_train.wait_event(sl["sampled"])
+        if timed and not fused:
+            a, b, c = ev(), ev(), ev()
+            a.record(st_train)
+        if not fused:
+            check(lib.nb_gather_rows_dyn(cs_train._h, ptr(x0), ptr(table), bot.source, ns[1], caps[1][2], F0, PITCH, PITCH))
             if timed:
-                a, b, c = ev(), ev(), ev()
-                a.record(stream)
-            check(lib.nb_gather_rows_dyn(cs._h, ptr(x0), ptr(table), bot.source, ns[1], caps[1][2], F0, F0, F0))
+                b.record(st_train)
+            check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(x0), ptr(y1), bot.edge_weight_forward, bot.row_indices,
+                                               bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
             if timed:
-                b.record(stream)
-            check(lib.nb_aggregate_csc_fwd_dyn(cs._h, ptr(x0), ptr(y1), bot.edge_weight_forward, bot.row_indices,
-                                               bot.column_offset, nd[1], caps[1][0], F0, F0, F0))
-            if timed:
-                c.record(stream)
+                c.record(st_train)
                 kern_ev["gather"].append((a, b))
                 kern_ev["agg_fwd_602"].append((b, c))
-            check(lib.nb_aggregate_csc_fwd_dyn(cs._h, ptr(h1), ptr(y0), top.edge_weight_forward, top.row_indices,
-                                               top.column_offset, nd[0], caps[0][0], F1, F1, F1))
-            check(lib.nb_aggregate_csr_bwd_dyn(cs._h, ptr(dy0), ptr(dh1), top.edge_weight_backward, top.row_offset,
-                                               top.column_indices, ns[0], caps[0][2], F1, F1, F1))
-            check(lib.nb_memcpy_d2h(cs._h, ptr(sizes_pin[i]), nd[1].value, 32, 0))
-            check(lib.nb_memcpy_d2h(cs._h, ptr(sizes_top[i]), nd[0].value, 32, 0))
-            if world > 1:
+        else:  # bottom hop aggregated straight from the feature table through the global ids: X0 is never materialised
+            check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
+                                               bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
+        check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(h1), ptr(y0), top.edge_weight_forward, top.row_indices,
+                                           top.column_offset, nd[0], caps[0][0], F1, F1, F1))
+        check(lib.nb_aggregate_csr_bwd_dyn(cs_train._h, ptr(dy0), ptr(dh1), top.edge_weight_backward, top.row_offset,
+                                           top.column_indices, ns[0], caps[0][2], F1, F1, F1))
+        check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_pin[i]), nd[1].value, 32, 0))
+        check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_top[i]), nd[0].value, 32, 0))
+        sl["consumed"].record(st_train)
+        if world > 1:
+            with torch.cuda.stream(st_train):
                 dist.all_reduce(grads)
 
-        def step_api(i, timed):
-            """e2e: the call sequence a user of the reference-shaped API makes (host seeds in, sizes and the batch's
-            top-layer output back on the host), including its synchronisation on the sampled sizes."""
-            fast.work_offset = i * BATCH
-            sg = fast.sample_gpu_fast(BATCH)                        # H2D seeds; syncs for the sizes
-            t, bt = sg.sampled_sgs
-            xx = x0[:bt.src_size]
-            fast.load_feature_gpu(cs, sg, xx, table)
-            yy1 = op_bot_cls(sg, 1, cs).forward(xx)
-            op_top = op_bot_cls(sg, 0, cs)
-            yy0 = op_top.forward(h1[:t.src_size])
-            op_top.backward(dy0)
-            if world > 1:
-                dist.all_reduce(grads)
-            y0_host.copy_(yy0, non_blocking=True)
-            stream.synchronize()
-            sizes_pin[i, 0], sizes_pin[i, 1], sizes_pin[i, 2] = bt.v_size, bt.e_size, bt.src_size
-            sizes_top[i, 1] = t.e_size
-            del yy1
+    def step_api(i, timed):
+        """e2e: the call sequence a user of the reference-shaped API makes -- host seeds in, sizes and the batch's top-layer
+        output back on the host -- including its synchronisation on the sampled sizes."""
+        fast.work_offset = i * BATCH
+        sg = fast.sample_gpu_fast(BATCH)                        # stages + uploads the seeds; syncs for the sizes
+        t, bt = sg.sampled_sgs
+        xx = x0[:bt.src_size, :F0]
+        fast.load_feature_gpu(cs_train, sg, xx, table[:, :F0])
+        yy1 = nts.SingleGPUAllSampleGraphOp(sg, 1, cs_train).forward(xx)
+        op_top = nts.SingleGPUAllSampleGraphOp(sg, 0, cs_train)
+        yy0 = op_top.forward(h1[:t.src_size])
+        op_top.backward(dy0)
+        if world > 1:
+            dist.all_reduce(grads)
+        y0_host.copy_(yy0, non_blocking=True)
+        st_train.synchronize()
+        sizes_pin[i, 0], sizes_pin[i, 1], sizes_pin[i, 2] = bt.v_size, bt.e_size, bt.src_size
+        sizes_top[i, 1] = t.e_size
+        del yy1
 
-        clock_box = [None]
+    clock_box = [None]
 
-        def run(from_host, sample_clocks=False):
-            step = step_api if from_host else step_async
-            for k in kern_ev.values():
-                k.clear()
+    def run(mode, sample_clocks=False):
+        step = {"async": step_async, "fused": lambda i, t: step_async(i, t, True), "api": step_api}[mode]
+        for k in kern_ev.values():
+            k.clear()
+        with torch.cuda.stream(st_train):
             for i in range(args.warmup):
                 step(i, False)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            launches0 = cs.launch_count() + sum(c.launch_count() for c in set(fast.cs_array) if c is not cs)
+            launches0 = cs_sample.launch_count() + cs_train.launch_count()
             clocks = ClockSampler(local) if sample_clocks else None
             if clocks:
                 clocks.start()
             t0, t1 = ev(), ev()
-            t0.record(stream)
+            t0.record(st_train)
             for i in range(args.warmup, n_steps):
                 step(i, True)
-            t1.record(stream)
+            t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes both streams
             torch.cuda.synchronize()
             if clocks:
                 clock_box[0] = clocks.summary()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            ms = t0.elapsed_time(t1)
-            sp, st_ = sizes_pin[args.warmup:n_steps].numpy().astype(np.int64), sizes_top[args.warmup:n_steps].numpy().astype(np.int64)
-            work = {"edges": int(sp[:, 1].sum() + st_[:, 1].sum()), "V1": int(sp[:, 0].sum()), "E1": int(sp[:, 1].sum()),
-                    "S1": int(sp[:, 2].sum())}
-            return ms, cs.launch_count() - launches0, work, {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1)
-                                                            for k, v in kern_ev.items()}
+        ms = t0.elapsed_time(t1)
+        sp, st_ = sizes_pin[args.warmup:n_steps].numpy().astype(np.int64), sizes_top[args.warmup:n_steps].numpy().astype(np.int64)
+        work = {"edges": int(sp[:, 1].sum() + st_[:, 1].sum()), "V1": int(sp[:, 0].sum()), "E1": int(sp[:, 1].sum()),
+                "S1": int(sp[:, 2].sum())}
+        launches = cs_sample.launch_count() + cs_train.launch_count() - launches0
+        return ms, launches, work, {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in kern_ev.items()}
 
-        ms, launches, work, kms = run(False, sample_clocks=True)
-        clk = clock_box[0]
-        ms_e2e, _, work_e2e, _ = run(True)
+    ms, launches, work, kms = run("async", sample_clocks=True)
+    clk = clock_box[0]
+    ms_e2e, _, work_e2e, _ = run("api")
+    ms_fused, _, work_fused, _ = run("fused")
 
-    def reduce_max(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def reduce_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    ms_max, ms_e2e_max = reduce_max(ms), reduce_max(ms_e2e)
-    edges_all, edges_e2e_all = reduce_sum(work["edges"]), reduce_sum(work_e2e["edges"])
-    launches_all = reduce_sum(launches)
+    MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
+    ms_max, ms_e2e_max, ms_fused_max = reduce(ms, MAX), reduce(ms_e2e, MAX), reduce(ms_fused, MAX)
+    edges_all, edges_e2e_all, edges_fused_all = reduce(work["edges"], SUM), reduce(work_e2e["edges"], SUM), reduce(work_fused["edges"], SUM)
+    launches_all = reduce(launches, SUM)
     value = edges_all / (ms_max * 1e-3)
     e2e_value = edges_e2e_all / (ms_e2e_max * 1e-3)
 
@@ -347,11 +362,14 @@ def main_b200(args):
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "kernels": {k: {"gbs": round(x["gbs"], 1), "frac": round(x["gbs"] / peak, 3), "ms": round(x["ms"], 4)} for k, x in kernels.items()}}
+                "kernels": {k: {"gbs": round(x["gbs"], 1), "frac": round(x["gbs"] / peak, 3), "ms": round(x["ms"], 4),
+                                "algorithmic_bytes": int(x["algorithmic_bytes"])} for k, x in kernels.items()}}
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
-                roof["traffic"] = json.load(open(traffic_file)).get(dom)
+                tr = json.load(open(traffic_file))
+                roof["traffic"] = tr.get(dom)
+                roof["traffic_note"] = tr.get("note")
             except Exception:
                 pass
         cpu = None
@@ -369,13 +387,19 @@ def main_b200(args):
         line = {"metric": "sampled_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(v, e_total, {"per_gpu_batch": BATCH, "parallelism": f"dp{world}: seeds sharded, "
-                                                   "one bucketed NCCL allreduce of dense grads per step" if world > 1 else "single GPU",
-                                                   "avg_E_per_step": work["edges"] / n, "avg_S1": S1, "avg_E1": E1, "avg_V1": V1,
-                                                   "epoch_ms_est": (ms_max / args.steps) * (all_seeds.size / BATCH / world)}),
-                "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": BATCH * 4,
-                        "d2h_bytes_per_step": BATCH * F1 * 4 + 2 * 32, "ms_per_step": ms_e2e_max / args.steps},
-                "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "config": config_dict(v, e_total, {
+                    "per_gpu_batch": BATCH, "pipeline_num": P, "row_pitch_floats": PITCH,
+                    "parallelism": (f"dp{world}: seeds sharded contiguously, one bucketed NCCL allreduce of the dense grads per step"
+                                    if world > 1 else "single GPU"),
+                    "avg_E_per_step": work["edges"] / n, "avg_S1": S1, "avg_E1": E1, "avg_V1": V1,
+                    "epoch_ms_est": (ms_max / args.steps) * (all_seeds.size / BATCH / world)}),
+                "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": BATCH * 4 + 64,
+                        "d2h_bytes_per_step": BATCH * F1 * 4 + 3 * 32, "ms_per_step": ms_e2e_max / args.steps,
+                        "path": "FastSampler.sample_gpu_fast (sync on sizes) -> load_feature_gpu -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H"},
+                "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "fused_gather_aggregate": {"value": edges_fused_all / (ms_fused_max * 1e-3), "unit": "edges/s",
+                                           "ms_per_step": ms_fused_max / args.steps,
+                                           "note": "same results; the bottom hop aggregates straight from the feature table, X0 is never written"}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -389,6 +413,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only; the metric is quoted at 1.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2, help="PIPELINE_NUM: sampler arenas in flight (sampling overlaps training)")
+    ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -89,6 +89,9 @@ typedef struct nb_layer_view {
 int nb_abi_version(void);
 const char *nb_last_error(void); /* thread-local, valid until the next failing call */
 int nb_device_count(int *count);
+/* tuning knobs (also readable from the environment at first use):
+ *   "gather_variant" / NB_GATHER_VARIANT : 0 = register path (LDG/STG), 1 = TMA bulk copies when rows are 16-byte aligned (default) */
+int nb_set_option(const char *name, int value);
 
 /* ---- context: class Cuda_Stream (cuda/ntsCUDA.hpp:177-199; cuda/ntsCUDAGraphOP.cu:203-262) ----
  * nb_ctx_create      <- Cuda_Stream::Cuda_Stream()     (adopt_stream == 0: creates a non-blocking stream;
@@ -238,7 +241,8 @@ int nb_aggregate_csc_fwd(nb_ctx *ctx, const float *input, float *output, const f
 int nb_aggregate_csr_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
                          const uint32_t *row_offset, const uint32_t *column_indices, uint32_t n_src, uint32_t n_dst,
                          uint32_t feature_size);
-/* same operators with the row count read from device memory and explicit row pitches (in floats) */
+/* same operators with explicit row pitches (in floats) and the row count read from device memory
+ * (n_*_dev == NULL: the max_* argument is the row count) */
 int nb_aggregate_csc_fwd_dyn(nb_ctx *ctx, const float *input, float *output, const float *weight_forward,
                              const uint32_t *row_indices, const uint32_t *column_offset, const uint32_t *n_dst_dev,
                              uint32_t max_dst, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch);

@@ -33,6 +33,22 @@ class WeightType:  # core/ntsFastSampler.hpp:27
     Sum, Mean, None_, MeanSampled = NB_WEIGHT_SUM, NB_WEIGHT_MEAN, NB_WEIGHT_NONE, NB_WEIGHT_MEAN_SAMPLED
 
 
+def _pitch(t, F):
+    """row pitch in floats of a [rows, F] tensor (a [:, :F] view of a wider, row-padded allocation is allowed)"""
+    if hasattr(t, "stride") and t.dim() == 2:
+        assert t.stride(1) == 1, "rows must be contiguous"
+        return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), F)
+    return F
+
+
+def _alloc_like_rows(n, F, like):
+    """[n, F] output with the same row pitch as `like` (padded in -> padded out)"""
+    p = _pitch(like, F)
+    if p == F:
+        return torch.empty((n, F), dtype=torch.float32, device=like.device)
+    return torch.empty((n, p), dtype=torch.float32, device=like.device)[:, :F]
+
+
 class _DevArray:
     """zero-copy view of sampler-owned device memory for torch.as_tensor (CUDA array interface)."""
 
@@ -110,6 +126,17 @@ class Cuda_Stream:
     Gather_By_Src_From_Dst = lambda self, input, output, weight_backward, row_offset, column_indices, src_start=0, src_end=0, dst_start=0, dst_end=0, edges=0, batch_size=0, feature_size=0, with_weight=False, tensor_weight=False: \
         self.Gather_By_Src_From_Dst_Spmm(input, output, weight_backward, row_offset, column_indices, 0, 0, 0, 0, 0, edges, batch_size, feature_size, with_weight, tensor_weight)
     Gather_By_Src_From_Dst_Optim = Gather_By_Src_From_Dst
+
+    def aggregate_fwd_pitched(self, input, output, weight, row_indices, column_offset, n_dst, feature_size, in_pitch, out_pitch,
+                              n_dst_dev=None):
+        """CSC forward on row-padded tensors (pitch in floats); n_dst_dev: device address of the row count, or None."""
+        check(lib().nb_aggregate_csc_fwd_dyn(self._h, ptr(input), ptr(output), ptr(weight), ptr(row_indices), ptr(column_offset),
+                                             ptr(n_dst_dev), n_dst, feature_size, in_pitch, out_pitch))
+
+    def aggregate_bwd_pitched(self, input, output, weight_b, row_offset, column_indices, n_src, feature_size, in_pitch, out_pitch,
+                              n_src_dev=None):
+        check(lib().nb_aggregate_csr_bwd_dyn(self._h, ptr(input), ptr(output), ptr(weight_b), ptr(row_offset), ptr(column_indices),
+                                             ptr(n_src_dev), n_src, feature_size, in_pitch, out_pitch))
 
     def Push_From_Dst_To_Src_Spmm(self, input, output, weight, row_indices, column_offset, column_num, src_start=0,
                                   src_end=0, dst_start=0, dst_end=0, edges=0, batch_size=0, feature_size=0,
@@ -369,7 +396,8 @@ class FastSampler:
         F = local_feature.shape[1]
         if local_feature.shape[0] != l.src_size:
             local_feature.resize_(l.src_size, F)
-        cuda_stream.zero_copy_feature_move_gpu(local_feature, global_feature_buffer, l.dev_source, F, l.src_size)
+        cuda_stream.zero_copy_feature_move_gpu(local_feature, global_feature_buffer, l.dev_source, F, l.src_size,
+                                               _pitch(global_feature_buffer, F), _pitch(local_feature, F))
         return local_feature
 
     def load_feature_gpu_cache(self, cuda_stream, subgraph, local_feature, global_feature_buffer, dev_cache_feature,
@@ -431,7 +459,7 @@ class _AggFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        return ctx.op.backward(dy.contiguous()), None
+        return ctx.op.backward(dy if dy.stride(-1) == 1 else dy.contiguous()), None
 
 
 class SingleGPUAllSampleGraphOp:
@@ -445,18 +473,26 @@ class SingleGPUAllSampleGraphOp:
     def forward(self, f_input):
         l = self.subgraphs.sampled_sgs[self.layer]
         F = f_input.shape[1]
-        assert f_input.is_contiguous() and f_input.shape[0] == l.src_size
-        out = torch.empty((l.v_size, F), dtype=torch.float32, device=f_input.device)
-        self.cuda_stream.Gather_By_Dst_From_Src_Spmm(f_input, out, l.dev_e_w(), l.dev_r_i(), l.dev_c_o(), l.src_size,
-                                                     0, 0, 0, 0, l.e_size, l.v_size, F, self.with_weight, False)
+        assert f_input.shape[0] == l.src_size
+        out = _alloc_like_rows(l.v_size, F, f_input)
+        if _pitch(f_input, F) == F:
+            self.cuda_stream.Gather_By_Dst_From_Src_Spmm(f_input, out, l.dev_e_w(), l.dev_r_i(), l.dev_c_o(), l.src_size,
+                                                         0, 0, 0, 0, l.e_size, l.v_size, F, self.with_weight, False)
+        else:
+            self.cuda_stream.aggregate_fwd_pitched(f_input, out, l.dev_e_w() if self.with_weight else None, l.dev_r_i(),
+                                                   l.dev_c_o(), l.v_size, F, _pitch(f_input, F), _pitch(out, F))
         return out
 
     def backward(self, f_output_grad):
         l = self.subgraphs.sampled_sgs[self.layer]
         F = f_output_grad.shape[1]
         assert f_output_grad.shape[0] == l.v_size
-        grad = torch.empty((l.src_size, F), dtype=torch.float32, device=f_output_grad.device)
-        if l.dev_row_offset is not None:
+        grad = _alloc_like_rows(l.src_size, F, f_output_grad)
+        if _pitch(f_output_grad, F) != F:
+            assert l.dev_row_offset is not None, "padded tensors need the CSR (build_csr=True)"
+            self.cuda_stream.aggregate_bwd_pitched(f_output_grad, grad, l.dev_e_w_b() if self.with_weight else None, l.dev_r_o(),
+                                                   l.dev_c_i(), l.src_size, F, _pitch(f_output_grad, F), _pitch(grad, F))
+        elif l.dev_row_offset is not None:
             self.cuda_stream.Gather_By_Src_From_Dst_Spmm(f_output_grad, grad, l.dev_e_w_b(), l.dev_r_o(), l.dev_c_i(),
                                                          l.v_size, 0, 0, 0, 0, l.e_size, l.src_size, F, self.with_weight, False)
         else:

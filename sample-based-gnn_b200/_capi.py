@@ -38,6 +38,7 @@ _SIGS = {
     "nb_abi_version": (I32, []),
     "nb_last_error": (C.c_char_p, []),
     "nb_device_count": (I32, [C.POINTER(I32)]),
+    "nb_set_option": (I32, [C.c_char_p, I32]),
     "nb_ctx_create": (I32, [I32, P, I32, C.POINTER(P)]),
     "nb_ctx_destroy": (I32, [P]),
     "nb_ctx_set_stream": (I32, [P, P]),

@@ -153,10 +153,11 @@ static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, cons
   if (n_rows == 0) return NB_OK;
   if (!in_pitch) in_pitch = F;
   if (!out_pitch) out_pitch = F;
-  int vec = nb_pick_vec(F, in, in_pitch, out, out_pitch);
-  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch);
-  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch);
-  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch);
+  uint32_t fe = F;
+  int vec = push ? nb_pick_vec(F, in, in_pitch, out, out_pitch) : nb_pick_vec(F, in, in_pitch, out, out_pitch, &fe);
+  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch);
+  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch);
+  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch);
 }
 
 extern "C" {
@@ -185,7 +186,7 @@ int nb_aggregate_csr_bwd(nb_ctx *ctx, const float *input, float *output, const f
 int nb_aggregate_csc_fwd_dyn(nb_ctx *ctx, const float *input, float *output, const float *weight_forward,
                              const uint32_t *row_indices, const uint32_t *column_offset, const uint32_t *n_dst_dev,
                              uint32_t max_dst, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch) {
-  NB_REQUIRE(ctx && input && output && row_indices && column_offset && n_dst_dev, NB_ERR_ARG, "nb_aggregate_csc_fwd_dyn: NULL argument");
+  NB_REQUIRE(ctx && (max_dst == 0 || (output && column_offset)), NB_ERR_ARG, "nb_aggregate_csc_fwd_dyn: NULL argument");
   NB_REQUIRE(feature_size > 0 && input_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
   NB_GUARD(ctx);
   return run_segment(ctx, false, input, output, weight_forward, row_indices, column_offset, max_dst, feature_size, n_dst_dev, input_pitch, output_pitch);
@@ -194,7 +195,7 @@ int nb_aggregate_csc_fwd_dyn(nb_ctx *ctx, const float *input, float *output, con
 int nb_aggregate_csr_bwd_dyn(nb_ctx *ctx, const float *input, float *output, const float *weight_backward,
                              const uint32_t *row_offset, const uint32_t *column_indices, const uint32_t *n_src_dev,
                              uint32_t max_src, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch) {
-  NB_REQUIRE(ctx && input && output && row_offset && column_indices && n_src_dev, NB_ERR_ARG, "nb_aggregate_csr_bwd_dyn: NULL argument");
+  NB_REQUIRE(ctx && (max_src == 0 || (output && row_offset)), NB_ERR_ARG, "nb_aggregate_csr_bwd_dyn: NULL argument");
   NB_REQUIRE(feature_size > 0 && input_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
   NB_GUARD(ctx);
   return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, max_src, feature_size, n_src_dev, input_pitch, output_pitch);

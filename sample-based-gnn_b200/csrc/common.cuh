@@ -168,10 +168,21 @@ struct Philox {
 };
 #endif  // __CUDACC__
 
-// vector width usable for rows of `feature_size` floats at pitches/pointers given (4, 2 or 1)
-static inline int nb_pick_vec(uint32_t feature_size, const void *a, uint64_t pitch_a, const void *b, uint64_t pitch_b) {
+// Vector width (4, 2 or 1 floats) usable for rows of `feature_size` floats at the given pitches / base pointers.
+// *f_eff is the row length the kernel should process: when the rows are padded (pitch >= feature_size rounded
+// up to the vector width, pitch a multiple of it) the pad columns are carried along so that a 602-float row at
+// pitch 608 still moves as 128-bit vectors. Pad columns only ever flow into pad columns.
+static inline int nb_pick_vec(uint32_t feature_size, const void *a, uint64_t pitch_a, const void *b, uint64_t pitch_b,
+                              uint32_t *f_eff = nullptr) {
   uintptr_t pa = (uintptr_t)a, pb = (uintptr_t)b;
-  if (feature_size % 4 == 0 && pitch_a % 4 == 0 && pitch_b % 4 == 0 && pa % 16 == 0 && pb % 16 == 0) return 4;
-  if (feature_size % 2 == 0 && pitch_a % 2 == 0 && pitch_b % 2 == 0 && pa % 8 == 0 && pb % 8 == 0) return 2;
+  for (int vec = 4; vec >= 2; vec >>= 1) {
+    const uint32_t up = (feature_size + vec - 1) / vec * vec;
+    if (pitch_a % vec == 0 && pitch_b % vec == 0 && pitch_a >= up && pitch_b >= up && pa % (4 * vec) == 0 && pb % (4 * vec) == 0) {
+      if (f_eff) *f_eff = up;
+      else if (up != feature_size) continue;
+      return vec;
+    }
+  }
+  if (f_eff) *f_eff = feature_size;
   return 1;
 }

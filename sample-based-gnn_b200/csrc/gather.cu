@@ -10,6 +10,8 @@
 // HBM bound. Algorithmic bytes per row: 4 (id) + 2*4F (read row + write row). One warp moves one
 // row with 128-/64-bit read-only streaming loads, ROWS_IN_FLIGHT rows per warp iteration so that
 // every lane has >= 4 independent 16-byte requests outstanding; grid = resident warps of 148 SMs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 struct nb_table {
@@ -63,6 +65,102 @@ k_gather_rows(float *__restrict__ out, const float *__restrict__ table, uint64_t
     }
   }
   if (MODE == 1 && hit_count && lane == 0 && hits) atomicAdd(hit_count, hits);
+}
+
+// ---- TMA variant -------------------------------------------------------------------------------
+// Rows whose byte length and addresses are 16-byte aligned (row pitches that are multiples of 4 floats, e.g. the
+// 602-float Reddit row stored at pitch 608 = 19 x 128 B) move global -> shared -> global with bulk async copies
+// (cp.async.bulk, SASS UBLKCP) and never touch registers. One thread owns one shared-memory row slot and its
+// mbarrier; SLOTS rows (~2.4 KB each) are in flight per CTA, one CTA per SM, i.e. ~150 KB in flight per SM versus
+// the <= 64 KB the register path can hold.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 1)
+k_gather_rows_tma(float *__restrict__ out, const float *__restrict__ table, uint64_t table_pitch, const float *__restrict__ cache,
+                  uint64_t cache_pitch, const uint32_t *__restrict__ cache_map, const float *const *__restrict__ shards,
+                  uint32_t n_shards, const uint32_t *__restrict__ ids, uint32_t n_rows, const uint32_t *__restrict__ n_rows_dev,
+                  uint32_t copy_bytes, uint32_t slot_bytes, uint64_t out_pitch, int slots) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t *bars = (uint64_t *)smem;                  // [slots]
+  uint8_t *rows = smem + ((slots * 8 + 127) & ~127);  // [slots][slot_bytes]
+  if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
+  const int t = threadIdx.x;
+  if (t >= slots) return;
+  const uint32_t bar = smem_u32(&bars[t]);
+  const uint32_t slot = smem_u32(rows + (size_t)t * slot_bytes);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const unsigned stride = gridDim.x * slots;
+  unsigned i = blockIdx.x * slots + t;
+  uint32_t v_next = i < n_rows ? ids[i] : 0;
+  uint32_t phase = 0;
+  for (; i < n_rows; i += stride) {
+    const uint32_t v = v_next;
+    if (i + stride < n_rows) v_next = ids[i + stride];
+    const float *src;
+    if (MODE == 0) src = table + (uint64_t)v * table_pitch;
+    else if (MODE == 1) {
+      const uint32_t s = cache_map[v];
+      src = s != 0xffffffffu ? cache + (uint64_t)s * cache_pitch : table + (uint64_t)v * table_pitch;
+    } else src = shards[v % n_shards] + (uint64_t)(v / n_shards) * table_pitch;
+    // the previous store out of this slot must have finished reading it
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(copy_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(slot), "l"(src), "r"(copy_bytes), "r"(bar) : "memory");
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    }
+    phase ^= 1;
+    float *dst = out + (uint64_t)i * out_pitch;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(slot), "r"(copy_bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// returns the number of bytes a bulk row copy may move (0 = layout not eligible)
+static uint32_t tma_row_bytes(uint32_t F, const void *a, uint64_t pitch_a, const void *b, uint64_t pitch_b, const void *c = nullptr, uint64_t pitch_c = 4) {
+  const uint32_t bytes = (F * 4 + 15) & ~15u;
+  if (pitch_a % 4 || pitch_b % 4 || pitch_c % 4) return 0;
+  if (pitch_a * 4 < bytes || pitch_b * 4 < bytes || (c && pitch_c * 4 < bytes)) return 0;
+  if ((uintptr_t)a % 16 || (uintptr_t)b % 16 || (uintptr_t)c % 16) return 0;
+  return bytes;
+}
+
+static int g_gather_variant = -1;  // NB_GATHER_VARIANT: 0 = registers (LDG/STG), 1 = TMA bulk when eligible (default)
+static int gather_variant() {
+  if (g_gather_variant < 0) {
+    const char *e = getenv("NB_GATHER_VARIANT");
+    g_gather_variant = e ? atoi(e) : 1;
+  }
+  return g_gather_variant;
+}
+
+template <int MODE>
+static int launch_gather_tma(nb_ctx *ctx, float *out, const float *table, uint64_t table_pitch, const float *cache, uint64_t cache_pitch,
+                             const uint32_t *cache_map, const float *const *shards, uint32_t n_shards, const uint32_t *ids,
+                             uint32_t n_rows, const uint32_t *n_rows_dev, uint32_t copy_bytes, uint64_t out_pitch) {
+  const uint32_t slot_bytes = (copy_bytes + 127) & ~127u;
+  int slots = (int)((200 * 1024) / slot_bytes);
+  if (slots > 128) slots = 128;
+  if (slots < 1) return NB_ERR_UNSUPPORTED;
+  const size_t smem = ((slots * 8 + 127) & ~127) + (size_t)slots * slot_bytes;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[MODE]) {
+    NB_CUDA(cudaFuncSetAttribute(k_gather_rows_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set[MODE] = true;
+  }
+  unsigned grid = (n_rows + slots - 1) / slots;
+  if (grid > (unsigned)ctx->sm_count) grid = ctx->sm_count;
+  k_gather_rows_tma<MODE><<<grid, 128, smem, ctx->stream>>>(out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids,
+                                                           n_rows, n_rows_dev, copy_bytes, slot_bytes, out_pitch, slots);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
 }
 
 __global__ void k_gather_labels(int64_t *__restrict__ out, const int64_t *__restrict__ labels, const uint32_t *__restrict__ ids, uint32_t n) {
@@ -127,22 +225,37 @@ static int launch_gather(nb_ctx *ctx, float *out, const float *table, uint64_t t
 
 extern "C" {
 
+int nb_set_option(const char *name, int value) {
+  NB_REQUIRE(name, NB_ERR_ARG, "nb_set_option: NULL name");
+  if (!strcmp(name, "gather_variant")) { g_gather_variant = value; return NB_OK; }
+  nb_set_error("nb_set_option: unknown option %s", name);
+  return NB_ERR_ARG;
+}
+
 int nb_gather_rows(nb_ctx *ctx, float *out, const float *table, const uint32_t *ids_dev, uint32_t n_rows,
                    uint32_t feature_size, uint32_t table_pitch, uint32_t out_pitch) {
   NB_REQUIRE(ctx && (n_rows == 0 || (out && table && ids_dev)), NB_ERR_ARG, "nb_gather_rows: NULL argument");
   NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && out_pitch >= feature_size, NB_ERR_ARG, "nb_gather_rows: bad pitch");
   NB_GUARD(ctx);
-  int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch);
-  return launch_gather<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, n_rows, feature_size, out_pitch, nullptr, vec);
+  if (n_rows == 0) return NB_OK;
+  const uint32_t tb = gather_variant() == 1 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
+  if (tb) return launch_gather_tma<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, n_rows, nullptr, tb, out_pitch);
+  uint32_t fe = feature_size;
+  int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch, &fe);
+  return launch_gather<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, n_rows, fe, out_pitch, nullptr, vec);
 }
 
 int nb_gather_rows_dyn(nb_ctx *ctx, float *out, const float *table, const uint32_t *ids_dev, const uint32_t *n_rows_dev,
                        uint32_t max_rows, uint32_t feature_size, uint32_t table_pitch, uint32_t out_pitch) {
-  NB_REQUIRE(ctx && out && table && ids_dev && n_rows_dev, NB_ERR_ARG, "nb_gather_rows_dyn: NULL argument");
+  NB_REQUIRE(ctx && (max_rows == 0 || (out && table && ids_dev)), NB_ERR_ARG, "nb_gather_rows_dyn: NULL argument");
   NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && out_pitch >= feature_size, NB_ERR_ARG, "nb_gather_rows_dyn: bad pitch");
   NB_GUARD(ctx);
-  int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch);
-  return launch_gather<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, max_rows, feature_size, out_pitch, nullptr, vec, n_rows_dev);
+  if (max_rows == 0) return NB_OK;
+  const uint32_t tb = gather_variant() == 1 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
+  if (tb) return launch_gather_tma<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, max_rows, n_rows_dev, tb, out_pitch);
+  uint32_t fe = feature_size;
+  int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch, &fe);
+  return launch_gather<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, max_rows, fe, out_pitch, nullptr, vec, n_rows_dev);
 }
 
 int nb_gather_rows_cached(nb_ctx *ctx, float *out, const float *cold_table, uint32_t cold_pitch, const float *cache_table,

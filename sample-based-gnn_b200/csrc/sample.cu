@@ -128,24 +128,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
       if (w < warp) warp_base += t;
       block_total += t;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+      // warp-parallel decoupled look-back: lane l inspects tile (first_pred - l); the window slides back by 32
       unsigned prefix = 0;
       if (tile == 0) {
-        atomicExch(&ws.tile_state[0], tag | (2ull << 32) | block_total);
+        if (lane == 0) atomicExch(&ws.tile_state[0], tag | (2ull << 32) | block_total);
       } else {
-        atomicExch(&ws.tile_state[tile], tag | (1ull << 32) | block_total);
-        int p = (int)tile - 1;
+        if (lane == 0) atomicExch(&ws.tile_state[tile], tag | (1ull << 32) | block_total);
+        int hi = (int)tile - 1;  // nearest predecessor not yet accounted for
         while (true) {
-          unsigned long long st = *((volatile unsigned long long *)&ws.tile_state[p]);
-          if ((st >> 34 << 34) != tag) continue;  // not written in this batch yet
-          unsigned flag = (unsigned)(st >> 32) & 3u;
-          prefix += (unsigned)st;
-          if (flag == 2) break;
-          p--;
+          const int p = hi - (int)lane;
+          unsigned long long st = 0;
+          bool ready = true;
+          if (p >= 0) {
+            st = *((volatile unsigned long long *)&ws.tile_state[p]);
+            ready = (st >> 34 << 34) == tag;
+          }
+          if (!__all_sync(FULL_MASK, ready)) continue;  // some predecessor has not published yet: poll again
+          const unsigned flag = p >= 0 ? ((unsigned)(st >> 32) & 3u) : 2u;  // "tile -1" acts as an inclusive prefix of 0
+          const unsigned incl_mask = __ballot_sync(FULL_MASK, flag == 2u);
+          const unsigned val = p >= 0 ? (unsigned)st : 0u;
+          const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;  // nearest lane holding an inclusive prefix
+          prefix += warp_sum_u32(lane <= (unsigned)stop ? val : 0u);
+          if (incl_mask) break;
+          hi -= 32;
         }
-        atomicExch(&ws.tile_state[tile], tag | (2ull << 32) | (unsigned long long)(prefix + block_total));
+        if (lane == 0) atomicExch(&ws.tile_state[tile], tag | (2ull << 32) | (unsigned long long)(prefix + block_total));
       }
-      s_prefix = prefix;
+      if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
     unsigned base = s_prefix + warp_base + (incl - sum);

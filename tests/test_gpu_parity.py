@@ -480,7 +480,7 @@ def test_full_size_reddit_shaped_properties(nts, cs):
     gy = torch.randn_like(y)
     gx = op.backward(gy)
     lhs, rhs = (y.double() * gy.double()).sum(), (x0.double() * gx.double()).sum()
-    assert abs(float(lhs - rhs)) <= 1e-6 * max(1.0, abs(float(lhs)))
+    assert abs(float(lhs - rhs)) <= 1e-6 * float((y.double().abs() * gy.double().abs()).sum())
     refb = torch.zeros((bottom.src_size, F), dtype=torch.float64, device="cuda")
     refb.index_add_(0, bottom.dev_row_indices.long(), gy.double()[e_dst] * w[:, None])
     torch.testing.assert_close(gx.double(), refb, rtol=1e-5, atol=1e-5)
