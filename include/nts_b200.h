@@ -182,6 +182,35 @@ int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out);
 int nb_sampler_sizes_dev(nb_sampler *s, int layer, const uint32_t **n_dst_dev, const uint32_t **n_edges_dev,
                          const uint32_t **n_src_dev, uint32_t *cap_dst, uint32_t *cap_edges, uint32_t *cap_src);
 
+/* ---- stage-by-stage sampling, in the reference's own call shapes ------------------------------------------------
+ * For callers that drive the stages themselves with host round trips in between (SampledSubgraph::gpu_sampling_init_co,
+ * gpu_sampling, update_degrees_GPU, Get_Weight -- core/FullyRepGraph.hpp:213-239, 326-524). Same kernels as
+ * nb_sampler_sample, on caller-owned arrays; transient state lives in the ctx scratch buffer.
+ * nb_sample_count        <- Cuda_Stream::sample_processing_get_co_gpu / _omit (cuda/ntsCUDA.hpp:331-349, 514-519); synchronises
+ *                           and returns the edge count, as the reference does through its VertexId_CUDA& edge_size.
+ * nb_sample_traverse     <- Cuda_Stream::sample_processing_traverse_gpu (:355-368): r_i receives GLOBAL src ids per edge;
+ *                           src receives the distinct ids ASCENDING (reference: atomic arrival order); src_index[v] = local id
+ *                           of every sampled v (reference: the same |V| map); *src_count_dev = number of distinct ids.
+ * nb_sample_update_ri    <- Cuda_Stream::sample_processing_update_ri_gpu (:351-354): r_i[e] = src_index[r_i[e]].
+ * nb_set_dst_local_index <- Cuda_Stream::set_dst_local_index (:562-563).
+ * nb_update_degree       <- Cuda_Stream::ReFreshDegree + UpdateDegree / UpdateDegreeCache (:420-429, 506-508).
+ * nb_edge_weight         <- Cuda_Stream::GetWeight / GetMeanWeight (:430-437, 510-512). */
+int nb_sample_count(nb_ctx *ctx, const uint32_t *dst_dev, uint32_t *local_column_offset_dev, const uint32_t *global_column_offset_dev,
+                    uint32_t dst_size, uint32_t fanout, const uint32_t *omit_flag_dev, uint32_t omit_value, uint32_t *edge_size_out);
+int nb_sample_traverse(nb_ctx *ctx, const uint32_t *destination_dev, const uint32_t *column_offset_dev, uint32_t *r_i_dev,
+                       const uint32_t *global_column_offset_dev, const uint32_t *global_row_indices_dev, uint32_t *src_index_dev,
+                       uint32_t vtx_size, uint32_t edge_size, uint32_t n_vertices, uint32_t *src_dev, uint32_t *src_count_dev,
+                       uint32_t layer, uint32_t fanout, int add_dst_to_src, uint64_t rng_seed, uint64_t rng_offset);
+int nb_sample_update_ri(nb_ctx *ctx, uint32_t *r_i_dev, const uint32_t *src_index_dev, uint32_t edge_size);
+int nb_set_dst_local_index(nb_ctx *ctx, const uint32_t *src_index_dev, const uint32_t *destination_dev, uint32_t n_dst,
+                           uint32_t *dst_to_local_dev);
+int nb_update_degree(nb_ctx *ctx, uint32_t *out_degree_dev, uint32_t *in_degree_dev, uint32_t n_vertices, uint32_t n_dst,
+                     const uint32_t *destination_dev, const uint32_t *source_dev, const uint32_t *column_offset_dev,
+                     const uint32_t *row_indices_dev, int cache_fanout);
+int nb_edge_weight(nb_ctx *ctx, float *edge_weight_dev, const uint32_t *out_degree_dev, const uint32_t *in_degree_dev, uint32_t n_dst,
+                   const uint32_t *destination_dev, const uint32_t *source_dev, const uint32_t *column_offset_dev,
+                   const uint32_t *row_indices_dev, int mean);
+
 /* ---- feature / label gather ----------------------------------------------------------------
  * nb_gather_rows        <- Cuda_Stream::zero_copy_feature_move_gpu (cuda/ntsCUDA.hpp:370-374): out[i,:] = table[ids[i],:].
  *                          `table` may be device memory or mapped pinned host memory; table_pitch

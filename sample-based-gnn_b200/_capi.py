@@ -63,6 +63,12 @@ _SIGS = {
     "nb_sampler_replay": (I32, [P, P, U32, C.POINTER(P), C.POINTER(U32), I32, C.POINTER(LayerView)]),
     "nb_sampler_layer": (I32, [P, I32, C.POINTER(LayerView)]),
     "nb_sampler_sizes_dev": (I32, [P, I32, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(U32), C.POINTER(U32), C.POINTER(U32)]),
+    "nb_sample_count": (I32, [P, P, P, P, U32, U32, P, U32, C.POINTER(U32)]),
+    "nb_sample_traverse": (I32, [P, P, P, P, P, P, P, U32, U32, U32, P, P, U32, U32, I32, U64, U64]),
+    "nb_sample_update_ri": (I32, [P, P, P, U32]),
+    "nb_set_dst_local_index": (I32, [P, P, P, U32, P]),
+    "nb_update_degree": (I32, [P, P, P, U32, U32, P, P, P, P, I32]),
+    "nb_edge_weight": (I32, [P, P, P, P, U32, P, P, P, P, I32]),
     "nb_gather_rows": (I32, [P, P, P, P, U32, U32, U32, U32]),
     "nb_gather_rows_dyn": (I32, [P, P, P, P, P, U32, U32, U32, U32]),
     "nb_aggregate_csc_fwd_dyn": (I32, [P, P, P, P, P, P, P, U32, U32, U32, U32]),

@@ -223,7 +223,7 @@ struct BitmapOp {
 __global__ void __launch_bounds__(256)
 k_emit_sources(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ word_rank, uint32_t *__restrict__ source,
                uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor, uint32_t *__restrict__ src_to_dst,
-               const LayerMeta *meta, uint32_t n_words) {
+               const LayerMeta *meta, uint32_t n_words, uint32_t *__restrict__ src_index_out = nullptr) {
   if (meta->err) return;
   const unsigned lane = lane_id();
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
@@ -232,9 +232,9 @@ k_emit_sources(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__
     if (bits & (1u << lane)) {
       const uint32_t k = word_rank[w] + __popc(bits & ((1u << lane) - 1u));
       source[k] = w * 32u + lane;
-      row_count[k] = 0;
-      row_cursor[k] = 0;
+      if (row_count) { row_count[k] = 0; row_cursor[k] = 0; }
       if (src_to_dst) src_to_dst[k] = 0xffffffffu;
+      if (src_index_out) src_index_out[w * 32u + lane] = k;  // legacy |V|-sized global -> local map
     }
   }
 }
@@ -371,7 +371,7 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
 // global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
 // Reference: sample_processing_update_ri_gpu_kernel cuda/ntsCUDATransferKernel.cuh:1136-1150,
 // sample_set_dst_local :1189-1196; CPU :1085-1099.
-__device__ __forceinline__ float edge_weight(uint32_t od, uint32_t id, uint32_t col_len, int weight_type) {
+__device__ __forceinline__ float edge_weight_fn(uint32_t od, uint32_t id, uint32_t col_len, int weight_type) {
   float w = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn((float)od), __fsqrt_rn((float)id)));
   if (weight_type == NB_WEIGHT_MEAN) w = __fdiv_rn(w, (float)id);
   else if (weight_type == NB_WEIGHT_MEAN_SAMPLED) w = __fdiv_rn(w, (float)col_len);
@@ -399,7 +399,7 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
     if (histogram) atomicAdd(&row_count[local], 1u);
     if (fuse_weights && weight_type != NB_WEIGHT_NONE) {
       const uint32_t j = edge_dst[e];
-      ewf[e] = edge_weight(out_deg[v], in_deg[dst[j]], col_off[j + 1] - col_off[j], weight_type);
+      ewf[e] = edge_weight_fn(out_deg[v], in_deg[dst[j]], col_off[j + 1] - col_off[j], weight_type);
     }
   }
   if (dst_local_id)
@@ -423,7 +423,7 @@ k_weights_sampled(float *__restrict__ ewf, const uint32_t *__restrict__ row_indi
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
     const uint32_t j = edge_dst[e];
     const uint32_t col_len = col_off[j + 1] - col_off[j];
-    ewf[e] = edge_weight(row_count[row_indices[e]], col_len, col_len, weight_type);
+    ewf[e] = edge_weight_fn(row_count[row_indices[e]], col_len, col_len, weight_type);
   }
 }
 
@@ -864,6 +864,168 @@ int nb_sampler_sizes_dev(nb_sampler *s, int layer, const uint32_t **n_dst_dev, c
   if (cap_dst) *cap_dst = s->lay[layer].cap_dst;
   if (cap_edges) *cap_edges = s->lay[layer].cap_edges;
   if (cap_src) *cap_src = s->lay[layer].cap_src;
+  return NB_OK;
+}
+
+
+// =============================================================================================
+// Stage-by-stage entry points with the reference's own call shapes, for unmodified callers of
+// Cuda_Stream::sample_processing_* (core/FullyRepGraph.hpp:326-524 drives them one stage at a time
+// with host round trips in between). They run the same kernels as nb_sampler_sample on caller-owned
+// arrays; transient state (bitmap, ranks, scan tiles) lives in the ctx scratch buffer.
+struct LegacyState {
+  LayerMeta meta[2];
+  BatchParams params;
+};
+
+__global__ void k_update_ri(uint32_t *r_i, const uint32_t *__restrict__ src_index, uint32_t n) {
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) r_i[e] = src_index[r_i[e]];
+}
+__global__ void k_map_ids(uint32_t *out, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ map, uint32_t n) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = map[ids[i]];
+}
+// in_degree[dst] = sampled column length (fanout when 0 and cache_fanout > 0), out_degree[src]++ per sampled edge
+// (up_date_degree / update_cache_degree, cuda/ntsCUDATransferKernel.cuh:238-292)
+__global__ void k_update_degree(uint32_t *out_degree, uint32_t *in_degree, uint32_t n_dst, const uint32_t *__restrict__ destination,
+                                const uint32_t *__restrict__ source, const uint32_t *__restrict__ col_off,
+                                const uint32_t *__restrict__ row_indices, int cache_fanout) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_dst; i += gridDim.x * blockDim.x) {
+    const uint32_t b = col_off[i], e = col_off[i + 1];
+    uint32_t len = e - b;
+    if (len == 0 && cache_fanout > 0) len = (uint32_t)cache_fanout;
+    in_degree[destination[i]] = len;
+    for (uint32_t j = b; j < e; j++) atomicAdd(&out_degree[source[row_indices[j]]], 1u);
+  }
+}
+// get_weight / get_mean_weight (ibid. :294-342) on caller-owned |V| degree arrays
+__global__ void k_legacy_weight(float *edge_weight, const uint32_t *__restrict__ out_degree, const uint32_t *__restrict__ in_degree,
+                                uint32_t n_dst, const uint32_t *__restrict__ destination, const uint32_t *__restrict__ source,
+                                const uint32_t *__restrict__ col_off, const uint32_t *__restrict__ row_indices, int mean) {
+  const unsigned lane = lane_id(), warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; d < n_dst; d += warps) {
+    const uint32_t b = col_off[d], e = col_off[d + 1], id = in_degree[destination[d]];
+    for (uint32_t j = b + lane; j < e; j += 32)
+      edge_weight[j] = edge_weight_fn(out_degree[source[row_indices[j]]], id, e - b, mean ? NB_WEIGHT_MEAN_SAMPLED : NB_WEIGHT_SUM);
+  }
+}
+
+static int legacy_state(nb_ctx *ctx, uint32_t n_items_for_scan, uint32_t n_vertices, uint64_t n_edges, LegacyState **st,
+                        unsigned long long **tiles, uint32_t **bitmap, uint32_t **word_rank, uint32_t **edge_dst) {
+  const uint32_t n_words = (n_vertices + 31) / 32;
+  uint32_t items = n_items_for_scan > n_words ? n_items_for_scan : n_words;
+  const size_t n_tiles = (items + SCAN_TILE - 1) / SCAN_TILE + 1;
+  size_t bytes = 1024 + n_tiles * 8 + ((size_t)n_words + 64) * 8 + (size_t)n_edges * 4 + 256;
+  uint8_t *p;
+  int rc = nb_ctx_scratch(ctx, bytes, (void **)&p);
+  if (rc) return rc;
+  *st = (LegacyState *)p;
+  *tiles = (unsigned long long *)(p + 1024);
+  *bitmap = (uint32_t *)(p + 1024 + n_tiles * 8);
+  *word_rank = *bitmap + n_words + 32;
+  *edge_dst = *word_rank + n_words + 32;
+  NB_CUDA(cudaMemsetAsync(*tiles, 0, n_tiles * 8, ctx->stream));
+  return NB_OK;
+}
+
+int nb_sample_count(nb_ctx *ctx, const uint32_t *dst_dev, uint32_t *local_column_offset_dev, const uint32_t *global_column_offset_dev,
+                    uint32_t dst_size, uint32_t fanout, const uint32_t *omit_flag_dev, uint32_t omit_value, uint32_t *edge_size_out) {
+  NB_REQUIRE(ctx && local_column_offset_dev && global_column_offset_dev && edge_size_out && (dst_dev || dst_size == 0), NB_ERR_ARG,
+             "nb_sample_count: NULL argument");
+  NB_GUARD(ctx);
+  LegacyState *st; unsigned long long *tiles; uint32_t *bitmap, *rank, *edge_dst;
+  int rc = legacy_state(ctx, dst_size, 32, 0, &st, &tiles, &bitmap, &rank, &edge_dst);
+  if (rc) return rc;
+  LegacyState h;
+  memset(&h, 0, sizeof(h));
+  h.meta[0].n_dst = dst_size;
+  h.params.omit = omit_flag_dev; h.params.omit_value = omit_value; h.params.epoch = 1;
+  NB_CUDA(cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  CountOp cop{global_column_offset_dev, dst_dev, &st->params, local_column_offset_dev, &st->meta[0], 0xffffffffu, (int)fanout, 1};
+  ScanWs ws{tiles, &st->params};
+  k_scan<CountOp><<<nb_grid(dst_size, SCAN_TILE, 4), SCAN_THREADS, 0, ctx->stream>>>(cop, ws);
+  NB_LAUNCH_CHECK(ctx);
+  NB_CUDA(cudaMemcpyAsync(edge_size_out, &st->meta[0].n_edges, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(cudaStreamSynchronize(ctx->stream));  // the reference returns edge_size by reference
+  return NB_OK;
+}
+
+int nb_sample_traverse(nb_ctx *ctx, const uint32_t *destination_dev, const uint32_t *column_offset_dev, uint32_t *r_i_dev,
+                       const uint32_t *global_column_offset_dev, const uint32_t *global_row_indices_dev, uint32_t *src_index_dev,
+                       uint32_t vtx_size, uint32_t edge_size, uint32_t n_vertices, uint32_t *src_dev, uint32_t *src_count_dev,
+                       uint32_t layer, uint32_t fanout, int add_dst_to_src, uint64_t rng_seed, uint64_t rng_offset) {
+  NB_REQUIRE(ctx && column_offset_dev && global_column_offset_dev && global_row_indices_dev && src_index_dev && src_dev && src_count_dev,
+             NB_ERR_ARG, "nb_sample_traverse: NULL argument");
+  NB_REQUIRE(fanout >= 1 && fanout <= 512, NB_ERR_UNSUPPORTED, "fanout %u: supported values are 1..512", fanout);
+  NB_GUARD(ctx);
+  LegacyState *st; unsigned long long *tiles; uint32_t *bitmap, *rank, *edge_dst;
+  int rc = legacy_state(ctx, vtx_size, n_vertices, edge_size, &st, &tiles, &bitmap, &rank, &edge_dst);
+  if (rc) return rc;
+  const uint32_t n_words = (n_vertices + 31) / 32;
+  LegacyState h;
+  memset(&h, 0, sizeof(h));
+  h.meta[0].n_dst = vtx_size; h.meta[0].n_edges = edge_size;
+  h.params.rng_seed = rng_seed; h.params.rng_offset = rng_offset; h.params.epoch = 1;
+  NB_CUDA(cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  NB_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)(n_words + 1) * 4, ctx->stream));
+  int hash_slots = fanout > 32 ? (int)pow2_ceil(2u * fanout) : 0;
+  k_sample<<<nb_grid(vtx_size, SAMPLE_WARPS, 8), SAMPLE_WARPS * 32, (size_t)hash_slots * SAMPLE_WARPS * 4, ctx->stream>>>(
+      global_column_offset_dev, global_row_indices_dev, destination_dev, column_offset_dev, r_i_dev, edge_dst, bitmap, &st->meta[0],
+      (int)fanout, &st->params, layer, add_dst_to_src ? 1 : 0, hash_slots);
+  NB_LAUNCH_CHECK(ctx);
+  BitmapOp bop{bitmap, rank, &st->meta[0], &st->meta[1], n_words, 0xffffffffu};
+  ScanWs ws{tiles, &st->params};
+  k_scan<BitmapOp><<<nb_grid(n_words, SCAN_TILE, 4), SCAN_THREADS, 0, ctx->stream>>>(bop, ws);
+  NB_LAUNCH_CHECK(ctx);
+  k_emit_sources<<<nb_grid(n_words, 8, 8), 256, 0, ctx->stream>>>(bitmap, rank, src_dev, nullptr, nullptr, nullptr, &st->meta[0], n_words, src_index_dev);
+  NB_LAUNCH_CHECK(ctx);
+  NB_CUDA(cudaMemcpyAsync(src_count_dev, &st->meta[0].n_src, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  return NB_OK;
+}
+
+int nb_sample_update_ri(nb_ctx *ctx, uint32_t *r_i_dev, const uint32_t *src_index_dev, uint32_t edge_size) {
+  NB_REQUIRE(ctx && (edge_size == 0 || (r_i_dev && src_index_dev)), NB_ERR_ARG, "nb_sample_update_ri: NULL argument");
+  NB_GUARD(ctx);
+  if (!edge_size) return NB_OK;
+  k_update_ri<<<nb_grid(edge_size, 256, 8), 256, 0, ctx->stream>>>(r_i_dev, src_index_dev, edge_size);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_set_dst_local_index(nb_ctx *ctx, const uint32_t *src_index_dev, const uint32_t *destination_dev, uint32_t n_dst, uint32_t *dst_to_local_dev) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (src_index_dev && destination_dev && dst_to_local_dev)), NB_ERR_ARG, "nb_set_dst_local_index: NULL argument");
+  NB_GUARD(ctx);
+  if (!n_dst) return NB_OK;
+  k_map_ids<<<nb_grid(n_dst, 256, 8), 256, 0, ctx->stream>>>(dst_to_local_dev, destination_dev, src_index_dev, n_dst);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_update_degree(nb_ctx *ctx, uint32_t *out_degree_dev, uint32_t *in_degree_dev, uint32_t n_vertices, uint32_t n_dst,
+                     const uint32_t *destination_dev, const uint32_t *source_dev, const uint32_t *column_offset_dev,
+                     const uint32_t *row_indices_dev, int cache_fanout) {
+  NB_REQUIRE(ctx && out_degree_dev && in_degree_dev, NB_ERR_ARG, "nb_update_degree: NULL argument");
+  NB_GUARD(ctx);
+  if (n_vertices) {  // ReFreshDegree
+    NB_CUDA(cudaMemsetAsync(out_degree_dev, 0, (size_t)n_vertices * 4, ctx->stream));
+    NB_CUDA(cudaMemsetAsync(in_degree_dev, 0, (size_t)n_vertices * 4, ctx->stream));
+  }
+  if (!n_dst) return NB_OK;
+  k_update_degree<<<nb_grid(n_dst, 256, 8), 256, 0, ctx->stream>>>(out_degree_dev, in_degree_dev, n_dst, destination_dev, source_dev,
+                                                                   column_offset_dev, row_indices_dev, cache_fanout);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+int nb_edge_weight(nb_ctx *ctx, float *edge_weight_dev, const uint32_t *out_degree_dev, const uint32_t *in_degree_dev, uint32_t n_dst,
+                   const uint32_t *destination_dev, const uint32_t *source_dev, const uint32_t *column_offset_dev,
+                   const uint32_t *row_indices_dev, int mean) {
+  NB_REQUIRE(ctx && (n_dst == 0 || (edge_weight_dev && out_degree_dev && in_degree_dev && destination_dev && source_dev && column_offset_dev)),
+             NB_ERR_ARG, "nb_edge_weight: NULL argument");
+  NB_GUARD(ctx);
+  if (!n_dst) return NB_OK;
+  k_legacy_weight<<<nb_grid(n_dst, 8, 8), 256, 0, ctx->stream>>>(edge_weight_dev, out_degree_dev, in_degree_dev, n_dst, destination_dev,
+                                                                 source_dev, column_offset_dev, row_indices_dev, mean);
+  NB_LAUNCH_CHECK(ctx);
   return NB_OK;
 }
 

@@ -484,3 +484,94 @@ def test_full_size_reddit_shaped_properties(nts, cs):
     refb = torch.zeros((bottom.src_size, F), dtype=torch.float64, device="cuda")
     refb.index_add_(0, bottom.dev_row_indices.long(), gy.double()[e_dst] * w[:, None])
     torch.testing.assert_close(gx.double(), refb, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_stage_by_stage_entry_points_match_oracle(nts, cs):
+    """The reference's own call sequence (SampledSubgraph::gpu_sampling_init_co -> gpu_sampling -> update_degrees_GPU ->
+    Get_Weight, core/FullyRepGraph.hpp:213-239, 326-524) through the stage-shaped entry points."""
+    import ctypes as C
+    lib, check, ptr = nts._capi.lib(), nts._capi.check, nts._capi.ptr
+    V = 8000
+    pairs, graph = make_graph(nts, cs, V, 25, seed=21)
+    co, ri = oracle.build_csc(pairs, V)
+    ind, outd = oracle.degrees(pairs, V)
+    g_co, g_ri, g_in, g_out = graph.device_arrays()
+    rng = np.random.default_rng(9)
+    dst_np = rng.permutation(V)[:600].astype(np.uint32)
+    dev = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
+    for fanout, merge in ((7, False), (40, True)):
+        dst = dev(dst_np)
+        lco = torch.zeros(dst_np.size + 1, dtype=torch.int32, device="cuda")
+        e = C.c_uint32()
+        check(lib.nb_sample_count(cs._h, ptr(dst), ptr(lco), ptr(g_co), dst_np.size, fanout, None, 0, C.byref(e)))
+        ref_co, ref_e = oracle.count_offsets(dst_np, co, fanout)
+        assert e.value == ref_e and np.array_equal(u32(lco), ref_co)
+        r_i = torch.zeros(max(e.value, 1), dtype=torch.int32, device="cuda")
+        src_index = torch.full((V,), -1, dtype=torch.int32, device="cuda")
+        src = torch.zeros(e.value + dst_np.size, dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        check(lib.nb_sample_traverse(cs._h, ptr(dst), ptr(lco), ptr(r_i), ptr(g_co), ptr(g_ri), ptr(src_index), dst_np.size,
+                                     e.value, V, ptr(src), ptr(cnt), 0, fanout, 1 if merge else 0, 77, 5))
+        ans = u32(r_i)[:e.value].copy()
+        S = int(cnt.item())
+        rsrc, rri, rdl = oracle.reindex(ans, dst_np, V, merge_src_dst=merge)
+        assert S == rsrc.size and np.array_equal(u32(src)[:S], rsrc)
+        assert np.array_equal(u32(src_index)[rsrc], np.arange(S, dtype=np.uint32))
+        check(lib.nb_sample_update_ri(cs._h, ptr(r_i), ptr(src_index), e.value))
+        assert np.array_equal(u32(r_i)[:e.value], rri)
+        if merge:
+            dl = torch.zeros(dst_np.size, dtype=torch.int32, device="cuda")
+            check(lib.nb_set_dst_local_index(cs._h, ptr(src_index), ptr(dst), dst_np.size, ptr(dl)))
+            assert np.array_equal(u32(dl), rdl)
+        # sampling rule
+        for j, d in enumerate(dst_np[:200]):
+            nb = ri[co[d]:co[d + 1]]
+            got = ans[ref_co[j]:ref_co[j + 1]]
+            assert np.array_equal(got, nb) if nb.size <= fanout else (np.unique(got).size == fanout and np.isin(got, nb).all())
+        # weights from the graph's degrees, then from per-batch sampled degrees
+        w = torch.zeros(max(e.value, 1), device="cuda")
+        check(lib.nb_edge_weight(cs._h, ptr(w), ptr(g_out), ptr(g_in), dst_np.size, ptr(dst), ptr(src), ptr(lco), ptr(r_i), 0))
+        ewf, _ = oracle.weights(dst_np, rsrc, ref_co, rri, None, None, ind, outd, 0)
+        assert np.array_equal(bits(f32(w)[:e.value]), bits(ewf))
+        d_in, d_out = torch.full((V,), 9, dtype=torch.int32, device="cuda"), torch.full((V,), 9, dtype=torch.int32, device="cuda")
+        check(lib.nb_update_degree(cs._h, ptr(d_out), ptr(d_in), V, dst_np.size, ptr(dst), ptr(src), ptr(lco), ptr(r_i), 0))
+        s_in, s_out = oracle.update_degrees(dst_np, rsrc, ref_co, rri, V)
+        assert np.array_equal(u32(d_in), s_in) and np.array_equal(u32(d_out), s_out)
+        check(lib.nb_edge_weight(cs._h, ptr(w), ptr(d_out), ptr(d_in), dst_np.size, ptr(dst), ptr(src), ptr(lco), ptr(r_i), 1))
+        ewf2, _ = oracle.weights(dst_np, rsrc, ref_co, rri, None, None, s_in, s_out, 2)
+        assert np.array_equal(bits(f32(w)[:e.value]), bits(ewf2))
+
+
+def test_padded_rows_and_tma_gather_match_dense(nts, cs):
+    """Row-padded layouts (pitch 608 for 602-wide rows) take the 128-bit / TMA bulk-copy paths and must give the same bits."""
+    lib, check, ptr = nts._capi.lib(), nts._capi.check, nts._capi.ptr
+    V, F, P = 5000, 602, 608
+    pairs, graph = make_graph(nts, cs, V, 25, seed=5)
+    rng = np.random.default_rng(1)
+    seeds = rng.permutation(V)[:300].astype(np.uint32)
+    sampler = nts.FastSampler(graph, seeds, 2, 300, [8, 6], cuda_stream=cs)
+    sg = sampler.sample_gpu_fast(300)
+    lay = sg.sampled_sgs[1]
+    dense = torch.randn((V, F), device="cuda")
+    padded = torch.zeros((V, P), device="cuda")
+    padded[:, :F] = dense
+    x_d = torch.empty((lay.src_size, F), device="cuda")
+    sampler.load_feature_gpu(cs, sg, x_d, dense)
+    for variant in (0, 1):
+        check(lib.nb_set_option(b"gather_variant", variant))
+        x_p = torch.full((lay.src_size, P), 7.0, device="cuda")
+        sampler.load_feature_gpu(cs, sg, x_p[:, :F], padded[:, :F])
+        assert torch.equal(x_p[:, :F], x_d)
+    op = nts.SingleGPUAllSampleGraphOp(sg, 1, cs)
+    y_d = op.forward(x_d)
+    y_p = op.forward(x_p[:, :F])
+    assert y_p.stride(0) == P and torch.equal(y_p, y_d)
+    dy = torch.randn((lay.v_size, P), device="cuda")
+    g_p = op.backward(dy[:, :F])
+    g_d = op.backward(dy[:, :F].contiguous())
+    assert torch.equal(g_p, g_d)
+    # the bottom hop straight from the feature table (no X0): identical bits
+    y_f = torch.empty((lay.v_size, P), device="cuda")
+    cs.aggregate_fwd_pitched(padded, y_f, lay.dev_e_w(), lay.dev_sample_ans, lay.dev_c_o(), lay.v_size, F, P, P)
+    assert torch.equal(y_f[:, :F], y_d)
