@@ -4,7 +4,7 @@
  * product (sample-based-gnn_b200/, include/): only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may use it, and only as the checker.
  *
- * Parity status: PINNED. Every function below is checked (tests/test_oracle_vs_reference.py)
+ * Parity status: PINNED. Every function below is checked (tests/test_oracle_golden.py)
  * against outputs of the reference's own code (oracle/_ref/ref_driver, built from the sources
  * under /root/reference by oracle/Makefile) recorded into tests/golden/ by
  * oracle/make_golden.py. Integer outputs match bit for bit; fp32 aggregation matches bit for
