@@ -438,7 +438,7 @@ class FeatureTable:
         self._keep = keepalive
 
     def gather(self, out, ids, n_rows):
-        check(lib().nb_table_gather(self.cs._h, self._h, ptr(out), ptr(ids), n_rows, out.shape[1]))
+        check(lib().nb_table_gather(self.cs._h, self._h, ptr(out), ptr(ids), n_rows, _pitch(out, self.feature_size)))
         return out
 
     def __del__(self):

@@ -1,0 +1,44 @@
+"""Launched by tests/test_gpu_multi.py under torch.distributed.run: one rank per GPU. Checks the row-sharded HBM feature
+table read peer-to-peer inside the gather kernel, and the bucketed NCCL gradient exchange."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nts = ge.load_package()
+    from sample_based_gnn_b200 import dist as nd
+    cs = nts.Cuda_Stream.on_torch_stream(local)
+    V, F = 50000, 128
+    full = torch.from_numpy(np.random.default_rng(1).standard_normal((V, F)).astype(np.float32))
+    mine = full[rank::world].cuda()
+    for pitch in (F, F + 4):
+        st = nd.ShardedTable(cs, mine, V, F, pitch=pitch)
+        ids = torch.from_numpy(np.random.default_rng(2 + rank).integers(0, V, 20000).astype(np.int32)).cuda()
+        out = torch.empty((20000, F), device="cuda")
+        st.gather(out, ids, 20000)
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), full[ids.cpu().long()]), f"rank {rank}: sharded gather mismatch (pitch {pitch})"
+        st.close()
+    w = torch.nn.Parameter(torch.zeros(602, 128, device="cuda"))
+    w.grad = torch.full_like(w, float(rank + 1))
+    nd.GradBucket([w]).all_reduce()
+    assert torch.equal(w.grad, torch.full_like(w, float(world * (world + 1) // 2)))
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
