@@ -178,6 +178,7 @@ def main_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     v, col_off, src = reddit_shaped_graph(args.scale)
     e_total = int(src.size)
@@ -194,9 +195,12 @@ def main_b200(args):
     with torch.cuda.stream(st_train):
         graph = nts.FullyRepGraph(cs_sample, v, column_offset=col_off, row_indices=src)
         # one sampler (arena) per pipeline slot, all on the sampling stream (the reference's PIPELINE_NUM SampledSubgraphs)
+        # bottom_csr=False: the bottom hop's backward never runs in the GCN toolkits (core/ntsContext.hpp:443), so its CSR is not built
         sampler = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=P, cuda_stream=[cs_sample] * P, build_csr=True,
-                                  rng_seed=SEED_SAMPLER + rank)
-        fast = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, cuda_stream=cs_train, build_csr=True, rng_seed=SEED_SAMPLER + rank)
+                                  bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
+        fast = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=2, cuda_stream=[cs_sample] * 2, build_csr=True,
+                               bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
+        api_ev = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
         gen = torch.Generator(device=dev).manual_seed(0x5EED0002)
         table = torch.zeros((v, PITCH), device=dev)                               # HBM-resident feature table
         table[:, :F0] = torch.rand((v, F0), generator=gen, device=dev) * 2 - 1
@@ -269,11 +273,28 @@ def main_b200(args):
             with torch.cuda.stream(st_train):
                 dist.all_reduce(grads)
 
-    def step_api(i, timed):
-        """e2e: the call sequence a user of the reference-shaped API makes -- host seeds in, sizes and the batch's top-layer
-        output back on the host -- including its synchronisation on the sampled sizes."""
+    api_state = {"issued": -1}
+
+    def api_issue(i):
+        """sample batch i asynchronously on the sampling stream into slot i % 2 (FastSampler pipeline slot, as PIPELINE_NUM=2)"""
+        k = i % 2
+        st_sample.wait_event(api_ev[k]["consumed"])
         fast.work_offset = i * BATCH
-        sg = fast.sample_gpu_fast(BATCH)                        # stages + uploads the seeds; syncs for the sizes
+        with torch.cuda.stream(st_sample):
+            fast.sample_gpu_fast(BATCH, ssg_id=k, sync=False)          # stages + uploads the seeds from host memory
+        api_ev[k]["sampled"].record(st_sample)
+        api_state["issued"] = i
+
+    def step_api(i, timed):
+        """e2e: the reference-shaped API a user calls -- host seeds in, sizes and the batch's top-layer output back on the
+        host every step. Batch i+1 is sampled (pipeline slot (i+1) % 2) while batch i is gathered / aggregated."""
+        if api_state["issued"] < i:
+            api_issue(i)
+        k = i % 2
+        sg = fast.wait(k)                                           # host waits for the sizes of batch i only
+        if i + 1 < n_steps:
+            api_issue(i + 1)
+        st_train.wait_event(api_ev[k]["sampled"])
         t, bt = sg.sampled_sgs
         xx = x0[:bt.src_size, :F0]
         fast.load_feature_gpu(cs_train, sg, xx, table[:, :F0])
@@ -281,10 +302,11 @@ def main_b200(args):
         op_top = nts.SingleGPUAllSampleGraphOp(sg, 0, cs_train)
         yy0 = op_top.forward(h1[:t.src_size])
         op_top.backward(dy0)
+        api_ev[k]["consumed"].record(st_train)
         if world > 1:
             dist.all_reduce(grads)
         y0_host.copy_(yy0, non_blocking=True)
-        st_train.synchronize()
+        st_train.synchronize()                                       # the host reads this step's result
         sizes_pin[i, 0], sizes_pin[i, 1], sizes_pin[i, 2] = bt.v_size, bt.e_size, bt.src_size
         sizes_top[i, 1] = t.e_size
         del yy1
@@ -293,6 +315,7 @@ def main_b200(args):
 
     def run(mode, sample_clocks=False):
         step = {"async": step_async, "fused": lambda i, t: step_async(i, t, True), "api": step_api}[mode]
+        api_state["issued"] = -1
         for k in kern_ev.values():
             k.clear()
         with torch.cuda.stream(st_train):
@@ -395,7 +418,7 @@ def main_b200(args):
                     "epoch_ms_est": (ms_max / args.steps) * (all_seeds.size / BATCH / world)}),
                 "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": BATCH * 4 + 64,
                         "d2h_bytes_per_step": BATCH * F1 * 4 + 3 * 32, "ms_per_step": ms_e2e_max / args.steps,
-                        "path": "FastSampler.sample_gpu_fast (sync on sizes) -> load_feature_gpu -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H"},
+                        "path": "FastSampler.sample_gpu_fast(slot i+1, async) || wait(slot i) -> load_feature_gpu -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H + sync, every step"},
                 "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "fused_gather_aggregate": {"value": edges_fused_all / (ms_fused_max * 1e-3), "unit": "edges/s",
                                            "ms_per_step": ms_fused_max / args.steps,

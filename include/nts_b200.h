@@ -57,6 +57,10 @@ typedef enum nb_weight_type {
 #define NB_SAMPLER_BUILD_CSR     4u /* also build row_offset / column_indices / e_w_b
                                        (sampCSC::csc_to_csr, core/coocsc.hpp:82-111)             */
 
+#define NB_SAMPLER_NO_BOTTOM_CSR  8u /* with BUILD_CSR: skip the CSR of the bottom layer. Its backward runs only when the
+                                       bottom op's input needs a gradient, which it never does when that input is the gathered
+                                       feature leaf (GCN/GraphSAGE toolkits; core/ntsContext.hpp:443 stops before the first op) */
+
 typedef struct nb_ctx nb_ctx;         /* replaces class Cuda_Stream, cuda/ntsCUDA.hpp:177-199     */
 typedef struct nb_graph nb_graph;     /* replaces the device side of FullyRepGraph +
                                          FastSampler's GPU ctor, core/ntsFastSampler.hpp:125-176  */
@@ -174,6 +178,7 @@ int nb_sampler_sample(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, in
                       nb_layer_view *views_out, int sync);
 int nb_sampler_replay(nb_sampler *s, const uint32_t *seeds_host, uint32_t n_seeds, const uint32_t *const *sample_ans_host,
                       const uint32_t *n_edges_host, int weight_type, nb_layer_view *views_out);
+int nb_sampler_wait(nb_sampler *s, nb_layer_view *views_out); /* completes a sync == 0 nb_sampler_sample (event wait on that batch only) */
 int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out);
 /* Device addresses of layer sizes (and the arena capacities that bound them), for the *_dyn entry points below:
  * kernels that consume a sampled layer read their extents from device memory, so sampling, gather and

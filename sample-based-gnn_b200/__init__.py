@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import (NB_SAMPLER_BUILD_CSR, NB_SAMPLER_MERGE_SRC_DST, NB_SAMPLER_UP_DEGREE, NB_WEIGHT_MEAN,
+from ._capi import (NB_SAMPLER_BUILD_CSR, NB_SAMPLER_MERGE_SRC_DST, NB_SAMPLER_NO_BOTTOM_CSR, NB_SAMPLER_UP_DEGREE, NB_WEIGHT_MEAN,
                     NB_WEIGHT_MEAN_SAMPLED, NB_WEIGHT_NONE, NB_WEIGHT_SUM, LayerView, NtsError, check, lib, ptr)
 
 __all__ = ["Cuda_Stream", "FullyRepGraph", "FastSampler", "SampledSubgraph", "sampCSC", "WeightType",
@@ -316,7 +316,7 @@ class FastSampler:
     """GPU FastSampler (core/ntsFastSampler.hpp:125-176, 648-915). One nb_sampler per pipeline slot."""
 
     def __init__(self, whole_graph, index, layers, batch_size, fanout, pipeline_num=1, cuda_stream=None,
-                 merge_src_dst=False, up_degree=False, build_csr=True, rng_seed=0x5EED0004):
+                 merge_src_dst=False, up_degree=False, build_csr=True, rng_seed=0x5EED0004, bottom_csr=True):
         assert len(index) > 0
         self.whole_graph = whole_graph
         self.sample_nids = np.ascontiguousarray(index, dtype=np.uint32).copy()
@@ -330,7 +330,7 @@ class FastSampler:
         self.cs_array = list(streams) + [streams[0]] * max(0, pipeline_num - len(streams))
         self.cs = self.cs_array[0]
         self.flags = (NB_SAMPLER_MERGE_SRC_DST if merge_src_dst else 0) | (NB_SAMPLER_UP_DEGREE if up_degree else 0) | \
-                     (NB_SAMPLER_BUILD_CSR if build_csr else 0)
+                     (NB_SAMPLER_BUILD_CSR if build_csr else 0) | (0 if bottom_csr else NB_SAMPLER_NO_BOTTOM_CSR)
         fan = (C.c_int * self.layer)(*self.fanout)
         self._samplers = []
         for i in range(max(1, pipeline_num)):
@@ -376,6 +376,12 @@ class FastSampler:
         self.work_offset += n
         self.batch_counter += 1
         return self._finish(ssg_id, views) if sync else None
+
+    def wait(self, ssg_id=0):
+        """Completes a sample_gpu_fast(..., sync=False) on pipeline slot ssg_id and returns its SampledSubgraph."""
+        views = (LayerView * self.layer)()
+        check(lib().nb_sampler_wait(self._samplers[ssg_id], views))
+        return self._finish(ssg_id, views)
 
     def sample_gpu_fast_omit(self, batch_size_, CacheFlag, super_batch_id=0xFFFFFFFF, weightType=WeightType.Sum, ssg_id=0):
         return self.sample_gpu_fast(batch_size_, ssg_id, weightType, CacheFlag, super_batch_id)

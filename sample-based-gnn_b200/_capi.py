@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnts_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "nts_b200.h")
 
 NB_WEIGHT_SUM, NB_WEIGHT_MEAN, NB_WEIGHT_NONE, NB_WEIGHT_MEAN_SAMPLED = 0, 1, 2, 3
-NB_SAMPLER_MERGE_SRC_DST, NB_SAMPLER_UP_DEGREE, NB_SAMPLER_BUILD_CSR = 1, 2, 4
+NB_SAMPLER_MERGE_SRC_DST, NB_SAMPLER_UP_DEGREE, NB_SAMPLER_BUILD_CSR, NB_SAMPLER_NO_BOTTOM_CSR = 1, 2, 4, 8
 
 
 class NtsError(RuntimeError):
@@ -61,6 +61,7 @@ _SIGS = {
     "nb_sampler_destroy": (I32, [P]),
     "nb_sampler_sample": (I32, [P, P, U32, I32, U64, U64, I32, P, U32, C.POINTER(LayerView), I32]),
     "nb_sampler_replay": (I32, [P, P, U32, C.POINTER(P), C.POINTER(U32), I32, C.POINTER(LayerView)]),
+    "nb_sampler_wait": (I32, [P, C.POINTER(LayerView)]),
     "nb_sampler_layer": (I32, [P, I32, C.POINTER(LayerView)]),
     "nb_sampler_sizes_dev": (I32, [P, I32, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(U32), C.POINTER(U32), C.POINTER(U32)]),
     "nb_sample_count": (I32, [P, P, P, P, U32, U32, P, U32, C.POINTER(U32)]),

@@ -20,7 +20,10 @@
 
 constexpr int AGG_THREADS = 256;
 
-template <int VEC, int CHUNK>
+// UNR = segment entries whose row loads are issued before the first accumulate (UNR*CHUNK independent vector loads per
+// lane in flight); narrow rows (CHUNK 1-2, e.g. F=128) take 8 entries at a time, wide rows 2. Accumulation stays in
+// stored order, so the result does not depend on UNR.
+template <int VEC, int CHUNK, int UNR>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
                  const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
@@ -43,31 +46,33 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
           my_idx = idx[j0 + lane];
           if (weight) my_w = weight[j0 + lane];
         }
-        uint32_t t = 0;
-        for (; t + 1 < cnt; t += 2) {
-          const uint32_t s0 = __shfl_sync(FULL_MASK, my_idx, t), s1 = __shfl_sync(FULL_MASK, my_idx, t + 1);
-          const float w0 = __shfl_sync(FULL_MASK, my_w, t), w1 = __shfl_sync(FULL_MASK, my_w, t + 1);
-          const float *p0 = in + (uint64_t)s0 * pitch, *p1 = in + (uint64_t)s1 * pitch;
-          Vec<VEC> x0[CHUNK], x1[CHUNK];
+        for (uint32_t t = 0; t < cnt; t += UNR) {
+          Vec<VEC> x[UNR][CHUNK];
+          float w[UNR];
 #pragma unroll
-          for (int c = 0; c < CHUNK; c++) {
-            const unsigned k = c0 + c * 32 + lane;
-            if (k < nvec) { x0[c].load(p0 + (uint64_t)k * VEC); x1[c].load(p1 + (uint64_t)k * VEC); }
+          for (int u = 0; u < UNR; u++) {
+            // entries past the end of the batch re-read entry t (cheap, cached) and are not accumulated
+            const uint32_t tt = t + u < cnt ? t + u : t;
+            const uint32_t s = __shfl_sync(FULL_MASK, my_idx, tt);
+            w[u] = __shfl_sync(FULL_MASK, my_w, tt);
+            const float *p = in + (uint64_t)s * pitch;
+            if (t + u < cnt) {
+#pragma unroll
+              for (int c = 0; c < CHUNK; c++) {
+                const unsigned k = c0 + c * 32 + lane;
+                if (k < nvec) x[u][c].load(p + (uint64_t)k * VEC);
+              }
+            }
           }
 #pragma unroll
-          for (int c = 0; c < CHUNK; c++) {
-            const unsigned k = c0 + c * 32 + lane;
-            if (k < nvec) { acc[c].axpy(x0[c], w0); acc[c].axpy(x1[c], w1); }
-          }
-        }
-        if (t < cnt) {
-          const uint32_t s0 = __shfl_sync(FULL_MASK, my_idx, t);
-          const float w0 = __shfl_sync(FULL_MASK, my_w, t);
-          const float *p0 = in + (uint64_t)s0 * pitch;
+          for (int u = 0; u < UNR; u++) {
+            if (t + u < cnt) {
 #pragma unroll
-          for (int c = 0; c < CHUNK; c++) {
-            const unsigned k = c0 + c * 32 + lane;
-            if (k < nvec) { Vec<VEC> x; x.load(p0 + (uint64_t)k * VEC); acc[c].axpy(x, w0); }
+              for (int c = 0; c < CHUNK; c++) {
+                const unsigned k = c0 + c * 32 + lane;
+                if (k < nvec) acc[c].axpy(x[u][c], w[u]);
+              }
+            }
           }
         }
       }
@@ -133,11 +138,12 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
 #define NB_SEG(C)                                                                                              \
   do {                                                                                                         \
     if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
-    else k_segment_reduce<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch); \
+    else k_segment_reduce<VEC, C, (C <= 2 ? 8 : C <= 4 ? 3 : 2)><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch); \
   } while (0)
   if (per_lane <= 1) NB_SEG(1);
   else if (per_lane <= 2) NB_SEG(2);
   else if (per_lane <= 4) NB_SEG(4);
+  else if (per_lane <= 5) NB_SEG(5);
   else if (per_lane <= 6) NB_SEG(6);
   else if (per_lane <= 8) NB_SEG(8);
   else if (per_lane <= 10) NB_SEG(10);

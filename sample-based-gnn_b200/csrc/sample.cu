@@ -81,9 +81,11 @@ struct nb_sampler {
   static const int RING = 8;
   uint8_t *stage[RING];
   cudaEvent_t stage_done[RING];
+  cudaEvent_t meta_ready;  // recorded after the sizes of the latest batch reached meta_host
   int stage_next;
   uint32_t epoch;
   cudaGraphExec_t graph_exec;
+  uint64_t graph_kernels;
   bool use_graph;
 };
 
@@ -270,6 +272,9 @@ __global__ void k_init_meta(LayerMeta *meta, int L, const BatchParams *params) {
 // mode 1 (replay): sample_ans was supplied; only edge_dst and the bitmap marks are produced.
 constexpr int SAMPLE_WARPS = 8;
 
+// GROUP lanes cooperate on one dst (GROUP = 8, 16 or 32 >= fanout for the register path; 32 for the hash path), so a
+// fanout-10 layer keeps two dst per warp busy instead of idling 22 lanes.
+template <int GROUP>
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32)
 k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_row_idx, const uint32_t *__restrict__ dst,
          const uint32_t *__restrict__ col_off, uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst,
@@ -282,39 +287,42 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
   const int replay = params->replay;
   const unsigned n_dst = meta->n_dst;
   const unsigned lane = lane_id();
-  const unsigned warps = gridDim.x * SAMPLE_WARPS;
+  constexpr unsigned GPW = 32 / GROUP;                       // groups per warp
+  const unsigned gl = lane % GROUP, gid = lane / GROUP;      // lane in group, group in warp
+  const unsigned gmask = GROUP == 32 ? FULL_MASK : (((1u << GROUP) - 1u) << (gid * GROUP));
+  const unsigned groups = gridDim.x * SAMPLE_WARPS * GPW;
   uint32_t *my_hash = s_hash + (threadIdx.x >> 5) * hash_slots;
   const Philox rng(key);
-  for (unsigned j = blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5); j < n_dst; j += warps) {
+  for (unsigned j = (blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5)) * GPW + gid; j < n_dst; j += groups) {
     const uint32_t d = dst[j];
     const uint32_t base = g_col_off[d];
     const uint32_t deg = g_col_off[d + 1] - base;
     const uint32_t off = col_off[j];
     const uint32_t num = col_off[j + 1] - off;
-    if (merge && lane == 0) atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+    if (merge && gl == 0) atomicOr(&bitmap[d >> 5], 1u << (d & 31));
     if (num == 0) continue;
     if (replay) {
-      for (uint32_t t = lane; t < num; t += 32) {
+      for (uint32_t t = gl; t < num; t += GROUP) {
         uint32_t v = sample_ans[off + t];
         edge_dst[off + t] = j;
         atomicOr(&bitmap[v >> 5], 1u << (v & 31));
       }
     } else if (num == deg) {  // take all, stored order
-      for (uint32_t t = lane; t < num; t += 32) {
+      for (uint32_t t = gl; t < num; t += GROUP) {
         uint32_t v = g_row_idx[base + t];
         sample_ans[off + t] = v;
         edge_dst[off + t] = j;
         atomicOr(&bitmap[v >> 5], 1u << (v & 31));
       }
-    } else if (num <= 32) {
-      const bool holder = lane < num;
-      const unsigned holders = __ballot_sync(FULL_MASK, holder);
+    } else if (num <= GROUP) {
+      const bool holder = gl < num;
+      const unsigned holders = __ballot_sync(gmask, holder) & gmask;
       bool need = holder;
       uint32_t pos = 0xffffffffu;
       uint4 r = make_uint4(0, 0, 0, 0);
       for (unsigned round = 0;; round++) {
         if (need) {
-          if ((round & 3) == 0) r = rng(j, lane + 32u * (round >> 2), layer, rng_offset);
+          if ((round & 3) == 0) r = rng(j, gl + 32u * (round >> 2), layer, rng_offset);
           uint32_t x = (round & 3) == 0 ? r.x : (round & 3) == 1 ? r.y : (round & 3) == 2 ? r.z : r.w;
           pos = __umulhi(x, deg);
         }
@@ -325,15 +333,15 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
           keep = !need || ((grp & settled) == 0 && lane == (unsigned)(__ffs(grp) - 1));
         }
         need = !keep;
-        if (!__any_sync(FULL_MASK, need)) break;
+        if (!__any_sync(gmask, need)) break;
       }
       if (holder) {
         uint32_t v = g_row_idx[base + pos];
-        sample_ans[off + lane] = v;
-        edge_dst[off + lane] = j;
+        sample_ans[off + gl] = v;
+        edge_dst[off + gl] = j;
         atomicOr(&bitmap[v >> 5], 1u << (v & 31));
       }
-    } else {  // fanout > 32: shared-memory set, 32 draws per round
+    } else if (GROUP == 32) {  // fanout > 32: shared-memory set, 32 draws per round
       for (int t = lane; t < hash_slots; t += 32) my_hash[t] = 0xffffffffu;
       __syncwarp();
       uint32_t have = 0;
@@ -366,6 +374,20 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
       }
     }
   }
+}
+
+static void launch_sample(cudaStream_t st, unsigned cap_dst, int fanout, const uint32_t *g_col_off, const uint32_t *g_row_idx,
+                          const uint32_t *dst, const uint32_t *col_off, uint32_t *sample_ans, uint32_t *edge_dst, uint32_t *bitmap,
+                          const LayerMeta *meta, const BatchParams *params, uint32_t layer, int merge) {
+  uint32_t hs = 1; while (fanout > 32 && hs < 2u * (uint32_t)fanout) hs <<= 1;
+  const int hash_slots = fanout > 32 ? (int)hs : 0;
+  const int group = (fanout < 0 || fanout > 16) ? 32 : (fanout > 8 ? 16 : 8);
+  const unsigned per_block = SAMPLE_WARPS * (32 / group);
+  const unsigned grid = nb_grid(cap_dst, per_block, 8);
+  const size_t smem = (size_t)hash_slots * SAMPLE_WARPS * 4;
+  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots);
+  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots);
+  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots);
 }
 
 // global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
@@ -657,6 +679,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     NB_CUDA(cudaHostAlloc(&s->stage[r], sizeof(BatchParams) + (size_t)max_batch * 4, cudaHostAllocDefault));
     NB_CUDA(cudaEventCreateWithFlags(&s->stage_done[r], cudaEventDisableTiming));
   }
+  NB_CUDA(cudaEventCreateWithFlags(&s->meta_ready, cudaEventDisableTiming));
   const char *ng = getenv("NB_NO_GRAPH");
   s->use_graph = !(ng && ng[0] == '1');
   NB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -670,6 +693,7 @@ int nb_sampler_destroy(nb_sampler *s) {
   cudaStreamSynchronize(s->ctx->stream);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   for (int r = 0; r < nb_sampler::RING; r++) { cudaFreeHost(s->stage[r]); cudaEventDestroy(s->stage_done[r]); }
+  cudaEventDestroy(s->meta_ready);
   cudaFree(s->arena);
   cudaFreeHost(s->meta_host);
   delete s;
@@ -679,7 +703,8 @@ int nb_sampler_destroy(nb_sampler *s) {
 static void fill_view(nb_sampler *s, int i, nb_layer_view *v) {
   const LayerBuf &b = s->lay[i];
   const LayerMeta &m = s->meta_host[i];
-  const bool csr = s->flags & NB_SAMPLER_BUILD_CSR, merge = s->flags & NB_SAMPLER_MERGE_SRC_DST;
+  const bool csr = (s->flags & NB_SAMPLER_BUILD_CSR) && !(i == s->L - 1 && s->L > 1 && (s->flags & NB_SAMPLER_NO_BOTTOM_CSR));
+  const bool merge = s->flags & NB_SAMPLER_MERGE_SRC_DST;
   v->n_dst = m.n_dst; v->n_edges = m.n_edges; v->n_src = m.n_src; v->reserved = 0;
   v->destination = b.destination; v->column_offset = b.column_offset; v->sample_ans = b.sample_ans;
   v->row_indices = b.row_indices; v->source = b.source;
@@ -708,10 +733,8 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
     CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, b.cap_edges, s->fanout[i], i == s->L - 1 ? 1 : 0};
     k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
     NB_LAUNCH_CHECK(ctx);
-    int hash_slots = s->fanout[i] > 32 ? (int)pow2_ceil(2u * (uint32_t)s->fanout[i]) : 0;
-    k_sample<<<nb_grid(b.cap_dst, SAMPLE_WARPS, 8), SAMPLE_WARPS * 32, (size_t)hash_slots * SAMPLE_WARPS * 4, st>>>(
-        g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, s->bitmap, m, s->fanout[i], pp,
-        (uint32_t)i, merge ? 1 : 0, hash_slots);
+    launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst,
+                  s->bitmap, m, pp, (uint32_t)i, merge ? 1 : 0);
     NB_LAUNCH_CHECK(ctx);
     BitmapOp bop{s->bitmap, s->word_rank, m, m + 1, s->n_words, b.cap_src};
     k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
@@ -728,7 +751,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
       k_weights_sampled<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
-    if (csr) {
+    if (csr && !(i == s->L - 1 && s->L > 1 && (s->flags & NB_SAMPLER_NO_BOTTOM_CSR))) {
       RowOp rop{b.row_count, b.row_offset, m};
       k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, ws2);
       NB_LAUNCH_CHECK(ctx);
@@ -781,6 +804,7 @@ static int run_batch(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int
       int rc = enqueue_kernels(s, cst);
       cudaError_t ce = cudaStreamEndCapture(cst, &graph);
       cudaStreamDestroy(cst);
+      s->graph_kernels = ctx->launches - launches0;  // kernels per replay (what NB_LAUNCH_CHECK counted during capture)
       s->ctx->launches = launches0;
       if (rc != NB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
       NB_CUDA(ce);
@@ -788,17 +812,18 @@ static int run_batch(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int
       NB_CUDA(cudaGraphDestroy(graph));
     }
     NB_CUDA(cudaGraphLaunch(s->graph_exec, st));
-    ctx->launches += (uint64_t)1 + (uint64_t)s->L * (5 + ((s->flags & NB_SAMPLER_UP_DEGREE) ? 1 : 0) + ((s->flags & NB_SAMPLER_BUILD_CSR) ? 4 : 0));
+    ctx->launches += s->graph_kernels;
   } else {
     int rc = enqueue_kernels(s, st);
     if (rc != NB_OK) return rc;
   }
   NB_CUDA(cudaMemcpyAsync(s->meta_host, s->meta_dev, sizeof(LayerMeta) * (s->L + 1), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaEventRecord(s->meta_ready, st));
   return NB_OK;
 }
 
 static int finish_batch(nb_sampler *s, nb_layer_view *views_out) {
-  NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  NB_CUDA(cudaEventSynchronize(s->meta_ready));  // waits for this sampler's batch only, not for later work on the stream
   for (int i = 0; i < s->L; i++) {
     if (s->meta_host[i].err) {
       nb_set_error("sampler layer %d: %s capacity exceeded (E=%u cap %u, S=%u cap %u)", i,
@@ -843,6 +868,14 @@ int nb_sampler_replay(nb_sampler *s, const uint32_t *seeds_host, uint32_t n_seed
     NB_REQUIRE(s->meta_host[i].n_edges == n_edges_host[i], NB_ERR_ARG, "replay layer %d: supplied %u edges, column offsets total %u", i,
                n_edges_host[i], s->meta_host[i].n_edges);
   return NB_OK;
+}
+
+// Completes an nb_sampler_sample(..., sync = 0): blocks until that batch's sizes are on the host, reports arena
+// overflow, fills the views. Lets a caller overlap the sampling of batch i+1 with its work on batch i.
+int nb_sampler_wait(nb_sampler *s, nb_layer_view *views_out) {
+  NB_REQUIRE(s, NB_ERR_ARG, "nb_sampler_wait: NULL sampler");
+  NB_GUARD(s->ctx);
+  return finish_batch(s, views_out);
 }
 
 int nb_sampler_layer(nb_sampler *s, int layer, nb_layer_view *out) {
@@ -967,10 +1000,8 @@ int nb_sample_traverse(nb_ctx *ctx, const uint32_t *destination_dev, const uint3
   h.params.rng_seed = rng_seed; h.params.rng_offset = rng_offset; h.params.epoch = 1;
   NB_CUDA(cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
   NB_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)(n_words + 1) * 4, ctx->stream));
-  int hash_slots = fanout > 32 ? (int)pow2_ceil(2u * fanout) : 0;
-  k_sample<<<nb_grid(vtx_size, SAMPLE_WARPS, 8), SAMPLE_WARPS * 32, (size_t)hash_slots * SAMPLE_WARPS * 4, ctx->stream>>>(
-      global_column_offset_dev, global_row_indices_dev, destination_dev, column_offset_dev, r_i_dev, edge_dst, bitmap, &st->meta[0],
-      (int)fanout, &st->params, layer, add_dst_to_src ? 1 : 0, hash_slots);
+  launch_sample(ctx->stream, vtx_size, (int)fanout, global_column_offset_dev, global_row_indices_dev, destination_dev, column_offset_dev,
+                r_i_dev, edge_dst, bitmap, &st->meta[0], &st->params, layer, add_dst_to_src ? 1 : 0);
   NB_LAUNCH_CHECK(ctx);
   BitmapOp bop{bitmap, rank, &st->meta[0], &st->meta[1], n_words, 0xffffffffu};
   ScanWs ws{tiles, &st->params};

@@ -575,3 +575,24 @@ def test_padded_rows_and_tma_gather_match_dense(nts, cs):
     y_f = torch.empty((lay.v_size, P), device="cuda")
     cs.aggregate_fwd_pitched(padded, y_f, lay.dev_e_w(), lay.dev_sample_ans, lay.dev_c_o(), lay.v_size, F, P, P)
     assert torch.equal(y_f[:, :F], y_d)
+
+
+def test_async_sampling_pipeline_slots_and_no_bottom_csr(nts, cs):
+    """sample_gpu_fast(sync=False) + wait(): two pipeline slots in flight give the same subgraphs as the synchronous call;
+    bottom_csr=False drops only the bottom layer's CSR."""
+    V = 6000
+    pairs, graph = make_graph(nts, cs, V, 30, seed=17)
+    seeds = np.random.default_rng(3).permutation(V)[:1024].astype(np.uint32)
+    a = nts.FastSampler(graph, seeds, 2, 256, [9, 5], pipeline_num=2, cuda_stream=[cs, cs], rng_seed=5, bottom_csr=False)
+    b = nts.FastSampler(graph, seeds, 2, 256, [9, 5], cuda_stream=cs, rng_seed=5)
+    a.sample_gpu_fast(256, ssg_id=0, sync=False)
+    a.sample_gpu_fast(256, ssg_id=1, sync=False)
+    for slot in (0, 1):
+        sa = a.wait(slot)
+        sb = b.sample_gpu_fast(256)
+        for la, lb in zip(sa.sampled_sgs, sb.sampled_sgs):
+            assert (la.v_size, la.e_size, la.src_size) == (lb.v_size, lb.e_size, lb.src_size)
+            assert torch.equal(la.dev_sample_ans, lb.dev_sample_ans) and torch.equal(la.dev_row_indices, lb.dev_row_indices)
+            assert torch.equal(la.dev_source, lb.dev_source) and torch.equal(la.dev_edge_weight_forward, lb.dev_edge_weight_forward)
+        assert sa.sampled_sgs[1].dev_row_offset is None and sa.sampled_sgs[0].dev_row_offset is not None
+        assert torch.equal(sa.sampled_sgs[0].dev_column_indices, sb.sampled_sgs[0].dev_column_indices)
