@@ -45,7 +45,9 @@ struct nb_ctx {
   void *scratch;         // grow-only device scratch (replaces Cuda_Stream::cuda_buffer, cuda/ntsCUDA.hpp:195-196)
   size_t scratch_bytes;
 };
-int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);  // stream-ordered reuse; grows with cudaMalloc
+int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);
+const void *nb_mirror_host(nb_ctx *ctx, const void *p);  // HBM copy of a mapped-host allocation (or p itself)
+void nb_mirror_host_enable(int on);  // stream-ordered reuse; grows with cudaMalloc
 
 struct DeviceGuard {
   int prev;

@@ -29,6 +29,61 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out) {
   return NB_OK;
 }
 
+#include <stdlib.h>
+// ---- HBM mirror of host-resident tables (features, adjacency) --------------------------------------
+// The reference keeps the feature table and the adjacency (row_indices) in mapped pinned host memory and reads them over
+// PCIe (zero copy: core/ntsDataloador.hpp:187,483; core/FullyRepGraph.hpp:727 + core/ntsFastSampler.hpp:159-166). On a 180 GB part the table fits in HBM, so the first
+// gather that sees a host-resident table copies the whole allocation to the device once and every later gather reads
+// HBM. The table is treated as immutable after that first gather (it is, in every sampled toolkit).
+// NB_MIRROR_HOST_TABLES=0 / nb_set_option("mirror_host_tables", 0) keeps the zero-copy behaviour.
+#include <map>
+#include <mutex>
+static int g_mirror_tables = -1;
+static std::mutex g_mirror_mutex;
+struct MirrorEntry { uintptr_t dev_base; size_t size; void *mirror; };
+static std::map<std::pair<int, uintptr_t>, MirrorEntry> g_mirrors;  // (device, device-visible base of the host allocation)
+
+const void *nb_mirror_host(nb_ctx *ctx, const void *table) {
+  if (g_mirror_tables < 0) {
+    const char *e = getenv("NB_MIRROR_HOST_TABLES");
+    g_mirror_tables = e ? atoi(e) : 1;
+  }
+  if (!g_mirror_tables || !table) return table;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, table) != cudaSuccess) { cudaGetLastError(); return table; }
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return table;
+  typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+  static range_fn get_range = nullptr;
+  if (!get_range) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { cudaGetLastError(); return table; }
+    get_range = (range_fn)fn;
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, (unsigned long long)(uintptr_t)attr.devicePointer) != 0 || !size) return table;
+  std::lock_guard<std::mutex> lock(g_mirror_mutex);
+  auto key = std::make_pair(ctx->device, (uintptr_t)base);
+  auto it = g_mirrors.find(key);
+  if (it == g_mirrors.end()) {
+    void *m = nullptr;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || size > free_b / 2 || cudaMalloc(&m, size) != cudaSuccess) {
+      cudaGetLastError();
+      g_mirrors[key] = MirrorEntry{(uintptr_t)base, size, nullptr};  // remember the refusal, stay zero-copy
+      return table;
+    }
+    if (cudaMemcpyAsync(m, (const void *)(uintptr_t)base, size, cudaMemcpyDefault, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(m); return table; }
+    it = g_mirrors.insert(std::make_pair(key, MirrorEntry{(uintptr_t)base, size, m})).first;
+  }
+  if (!it->second.mirror) return table;
+  return (const void *)((const char *)it->second.mirror + ((uintptr_t)attr.devicePointer - it->second.dev_base));
+}
+void nb_mirror_host_enable(int on) { g_mirror_tables = on; }
+
+
 extern "C" {
 
 int nb_abi_version(void) { return NB_ABI_VERSION; }

@@ -228,6 +228,7 @@ extern "C" {
 int nb_set_option(const char *name, int value) {
   NB_REQUIRE(name, NB_ERR_ARG, "nb_set_option: NULL name");
   if (!strcmp(name, "gather_variant")) { g_gather_variant = value; return NB_OK; }
+  if (!strcmp(name, "mirror_host_tables")) { nb_mirror_host_enable(value); return NB_OK; }
   nb_set_error("nb_set_option: unknown option %s", name);
   return NB_ERR_ARG;
 }
@@ -238,6 +239,7 @@ int nb_gather_rows(nb_ctx *ctx, float *out, const float *table, const uint32_t *
   NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && out_pitch >= feature_size, NB_ERR_ARG, "nb_gather_rows: bad pitch");
   NB_GUARD(ctx);
   if (n_rows == 0) return NB_OK;
+  table = (const float *)nb_mirror_host(ctx, table);
   const uint32_t tb = gather_variant() == 1 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
   if (tb) return launch_gather_tma<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, n_rows, nullptr, tb, out_pitch);
   uint32_t fe = feature_size;
@@ -251,6 +253,7 @@ int nb_gather_rows_dyn(nb_ctx *ctx, float *out, const float *table, const uint32
   NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && out_pitch >= feature_size, NB_ERR_ARG, "nb_gather_rows_dyn: bad pitch");
   NB_GUARD(ctx);
   if (max_rows == 0) return NB_OK;
+  table = (const float *)nb_mirror_host(ctx, table);
   const uint32_t tb = gather_variant() == 1 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
   if (tb) return launch_gather_tma<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, max_rows, n_rows_dev, tb, out_pitch);
   uint32_t fe = feature_size;
@@ -265,6 +268,7 @@ int nb_gather_rows_cached(nb_ctx *ctx, float *out, const float *cold_table, uint
              "nb_gather_rows_cached: NULL argument");
   NB_REQUIRE(feature_size > 0 && cold_pitch >= feature_size && cache_pitch >= feature_size && out_pitch >= feature_size, NB_ERR_ARG, "bad pitch");
   NB_GUARD(ctx);
+  cold_table = (const float *)nb_mirror_host(ctx, cold_table);
   int v1 = nb_pick_vec(feature_size, cold_table, cold_pitch, out, out_pitch);
   int v2 = nb_pick_vec(feature_size, cache_table, cache_pitch, out, out_pitch);
   return launch_gather<1>(ctx, out, cold_table, cold_pitch, cache_table, cache_pitch, cache_node_hashmap_dev, nullptr, 0, ids_dev,
