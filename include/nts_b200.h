@@ -95,9 +95,11 @@ const char *nb_last_error(void); /* thread-local, valid until the next failing c
 int nb_device_count(int *count);
 /* tuning knobs (also readable from the environment at first use):
  *   "gather_variant" / NB_GATHER_VARIANT : 0 = register path (LDG/STG), 1 = TMA bulk copies when rows are 16-byte aligned (default)
- *   "mirror_host_tables" / NB_MIRROR_HOST_TABLES : 1 (default) = a feature table found in mapped pinned HOST memory (the reference's
- *       zero-copy table, core/ntsDataloador.hpp:187) is copied to HBM once, on the first gather that sees it, and read from HBM
- *       afterwards (the table must not change after that); 0 = gather over PCIe like the reference */
+ *   "mirror_host_tables" / NB_MIRROR_HOST_TABLES : 1 = a feature table found in mapped pinned HOST memory (the reference's zero-copy
+ *       table, core/ntsDataloador.hpp:187) is copied to HBM once, on the first gather that sees it, and read from HBM afterwards
+ *       (the buffer must not change after that); 0 (default) = gather over PCIe like the reference
+ *   "mirror_host_adjacency" / NB_MIRROR_HOST_ADJACENCY : 1 (default) = the same for the adjacency array that the stage-shaped
+ *       sampling calls receive as a mapped host pointer (core/ntsFastSampler.hpp:159-166); the topology never changes after load */
 int nb_set_option(const char *name, int value);
 
 /* ---- context: class Cuda_Stream (cuda/ntsCUDA.hpp:177-199; cuda/ntsCUDAGraphOP.cu:203-262) ----

@@ -55,7 +55,8 @@ CACHE:0
 GPU_NUM:1
 """)
         t0 = time.time()
-        r = subprocess.run([os.path.join(HERE, "_ref", "nts_b200"), cfg], cwd=os.path.join(HERE, "_ref"), capture_output=True, text=True)
+        r = subprocess.run([os.path.join(HERE, "_ref", "nts_b200"), cfg], cwd=os.path.join(HERE, "_ref"), capture_output=True, text=True,
+                           env=dict(os.environ, NB_MIRROR_HOST_TABLES=os.environ.get("NB_MIRROR_HOST_TABLES", "1")))
         wall = time.time() - t0
     out = r.stdout + r.stderr
     times = [float(m.group(1)) for m in re.finditer(r"Epoch\[\d+\]:Times\[([0-9.eE+-]+)\(s\)\]", out)]

@@ -46,8 +46,8 @@ struct nb_ctx {
   size_t scratch_bytes;
 };
 int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);
-const void *nb_mirror_host(nb_ctx *ctx, const void *p);  // HBM copy of a mapped-host allocation (or p itself)
-void nb_mirror_host_enable(int on);  // stream-ordered reuse; grows with cudaMalloc
+const void *nb_mirror_host(nb_ctx *ctx, const void *p, int is_adjacency = 0);  // HBM copy of a mapped-host allocation (or p itself)
+void nb_mirror_host_enable(int on, int adjacency);  // stream-ordered reuse; grows with cudaMalloc
 
 struct DeviceGuard {
   int prev;

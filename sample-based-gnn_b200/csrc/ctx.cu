@@ -35,7 +35,8 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out) {
 // PCIe (zero copy: core/ntsDataloador.hpp:187,483; core/FullyRepGraph.hpp:727 + core/ntsFastSampler.hpp:159-166). On a 180 GB part the table fits in HBM, so the first
 // gather that sees a host-resident table copies the whole allocation to the device once and every later gather reads
 // HBM. The table is treated as immutable after that first gather (it is, in every sampled toolkit).
-// NB_MIRROR_HOST_TABLES=0 / nb_set_option("mirror_host_tables", 0) keeps the zero-copy behaviour.
+// Opt-in for feature tables (NB_MIRROR_HOST_TABLES=1 / nb_set_option("mirror_host_tables", 1)): some toolkits also push
+// host buffers that the CPU rewrites every super-batch through the same call. On by default for the adjacency.
 #include <map>
 #include <mutex>
 static int g_mirror_tables = -1;
@@ -43,12 +44,17 @@ static std::mutex g_mirror_mutex;
 struct MirrorEntry { uintptr_t dev_base; size_t size; void *mirror; };
 static std::map<std::pair<int, uintptr_t>, MirrorEntry> g_mirrors;  // (device, device-visible base of the host allocation)
 
-const void *nb_mirror_host(nb_ctx *ctx, const void *table) {
+static int g_mirror_adjacency = -1;
+const void *nb_mirror_host(nb_ctx *ctx, const void *table, int is_adjacency) {
   if (g_mirror_tables < 0) {
     const char *e = getenv("NB_MIRROR_HOST_TABLES");
-    g_mirror_tables = e ? atoi(e) : 1;
+    g_mirror_tables = e ? atoi(e) : 0;   // feature-like buffers may be rewritten by the host (CPU-computed hot embeddings): opt-in
   }
-  if (!g_mirror_tables || !table) return table;
+  if (g_mirror_adjacency < 0) {
+    const char *e = getenv("NB_MIRROR_HOST_ADJACENCY");
+    g_mirror_adjacency = e ? atoi(e) : 1;  // the topology never changes after load: on by default
+  }
+  if (!(is_adjacency ? g_mirror_adjacency : g_mirror_tables) || !table) return table;
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, table) != cudaSuccess) { cudaGetLastError(); return table; }
   if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return table;
@@ -81,7 +87,7 @@ const void *nb_mirror_host(nb_ctx *ctx, const void *table) {
   if (!it->second.mirror) return table;
   return (const void *)((const char *)it->second.mirror + ((uintptr_t)attr.devicePointer - it->second.dev_base));
 }
-void nb_mirror_host_enable(int on) { g_mirror_tables = on; }
+void nb_mirror_host_enable(int on, int adjacency) { if (adjacency) g_mirror_adjacency = on; else g_mirror_tables = on; }
 
 
 extern "C" {

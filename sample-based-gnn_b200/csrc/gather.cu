@@ -228,7 +228,8 @@ extern "C" {
 int nb_set_option(const char *name, int value) {
   NB_REQUIRE(name, NB_ERR_ARG, "nb_set_option: NULL name");
   if (!strcmp(name, "gather_variant")) { g_gather_variant = value; return NB_OK; }
-  if (!strcmp(name, "mirror_host_tables")) { nb_mirror_host_enable(value); return NB_OK; }
+  if (!strcmp(name, "mirror_host_tables")) { nb_mirror_host_enable(value, 0); return NB_OK; }
+  if (!strcmp(name, "mirror_host_adjacency")) { nb_mirror_host_enable(value, 1); return NB_OK; }
   nb_set_error("nb_set_option: unknown option %s", name);
   return NB_ERR_ARG;
 }

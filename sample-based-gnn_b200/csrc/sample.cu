@@ -990,7 +990,7 @@ int nb_sample_traverse(nb_ctx *ctx, const uint32_t *destination_dev, const uint3
              NB_ERR_ARG, "nb_sample_traverse: NULL argument");
   NB_REQUIRE(fanout >= 1 && fanout <= 512, NB_ERR_UNSUPPORTED, "fanout %u: supported values are 1..512", fanout);
   NB_GUARD(ctx);
-  global_row_indices_dev = (const uint32_t *)nb_mirror_host(ctx, global_row_indices_dev);  // adjacency left in pinned host memory by the caller
+  global_row_indices_dev = (const uint32_t *)nb_mirror_host(ctx, global_row_indices_dev, 1);  // adjacency left in pinned host memory by the caller
   LegacyState *st; unsigned long long *tiles; uint32_t *bitmap, *rank, *edge_dst;
   int rc = legacy_state(ctx, vtx_size, n_vertices, edge_size, &st, &tiles, &bitmap, &rank, &edge_dst);
   if (rc) return rc;
