@@ -235,6 +235,8 @@ def main_b200(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_ev = {"gather": [], "agg_fwd_602": []}
+    st_comm = torch.cuda.Stream(dev)
+    comm_box = [None]
 
     def step_async(i, timed, fused=False):
         """value: inputs resident in HBM, no host synchronisation anywhere (sizes stay on the device). Batch i is sampled on
@@ -262,6 +264,8 @@ def main_b200(args):
         else:  # bottom hop aggregated straight from the feature table through the global ids: X0 is never materialised
             check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
                                                bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
+        if comm_box[0] is not None:
+            st_train.wait_event(comm_box[0])
         check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(h1), ptr(y0), top.edge_weight_forward, top.row_indices,
                                            top.column_offset, nd[0], caps[0][0], F1, F1, F1))
         check(lib.nb_aggregate_csr_bwd_dyn(cs_train._h, ptr(dy0), ptr(dh1), top.edge_weight_backward, top.row_offset,
@@ -270,8 +274,15 @@ def main_b200(args):
         check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_top[i]), nd[0].value, 32, 0))
         sl["consumed"].record(st_train)
         if world > 1:
-            with torch.cuda.stream(st_train):
+            # the dense-gradient exchange runs on its own stream behind this step's backward and overlaps the next step's
+            # gather / bottom aggregation; the next step's top hop (the first consumer of updated weights) waits for it
+            bwd_done = torch.cuda.Event()
+            bwd_done.record(st_train)
+            st_comm.wait_event(bwd_done)
+            with torch.cuda.stream(st_comm):
                 dist.all_reduce(grads)
+            comm_box[0] = torch.cuda.Event()
+            comm_box[0].record(st_comm)
 
     api_state = {"issued": -1}
 
@@ -316,6 +327,7 @@ def main_b200(args):
     def run(mode, sample_clocks=False):
         step = {"async": step_async, "fused": lambda i, t: step_async(i, t, True), "api": step_api}[mode]
         api_state["issued"] = -1
+        comm_box[0] = None
         for k in kern_ev.values():
             k.clear()
         with torch.cuda.stream(st_train):
@@ -333,7 +345,9 @@ def main_b200(args):
             t0.record(st_train)
             for i in range(args.warmup, n_steps):
                 step(i, True)
-            t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes both streams
+            if comm_box[0] is not None:
+                st_train.wait_event(comm_box[0])
+            t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes all streams
             torch.cuda.synchronize()
             if clocks:
                 clock_box[0] = clocks.summary()

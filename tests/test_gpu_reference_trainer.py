@@ -14,11 +14,22 @@ REFDIR = os.path.join(ROOT, "oracle", "_ref")
 BIN = os.path.join(REFDIR, "nts_b200")
 
 TOOLKITS = ["GCNSAMPLEALLGPU", "GCNSAMPLEGPU", "GSSAMPLEALLGPU", "GATSAMPLEALLGPU", "GSSAMPLECACHE", "GCNSAMPLEPDCACHE"]
+MULTI_GPU_TOOLKITS = ["GCNSAMPLEALLMULTI", "GATSAMPLEALLMULTI"]   # GPU_NUM:2 -- one thread per GPU + NCCL_Communicator of the adaptor
+
+
+def _gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/nts_b200 not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("alg", TOOLKITS)
+@pytest.mark.parametrize("alg", TOOLKITS + MULTI_GPU_TOOLKITS)
 def test_reference_trainer_runs_on_libnts_b200(alg):
+    if alg in MULTI_GPU_TOOLKITS and _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
     import glob
     for f in glob.glob(os.path.join(REFDIR, "data", "*pre_sample*.bin")):   # hot-vertex lists a previous toolkit left behind
         os.remove(f)
