@@ -221,6 +221,19 @@ int nb_edge_weight(nb_ctx *ctx, float *edge_weight_dev, const uint32_t *out_degr
                    const uint32_t *destination_dev, const uint32_t *source_dev, const uint32_t *column_offset_dev,
                    const uint32_t *row_indices_dev, int mean);
 
+/* ---- hotness-aware cache selection ------------------------------------------------------------------------------
+ * nb_hotness         <- nts::op::get_most_neighbor (core/ntsBaseOp.hpp:333-399; per super-batch, CPU in the reference): counts start
+ *                       as the indicator of the super-batch seeds, are pushed `layers-1` hops along the in-edges of the full graph,
+ *                       cache_num = (u32)((#non-zero counts + 1) * cache_rate) (or fixed_cache_num when != 0xffffffff, the
+ *                       overload :266-330), pivot = count at descending rank cache_num, output = the first cache_num vertex ids
+ *                       (ASCENDING, the serial order of the reference loop) whose count >= pivot. Synchronises to return cache_num.
+ * nb_set_cache_index <- GNNDatum::set_cache_index (core/ntsDataloador.hpp:440-478) on device arrays:
+ *                       cache_map[id] = super_batch_id, cache_location[id] = position in the list. */
+int nb_hotness(nb_ctx *ctx, nb_graph *g, const uint32_t *seeds, uint32_t n_seeds, int seeds_on_device, int layers, float cache_rate,
+               uint32_t fixed_cache_num, uint32_t *cache_ids_dev, uint32_t capacity, uint32_t *cache_num_out, uint32_t *counts_dev_or_null);
+int nb_set_cache_index(nb_ctx *ctx, uint32_t *cache_map_dev, uint32_t *cache_location_dev, uint32_t super_batch_id,
+                       const uint32_t *cache_ids_dev, uint32_t n);
+
 /* ---- feature / label gather ----------------------------------------------------------------
  * nb_gather_rows        <- Cuda_Stream::zero_copy_feature_move_gpu (cuda/ntsCUDA.hpp:370-374): out[i,:] = table[ids[i],:].
  *                          `table` may be device memory or mapped pinned host memory; table_pitch

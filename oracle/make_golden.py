@@ -73,6 +73,24 @@ def run_record(name, pairs, V, seeds, batch, fanout, F, up_degree=0, weight="sum
     print(name, os.path.getsize(path) // 1024, "KiB", len(rec["batches"]), "batches")
 
 
+def run_hotness(name, pairs, V, seeds, batch, pipeline, layers):
+    """nts::op::preSample through the reference driver: per-super-batch hot-vertex lists + the .bin file it writes."""
+    with tempfile.TemporaryDirectory() as td:
+        ef, sf, of = os.path.join(td, "g.edge"), os.path.join(td, "seeds.u32"), os.path.join(td, "rec.bin")
+        np.ascontiguousarray(pairs, dtype=np.uint32).tofile(ef)
+        np.ascontiguousarray(seeds, dtype=np.uint32).tofile(sf)
+        # one OpenMP thread: the reference collects the hot ids from a parallel loop in arrival order (core/ntsBaseOp.hpp:384-395)
+        env = dict(os.environ, OMP_NUM_THREADS="1", NTS_ORACLE_CPUS="1")
+        subprocess.check_call([DRIVER, "hotness", ef, str(V), sf, str(batch), str(pipeline), str(layers), of], env=env,
+                              stdout=subprocess.DEVNULL)
+        rec = refio.read_record(of)["graph"]
+        raw = np.fromfile(os.path.join(td, f"g.pre_sample_b{batch}_fx_p{pipeline}.bin"), dtype=np.uint32)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, meta=np.array([V, batch, pipeline, layers], np.int64), pairs=np.ascontiguousarray(pairs, np.uint32),
+                        seeds=np.ascontiguousarray(seeds, np.uint32), counts=rec["counts"], ids=rec["ids"], top=rec["top"], bin_file=raw)
+    print(name, os.path.getsize(path) // 1024, "KiB", rec["counts"].tolist())
+
+
 def main():
     if not os.path.exists(DRIVER):
         subprocess.check_call(["make", "-C", HERE, "ref"])
@@ -93,6 +111,9 @@ def main():
     run_record("synth300_takeall_3layer", g2, 300, rng.permutation(300)[:90], 45, [-1, 3, 2], 4)
     # 5. Mean weights with global degrees
     run_record("synth300_mean", g2, 300, rng.permutation(300)[:64], 64, [3, 3], 8, weight="mean")
+    # 5b. hotness pre-sampling (a11): one hop (2 layers) and two hops (3 layers), ragged last super-batch
+    run_hotness("hotness_synth600_l2", g, 600, rng.permutation(600)[:250], 64, 2, 2)
+    run_hotness("hotness_synth300_l3", g2, 300, rng.permutation(300)[:100], 16, 3, 3)
     # 6. the shipped hot-vertex list (a11 on-disk layout: u32 counts[] || u32 ids[]), kept as data
     raw = np.fromfile(os.path.join(REF, "data", "cora.2708.edge.pre_sample_b1024_f25-10_p1.bin"), dtype=np.uint32)
     np.savez_compressed(os.path.join(GOLD, "cora_pre_sample_bin.npz"), raw=raw)

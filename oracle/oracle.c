@@ -446,3 +446,42 @@ void orc_gat_layer_bwd(const float *h, const float *att, const float *dout /*[V,
 void orc_set_cache_index(vid_t *cache_map, vid_t *cache_location, vid_t super_batch_id, const vid_t *cache_ids, vid_t n) {
   for (vid_t i = 0; i < n; i++) { cache_map[cache_ids[i]] = super_batch_id; cache_location[cache_ids[i]] = i; }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Hotness pre-sampling. core/ntsBaseOp.hpp:333-399 (get_most_neighbor, the overload preSample
+ * :415-541 calls): counts start as the indicator of the super-batch's seeds and are pushed
+ * `layers-1` times along the in-edges of the FULL graph (new[src] += old[dst] for every
+ * in-neighbour src of every dst with old[dst] > 0); the counts are sorted descending,
+ * total_sample_num = (index of the first zero) + 1, cache_num = (u32)(total_sample_num * cache_rate)
+ * in float arithmetic, pivot = sorted[cache_num]; the ids with count >= pivot are collected, at most
+ * cache_num of them. The reference collects them from an OpenMP loop (arrival order); the serial,
+ * ascending-id order is restated (it is what the shipped .bin and the 1-thread run contain).
+ * Returns cache_num; writes the final counts to counts_out[V] if not NULL. */
+static int cmp_desc_u32(const void *a, const void *b) {
+  vid_t x = *(const vid_t *)a, y = *(const vid_t *)b;
+  return x < y ? 1 : (x > y ? -1 : 0);
+}
+vid_t orc_hotness(const vid_t *seeds, vid_t n_seeds, const vid_t *g_column_offset, const vid_t *g_row_indices, vid_t n_vertices,
+                  int layers, float cache_rate, vid_t *cache_ids /*[n_vertices]*/, vid_t *counts_out) {
+  vid_t *oldc = (vid_t *)calloc(n_vertices, sizeof(vid_t)), *newc = (vid_t *)calloc(n_vertices, sizeof(vid_t));
+  for (vid_t i = 0; i < n_seeds; i++) oldc[seeds[i]] = 1;
+  for (int layer = 1; layer < layers; layer++) {
+    if (layer != 1) { vid_t *t = oldc; oldc = newc; newc = t; memset(newc, 0, sizeof(vid_t) * n_vertices); }
+    for (vid_t i = 0; i < n_vertices; i++)
+      if (oldc[i] > 0)
+        for (vid_t e = g_column_offset[i]; e < g_column_offset[i + 1]; e++) newc[g_row_indices[e]] += oldc[i];
+  }
+  if (counts_out) memcpy(counts_out, newc, sizeof(vid_t) * n_vertices);
+  memcpy(oldc, newc, sizeof(vid_t) * n_vertices);
+  qsort(oldc, n_vertices, sizeof(vid_t), cmp_desc_u32);
+  vid_t total = n_vertices; /* the reference leaves it uninitialised when no count is zero */
+  for (vid_t i = 0; i < n_vertices; i++) if (oldc[i] == 0) { total = i + 1; break; }
+  vid_t cache_num = (vid_t)((float)total * cache_rate);
+  if (cache_num >= n_vertices) cache_num = n_vertices - 1;
+  vid_t pivot = oldc[cache_num], idx = 0;
+  for (vid_t i = 0; i < n_vertices && idx < cache_num; i++)
+    if (newc[i] >= pivot) cache_ids[idx++] = i;
+  free(oldc);
+  free(newc);
+  return cache_num;
+}

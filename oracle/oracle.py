@@ -338,3 +338,42 @@ def sample_batch(seeds, g_column_offset, g_row_indices, fanouts, n_vertices, in_
                            in_deg=ind.copy() if up_degree else None, out_deg=outd.copy() if up_degree else None))
         dst = src
     return layers
+
+
+def hotness(seeds, g_column_offset, g_row_indices, n_vertices, layers, cache_rate):
+    """one super-batch of core/ntsBaseOp.hpp:333-399 -> (hot ids ascending, final counts)"""
+    seeds = _u32(seeds)
+    ids = np.zeros(n_vertices, U32)
+    counts = np.zeros(n_vertices, U32)
+    n = _call("orc_hotness", c_u32, seeds, c_u32(seeds.size), _u32(g_column_offset), _u32(g_row_indices), c_u32(n_vertices),
+              c_int(layers), ctypes.c_float(cache_rate), ids, counts)
+    return ids[:n].copy(), counts
+
+
+def pre_sample(train_ids, batch_size, pipeline_num, g_column_offset, g_row_indices, n_vertices, layers, cache_rate=0.8):
+    """nts::op::preSample (core/ntsBaseOp.hpp:415-470): per super-batch (= batch_size * pipeline_num seeds) hot lists."""
+    train_ids = _u32(train_ids)
+    sb = batch_size * pipeline_num
+    counts, ids = [], []
+    for start in range(0, train_ids.size, sb):
+        h, _ = hotness(train_ids[start:start + sb], g_column_offset, g_row_indices, n_vertices, layers, cache_rate)
+        counts.append(h.size)
+        ids.append(h)
+    return np.array(counts, U32), (np.concatenate(ids) if ids else np.zeros(0, U32))
+
+
+def pre_sample_file_pack(counts, ids):
+    """on-disk layout (core/ntsBaseOp.hpp:477-495): u32 counts[#super_batches] || u32 ids[sum(counts)]"""
+    return np.concatenate([_u32(counts), _u32(ids)])
+
+
+def pre_sample_file_unpack(raw, n_super_batches, of_rate=1.0):
+    """reader (core/ntsBaseOp.hpp:497-538): the first counts[i]*of_rate ids of every group"""
+    raw = _u32(raw)
+    counts = raw[:n_super_batches]
+    take = (counts.astype(np.float32) * np.float32(of_rate)).astype(U32)
+    out, pos = [], n_super_batches
+    for c, t in zip(counts, take):
+        out.append(raw[pos:pos + t])
+        pos += int(c)
+    return take, (np.concatenate(out) if out else np.zeros(0, U32))

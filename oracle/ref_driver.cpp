@@ -223,5 +223,33 @@ int main(int argc, char **argv) {
     printf("}\n");
     return 0;
   }
+  if (mode == "hotness") {
+    /* hotness <edge_file> <V> <seed_file> <batch> <pipeline> <layers> <out.bin>
+     * nts::op::preSample (core/ntsBaseOp.hpp:415-541), the overload the *_CACHE toolkits call: per super-batch
+     * get_most_neighbor (:333-399) and the counts||ids file. The file name is derived from the edge file by the
+     * reference itself (:420-428, which also forces cache_rate = 0.8 when the file does not exist yet). */
+    if (argc < 9) return 2;
+    const char *edge_file = argv[2]; VertexId V = atoi(argv[3]);
+    std::vector<VertexId> seeds = read_u32(argv[4]);
+    int batch = atoi(argv[5]), pipeline = atoi(argv[6]), layers = atoi(argv[7]);
+    std::vector<int> layer_size(layers + 1, 4);
+    Env e = setup(edge_file, V, layer_size, false, false);
+    e.graph->config->edge_file = edge_file;
+    e.graph->config->pre_sample_file = "";
+    e.graph->config->batch_size = batch;
+    e.graph->config->fanout_string = "x";
+    std::vector<VertexId> batch_cache_num;
+    VertexId top_cache_num = 0;
+    std::vector<VertexId> ids = nts::op::preSample(seeds, batch, batch_cache_num, 0.5f, top_cache_num, layers, e.full, 1.0f, e.graph, pipeline);
+    Out o{fopen(argv[8], "wb")};
+    uint32_t hdr[4] = {0x4e545352u, (uint32_t)layers, (uint32_t)batch, (uint32_t)pipeline};
+    fwrite(hdr, 4, 4, o.f);
+    o.u32("counts", batch_cache_num.data(), batch_cache_num.size());
+    o.u32("ids", ids.data(), ids.size());
+    o.u32("top", &top_cache_num, 1);
+    o.tag("end", 0, 0);
+    fclose(o.f);
+    return 0;
+  }
   return 2;
 }

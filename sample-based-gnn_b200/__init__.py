@@ -24,7 +24,7 @@ from . import _capi
 from ._capi import (NB_SAMPLER_BUILD_CSR, NB_SAMPLER_MERGE_SRC_DST, NB_SAMPLER_NO_BOTTOM_CSR, NB_SAMPLER_UP_DEGREE, NB_WEIGHT_MEAN,
                     NB_WEIGHT_MEAN_SAMPLED, NB_WEIGHT_NONE, NB_WEIGHT_SUM, LayerView, NtsError, check, lib, ptr)
 
-__all__ = ["Cuda_Stream", "FullyRepGraph", "FastSampler", "SampledSubgraph", "sampCSC", "WeightType",
+__all__ = ["preSample", "write_pre_sample_file", "read_pre_sample_file", "set_cache_index", "Cuda_Stream", "FullyRepGraph", "FastSampler", "SampledSubgraph", "sampCSC", "WeightType",
            "SingleGPUAllSampleGraphOp", "SingleGPUSampleGraphOp", "GATFusedOp", "BatchGPUSrcDstScatterOp",
            "BatchGPUEdgeSoftMax", "BatchGPUAggregateDst", "FeatureTable", "NtsError"]
 
@@ -428,6 +428,47 @@ class FastSampler:
         l = subgraph.sampled_sgs[self.layer - 1]
         cuda_stream.dev_load_share_embedding(dev_embedding, share_embedding, dev_cache_map, dev_cache_location,
                                              dev_embedding.shape[1], l.dev_destination, l.v_size, super_batch_id)
+
+
+def preSample(train_ids, batch_size, pipeline_num, layers, whole_graph, cache_rate=0.8, cuda_stream=None):
+    """nts::op::preSample (core/ntsBaseOp.hpp:415-470) on the GPU: for every super-batch (batch_size * pipeline_num seeds) the hot
+    vertices of its (layers-1)-hop in-neighbourhood. Returns (batch_cache_num u32[#super_batches], batch_cache_ids u32[sum])."""
+    cs = cuda_stream or whole_graph.cs
+    train_ids = np.ascontiguousarray(train_ids, dtype=np.uint32)
+    sb = int(batch_size) * int(pipeline_num)
+    V = whole_graph.global_vertices
+    out = torch.empty(V, dtype=torch.int32, device=cs.device)
+    counts, ids = [], []
+    for start in range(0, train_ids.size, sb):
+        seeds = train_ids[start:start + sb]
+        n = C.c_uint32()
+        check(lib().nb_hotness(cs._h, whole_graph._h, ptr(seeds), seeds.size, 0, int(layers), float(cache_rate), 0xFFFFFFFF,
+                               ptr(out), V, C.byref(n), None))
+        counts.append(n.value)
+        ids.append(out[:n.value].cpu().numpy().view(np.uint32).copy())
+    return np.array(counts, np.uint32), (np.concatenate(ids) if ids else np.zeros(0, np.uint32))
+
+
+def write_pre_sample_file(path, batch_cache_num, batch_cache_ids):
+    """PRE_SAMPLE_FILE layout (core/ntsBaseOp.hpp:477-495): u32 counts[#super_batches] || u32 ids[sum(counts)]"""
+    np.concatenate([np.asarray(batch_cache_num, np.uint32), np.asarray(batch_cache_ids, np.uint32)]).tofile(path)
+
+
+def read_pre_sample_file(path, n_super_batches, of_rate=1.0):
+    """reader (core/ntsBaseOp.hpp:497-538): the first counts[i]*of_rate ids of every super-batch group"""
+    raw = np.fromfile(path, dtype=np.uint32)
+    counts = raw[:n_super_batches]
+    take = (counts.astype(np.float32) * np.float32(of_rate)).astype(np.uint32)
+    out, pos = [], n_super_batches
+    for c, t in zip(counts, take):
+        out.append(raw[pos:pos + t])
+        pos += int(c)
+    return take, (np.concatenate(out) if out else np.zeros(0, np.uint32))
+
+
+def set_cache_index(cuda_stream, cache_map, cache_location, super_batch_id, cache_ids_dev, n):
+    """GNNDatum::set_cache_index (core/ntsDataloador.hpp:440-478) on device arrays"""
+    check(lib().nb_set_cache_index(cuda_stream._h, ptr(cache_map), ptr(cache_location), super_batch_id, ptr(cache_ids_dev), n))
 
 
 class FeatureTable:

@@ -70,6 +70,8 @@ _SIGS = {
     "nb_set_dst_local_index": (I32, [P, P, P, U32, P]),
     "nb_update_degree": (I32, [P, P, P, U32, U32, P, P, P, P, I32]),
     "nb_edge_weight": (I32, [P, P, P, P, U32, P, P, P, P, I32]),
+    "nb_hotness": (I32, [P, P, P, U32, I32, I32, F32, U32, P, U32, C.POINTER(U32), P]),
+    "nb_set_cache_index": (I32, [P, P, P, U32, P, U32]),
     "nb_gather_rows": (I32, [P, P, P, P, U32, U32, U32, U32]),
     "nb_gather_rows_dyn": (I32, [P, P, P, P, P, U32, U32, U32, U32]),
     "nb_aggregate_csc_fwd_dyn": (I32, [P, P, P, P, P, P, P, U32, U32, U32, U32]),

@@ -25,11 +25,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
-
-struct LayerMeta {  // device resident, one per layer (+1 sentinel)
-  uint32_t n_dst, n_edges, n_src, err;
-  uint32_t long_rows, pad0, pad1, pad2;
-};
+#include "scan.cuh"
 
 struct LayerBuf {
   uint32_t cap_dst, cap_edges, cap_src;
@@ -37,28 +33,6 @@ struct LayerBuf {
   uint32_t *row_offset, *row_count, *row_cursor, *column_indices, *csr_tmp, *csr_to_csc, *long_rows;
   uint32_t *dst_local_id, *src_to_dst;
   float *ewf, *ewb;
-};
-
-// Everything that changes from batch to batch lives in device memory so that the kernel
-// arguments are constant and the whole batch can be replayed as one CUDA graph.
-struct BatchParams {
-  uint64_t rng_seed, rng_offset;
-  const uint32_t *omit;  // device, [|V|] or NULL
-  uint32_t n_seeds, weight_type, omit_value, replay;
-  uint32_t epoch, pad[3];
-};
-
-struct ScanWs {
-  unsigned long long *tile_state;  // one array per scan launch of a batch; entries are tagged with the batch epoch
-  const BatchParams *params;
-};
-
-struct nb_graph {
-  nb_ctx *ctx;
-  uint32_t V;
-  uint64_t E;
-  uint32_t *col_off, *row_idx, *in_deg, *out_deg;
-  uint32_t max_in_degree;
 };
 
 #define NB_MAX_LAYERS 8
@@ -88,88 +62,6 @@ struct nb_sampler {
   uint64_t graph_kernels;
   bool use_graph;
 };
-
-// ---------------------------------------------------------------------------------------------
-// Single-pass exclusive scan (decoupled look-back, Merrill & Garland) over n items, n read from
-// device memory through Op. Tiles are handed out by an atomic ticket so a tile's predecessors are
-// always resident or finished; the last block to leave resets the workspace for the next launch.
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-template <class Op>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
-  __shared__ unsigned s_prefix, s_warp[SCAN_THREADS / 32];
-  const unsigned n = op.n();
-  const unsigned ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) op.total(0);
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // tile state word: [63:34] batch epoch, [33:32] 1 = aggregate, 2 = inclusive prefix, [31:0] value.
-  // The grid never exceeds the number of co-resident blocks, so waiting on a lower tile cannot deadlock.
-  const unsigned long long tag = ((unsigned long long)(ws.params->epoch & 0x3fffffffu)) << 34;
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    unsigned v[SCAN_ITEMS], sum = 0;
-    const unsigned first = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-      v[k] = (first + k < n) ? op.load(first + k) : 0u;
-      sum += v[k];
-    }
-    unsigned incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(FULL_MASK, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned warp_base = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; w++) {
-      unsigned t = s_warp[w];
-      if (w < warp) warp_base += t;
-      block_total += t;
-    }
-    if (warp == 0) {
-      // warp-parallel decoupled look-back: lane l inspects tile (first_pred - l); the window slides back by 32
-      unsigned prefix = 0;
-      if (tile == 0) {
-        if (lane == 0) atomicExch(&ws.tile_state[0], tag | (2ull << 32) | block_total);
-      } else {
-        if (lane == 0) atomicExch(&ws.tile_state[tile], tag | (1ull << 32) | block_total);
-        int hi = (int)tile - 1;  // nearest predecessor not yet accounted for
-        while (true) {
-          const int p = hi - (int)lane;
-          unsigned long long st = 0;
-          bool ready = true;
-          if (p >= 0) {
-            st = *((volatile unsigned long long *)&ws.tile_state[p]);
-            ready = (st >> 34 << 34) == tag;
-          }
-          if (!__all_sync(FULL_MASK, ready)) continue;  // some predecessor has not published yet: poll again
-          const unsigned flag = p >= 0 ? ((unsigned)(st >> 32) & 3u) : 2u;  // "tile -1" acts as an inclusive prefix of 0
-          const unsigned incl_mask = __ballot_sync(FULL_MASK, flag == 2u);
-          const unsigned val = p >= 0 ? (unsigned)st : 0u;
-          const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;  // nearest lane holding an inclusive prefix
-          prefix += warp_sum_u32(lane <= (unsigned)stop ? val : 0u);
-          if (incl_mask) break;
-          hi -= 32;
-        }
-        if (lane == 0) atomicExch(&ws.tile_state[tile], tag | (2ull << 32) | (unsigned long long)(prefix + block_total));
-      }
-      if (lane == 0) s_prefix = prefix;
-    }
-    __syncthreads();
-    unsigned base = s_prefix + warp_base + (incl - sum);
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-      if (first + k < n) op.store(first + k, base, v[k]);
-      base += v[k];
-    }
-    if (tile == ntiles - 1 && threadIdx.x == 0) op.total(s_prefix + block_total);
-    __syncthreads();
-  }
-}
 
 // counts = min(deg, fanout) (fanout -1: deg), 0 for omitted dst; scan -> column_offset; total -> E.
 // Reference: sample_processing_get_co_gpu_kernel[_omit] cuda/ntsCUDATransferKernel.cuh:754-822 and the

@@ -596,3 +596,38 @@ def test_async_sampling_pipeline_slots_and_no_bottom_csr(nts, cs):
             assert torch.equal(la.dev_source, lb.dev_source) and torch.equal(la.dev_edge_weight_forward, lb.dev_edge_weight_forward)
         assert sa.sampled_sgs[1].dev_row_offset is None and sa.sampled_sgs[0].dev_row_offset is not None
         assert torch.equal(sa.sampled_sgs[0].dev_column_indices, sb.sampled_sgs[0].dev_column_indices)
+
+
+@pytest.mark.parametrize("name", ["hotness_synth600_l2", "hotness_synth300_l3"])
+def test_hotness_pre_sampling_matches_reference_record(nts, cs, name, tmp_path):
+    """a11 on the GPU vs what the reference's own preSample wrote (tests/golden, 1 thread): counts, ids, and the .bin bytes."""
+    import os
+    from golden_util import GOLD
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    V, batch, pipeline, layers = (int(x) for x in z["meta"])
+    graph = nts.FullyRepGraph(cs, V, edge_pairs=z["pairs"])
+    counts, ids = nts.preSample(z["seeds"], batch, pipeline, layers, graph, cache_rate=0.8, cuda_stream=cs)
+    assert np.array_equal(counts, z["counts"]) and np.array_equal(ids, z["ids"])
+    path = str(tmp_path / "x.bin")
+    nts.write_pre_sample_file(path, counts, ids)
+    assert np.array_equal(np.fromfile(path, dtype=np.uint32), z["bin_file"])
+    take, sub = nts.read_pre_sample_file(path, counts.size, of_rate=0.25)
+    assert np.array_equal(take, (counts * 0.25).astype(np.uint32)) and sub.size == take.sum()
+
+
+def test_hotness_large_graph_and_cache_index(nts, cs):
+    V = 30000
+    pairs, graph = make_graph(nts, cs, V, 40, seed=31)
+    co, ri = oracle.build_csc(pairs, V)
+    seeds = np.random.default_rng(8).permutation(V)[:4096].astype(np.uint32)
+    for layers, rate in ((2, 0.1), (3, 0.01), (1, 0.5)):
+        counts, ids = nts.preSample(seeds, 1024, 2, layers, graph, cache_rate=rate, cuda_stream=cs)
+        rc, rids = oracle.pre_sample(seeds, 1024, 2, co, ri, V, layers, cache_rate=rate)
+        assert np.array_equal(counts, rc) and np.array_equal(ids, rids), (layers, rate)
+    cmap = torch.full((V,), -1, dtype=torch.int32, device="cuda")
+    cloc = torch.zeros(V, dtype=torch.int32, device="cuda")
+    hot = torch.from_numpy(ids[:counts[0]].view(np.int32)).cuda()
+    nts.set_cache_index(cs, cmap, cloc, 7, hot, hot.numel())
+    m, l = np.full(V, 0xFFFFFFFF, np.uint32), np.zeros(V, np.uint32)
+    oracle.set_cache_index(m, l, 7, ids[:counts[0]])
+    assert np.array_equal(u32(cmap), m) and np.array_equal(u32(cloc), l)

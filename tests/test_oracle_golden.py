@@ -158,3 +158,24 @@ def test_pre_sample_bin_layout():
         grp = ids[off:off + c]
         assert np.all(np.diff(grp.astype(np.int64)) > 0)
         off += c
+
+
+@pytest.mark.parametrize("name", ["hotness_synth600_l2", "hotness_synth300_l3"])
+def test_hotness_pre_sampling_matches_reference(name):
+    """a11: nts::op::preSample / get_most_neighbor recorded from the reference (1 thread) vs the restatement, and the .bin layout."""
+    import os
+    from golden_util import GOLD
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    V, batch, pipeline, layers = (int(x) for x in z["meta"])
+    co, ri = oracle.build_csc(z["pairs"], V)
+    counts, ids = oracle.pre_sample(z["seeds"], batch, pipeline, co, ri, V, layers, cache_rate=0.8)  # 0.8: forced by :426-427
+    assert np.array_equal(counts, z["counts"]) and np.array_equal(ids, z["ids"])
+    assert np.array_equal(oracle.pre_sample_file_pack(counts, ids), z["bin_file"])
+    take, sub = oracle.pre_sample_file_unpack(z["bin_file"], counts.size, of_rate=0.5)
+    assert np.array_equal(take, (counts * 0.5).astype(np.uint32))
+    off = 0
+    pos = 0
+    for c, t in zip(counts, take):
+        assert np.array_equal(sub[pos:pos + t], ids[off:off + t])
+        off += int(c)
+        pos += int(t)
