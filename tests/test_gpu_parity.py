@@ -631,3 +631,106 @@ def test_hotness_large_graph_and_cache_index(nts, cs):
     m, l = np.full(V, 0xFFFFFFFF, np.uint32), np.zeros(V, np.uint32)
     oracle.set_cache_index(m, l, 7, ids[:counts[0]])
     assert np.array_equal(u32(cmap), m) and np.array_equal(u32(cloc), l)
+
+
+# ---------------------------------------------------------------------------------------------
+def _power_law_graph_on_gpu(V, E, seed):
+    """in-edge CSC generated on the device: power-law in-degree, skewed sources (same recipe as bench.py, scaled)"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    w = torch.rand(V, generator=g, device="cuda").clamp_min(1e-6).pow(-0.65)
+    deg = (w / w.sum() * E).floor().clamp_(1, V - 1).to(torch.int64)
+    co = torch.zeros(V + 1, dtype=torch.int64, device="cuda")
+    co[1:] = deg.cumsum(0)
+    total = int(co[-1])
+    src = torch.empty(total, dtype=torch.int32, device="cuda")
+    chunk = 1 << 27
+    for a in range(0, total, chunk):
+        b = min(total, a + chunk)
+        src[a:b] = (torch.rand(b - a, generator=g, device="cuda").pow(1.6) * V).to(torch.int64).clamp_(0, V - 1).to(torch.int32)
+    return co.to(torch.int32).cpu().numpy().view(np.uint32), src.cpu().numpy().view(np.uint32)
+
+
+def test_full_size_products_shaped_cached_path(nts, cs):
+    """BASELINE.json configs[2] shape (2.45M vertices, ~62M edges, F=100): hotness -> cache index -> omit sampling -> cached gather
+    -> hot-row override, checked through invariants and against torch formulations of the same selections."""
+    V, E, F = 2449029, 61859140, 100
+    co, ri = _power_law_graph_on_gpu(V, E, 0xBEEF)
+    graph = nts.FullyRepGraph(cs, V, column_offset=co, row_indices=ri)
+    rng = np.random.default_rng(12)
+    train = rng.permutation(V)[:8192].astype(np.uint32)
+    counts, ids = nts.preSample(train, 1024, 4, 2, graph, cache_rate=0.05, cuda_stream=cs)   # 2 super-batches
+    assert counts.size == 2 and counts.sum() == ids.size and (np.diff(ids[:counts[0]].astype(np.int64)) > 0).all()
+    # hottest vertices really are the most frequent in-neighbours of the super-batch (fp64 torch formulation)
+    deg = np.diff(co.astype(np.int64))
+    sb = train[:4096]
+    nbr = np.concatenate([ri[co[d]:co[d + 1]] for d in sb])
+    cnt = np.bincount(nbr, minlength=V)
+    nnz = int((cnt > 0).sum())
+    assert counts[0] == int(np.float32(nnz + 1) * np.float32(0.05))
+    pivot = np.sort(cnt)[::-1][counts[0]]
+    assert np.array_equal(ids[:counts[0]], np.nonzero(cnt >= pivot)[0][:counts[0]].astype(np.uint32))
+    cmap = torch.full((V,), -1, dtype=torch.int32, device="cuda")
+    cloc = torch.zeros(V, dtype=torch.int32, device="cuda")
+    hot = torch.from_numpy(ids[:counts[0]].view(np.int32)).cuda()
+    nts.set_cache_index(cs, cmap, cloc, 0, hot, hot.numel())
+    sampler = nts.FastSampler(graph, sb, 2, 1024, [25, 10], cuda_stream=cs)
+    sg = sampler.sample_gpu_fast_omit(1024, cmap, 0)
+    top, bot = sg.sampled_sgs
+    lens = np.diff(u32(bot.dev_column_offset).astype(np.int64))
+    dstb = u32(bot.dev_destination)
+    is_hot = np.isin(dstb, ids[:counts[0]])
+    assert (lens[is_hot] == 0).all() and np.array_equal(lens[~is_hot], np.minimum(deg[dstb[~is_hot]], 10))
+    assert is_hot.sum() > 0
+    # cached gather: hot rows from the HBM cache table (slot = cache_location), cold rows from the full table
+    table = torch.randn((V, F), device="cuda")
+    cache_table = table[hot.long()] + 100.0
+    hashmap = torch.full((V,), -1, dtype=torch.int32, device="cuda")
+    hashmap[hot.long()] = torch.arange(hot.numel(), dtype=torch.int32, device="cuda")
+    x = torch.empty((bot.src_size, F), device="cuda")
+    hits = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sampler.load_feature_gpu_cache(cs, sg, x, table, cache_table, hashmap, hits)
+    srcl = bot.dev_source.long()
+    ref = torch.where((hashmap[srcl] >= 0)[:, None], table[srcl] + 100.0, table[srcl])
+    assert torch.equal(x, ref) and int(hits.item()) == int((hashmap[srcl] >= 0).sum())
+    # hot-row override of the aggregated output
+    y = nts.SingleGPUAllSampleGraphOp(sg, 1, cs).forward(x)
+    assert float(y[torch.from_numpy(is_hot).cuda()].abs().sum()) == 0.0        # omitted columns aggregate to zero rows
+    share = torch.randn((hot.numel(), F), device="cuda")
+    sampler.load_share_embedding(cs, sg, y, share, cmap, cloc, 0)
+    hot_rows = torch.from_numpy(np.nonzero(is_hot)[0]).cuda()
+    assert torch.equal(y[hot_rows], share[cloc[bot.dev_destination.long()[hot_rows]].long()])
+
+
+def test_full_size_papers100m_shaped_sampling(nts, cs):
+    """BASELINE.json configs[4] topology scale (111M vertices, ~1.6B edges): u32 offsets up to 1.6e9, a 3.5M-word dedup bitmap,
+    1,700 scan tiles. Sampling invariants only (the 57 GB feature table is the sharded-table test's business)."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs ~40 GB of free HBM")
+    V, E = 111059956, 1615685872
+    co, ri = _power_law_graph_on_gpu(V, E, 0xFACE)
+    torch.cuda.empty_cache()
+    assert int(co[-1]) == ri.size and ri.size > 1_500_000_000
+    graph = nts.FullyRepGraph(cs, V, column_offset=co, row_indices=ri)
+    rng = np.random.default_rng(4)
+    seeds = rng.integers(V // 2, V, 1024).astype(np.uint32)      # high ids: column offsets beyond 2^30
+    seeds = np.unique(seeds)
+    sampler = nts.FastSampler(graph, seeds, 2, seeds.size, [25, 10], cuda_stream=cs)
+    sg = sampler.sample_gpu_fast(seeds.size)
+    deg = np.diff(co.astype(np.int64))
+    for lay, f in zip(sg.sampled_sgs, (25, 10)):
+        dst = u32(lay.dev_destination)
+        lens = np.diff(u32(lay.dev_column_offset).astype(np.int64))
+        assert np.array_equal(lens, np.minimum(deg[dst], f))
+        src = u32(lay.dev_source).astype(np.int64)
+        ans = u32(lay.dev_sample_ans)
+        assert (np.diff(src) > 0).all() and np.array_equal(np.unique(ans), src)
+        assert np.array_equal(src[u32(lay.dev_row_indices)], ans)
+        lco = u32(lay.dev_column_offset)
+        for j in range(0, dst.size, max(1, dst.size // 300)):       # membership on a sample of columns
+            nb = ri[co[dst[j]]:co[dst[j] + 1]]
+            got = ans[lco[j]:lco[j + 1]]
+            assert np.isin(got, nb).all()
+        ro = u32(lay.dev_row_offset)
+        assert ro[-1] == lay.e_size
+    assert torch.equal(sg.sampled_sgs[1].dev_destination, sg.sampled_sgs[0].dev_source)
