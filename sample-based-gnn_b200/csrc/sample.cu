@@ -45,7 +45,7 @@ struct nb_sampler {
   LayerBuf lay[NB_MAX_LAYERS];
   LayerMeta *meta_dev;   // [L+1]
   LayerMeta *meta_host;  // pinned [L+1]
-  uint32_t *bitmap, *word_rank;
+  uint32_t *bitmap[2], *word_rank;  // layer i marks bitmap[i & 1]; its relabel pass clears the other one for layer i + 1
   uint32_t n_words;
   unsigned long long *tile_states;  // [3 * L][max_tiles]
   BatchParams *params_dev;
@@ -70,10 +70,14 @@ struct CountOp {
   const uint32_t *g_col_off, *dst;
   const BatchParams *params;
   uint32_t *col_off;
-  LayerMeta *meta;
+  LayerMeta *meta;       // this layer's; layer 0 takes its dst count from params, deeper layers from the previous bitmap scan
+  const LayerMeta *prev; // previous layer's (NULL for layer 0): an arena overflow there empties every later layer
   uint32_t cap_edges;
-  int fanout, bottom;  // omit applies to the bottom layer only (ntsFastSampler.hpp:747-763)
-  __device__ unsigned n() const { return meta->n_dst; }
+  int fanout, bottom;    // omit applies to the bottom layer only (ntsFastSampler.hpp:747-763)
+  __device__ unsigned n() const {
+    if (prev) return prev->err ? 0u : meta->n_dst;
+    return params->n_seeds;
+  }
   __device__ unsigned load(unsigned i) const {
     uint32_t d = dst[i];
     uint32_t deg = g_col_off[d + 1] - g_col_off[d];
@@ -87,11 +91,14 @@ struct CountOp {
     return c;
   }
   __device__ void store(unsigned i, unsigned excl, unsigned) const { col_off[i] = excl; }
-  __device__ void total(unsigned t) const {
-    col_off[meta->n_dst] = t;
+  __device__ void total(unsigned t) const {  // runs exactly once per batch and layer: (re)initialises the layer's meta
+    const unsigned nd = n();
+    col_off[nd] = t;
+    meta->n_dst = nd;
     meta->n_edges = t;
+    meta->n_src = 0;
     meta->long_rows = 0;
-    if (t > cap_edges) meta->err = 1;
+    meta->err = (prev && prev->err) ? prev->err : (t > cap_edges ? 1u : 0u);
   }
 };
 
@@ -143,14 +150,6 @@ struct RowOp {
   __device__ void total(unsigned t) const { row_offset[meta->err ? 0u : meta->n_src] = t; }
 };
 
-__global__ void k_init_meta(LayerMeta *meta, int L, const BatchParams *params) {
-  int i = threadIdx.x;
-  if (i <= L) {
-    meta[i].n_dst = i == 0 ? params->n_seeds : 0;
-    meta[i].n_edges = 0; meta[i].n_src = 0; meta[i].err = 0; meta[i].long_rows = 0;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Neighbour selection: one warp per dst.
 //   deg <= fanout (or fanout < 0): every in-neighbour in stored order (ntsFastSampler.hpp:1040-1048)
@@ -171,9 +170,18 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32)
 k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_row_idx, const uint32_t *__restrict__ dst,
          const uint32_t *__restrict__ col_off, uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst,
          uint32_t *__restrict__ bitmap, const LayerMeta *meta, int fanout, const BatchParams *params, uint32_t layer,
-         int merge, int hash_slots) {
+         int merge, int hash_slots, uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor,
+         uint32_t *__restrict__ src_to_dst, uint32_t cap_src) {
   extern __shared__ uint32_t s_hash[];
   if (meta->err) return;
+  if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
+    const unsigned bound = min(cap_src, meta->n_edges + (merge ? meta->n_dst : 0u));
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < bound; k += gridDim.x * blockDim.x) {
+      row_count[k] = 0;
+      row_cursor[k] = 0;
+      if (src_to_dst) src_to_dst[k] = 0xffffffffu;
+    }
+  }
   const uint64_t key = params->rng_seed ^ (params->rng_offset >> 32 << 32);
   const uint32_t rng_offset = (uint32_t)params->rng_offset;
   const int replay = params->replay;
@@ -270,16 +278,18 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
 
 static void launch_sample(cudaStream_t st, unsigned cap_dst, int fanout, const uint32_t *g_col_off, const uint32_t *g_row_idx,
                           const uint32_t *dst, const uint32_t *col_off, uint32_t *sample_ans, uint32_t *edge_dst, uint32_t *bitmap,
-                          const LayerMeta *meta, const BatchParams *params, uint32_t layer, int merge) {
+                          const LayerMeta *meta, const BatchParams *params, uint32_t layer, int merge, uint32_t *row_count = nullptr,
+                          uint32_t *row_cursor = nullptr, uint32_t *src_to_dst = nullptr, uint32_t cap_src = 0) {
   uint32_t hs = 1; while (fanout > 32 && hs < 2u * (uint32_t)fanout) hs <<= 1;
   const int hash_slots = fanout > 32 ? (int)hs : 0;
   const int group = (fanout < 0 || fanout > 16) ? 32 : (fanout > 8 ? 16 : 8);
   const unsigned per_block = SAMPLE_WARPS * (32 / group);
-  const unsigned grid = nb_grid(cap_dst, per_block, 8);
+  unsigned grid = nb_grid(cap_dst, per_block, 8);
+  if (row_count && grid < NB_SM_COUNT) grid = NB_SM_COUNT;  // enough threads for the scratch clear
   const size_t smem = (size_t)hash_slots * SAMPLE_WARPS * 4;
-  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots);
-  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots);
-  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots);
+  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src);
+  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src);
+  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src);
 }
 
 // global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
@@ -301,11 +311,23 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
           const uint32_t *__restrict__ word_rank, uint32_t *__restrict__ row_count, const uint32_t *__restrict__ dst,
           uint32_t *__restrict__ dst_local_id, uint32_t *__restrict__ src_to_dst, const LayerMeta *meta, int histogram,
           int fuse_weights, float *__restrict__ ewf, const uint32_t *__restrict__ edge_dst, const uint32_t *__restrict__ col_off,
-          const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg, const BatchParams *params) {
+          const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg, const BatchParams *params,
+          uint32_t *__restrict__ source, uint32_t n_words, uint32_t *__restrict__ other_bitmap) {
+  const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  // the next layer marks the other bitmap: clear it here, off the critical path (no memset node per layer)
+  if (other_bitmap)
+    for (unsigned w = tid; w <= n_words; w += stride) other_bitmap[w] = 0u;
   if (meta->err) return;
   const unsigned E = meta->n_edges, nd = meta->n_dst;
   const int weight_type = params->weight_type;
-  const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  // `source` in ascending global id: one thread per vertex bit, a warp covers one bitmap word (consecutive writes)
+  {
+    const unsigned lane = lane_id();
+    for (unsigned w = tid >> 5; w < n_words; w += stride >> 5) {
+      const uint32_t bits = bitmap[w];
+      if (bits & (1u << lane)) source[word_rank[w] + __popc(bits & ((1u << lane) - 1u))] = w * 32u + lane;
+    }
+  }
   for (unsigned e = tid; e < E; e += stride) {
     uint32_t v = sample_ans[e];
     uint32_t local = word_rank[v >> 5] + __popc(bitmap[v >> 5] & ((1u << (v & 31)) - 1u));
@@ -366,44 +388,42 @@ __device__ __forceinline__ void csr_emit(uint32_t pos, uint32_t e, uint32_t *col
 __global__ void __launch_bounds__(256)
 k_csr_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
            uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
-           const float *__restrict__ ewf, uint32_t *__restrict__ long_rows, LayerMeta *meta, const BatchParams *params) {
+           const float *__restrict__ ewf, LayerMeta *meta, const BatchParams *params) {
   if (meta->err) return;
   if (params->weight_type == NB_WEIGHT_NONE) ewb = nullptr;
   const unsigned S = meta->n_src;
-  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-    const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
-    if (n > CSR_SHORT) { long_rows[atomicAdd(&meta->long_rows, 1u)] = s; continue; }
-    uint32_t ev[CSR_SHORT];
+  const unsigned lane = lane_id();
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned s0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; s0 < S; s0 += stride) {  // a warp owns 32 consecutive rows
+    const unsigned s = s0 + lane;
+    uint32_t a = 0, n = 0;
+    if (s < S) { a = row_offset[s]; n = row_offset[s + 1] - a; }
+    if (n > 0 && n <= CSR_SHORT) {  // short row: one thread, rank counting in registers
+      uint32_t ev[CSR_SHORT];
 #pragma unroll
-    for (uint32_t i = 0; i < CSR_SHORT; i++) ev[i] = i < n ? csr_tmp[a + i] : 0xffffffffu;
+      for (uint32_t i = 0; i < CSR_SHORT; i++) ev[i] = i < n ? csr_tmp[a + i] : 0xffffffffu;
 #pragma unroll
-    for (uint32_t i = 0; i < CSR_SHORT; i++) {
-      if (i < n) {
-        uint32_t rank = 0;
+      for (uint32_t i = 0; i < CSR_SHORT; i++) {
+        if (i < n) {
+          uint32_t rank = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < CSR_SHORT; k++) rank += (ev[k] < ev[i]);
-        csr_emit(a + rank, ev[i], column_indices, csr_to_csc, edge_dst, ewb, ewf);
+          for (uint32_t k = 0; k < CSR_SHORT; k++) rank += (ev[k] < ev[i]);
+          csr_emit(a + rank, ev[i], column_indices, csr_to_csc, edge_dst, ewb, ewf);
+        }
       }
     }
-  }
-}
-__global__ void __launch_bounds__(256)
-k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
-                uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
-                const float *__restrict__ ewf, const uint32_t *__restrict__ long_rows, const LayerMeta *meta,
-                const BatchParams *params) {
-  if (meta->err) return;
-  if (params->weight_type == NB_WEIGHT_NONE) ewb = nullptr;
-  const unsigned n_long = meta->long_rows;
-  const unsigned lane = lane_id();
-  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_long; w += (gridDim.x * blockDim.x) >> 5) {
-    const uint32_t s = long_rows[w];
-    const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
-    for (uint32_t i = lane; i < n; i += 32) {
-      const uint32_t e = csr_tmp[a + i];
-      uint32_t rank = 0;
-      for (uint32_t k = 0; k < n; k++) rank += (__ldg(&csr_tmp[a + k]) < e);
-      csr_emit(a + rank, e, column_indices, csr_to_csc, edge_dst, ewb, ewf);
+    // long rows (hub sources): the whole warp ranks one row at a time
+    unsigned longs = __ballot_sync(FULL_MASK, n > CSR_SHORT);
+    while (longs) {
+      const int l = __ffs(longs) - 1;
+      longs &= longs - 1;
+      const uint32_t la = __shfl_sync(FULL_MASK, a, l), ln = __shfl_sync(FULL_MASK, n, l);
+      for (uint32_t i = lane; i < ln; i += 32) {
+        const uint32_t e = csr_tmp[la + i];
+        uint32_t rank = 0;
+        for (uint32_t k = 0; k < ln; k++) rank += (__ldg(&csr_tmp[la + k]) < e);
+        csr_emit(la + rank, e, column_indices, csr_to_csc, edge_dst, ewb, ewf);
+      }
     }
   }
 }
@@ -534,7 +554,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   s->n_words = (g->V + 31) / 32;
   if (s->n_words > max_items) max_items = s->n_words;
   s->max_tiles = (uint32_t)((max_items + SCAN_TILE - 1) / SCAN_TILE) + 1;
-  size_t o_bitmap = take(s->n_words + 1), o_rank = take(s->n_words + 1);
+  size_t o_bitmap = take(s->n_words + 1), o_bitmap1 = take(s->n_words + 1), o_rank = take(s->n_words + 1);
   size_t o_state = take((size_t)s->max_tiles * 2 * 3 * n_layers);
   size_t o_meta = take((sizeof(LayerMeta) / 4) * (NB_MAX_LAYERS + 1));
   size_t o_params = take(sizeof(BatchParams) / 4 + 8);
@@ -561,7 +581,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     b.ewf = (float *)(base + o.ewf); b.ewb = (float *)(base + o.ewb);
   }
   for (int i = 1; i < n_layers; i++) s->lay[i].destination = s->lay[i - 1].source;  // layer chaining (FullyRepGraph.hpp:309)
-  s->bitmap = base + o_bitmap; s->word_rank = base + o_rank;
+  s->bitmap[0] = base + o_bitmap; s->bitmap[1] = base + o_bitmap1; s->word_rank = base + o_rank;
   s->tile_states = (unsigned long long *)(base + o_state);
   s->meta_dev = (LayerMeta *)(base + o_meta);
   s->params_dev = (BatchParams *)(base + o_params);
@@ -614,46 +634,43 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
   const bool merge = s->flags & NB_SAMPLER_MERGE_SRC_DST, up = s->flags & NB_SAMPLER_UP_DEGREE,
              csr = s->flags & NB_SAMPLER_BUILD_CSR;
   const BatchParams *pp = s->params_dev;
-  k_init_meta<<<1, 32, 0, st>>>(s->meta_dev, s->L, pp);
-  NB_LAUNCH_CHECK(ctx);
+  // with an odd number of layers the last layer leaves bitmap[0] marked, and layer 0 of the next batch uses it
+  if (s->L & 1) NB_CUDA(cudaMemsetAsync(s->bitmap[0], 0, (size_t)(s->n_words + 1) * 4, st));
   for (int i = 0; i < s->L; i++) {
     LayerBuf &b = s->lay[i];
     LayerMeta *m = s->meta_dev + i;
+    uint32_t *bm = s->bitmap[i & 1], *bm_other = (s->L > 1) ? s->bitmap[(i + 1) & 1] : nullptr;
     ScanWs ws0{s->tile_states + (size_t)(3 * i + 0) * s->max_tiles, pp}, ws1{s->tile_states + (size_t)(3 * i + 1) * s->max_tiles, pp},
         ws2{s->tile_states + (size_t)(3 * i + 2) * s->max_tiles, pp};
-    NB_CUDA(cudaMemsetAsync(s->bitmap, 0, (size_t)(s->n_words + 1) * 4, st));
-    CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, b.cap_edges, s->fanout[i], i == s->L - 1 ? 1 : 0};
+    const bool layer_csr = csr && !(i == s->L - 1 && s->L > 1 && (s->flags & NB_SAMPLER_NO_BOTTOM_CSR));
+    const int histogram = (layer_csr || up) ? 1 : 0;
+    CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, i ? m - 1 : nullptr, b.cap_edges, s->fanout[i], i == s->L - 1 ? 1 : 0};
     k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
     NB_LAUNCH_CHECK(ctx);
-    launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst,
-                  s->bitmap, m, pp, (uint32_t)i, merge ? 1 : 0);
+    launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
+                  pp, (uint32_t)i, merge ? 1 : 0, (histogram || merge) ? b.row_count : nullptr, b.row_cursor,
+                  merge ? b.src_to_dst : nullptr, b.cap_src);
     NB_LAUNCH_CHECK(ctx);
-    BitmapOp bop{s->bitmap, s->word_rank, m, m + 1, s->n_words, b.cap_src};
+    BitmapOp bop{bm, s->word_rank, m, m + 1, s->n_words, b.cap_src};
     k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
     NB_LAUNCH_CHECK(ctx);
-    k_emit_sources<<<nb_grid(s->n_words, 8, 8), 256, 0, st>>>(s->bitmap, s->word_rank, b.source, b.row_count, b.row_cursor,
-                                                               merge ? b.src_to_dst : nullptr, m, s->n_words);
-    NB_LAUNCH_CHECK(ctx);
-    const int histogram = (csr || up) ? 1 : 0;
     k_relabel<<<nb_grid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
-        b.sample_ans, b.row_indices, s->bitmap, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
-        merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp);
+        b.sample_ans, b.row_indices, bm, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
+        merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp,
+        b.source, s->n_words, bm_other);
     NB_LAUNCH_CHECK(ctx);
     if (up) {
       k_weights_sampled<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
-    if (csr && !(i == s->L - 1 && s->L > 1 && (s->flags & NB_SAMPLER_NO_BOTTOM_CSR))) {
+    if (layer_csr) {
       RowOp rop{b.row_count, b.row_offset, m};
       k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, ws2);
       NB_LAUNCH_CHECK(ctx);
       k_csr_fill<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
       NB_LAUNCH_CHECK(ctx);
       k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
-                                                               b.ewb, b.ewf, b.long_rows, m, pp);
-      NB_LAUNCH_CHECK(ctx);
-      k_csr_long_rows<<<nb_grid(b.cap_src, 8, 2), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc,
-                                                                  b.edge_dst, b.ewb, b.ewf, b.long_rows, m, pp);
+                                                               b.ewb, b.ewf, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
   }
@@ -862,10 +879,10 @@ int nb_sample_count(nb_ctx *ctx, const uint32_t *dst_dev, uint32_t *local_column
   if (rc) return rc;
   LegacyState h;
   memset(&h, 0, sizeof(h));
-  h.meta[0].n_dst = dst_size;
+  h.params.n_seeds = dst_size;
   h.params.omit = omit_flag_dev; h.params.omit_value = omit_value; h.params.epoch = 1;
   NB_CUDA(cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-  CountOp cop{global_column_offset_dev, dst_dev, &st->params, local_column_offset_dev, &st->meta[0], 0xffffffffu, (int)fanout, 1};
+  CountOp cop{global_column_offset_dev, dst_dev, &st->params, local_column_offset_dev, &st->meta[0], nullptr, 0xffffffffu, (int)fanout, 1};
   ScanWs ws{tiles, &st->params};
   k_scan<CountOp><<<nb_grid(dst_size, SCAN_TILE, 4), SCAN_THREADS, 0, ctx->stream>>>(cop, ws);
   NB_LAUNCH_CHECK(ctx);
