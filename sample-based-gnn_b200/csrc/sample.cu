@@ -388,42 +388,45 @@ __device__ __forceinline__ void csr_emit(uint32_t pos, uint32_t e, uint32_t *col
 __global__ void __launch_bounds__(256)
 k_csr_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
            uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
-           const float *__restrict__ ewf, LayerMeta *meta, const BatchParams *params) {
+           const float *__restrict__ ewf, uint32_t *__restrict__ long_rows, LayerMeta *meta, const BatchParams *params) {
   if (meta->err) return;
   if (params->weight_type == NB_WEIGHT_NONE) ewb = nullptr;
   const unsigned S = meta->n_src;
-  const unsigned lane = lane_id();
-  const unsigned stride = gridDim.x * blockDim.x;
-  for (unsigned s0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; s0 < S; s0 += stride) {  // a warp owns 32 consecutive rows
-    const unsigned s = s0 + lane;
-    uint32_t a = 0, n = 0;
-    if (s < S) { a = row_offset[s]; n = row_offset[s + 1] - a; }
-    if (n > 0 && n <= CSR_SHORT) {  // short row: one thread, rank counting in registers
-      uint32_t ev[CSR_SHORT];
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
+    if (n > CSR_SHORT) { long_rows[atomicAdd(&meta->long_rows, 1u)] = s; continue; }  // hub source: queued for a whole warp
+    uint32_t ev[CSR_SHORT];
 #pragma unroll
-      for (uint32_t i = 0; i < CSR_SHORT; i++) ev[i] = i < n ? csr_tmp[a + i] : 0xffffffffu;
+    for (uint32_t i = 0; i < CSR_SHORT; i++) ev[i] = i < n ? csr_tmp[a + i] : 0xffffffffu;
 #pragma unroll
-      for (uint32_t i = 0; i < CSR_SHORT; i++) {
-        if (i < n) {
-          uint32_t rank = 0;
+    for (uint32_t i = 0; i < CSR_SHORT; i++) {
+      if (i < n) {
+        uint32_t rank = 0;
 #pragma unroll
-          for (uint32_t k = 0; k < CSR_SHORT; k++) rank += (ev[k] < ev[i]);
-          csr_emit(a + rank, ev[i], column_indices, csr_to_csc, edge_dst, ewb, ewf);
-        }
+        for (uint32_t k = 0; k < CSR_SHORT; k++) rank += (ev[k] < ev[i]);
+        csr_emit(a + rank, ev[i], column_indices, csr_to_csc, edge_dst, ewb, ewf);
       }
     }
-    // long rows (hub sources): the whole warp ranks one row at a time
-    unsigned longs = __ballot_sync(FULL_MASK, n > CSR_SHORT);
-    while (longs) {
-      const int l = __ffs(longs) - 1;
-      longs &= longs - 1;
-      const uint32_t la = __shfl_sync(FULL_MASK, a, l), ln = __shfl_sync(FULL_MASK, n, l);
-      for (uint32_t i = lane; i < ln; i += 32) {
-        const uint32_t e = csr_tmp[la + i];
-        uint32_t rank = 0;
-        for (uint32_t k = 0; k < ln; k++) rank += (__ldg(&csr_tmp[la + k]) < e);
-        csr_emit(la + rank, e, column_indices, csr_to_csc, edge_dst, ewb, ewf);
-      }
+  }
+}
+// one warp per queued long row, rank counting over the row (O(n^2/32), rows of a few hundred entries at most in practice)
+__global__ void __launch_bounds__(256)
+k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
+                uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
+                const float *__restrict__ ewf, const uint32_t *__restrict__ long_rows, const LayerMeta *meta,
+                const BatchParams *params) {
+  if (meta->err) return;
+  if (params->weight_type == NB_WEIGHT_NONE) ewb = nullptr;
+  const unsigned n_long = meta->long_rows;
+  const unsigned lane = lane_id();
+  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_long; w += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t s = long_rows[w];
+    const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t e = csr_tmp[a + i];
+      uint32_t rank = 0;
+      for (uint32_t k = 0; k < n; k++) rank += (__ldg(&csr_tmp[a + k]) < e);
+      csr_emit(a + rank, e, column_indices, csr_to_csc, edge_dst, ewb, ewf);
     }
   }
 }
@@ -670,7 +673,10 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
       k_csr_fill<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
       NB_LAUNCH_CHECK(ctx);
       k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
-                                                               b.ewb, b.ewf, m, pp);
+                                                               b.ewb, b.ewf, b.long_rows, m, pp);
+      NB_LAUNCH_CHECK(ctx);
+      k_csr_long_rows<<<nb_grid(b.cap_src, 8, 2), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc,
+                                                                  b.edge_dst, b.ewb, b.ewf, b.long_rows, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
   }
