@@ -263,6 +263,19 @@ int nb_row_override2(nb_ctx *ctx, float *out_feature, float *out_embedding, cons
                      const uint32_t *destination_dev, uint32_t n_dst, uint32_t feature_size, uint32_t embedding_size,
                      uint32_t super_batch_id);
 
+/* Cold-row staging (feature table too large for, or simply left in, host memory; hot rows in an HBM cache table).
+ * Replaces FastSampler::load_feature_gpu_cache's CPU split + zero-copy reads (core/ntsFastSampler.hpp:263-317):
+ * nb_stage_submit splits the id list on the device, ships only the cold ids to the host and returns; a worker thread packs
+ * those rows into pinned memory and issues ONE cudaMemcpyAsync on a side stream; nb_stage_gather orders the merge kernel
+ * (hot rows from the cache table, cold rows from the staged block) behind that copy. Two slots: submit batch i+1 while batch i
+ * trains. host_table may be any host memory (pinned or pageable); it is read by the worker thread only. */
+typedef struct nb_stage nb_stage;
+int nb_stage_create(nb_ctx *ctx, const float *host_table, uint32_t host_pitch, uint32_t feature_size, uint32_t max_rows, nb_stage **out);
+int nb_stage_destroy(nb_stage *s);
+int nb_stage_submit(nb_stage *s, int slot, const uint32_t *ids_dev, uint32_t n_rows, const uint32_t *cache_node_hashmap_dev);
+int nb_stage_gather(nb_stage *s, int slot, float *out, uint32_t out_pitch, const float *cache_table, uint32_t cache_pitch,
+                    const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out);
+
 /* Sharded HBM feature table (multi-GPU): row v lives on shard v % n_shards at local row
  * v / n_shards. shard_ptrs[k] is a device pointer valid on THIS device (local allocation or a
  * peer mapping obtained through CUDA IPC); the gather kernel reads peers directly over NVLink.

@@ -24,7 +24,7 @@ from . import _capi
 from ._capi import (NB_SAMPLER_BUILD_CSR, NB_SAMPLER_MERGE_SRC_DST, NB_SAMPLER_NO_BOTTOM_CSR, NB_SAMPLER_UP_DEGREE, NB_WEIGHT_MEAN,
                     NB_WEIGHT_MEAN_SAMPLED, NB_WEIGHT_NONE, NB_WEIGHT_SUM, LayerView, NtsError, check, lib, ptr)
 
-__all__ = ["preSample", "write_pre_sample_file", "read_pre_sample_file", "set_cache_index", "Cuda_Stream", "FullyRepGraph", "FastSampler", "SampledSubgraph", "sampCSC", "WeightType",
+__all__ = ["ColdStage", "preSample", "write_pre_sample_file", "read_pre_sample_file", "set_cache_index", "Cuda_Stream", "FullyRepGraph", "FastSampler", "SampledSubgraph", "sampCSC", "WeightType",
            "SingleGPUAllSampleGraphOp", "SingleGPUSampleGraphOp", "GATFusedOp", "BatchGPUSrcDstScatterOp",
            "BatchGPUEdgeSoftMax", "BatchGPUAggregateDst", "FeatureTable", "NtsError"]
 
@@ -469,6 +469,33 @@ def read_pre_sample_file(path, n_super_batches, of_rate=1.0):
 def set_cache_index(cuda_stream, cache_map, cache_location, super_batch_id, cache_ids_dev, n):
     """GNNDatum::set_cache_index (core/ntsDataloador.hpp:440-478) on device arrays"""
     check(lib().nb_set_cache_index(cuda_stream._h, ptr(cache_map), ptr(cache_location), super_batch_id, ptr(cache_ids_dev), n))
+
+
+class ColdStage:
+    """Cold rows from a host-resident feature table, staged per batch through pinned memory on a side stream while the previous
+    batch trains; hot rows from an HBM cache table (replaces load_feature_gpu_cache's CPU split + zero-copy, ntsFastSampler.hpp:263-317)."""
+
+    def __init__(self, cuda_stream, host_table, max_rows):
+        assert host_table.dim() == 2 and host_table.stride(1) == 1 and not host_table.is_cuda
+        self.cs, self.host_table, self.F = cuda_stream, host_table, host_table.shape[1]
+        h = C.c_void_p()
+        check(lib().nb_stage_create(cuda_stream._h, ptr(host_table), host_table.stride(0), self.F, int(max_rows), C.byref(h)))
+        self._h = h
+
+    def submit(self, slot, ids_dev, n_rows, cache_node_hashmap_dev):
+        check(lib().nb_stage_submit(self._h, slot, ptr(ids_dev), n_rows, ptr(cache_node_hashmap_dev)))
+
+    def gather(self, slot, out, cache_table, cache_node_hashmap_dev, ids_dev):
+        n_cold = C.c_uint32()
+        check(lib().nb_stage_gather(self._h, slot, ptr(out), _pitch(out, self.F), ptr(cache_table), _pitch(cache_table, self.F),
+                                    ptr(cache_node_hashmap_dev), ptr(ids_dev), C.byref(n_cold)))
+        return n_cold.value
+
+    def __del__(self):
+        try:
+            lib().nb_stage_destroy(self._h)
+        except Exception:
+            pass
 
 
 class FeatureTable:

@@ -43,6 +43,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 template <class Op>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
   __shared__ unsigned s_prefix, s_warp[SCAN_THREADS / 32];
+  __shared__ unsigned s_items[SCAN_TILE + SCAN_TILE / 32];
   const unsigned n = op.n();
   const unsigned ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) op.total(0);
@@ -51,11 +52,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
   // The grid never exceeds the number of co-resident blocks, so waiting on a lower tile cannot deadlock.
   const unsigned long long tag = ((unsigned long long)(ws.params->epoch & 0x3fffffffu)) << 34;
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // items are produced with coalesced (striped) indices and handed to their owner thread (blocked layout) through
+    // shared memory; the +i/32 padding keeps both access patterns nearly conflict free
     unsigned v[SCAN_ITEMS], sum = 0;
     const unsigned first = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-      v[k] = (first + k < n) ? op.load(first + k) : 0u;
+      const unsigned i = k * SCAN_THREADS + threadIdx.x, g = tile * SCAN_TILE + i;
+      s_items[i + (i >> 5)] = g < n ? op.load(g) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+      const unsigned i = threadIdx.x * SCAN_ITEMS + k;
+      v[k] = s_items[i + (i >> 5)];
       sum += v[k];
     }
     unsigned incl = sum;

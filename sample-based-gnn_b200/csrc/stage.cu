@@ -1,0 +1,225 @@
+// stage.cu -- cold-row staging for feature tables that stay in host memory.
+//
+// Hot rows live in an HBM cache table (cache_node_hashmap[v] = slot or -1, top-out-degree vertices:
+// toolkits/GS_SAMPLE_PC_MULTI.hpp:916-1015); cold rows come from the host table. The reference splits the id list on the CPU
+// after a synchronous D2H and then reads cold rows over PCIe 4 bytes at a time from a zero-copy mapping
+// (core/ntsFastSampler.hpp:263-317). Here the split happens on the device, only the cold ids travel to the host, a worker
+// thread packs those rows into a pinned staging buffer and ships them with one cudaMemcpyAsync on a side stream, and the merge
+// kernel (hot rows from the cache, cold rows from the staged block) waits on that copy's event. submit() returns immediately,
+// so the staging of batch i+1 overlaps the training of batch i (2 slots).
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+#include "common.cuh"
+
+constexpr int STAGE_SLOTS = 2;
+
+struct StageSlot {
+  uint32_t *cold_pos_dev, *cold_ids_dev, *count_dev;  // compacted cold rows: position in the batch, global id
+  uint32_t *cold_ids_host, *count_host;               // pinned
+  float *rows_host, *rows_dev;                        // pinned staging block and its device copy
+  cudaEvent_t ids_ready, rows_ready, consumed;
+  uint32_t n_rows, n_cold;
+  int state;  // 0 idle, 1 submitted (worker owns it), 2 staged (rows_ready recorded)
+};
+
+struct nb_stage {
+  nb_ctx *ctx;
+  cudaStream_t side;
+  const float *host_table;
+  uint64_t host_pitch;
+  uint32_t F, max_rows;
+  StageSlot slot[STAGE_SLOTS];
+  std::thread worker;
+  std::mutex m;
+  std::condition_variable cv;
+  int pending[STAGE_SLOTS + 1], n_pending;
+  bool stop;
+  char err[256];
+};
+
+// rows whose cache slot is -1: warp-ballot compaction, one atomic per warp. The order of the list does not matter to the
+// merge (each cold id travels with its position in the batch), so no scan is needed
+__global__ void __launch_bounds__(256)
+k_cold_split(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ cache_map, uint32_t n, uint32_t *__restrict__ cold_pos,
+             uint32_t *__restrict__ cold_ids, uint32_t *count) {
+  const unsigned lane = lane_id();
+  for (unsigned i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const unsigned i = i0 + lane;
+    uint32_t v = 0;
+    bool cold = false;
+    if (i < n) { v = ids[i]; cold = cache_map[v] == 0xffffffffu; }
+    const unsigned mask = __ballot_sync(FULL_MASK, cold);
+    if (!mask) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (cold) {
+      const uint32_t k = base + __popc(mask & ((1u << lane) - 1u));
+      cold_pos[k] = i;
+      cold_ids[k] = v;
+    }
+  }
+}
+
+// hot rows: out[i,:] = cache[slot,:]; cold rows: out[cold_pos[k],:] = staged[k,:]
+__global__ void __launch_bounds__(256)
+k_stage_merge(float *__restrict__ out, uint64_t out_pitch, const float *__restrict__ cache, uint64_t cache_pitch,
+              const uint32_t *__restrict__ cache_map, const uint32_t *__restrict__ ids, uint32_t n, const float *__restrict__ staged,
+              const uint32_t *__restrict__ cold_pos, const uint32_t *__restrict__ n_cold_dev, uint32_t F) {
+  const unsigned lane = lane_id(), warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_cold = *n_cold_dev;
+  for (unsigned w = warp; w < n + n_cold; w += warps) {
+    const float *src;
+    float *dst;
+    if (w < n) {
+      const uint32_t slot = cache_map[ids[w]];
+      if (slot == 0xffffffffu) continue;
+      src = cache + (uint64_t)slot * cache_pitch;
+      dst = out + (uint64_t)w * out_pitch;
+    } else {
+      const uint32_t k = w - n;
+      src = staged + (uint64_t)k * F;
+      dst = out + (uint64_t)cold_pos[k] * out_pitch;
+    }
+    for (unsigned j = lane; j < F; j += 32) dst[j] = src[j];
+  }
+}
+
+static void stage_worker(nb_stage *s) {
+  cudaSetDevice(s->ctx->device);
+  while (true) {
+    int k;
+    {
+      std::unique_lock<std::mutex> g(s->m);
+      s->cv.wait(g, [&] { return s->stop || s->n_pending > 0; });
+      if (s->stop && s->n_pending == 0) return;
+      k = s->pending[0];
+      for (int i = 1; i < s->n_pending; i++) s->pending[i - 1] = s->pending[i];
+      s->n_pending--;
+    }
+    StageSlot &sl = s->slot[k];
+    cudaError_t e = cudaEventSynchronize(sl.ids_ready);  // cold ids and their count are on the host
+    const uint32_t nc = e == cudaSuccess ? *sl.count_host : 0;
+    if (e == cudaSuccess) {
+      const size_t row_bytes = (size_t)s->F * sizeof(float);
+#pragma omp parallel for schedule(static)
+      for (long r = 0; r < (long)nc; r++)
+        memcpy(sl.rows_host + (size_t)r * s->F, s->host_table + (uint64_t)sl.cold_ids_host[r] * s->host_pitch, row_bytes);
+      if (nc) e = cudaMemcpyAsync(sl.rows_dev, sl.rows_host, (size_t)nc * row_bytes, cudaMemcpyHostToDevice, s->side);
+      if (e == cudaSuccess) e = cudaEventRecord(sl.rows_ready, s->side);
+    }
+    {
+      std::lock_guard<std::mutex> g(s->m);
+      sl.n_cold = nc;
+      sl.state = 2;
+      if (e != cudaSuccess) snprintf(s->err, sizeof(s->err), "stage worker: %s", cudaGetErrorString(e));
+    }
+    s->cv.notify_all();
+  }
+}
+
+extern "C" {
+
+int nb_stage_create(nb_ctx *ctx, const float *host_table, uint32_t host_pitch, uint32_t feature_size, uint32_t max_rows, nb_stage **out) {
+  NB_REQUIRE(ctx && host_table && out && feature_size > 0 && host_pitch >= feature_size && max_rows > 0, NB_ERR_ARG, "nb_stage_create: bad argument");
+  NB_GUARD(ctx);
+  nb_stage *s = new nb_stage();
+  s->ctx = ctx; s->host_table = host_table; s->host_pitch = host_pitch; s->F = feature_size; s->max_rows = max_rows;
+  s->n_pending = 0; s->stop = false; s->err[0] = 0;
+  NB_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+  for (int k = 0; k < STAGE_SLOTS; k++) {
+    StageSlot &sl = s->slot[k];
+    NB_CUDA(cudaMalloc(&sl.cold_pos_dev, (size_t)max_rows * 4));
+    NB_CUDA(cudaMalloc(&sl.cold_ids_dev, (size_t)max_rows * 4));
+    NB_CUDA(cudaMalloc(&sl.count_dev, 64));
+    NB_CUDA(cudaMalloc(&sl.rows_dev, (size_t)max_rows * feature_size * 4));
+    NB_CUDA(cudaHostAlloc(&sl.cold_ids_host, (size_t)max_rows * 4, cudaHostAllocDefault));
+    NB_CUDA(cudaHostAlloc(&sl.count_host, 64, cudaHostAllocDefault));
+    NB_CUDA(cudaHostAlloc(&sl.rows_host, (size_t)max_rows * feature_size * 4, cudaHostAllocDefault));
+    NB_CUDA(cudaEventCreateWithFlags(&sl.ids_ready, cudaEventDisableTiming));
+    NB_CUDA(cudaEventCreateWithFlags(&sl.rows_ready, cudaEventDisableTiming));
+    NB_CUDA(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
+    sl.state = 0; sl.n_rows = 0; sl.n_cold = 0;
+  }
+  s->worker = std::thread(stage_worker, s);
+  *out = s;
+  return NB_OK;
+}
+
+int nb_stage_destroy(nb_stage *s) {
+  if (!s) return NB_OK;
+  { std::lock_guard<std::mutex> g(s->m); s->stop = true; }
+  s->cv.notify_all();
+  if (s->worker.joinable()) s->worker.join();
+  DeviceGuard guard(s->ctx->device);
+  cudaStreamSynchronize(s->side);
+  for (int k = 0; k < STAGE_SLOTS; k++) {
+    StageSlot &sl = s->slot[k];
+    cudaFree(sl.cold_pos_dev); cudaFree(sl.cold_ids_dev); cudaFree(sl.count_dev); cudaFree(sl.rows_dev);
+    cudaFreeHost(sl.cold_ids_host); cudaFreeHost(sl.count_host); cudaFreeHost(sl.rows_host);
+    cudaEventDestroy(sl.ids_ready); cudaEventDestroy(sl.rows_ready); cudaEventDestroy(sl.consumed);
+  }
+  cudaStreamDestroy(s->side);
+  delete s;
+  return NB_OK;
+}
+
+// Enqueue the split of one id list on the ctx stream and hand the slot to the worker. Returns immediately.
+int nb_stage_submit(nb_stage *s, int slot, const uint32_t *ids_dev, uint32_t n_rows, const uint32_t *cache_node_hashmap_dev) {
+  NB_REQUIRE(s && slot >= 0 && slot < STAGE_SLOTS && (n_rows == 0 || (ids_dev && cache_node_hashmap_dev)), NB_ERR_ARG, "nb_stage_submit: bad argument");
+  NB_REQUIRE(n_rows <= s->max_rows, NB_ERR_CAPACITY, "nb_stage_submit: %u rows exceed the stage capacity %u", n_rows, s->max_rows);
+  nb_ctx *ctx = s->ctx;
+  NB_GUARD(ctx);
+  StageSlot &sl = s->slot[slot];
+  {
+    std::unique_lock<std::mutex> g(s->m);
+    NB_REQUIRE(sl.state != 1, NB_ERR_ARG, "nb_stage_submit: slot %d is still being staged", slot);
+    sl.state = 1;
+  }
+  NB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.consumed, 0));  // the merge that last read this slot's buffers has run
+  NB_CUDA(cudaMemsetAsync(sl.count_dev, 0, 4, ctx->stream));
+  if (n_rows) {
+    k_cold_split<<<nb_grid(n_rows, 256, 4), 256, 0, ctx->stream>>>(ids_dev, cache_node_hashmap_dev, n_rows, sl.cold_pos_dev, sl.cold_ids_dev, sl.count_dev);
+    NB_LAUNCH_CHECK(ctx);
+    NB_CUDA(cudaMemcpyAsync(sl.cold_ids_host, sl.cold_ids_dev, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  NB_CUDA(cudaMemcpyAsync(sl.count_host, sl.count_dev, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(cudaEventRecord(sl.ids_ready, ctx->stream));
+  sl.n_rows = n_rows;
+  {
+    std::lock_guard<std::mutex> g(s->m);
+    s->pending[s->n_pending++] = slot;
+  }
+  s->cv.notify_all();
+  return NB_OK;
+}
+
+// out[i,:] for the id list given to submit(): waits (host side) until the worker has issued the copy, then orders the merge
+// kernel behind it on the ctx stream. n_cold_out (may be NULL) receives the number of rows that came from the host.
+int nb_stage_gather(nb_stage *s, int slot, float *out, uint32_t out_pitch, const float *cache_table, uint32_t cache_pitch,
+                    const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out) {
+  NB_REQUIRE(s && slot >= 0 && slot < STAGE_SLOTS && out && out_pitch >= s->F, NB_ERR_ARG, "nb_stage_gather: bad argument");
+  nb_ctx *ctx = s->ctx;
+  NB_GUARD(ctx);
+  StageSlot &sl = s->slot[slot];
+  {
+    std::unique_lock<std::mutex> g(s->m);
+    NB_REQUIRE(sl.state != 0, NB_ERR_ARG, "nb_stage_gather: nothing was submitted on slot %d", slot);
+    s->cv.wait(g, [&] { return sl.state == 2; });
+    sl.state = 0;
+    if (s->err[0]) { nb_set_error("%s", s->err); s->err[0] = 0; return NB_ERR_CUDA; }
+  }
+  if (n_cold_out) *n_cold_out = sl.n_cold;
+  NB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.rows_ready, 0));
+  if (sl.n_rows) {
+    k_stage_merge<<<nb_grid((uint64_t)sl.n_rows + sl.n_cold, 8, 8), 256, 0, ctx->stream>>>(out, out_pitch, cache_table, cache_pitch,
+        cache_node_hashmap_dev, ids_dev, sl.n_rows, sl.rows_dev, sl.cold_pos_dev, sl.count_dev, s->F);
+    NB_LAUNCH_CHECK(ctx);
+  }
+  NB_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
+  return NB_OK;
+}
+
+}  // extern "C"

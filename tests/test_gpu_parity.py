@@ -734,3 +734,34 @@ def test_full_size_papers100m_shaped_sampling(nts, cs):
         ro = u32(lay.dev_row_offset)
         assert ro[-1] == lay.e_size
     assert torch.equal(sg.sampled_sgs[1].dev_destination, sg.sampled_sgs[0].dev_source)
+
+
+def test_cold_row_staging_overlapped_slots(nts, cs):
+    """Hot rows from the HBM cache table, cold rows staged from (pageable) host memory by the worker thread through pinned
+    memory + one async copy on a side stream; two slots in flight; result identical to the oracle's cached gather."""
+    V, F = 40000, 100
+    rng = np.random.default_rng(6)
+    table_np = rng.standard_normal((V, F)).astype(np.float32)
+    hot = np.sort(rng.permutation(V)[:6000]).astype(np.uint32)
+    cache_np = table_np[hot] + np.float32(50.0)
+    hashmap = np.full(V, 0xFFFFFFFF, np.uint32)
+    hashmap[hot] = np.arange(hot.size, dtype=np.uint32)
+    d_hash = torch.from_numpy(hashmap.view(np.int32)).cuda()
+    d_cache = torch.from_numpy(cache_np).cuda()
+    host_table = torch.from_numpy(table_np)                          # plain pageable host memory
+    stage = nts.ColdStage(cs, host_table, max_rows=30000)
+    batches = [rng.integers(0, V, n).astype(np.uint32) for n in (30000, 1, 17000, 0, 25000)]
+    d_ids = [torch.from_numpy(b.view(np.int32)).cuda() for b in batches]
+    outs = [torch.full((max(b.size, 1), F), 9.0, device="cuda") for b in batches]
+    stage.submit(0, d_ids[0], batches[0].size, d_hash)
+    for i, b in enumerate(batches):
+        if i + 1 < len(batches):
+            stage.submit((i + 1) % 2, d_ids[i + 1], batches[i + 1].size, d_hash)   # next batch stages while this one is merged
+        n_cold = stage.gather(i % 2, outs[i], d_cache, d_hash, d_ids[i])
+        assert n_cold == int((hashmap[b] == 0xFFFFFFFF).sum())
+    cs.CUDA_DEVICE_SYNCHRONIZE()
+    for b, o in zip(batches, outs):
+        if b.size:
+            assert np.array_equal(bits(f32(o)[:b.size]), bits(oracle.gather_rows_cached(table_np, cache_np, hashmap, b)))
+    with pytest.raises(nts.NtsError):
+        stage.submit(0, d_ids[0], 30001, d_hash)
