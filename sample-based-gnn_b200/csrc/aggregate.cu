@@ -21,7 +21,7 @@
 constexpr int AGG_THREADS = 256;
 
 // UNR = segment entries whose row loads are issued before the first accumulate (UNR*CHUNK independent vector loads per
-// lane in flight); narrow rows (CHUNK 1-2, e.g. F=128) take 8 entries at a time, wide rows 2. Accumulation stays in
+// lane in flight); narrow rows (CHUNK 1-2, e.g. F=128) take 4 entries at a time, wide rows 2. Accumulation stays in
 // stored order, so the result does not depend on UNR.
 template <int VEC, int CHUNK, int UNR>
 __global__ void __launch_bounds__(AGG_THREADS)
@@ -138,7 +138,7 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
 #define NB_SEG(C)                                                                                              \
   do {                                                                                                         \
     if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
-    else k_segment_reduce<VEC, C, (C <= 2 ? 8 : C <= 4 ? 3 : 2)><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch); \
+    else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2)><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch); \
   } while (0)
   if (per_lane <= 1) NB_SEG(1);
   else if (per_lane <= 2) NB_SEG(2);
