@@ -349,7 +349,7 @@ int nb_gat_fwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
 int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slope, const float *dout,
                const float *score_pre, const float *alpha, const uint32_t *column_offset, const uint32_t *row_indices,
                const uint32_t *dst_local_id, const uint32_t *row_offset, const uint32_t *column_indices,
-               const uint32_t *csr_to_csc, const uint32_t *src_to_dst, uint32_t n_dst, uint32_t n_src,
+               const uint32_t *csr_to_csc, const uint32_t *src_to_dst, uint32_t n_dst, uint32_t n_src, uint32_t n_edges,
                uint32_t feature_size, float *dh, float *datt);
 
 #ifdef __cplusplus

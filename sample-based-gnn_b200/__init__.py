@@ -623,7 +623,7 @@ class GATFusedOp:
         datt = torch.empty(2 * F, dtype=torch.float32, device=h.device)
         check(lib().nb_gat_bwd(self.cs._h, ptr(h), ptr(att.contiguous()), self.slope, ptr(dout), ptr(self.score_pre),
                                ptr(self.alpha), ptr(l.dev_c_o()), ptr(l.dev_r_i()), ptr(l.dev_dst_local_id), ptr(l.dev_r_o()),
-                               ptr(l.dev_c_i()), ptr(l.dev_csr_to_csc), ptr(l.dev_src_to_dst), l.v_size, l.src_size, F,
+                               ptr(l.dev_c_i()), ptr(l.dev_csr_to_csc), ptr(l.dev_src_to_dst), l.v_size, l.src_size, l.e_size, F,
                                ptr(dh), ptr(datt)))
         return dh, datt.view_as(att)
 

@@ -100,7 +100,7 @@ _SIGS = {
     "nb_gather_msg_to_dst": (I32, [P, P, P, P, U32, U32]),
     "nb_scatter_dst_to_msg": (I32, [P, P, P, P, U32, U32]),
     "nb_gat_fwd": (I32, [P, P, P, F32, P, P, P, U32, U32, U32, P, P, P]),
-    "nb_gat_bwd": (I32, [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, U32, U32, U32, P, P]),
+    "nb_gat_bwd": (I32, [P, P, P, F32, P, P, P, P, P, P, P, P, P, P, U32, U32, U32, U32, P, P]),
 }
 
 

@@ -23,11 +23,18 @@ constexpr int AGG_THREADS = 256;
 // UNR = segment entries whose row loads are issued before the first accumulate (UNR*CHUNK independent vector loads per
 // lane in flight); narrow rows (CHUNK 1-2, e.g. F=128) take 4 entries at a time, wide rows 2. Accumulation stays in
 // stored order, so the result does not depend on UNR.
+// Optional rank-2 epilogue (used by the fused GAT backward): out[r,:] += e1[r] * va[:] + e2[r] * vb[:].
+struct SegEpilogue {
+  const float *e1, *e2;  // per output row scalars (e2 may be NULL)
+  const float *va, *vb;  // feature-length vectors
+};
+
 template <int VEC, int CHUNK, int UNR>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
                  const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
-                 const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch) {
+                 const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch,
+                 SegEpilogue epi = SegEpilogue{nullptr, nullptr, nullptr, nullptr}) {
   const unsigned lane = lane_id();
   const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
   const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
@@ -73,6 +80,19 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
                 if (k < nvec) acc[c].axpy(x[u][c], w[u]);
               }
             }
+          }
+        }
+      }
+      if (epi.e1) {
+        const float s1 = epi.e1[r], s2 = epi.e2 ? epi.e2[r] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CHUNK; c++) {
+          const unsigned k = c0 + c * 32 + lane;
+          if (k < nvec) {
+            Vec<VEC> a, b;
+            a.load(epi.va + (uint64_t)k * VEC);
+            acc[c].axpy(a, s1);
+            if (epi.e2) { b.load(epi.vb + (uint64_t)k * VEC); acc[c].axpy(b, s2); }
           }
         }
       }
@@ -131,14 +151,14 @@ k_push(const float *__restrict__ in, float *__restrict__ out, const float *__res
 template <int VEC>
 static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                           const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
-                          uint64_t out_pitch) {
+                          uint64_t out_pitch, SegEpilogue epi) {
   const uint32_t nvec = F / VEC;
   const unsigned grid = nb_grid(n_rows, AGG_THREADS / 32, 8);
   const uint32_t per_lane = (nvec + 31) / 32;
 #define NB_SEG(C)                                                                                              \
   do {                                                                                                         \
     if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
-    else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2)><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch); \
+    else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2)><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
   } while (0)
   if (per_lane <= 1) NB_SEG(1);
   else if (per_lane <= 2) NB_SEG(2);
@@ -153,17 +173,25 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
   return NB_OK;
 }
 
-static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
-                       const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev = nullptr,
-                       uint64_t in_pitch = 0, uint64_t out_pitch = 0) {
+int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
+                   const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
+                   uint64_t out_pitch, const float *e1, const float *e2, const float *va, const float *vb) {
+  SegEpilogue epi{e1, e2, va, vb};
   if (n_rows == 0) return NB_OK;
   if (!in_pitch) in_pitch = F;
   if (!out_pitch) out_pitch = F;
   uint32_t fe = F;
-  int vec = push ? nb_pick_vec(F, in, in_pitch, out, out_pitch) : nb_pick_vec(F, in, in_pitch, out, out_pitch, &fe);
-  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch);
-  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch);
-  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch);
+  int vec = (push || e1) ? nb_pick_vec(F, in, in_pitch, out, out_pitch) : nb_pick_vec(F, in, in_pitch, out, out_pitch, &fe);
+  if (e1 && vec > 1 && (((uintptr_t)va | (uintptr_t)vb) % (4 * vec))) vec = 1;  // epilogue vectors must allow the same vector loads
+  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi);
+  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi);
+  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi);
+}
+
+static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
+                       const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev = nullptr,
+                       uint64_t in_pitch = 0, uint64_t out_pitch = 0) {
+  return nb_run_segment(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" {

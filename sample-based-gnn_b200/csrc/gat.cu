@@ -176,25 +176,53 @@ k_gat_fwd(const float *__restrict__ h, const float *__restrict__ al, const float
 }
 
 // per dst column: da_e = dout[d].h[src_e]; dm_e = alpha_e (da_e - sum_e' alpha_e' da_e'); ds_e = lrelu'(pre_e) dm_e
-// writes ds[E] and dsum[V] = sum_e ds_e
+// writes ds[E] and dsum[V] = sum_e ds_e. The dout row stays in registers; two h rows are in flight per step.
+template <int VEC, int CHUNK>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_edge(const float *__restrict__ h, const float *__restrict__ dout, const float *__restrict__ score_pre,
                const float *__restrict__ alpha, float slope, const uint32_t *__restrict__ col_off,
-               const uint32_t *__restrict__ row_indices, uint32_t n_dst, uint32_t F, float *__restrict__ ds, float *__restrict__ dsum) {
+               const uint32_t *__restrict__ row_indices, uint32_t n_dst, uint32_t nvec, uint64_t pitch, float *__restrict__ ds,
+               float *__restrict__ dsum) {
   const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
   for (unsigned d = warp; d < n_dst; d += warps) {
     const uint32_t beg = col_off[d], end = col_off[d + 1];
-    const float *g = dout + (uint64_t)d * F;
-    float agg = 0.f;
-    for (uint32_t e = beg; e < end; e++) {
-      const float *p = h + (uint64_t)row_indices[e] * F;
-      float da = 0.f;
-      for (unsigned k = lane; k < F; k += 32) da += g[k] * p[k];
-      da = warp_sum(da);
-      if (lane == 0) ds[e] = da;  // stash da
-      agg += da * alpha[e];
+    if (beg == end) { if (lane == 0) dsum[d] = 0.f; continue; }
+    Vec<VEC> g[CHUNK];
+#pragma unroll
+    for (int c = 0; c < CHUNK; c++) {
+      const unsigned k = c * 32 + lane;
+      if (k < nvec) g[c].load(dout + (uint64_t)d * pitch + (uint64_t)k * VEC); else g[c].zero();
     }
-    __syncwarp();
+    float agg = 0.f;
+    for (uint32_t j0 = beg; j0 < end; j0 += 32) {
+      const uint32_t cnt = min(32u, end - j0);
+      uint32_t my_idx = 0;
+      float my_alpha = 0.f, my_da = 0.f;
+      if (lane < cnt) { my_idx = row_indices[j0 + lane]; my_alpha = alpha[j0 + lane]; }
+      for (uint32_t t = 0; t < cnt; t += 2) {
+        const uint32_t t1 = t + 1 < cnt ? t + 1 : t;
+        const float *p0 = h + (uint64_t)__shfl_sync(FULL_MASK, my_idx, t) * pitch;
+        const float *p1 = h + (uint64_t)__shfl_sync(FULL_MASK, my_idx, t1) * pitch;
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CHUNK; c++) {
+          const unsigned k = c * 32 + lane;
+          if (k < nvec) {
+            Vec<VEC> x0, x1;
+            x0.load(p0 + (uint64_t)k * VEC);
+            x1.load(p1 + (uint64_t)k * VEC);
+            d0 += g[c].dot(x0);
+            d1 += g[c].dot(x1);
+          }
+        }
+        d0 = warp_sum(d0);
+        d1 = warp_sum(d1);
+        if (lane == t) my_da = d0;
+        if (lane == t1 && t1 != t) my_da = d1;
+      }
+      agg += warp_sum(lane < cnt ? my_da * my_alpha : 0.f);
+      if (lane < cnt) ds[j0 + lane] = my_da;  // stash da until the column total is known
+    }
     float tot = 0.f;
     for (uint32_t e = beg + lane; e < end; e += 32) {
       const float dm = alpha[e] * (ds[e] - agg);
@@ -207,47 +235,40 @@ k_gat_bwd_edge(const float *__restrict__ h, const float *__restrict__ dout, cons
   }
 }
 
-// per src row (CSR): dh[s,:] = sum_j alpha[e_j] dout[dst_j,:] + (sum_j ds[e_j]) att[0:F] + [s is dst d] dsum[d] att[F:2F]
+// CSR-order weights and per-src scalars for the segment reduction: w[j] = alpha[e_j], rs[s] = sum_j ds[e_j], dd[s] = dsum of the dst equal to s
 __global__ void __launch_bounds__(GAT_THREADS)
-k_gat_bwd_src(const float *__restrict__ dout, const float *__restrict__ att, const float *__restrict__ alpha,
-              const float *__restrict__ ds, const float *__restrict__ dsum, const uint32_t *__restrict__ row_offset,
-              const uint32_t *__restrict__ column_indices, const uint32_t *__restrict__ csr_to_csc,
-              const uint32_t *__restrict__ src_to_dst, uint32_t n_src, uint32_t F, float *__restrict__ dh, float *__restrict__ rs) {
-  const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
-  for (unsigned s = warp; s < n_src; s += warps) {
-    const uint32_t beg = row_offset[s], end = row_offset[s + 1];
-    float rsum = 0.f;
-    for (uint32_t j = beg + lane; j < end; j += 32) rsum += ds[csr_to_csc[j]];
-    rsum = warp_sum(rsum);
-    const uint32_t d = src_to_dst[s];
-    const float dd = d != 0xffffffffu ? dsum[d] : 0.f;
-    if (lane == 0) rs[s] = rsum;
-    for (unsigned k = lane; k < F; k += 32) {
-      float acc = 0.f;
-      for (uint32_t j = beg; j < end; j++) acc += alpha[csr_to_csc[j]] * dout[(uint64_t)column_indices[j] * F + k];
-      dh[(uint64_t)s * F + k] = acc + rsum * att[k] + dd * att[F + k];
+k_gat_bwd_rows(const float *__restrict__ alpha, const float *__restrict__ ds, const float *__restrict__ dsum,
+               const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ src_to_dst,
+               uint32_t n_src, float *__restrict__ wcsr, float *__restrict__ rs, float *__restrict__ dd) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n_src; s += gridDim.x * blockDim.x) {
+    float r = 0.f;
+    for (uint32_t j = row_offset[s]; j < row_offset[s + 1]; j++) {
+      const uint32_t e = csr_to_csc[j];
+      wcsr[j] = alpha[e];
+      r += ds[e];
     }
+    rs[s] = r;
+    const uint32_t d = src_to_dst[s];
+    dd[s] = d != 0xffffffffu ? dsum[d] : 0.f;
   }
 }
 
 // datt[0:F] += sum_s rs[s] h[s,:];  datt[F:2F] += sum_d dsum[d] h[dl[d],:]
 __global__ void __launch_bounds__(GAT_THREADS)
-k_gat_bwd_att(const float *__restrict__ h, const float *__restrict__ rs, const float *__restrict__ dsum,
-              const uint32_t *__restrict__ dl, uint32_t n_src, uint32_t n_dst, uint32_t F, float *__restrict__ datt) {
-  // each block owns a contiguous slice of rows; thread k sums feature column k (coalesced row reads)
+k_gat_bwd_att(const float *__restrict__ h, const float *__restrict__ rs, const float *__restrict__ dd, uint32_t n_src, uint32_t F,
+              float *__restrict__ datt) {
+  // one pass over H: each block owns a contiguous slice of rows; thread k sums feature column k (coalesced row reads);
+  // dd[s] is the column total of the dst that equals src s (0 if s is not a dst), so both halves come from the same read
   const unsigned rows_per_block = (n_src + gridDim.x - 1) / gridDim.x;
   const unsigned r0 = blockIdx.x * rows_per_block, r1 = min(n_src, r0 + rows_per_block);
   for (unsigned k = threadIdx.x; k < F; k += blockDim.x) {
-    float acc = 0.f;
-    for (unsigned s = r0; s < r1; s++) acc += rs[s] * h[(uint64_t)s * F + k];
-    if (r1 > r0) atomicAdd(&datt[k], acc);
-  }
-  const unsigned dpb = (n_dst + gridDim.x - 1) / gridDim.x;
-  const unsigned d0 = blockIdx.x * dpb, d1 = min(n_dst, d0 + dpb);
-  for (unsigned k = threadIdx.x; k < F; k += blockDim.x) {
-    float acc = 0.f;
-    for (unsigned d = d0; d < d1; d++) acc += dsum[d] * h[(uint64_t)dl[d] * F + k];
-    if (d1 > d0) atomicAdd(&datt[F + k], acc);
+    float a = 0.f, b = 0.f;
+    for (unsigned s = r0; s < r1; s++) {
+      const float x = h[(uint64_t)s * F + k];
+      a += rs[s] * x;
+      b += dd[s] * x;
+    }
+    if (r1 > r0) { atomicAdd(&datt[k], a); atomicAdd(&datt[F + k], b); }
   }
 }
 
@@ -346,29 +367,42 @@ int nb_gat_fwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
 int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slope, const float *dout,
                const float *score_pre, const float *alpha, const uint32_t *column_offset, const uint32_t *row_indices,
                const uint32_t *dst_local_id, const uint32_t *row_offset, const uint32_t *column_indices,
-               const uint32_t *csr_to_csc, const uint32_t *src_to_dst, uint32_t n_dst, uint32_t n_src,
+               const uint32_t *csr_to_csc, const uint32_t *src_to_dst, uint32_t n_dst, uint32_t n_src, uint32_t n_edges,
                uint32_t feature_size, float *dh, float *datt) {
   NB_REQUIRE(ctx && h && att && dout && score_pre && alpha && column_offset && row_indices && dst_local_id && row_offset &&
                  column_indices && csr_to_csc && src_to_dst && dh && datt, NB_ERR_ARG, "nb_gat_bwd: NULL argument (needs a sampler built with MERGE_SRC_DST|BUILD_CSR)");
   NB_GUARD(ctx);
-  NB_CUDA(cudaMemsetAsync(datt, 0, (size_t)2 * feature_size * 4, ctx->stream));
+  const uint32_t F = feature_size;
+  NB_CUDA(cudaMemsetAsync(datt, 0, (size_t)2 * F * 4, ctx->stream));
   if (n_src == 0) return NB_OK;
-  // n_edges is only on the device side of the caller's view; bound the scratch by the CSR: E <= what row_offset[n_src] says,
-  // so size ds[] from a host copy of that single word.
-  uint32_t E = 0;
-  NB_CUDA(cudaMemcpyAsync(&E, row_offset + n_src, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  NB_CUDA(cudaStreamSynchronize(ctx->stream));
   float *scratch;
-  int rc = nb_ctx_scratch(ctx, ((size_t)E + n_dst + n_src + 8) * sizeof(float), (void **)&scratch);
+  int rc = nb_ctx_scratch(ctx, ((size_t)2 * n_edges + n_dst + 2 * (size_t)n_src + 64) * sizeof(float), (void **)&scratch);
   if (rc) return rc;
-  float *ds = scratch, *dsum = scratch + E, *rs = dsum + n_dst;
+  float *ds = scratch, *wcsr = ds + n_edges, *dsum = wcsr + n_edges, *rs = dsum + n_dst + 8, *dd = rs + n_src + 8;
   if (n_dst) {
-    k_gat_bwd_edge<<<nb_grid(n_dst, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(h, dout, score_pre, alpha, negative_slope, column_offset, row_indices, n_dst, feature_size, ds, dsum);
-    NB_LAUNCH_CHECK(ctx);
+    const int vec = nb_pick_vec(F, h, F, dout, F);
+    const uint32_t nvec = F / vec, per_lane = (nvec + 31) / 32;
+    const unsigned grid = nb_grid(n_dst, GAT_THREADS / 32, 8);
+    bool done = false;
+#define NB_GBE(V, C)                                                                                                              \
+  if (!done && vec == V && per_lane <= C) {                                                                                        \
+    k_gat_bwd_edge<V, C><<<grid, GAT_THREADS, 0, ctx->stream>>>(h, dout, score_pre, alpha, negative_slope, column_offset, row_indices, \
+                                                               n_dst, nvec, F, ds, dsum);                                         \
+    done = true;                                                                                                                   \
   }
-  k_gat_bwd_src<<<nb_grid(n_src, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(dout, att, alpha, ds, dsum, row_offset, column_indices, csr_to_csc, src_to_dst, n_src, feature_size, dh, rs);
+    NB_GBE(4, 1) NB_GBE(4, 2) NB_GBE(4, 4) NB_GBE(4, 8) NB_GBE(2, 2) NB_GBE(2, 4) NB_GBE(2, 8) NB_GBE(2, 16) NB_GBE(1, 2) NB_GBE(1, 4) NB_GBE(1, 8) NB_GBE(1, 16) NB_GBE(1, 32)
+#undef NB_GBE
+    NB_REQUIRE(done, NB_ERR_UNSUPPORTED, "nb_gat_bwd: feature_size %u too wide for the fused backward (max 1024)", F);
+    NB_LAUNCH_CHECK(ctx);
+  } else {
+    NB_CUDA(cudaMemsetAsync(ds, 0, (size_t)n_edges * 4, ctx->stream));
+  }
+  k_gat_bwd_rows<<<nb_grid(n_src, GAT_THREADS, 8), GAT_THREADS, 0, ctx->stream>>>(alpha, ds, dsum, row_offset, csr_to_csc, src_to_dst, n_src, wcsr, rs, dd);
   NB_LAUNCH_CHECK(ctx);
-  k_gat_bwd_att<<<NB_SM_COUNT * 2, GAT_THREADS, 0, ctx->stream>>>(h, rs, dsum, dst_local_id, n_src, n_dst, feature_size, datt);
+  // dh[s,:] = sum_j alpha[e_j] dout[dst_j,:] + rs[s] att[0:F] + dd[s] att[F:2F]: the tuned CSR segment reduction with a rank-2 epilogue
+  rc = nb_run_segment(ctx, false, dout, dh, wcsr, column_indices, row_offset, n_src, F, nullptr, F, F, rs, dd, att, att + F);
+  if (rc) return rc;
+  k_gat_bwd_att<<<NB_SM_COUNT * 2, GAT_THREADS, 0, ctx->stream>>>(h, rs, dd, n_src, F, datt);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
 }
