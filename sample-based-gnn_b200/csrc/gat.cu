@@ -257,18 +257,41 @@ k_gat_bwd_rows(const float *__restrict__ alpha, const float *__restrict__ ds, co
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_att(const float *__restrict__ h, const float *__restrict__ rs, const float *__restrict__ dd, uint32_t n_src, uint32_t F,
               float *__restrict__ datt) {
-  // one pass over H: each block owns a contiguous slice of rows; thread k sums feature column k (coalesced row reads);
-  // dd[s] is the column total of the dst that equals src s (0 if s is not a dst), so both halves come from the same read
+  // one pass over H. A block owns a contiguous slice of rows; thread (g, k) sums feature column k over the rows g, g+G, ... of the
+  // slice (G = blockDim / F row groups when F <= blockDim), four rows in flight; the groups are combined in shared memory and
+  // the block adds its 2F partial sums to datt. dd[s] is the column total of the dst that equals src s (0 if s is not a dst).
+  __shared__ float s_a[GAT_THREADS], s_b[GAT_THREADS];
   const unsigned rows_per_block = (n_src + gridDim.x - 1) / gridDim.x;
   const unsigned r0 = blockIdx.x * rows_per_block, r1 = min(n_src, r0 + rows_per_block);
-  for (unsigned k = threadIdx.x; k < F; k += blockDim.x) {
+  if (r0 >= r1) return;
+  const unsigned G = F <= GAT_THREADS ? GAT_THREADS / F : 1;
+  const unsigned g = threadIdx.x / (F <= GAT_THREADS ? F : GAT_THREADS), lanes = F <= GAT_THREADS ? F : GAT_THREADS;
+  for (unsigned k0 = 0; k0 < F; k0 += lanes) {
+    const unsigned k = k0 + threadIdx.x % lanes;
     float a = 0.f, b = 0.f;
-    for (unsigned s = r0; s < r1; s++) {
-      const float x = h[(uint64_t)s * F + k];
-      a += rs[s] * x;
-      b += dd[s] * x;
+    if (g < G && k < F) {
+      unsigned s = r0 + g;
+      for (; s + 3 * G < r1; s += 4 * G) {
+        const float x0 = h[(uint64_t)s * F + k], x1 = h[(uint64_t)(s + G) * F + k], x2 = h[(uint64_t)(s + 2 * G) * F + k],
+                    x3 = h[(uint64_t)(s + 3 * G) * F + k];
+        a += rs[s] * x0 + rs[s + G] * x1 + rs[s + 2 * G] * x2 + rs[s + 3 * G] * x3;
+        b += dd[s] * x0 + dd[s + G] * x1 + dd[s + 2 * G] * x2 + dd[s + 3 * G] * x3;
+      }
+      for (; s < r1; s += G) {
+        const float x = h[(uint64_t)s * F + k];
+        a += rs[s] * x;
+        b += dd[s] * x;
+      }
     }
-    if (r1 > r0) { atomicAdd(&datt[k], a); atomicAdd(&datt[F + k], b); }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+    __syncthreads();
+    if (g == 0 && k < F) {
+      for (unsigned gg = 1; gg < G; gg++) { a += s_a[gg * lanes + threadIdx.x]; b += s_b[gg * lanes + threadIdx.x]; }
+      atomicAdd(&datt[k], a);
+      atomicAdd(&datt[F + k], b);
+    }
+    __syncthreads();
   }
 }
 
@@ -402,7 +425,7 @@ int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
   // dh[s,:] = sum_j alpha[e_j] dout[dst_j,:] + rs[s] att[0:F] + dd[s] att[F:2F]: the tuned CSR segment reduction with a rank-2 epilogue
   rc = nb_run_segment(ctx, false, dout, dh, wcsr, column_indices, row_offset, n_src, F, nullptr, F, F, rs, dd, att, att + F);
   if (rc) return rc;
-  k_gat_bwd_att<<<NB_SM_COUNT * 2, GAT_THREADS, 0, ctx->stream>>>(h, rs, dd, n_src, F, datt);
+  k_gat_bwd_att<<<NB_SM_COUNT * 8, GAT_THREADS, 0, ctx->stream>>>(h, rs, dd, n_src, F, datt);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
 }

@@ -13,7 +13,18 @@
  * full-graph (non-sampled) engine are declared for source compatibility and fail loudly if called:
  * they are outside the sampled hot path this library replaces.
  */
-#include "cuda_type.h"
+/* VertexId_CUDA and the launch constants core/ reads: taken from the reference tree's own cuda/cuda_type.h when it is on the
+ * include path (it is, when the reference is being built against this adaptor); otherwise the same names are defined here */
+#if __has_include("cuda/cuda_type.h")
+#include "cuda/cuda_type.h"
+#else
+#ifndef CUDA_TYPE_H
+#define CUDA_TYPE_H
+#include <stdint.h>
+typedef uint32_t VertexId_CUDA;
+static const int WARP_SIZE = 32, CUDA_NUM_THREADS = 512, CUDA_NUM_BLOCKS = 128, CUDA_NUM_THREADS_SOFTMAX = 32, CUDA_NUM_BLOCKS_SOFTMAX = 512;
+#endif
+#endif
 #define CUDA_ENABLE 1
 #include <cuda_runtime.h>
 #if __has_include(<nccl.h>)
