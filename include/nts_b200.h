@@ -288,6 +288,19 @@ int nb_table_gather(nb_ctx *ctx, nb_table *t, float *out, const uint32_t *ids_de
 int nb_ipc_get_handle(void *dev_ptr, void *handle64_out);
 int nb_ipc_open_handle(const void *handle64, void **dev_ptr_out);
 int nb_ipc_close_handle(void *dev_ptr);
+/* Peer-shareable HBM for the shards (CUDA virtual memory management, 2 MB pages on both sides of the link). Mappings made by
+ * cudaIpcOpenMemHandle are translated through small pages, and a random-row gather over a multi-GB remote shard becomes
+ * TLB-miss bound (measured ~45 GB/s per peer against ~740 GB/s through these mappings). nb_vmm_alloc returns device memory on
+ * ctx's device and, when fd_out != NULL, a POSIX file descriptor to hand to the other processes (SCM_RIGHTS / pidfd_getfd);
+ * nb_vmm_import maps the allocation behind such a descriptor for ctx's device (bytes = the exporter's request; both sides
+ * round up to nb_vmm_padded_size); nb_vmm_grant lets another device of THIS process read/write the mapping (the reference's
+ * one-process-many-GPUs threading); nb_vmm_free unmaps and releases either kind. There is no reference counterpart: the
+ * reference replicates its cache per GPU (GS_SAMPLE_PC_MULTI.hpp:916-1015). */
+size_t nb_vmm_padded_size(nb_ctx *ctx, size_t bytes);
+int nb_vmm_alloc(nb_ctx *ctx, size_t bytes, void **dev_ptr_out, int *fd_out);
+int nb_vmm_import(nb_ctx *ctx, int fd, size_t bytes, void **dev_ptr_out);
+int nb_vmm_grant(void *dev_ptr, int device);
+int nb_vmm_free(void *dev_ptr);
 
 /* ---- sparse aggregation ----------------------------------------------------------------------
  * nb_aggregate_csc_fwd <- Cuda_Stream::Gather_By_Dst_From_Src_Spmm (cuSPARSE, cuda/ntsCUDAGraphOP.cu:425-587) and

@@ -90,6 +90,11 @@ _SIGS = {
     "nb_ipc_get_handle": (I32, [P, P]),
     "nb_ipc_open_handle": (I32, [P, C.POINTER(P)]),
     "nb_ipc_close_handle": (I32, [P]),
+    "nb_vmm_padded_size": (SZ, [P, SZ]),
+    "nb_vmm_alloc": (I32, [P, SZ, C.POINTER(P), C.POINTER(I32)]),
+    "nb_vmm_import": (I32, [P, I32, SZ, C.POINTER(P)]),
+    "nb_vmm_grant": (I32, [P, I32]),
+    "nb_vmm_free": (I32, [P]),
     "nb_aggregate_csc_fwd": (I32, [P, P, P, P, P, P, U32, U32, U32]),
     "nb_aggregate_csr_bwd": (I32, [P, P, P, P, P, P, U32, U32, U32]),
     "nb_aggregate_push_bwd": (I32, [P, P, P, P, P, P, U32, U32, U32]),

@@ -90,6 +90,82 @@ const void *nb_mirror_host(nb_ctx *ctx, const void *table, int is_adjacency) {
 void nb_mirror_host_enable(int on, int adjacency) { if (adjacency) g_mirror_adjacency = on; else g_mirror_tables = on; }
 
 
+// ---- peer-shareable HBM (CUDA virtual memory management) -------------------------------------------
+// Shards of a row-sharded feature table are read by other processes' kernels over NVLink. Mappings made by
+// cudaIpcOpenMemHandle translate through small pages: a random-row gather over a multi-GB remote shard ran at ~45 GB/s
+// per peer on B200 (TLB-miss bound; tools/shard_bench.py), while the same rows reached through a 2 MB-granular
+// cuMemCreate/cuMemMap mapping run at the link rate (~740 GB/s, tools/p2p_probe.cu). So shards are allocated with
+// cuMemCreate, exported as POSIX file descriptors and mapped by the peers with cuMemMap.
+#include <cuda.h>
+#include <unistd.h>
+struct VmmEntry { size_t size; CUmemGenericAllocationHandle handle; int fd; };
+static std::map<uintptr_t, VmmEntry> g_vmm;
+static std::mutex g_vmm_mutex;
+
+template <typename Fn> static bool drv(const char *name, Fn &fn) {
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qr) != cudaSuccess || !p) { cudaGetLastError(); return false; }
+  fn = (Fn)p;
+  return true;
+}
+struct VmmApi {
+  CUresult (*GetGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags);
+  CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long);
+  CUresult (*Release)(CUmemGenericAllocationHandle);
+  CUresult (*AddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
+  CUresult (*AddressFree)(CUdeviceptr, size_t);
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+  CUresult (*Unmap)(CUdeviceptr, size_t);
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t);
+  CUresult (*Export)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+  CUresult (*Import)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType);
+  bool ok;
+};
+static VmmApi *vmm_api() {
+  static VmmApi api;
+  static bool init = false;
+  if (!init) {
+    api.ok = drv("cuMemGetAllocationGranularity", api.GetGranularity) && drv("cuMemCreate", api.Create) &&
+             drv("cuMemRelease", api.Release) && drv("cuMemAddressReserve", api.AddressReserve) &&
+             drv("cuMemAddressFree", api.AddressFree) && drv("cuMemMap", api.Map) && drv("cuMemUnmap", api.Unmap) &&
+             drv("cuMemSetAccess", api.SetAccess) && drv("cuMemExportToShareableHandle", api.Export) &&
+             drv("cuMemImportFromShareableHandle", api.Import);
+    init = true;
+  }
+  return &api;
+}
+#define NB_CU(call)                                                                      \
+  do {                                                                                   \
+    CUresult r_ = (call);                                                                \
+    if (r_ != CUDA_SUCCESS) { nb_set_error("%s failed: CUresult %d", #call, (int)r_); return NB_ERR_CUDA; } \
+  } while (0)
+
+static CUmemAllocationProp vmm_prop(int device) {
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  return prop;
+}
+static int vmm_map(VmmApi *a, int device, CUmemGenericAllocationHandle h, size_t size, size_t gran, void **out) {
+  CUdeviceptr va = 0;
+  NB_CU(a->AddressReserve(&va, size, gran, 0, 0));
+  if (a->Map(va, size, 0, h, 0) != CUDA_SUCCESS) { a->AddressFree(va, size); nb_set_error("cuMemMap failed"); return NB_ERR_CUDA; }
+  CUmemAccessDesc d = {};
+  d.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  d.location.id = device;
+  d.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (a->SetAccess(va, size, &d, 1) != CUDA_SUCCESS) {
+    a->Unmap(va, size); a->AddressFree(va, size);
+    nb_set_error("cuMemSetAccess(device %d) failed: no peer path to the owning GPU?", device);
+    return NB_ERR_CUDA;
+  }
+  *out = (void *)va;
+  return NB_OK;
+}
+
 extern "C" {
 
 int nb_abi_version(void) { return NB_ABI_VERSION; }
@@ -216,5 +292,101 @@ int nb_ipc_open_handle(const void *handle64, void **dev_ptr_out) {
   return NB_OK;
 }
 int nb_ipc_close_handle(void *dev_ptr) { NB_CUDA(cudaIpcCloseMemHandle(dev_ptr)); return NB_OK; }
+
+size_t nb_vmm_padded_size(nb_ctx *ctx, size_t bytes) {
+  if (!ctx) return 0;
+  DeviceGuard g(ctx->device);
+  VmmApi *a = vmm_api();
+  if (!a->ok) return 0;
+  CUmemAllocationProp prop = vmm_prop(ctx->device);
+  size_t gran = 0;
+  if (a->GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || !gran) return 0;
+  if (!bytes) bytes = 1;
+  return (bytes + gran - 1) / gran * gran;
+}
+
+int nb_vmm_alloc(nb_ctx *ctx, size_t bytes, void **dev_ptr_out, int *fd_out) {
+  NB_REQUIRE(ctx && dev_ptr_out, NB_ERR_ARG, "nb_vmm_alloc: NULL argument");
+  NB_GUARD(ctx);
+  NB_CUDA(cudaFree(0));
+  VmmApi *a = vmm_api();
+  NB_REQUIRE(a->ok, NB_ERR_UNSUPPORTED, "nb_vmm_alloc: the driver lacks the cuMem* virtual memory API");
+  CUmemAllocationProp prop = vmm_prop(ctx->device);
+  size_t gran = 0;
+  NB_CU(a->GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  const size_t size = ((bytes ? bytes : 1) + gran - 1) / gran * gran;
+  CUmemGenericAllocationHandle h;
+  NB_CU(a->Create(&h, size, &prop, 0));
+  void *p = nullptr;
+  int rc = vmm_map(a, ctx->device, h, size, gran, &p);
+  if (rc != NB_OK) { a->Release(h); return rc; }
+  int fd = -1;
+  if (fd_out) {
+    if (a->Export(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) {
+      a->Unmap((CUdeviceptr)p, size); a->AddressFree((CUdeviceptr)p, size); a->Release(h);
+      nb_set_error("cuMemExportToShareableHandle failed");
+      return NB_ERR_CUDA;
+    }
+    *fd_out = fd;
+  }
+  std::lock_guard<std::mutex> lock(g_vmm_mutex);
+  g_vmm[(uintptr_t)p] = VmmEntry{size, h, fd};
+  *dev_ptr_out = p;
+  return NB_OK;
+}
+
+int nb_vmm_import(nb_ctx *ctx, int fd, size_t bytes, void **dev_ptr_out) {
+  NB_REQUIRE(ctx && dev_ptr_out && fd >= 0, NB_ERR_ARG, "nb_vmm_import: bad argument");
+  NB_GUARD(ctx);
+  NB_CUDA(cudaFree(0));
+  VmmApi *a = vmm_api();
+  NB_REQUIRE(a->ok, NB_ERR_UNSUPPORTED, "nb_vmm_import: the driver lacks the cuMem* virtual memory API");
+  CUmemAllocationProp prop = vmm_prop(ctx->device);
+  size_t gran = 0;
+  NB_CU(a->GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  const size_t size = ((bytes ? bytes : 1) + gran - 1) / gran * gran;
+  CUmemGenericAllocationHandle h;
+  NB_CU(a->Import(&h, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  void *p = nullptr;
+  int rc = vmm_map(a, ctx->device, h, size, gran, &p);
+  if (rc != NB_OK) { a->Release(h); return rc; }
+  std::lock_guard<std::mutex> lock(g_vmm_mutex);
+  g_vmm[(uintptr_t)p] = VmmEntry{size, h, -1};
+  *dev_ptr_out = p;
+  return NB_OK;
+}
+
+int nb_vmm_grant(void *dev_ptr, int device) {
+  VmmApi *a = vmm_api();
+  NB_REQUIRE(a->ok, NB_ERR_UNSUPPORTED, "nb_vmm_grant: the driver lacks the cuMem* virtual memory API");
+  std::lock_guard<std::mutex> lock(g_vmm_mutex);
+  auto it = g_vmm.find((uintptr_t)dev_ptr);
+  NB_REQUIRE(it != g_vmm.end(), NB_ERR_ARG, "nb_vmm_grant: pointer was not returned by nb_vmm_alloc/import");
+  CUmemAccessDesc d = {};
+  d.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  d.location.id = device;
+  d.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  NB_CU(a->SetAccess((CUdeviceptr)dev_ptr, it->second.size, &d, 1));
+  return NB_OK;
+}
+
+int nb_vmm_free(void *dev_ptr) {
+  if (!dev_ptr) return NB_OK;
+  VmmApi *a = vmm_api();
+  NB_REQUIRE(a->ok, NB_ERR_UNSUPPORTED, "nb_vmm_free: the driver lacks the cuMem* virtual memory API");
+  VmmEntry e;
+  {
+    std::lock_guard<std::mutex> lock(g_vmm_mutex);
+    auto it = g_vmm.find((uintptr_t)dev_ptr);
+    NB_REQUIRE(it != g_vmm.end(), NB_ERR_ARG, "nb_vmm_free: pointer was not returned by nb_vmm_alloc/import");
+    e = it->second;
+    g_vmm.erase(it);
+  }
+  NB_CU(a->Unmap((CUdeviceptr)dev_ptr, e.size));
+  NB_CU(a->AddressFree((CUdeviceptr)dev_ptr, e.size));
+  NB_CU(a->Release(e.handle));
+  if (e.fd >= 0) close(e.fd);
+  return NB_OK;
+}
 
 }  // extern "C"

@@ -59,36 +59,77 @@ class GradBucket:
             off += p.numel()
 
 
+def exchange_fds(fd):
+    """Every rank hands `fd` to every other rank of the node; returns {rank: local duplicate of that rank's descriptor}.
+    Descriptors cross processes as SCM_RIGHTS ancillary data on unix stream sockets (abstract names, nothing left on disk).
+    A connect() completes once it is queued on the peer's listen backlog, so connect-all, then accept-and-send, then receive
+    cannot deadlock."""
+    import os
+    import socket
+    import uuid
+    rank, world = dist.get_rank(), dist.get_world_size()
+    name = f"\0nts_b200_{os.getpid()}_{uuid.uuid4().hex}"
+    listener = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    listener.bind(name)
+    listener.listen(world)
+    names = [None] * world
+    dist.all_gather_object(names, name)      # also orders every listen() before any connect()
+    links = {}
+    for r in range(world):
+        if r != rank:
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(names[r])
+            links[r] = c
+    served = []
+    for _ in range(world - 1):
+        conn, _addr = listener.accept()
+        socket.send_fds(conn, [b"f"], [fd])
+        served.append(conn)
+    got = {}
+    for r, c in links.items():
+        _msg, fds, _flags, _a = socket.recv_fds(c, 1, 1)
+        assert len(fds) == 1, f"rank {rank}: no descriptor from rank {r}"
+        got[r] = fds[0]
+        c.close()
+    for conn in served:
+        conn.close()
+    listener.close()
+    return got
+
+
 class ShardedTable:
-    """Row-sharded fp32 feature table over the ranks of one node, read peer-to-peer inside the gather kernel."""
+    """Row-sharded fp32 feature table over the ranks of one node, read peer-to-peer inside the gather kernel. Shards live in
+    cuMemCreate allocations shared through POSIX descriptors (nb_vmm_*): cudaIpc mappings of multi-GB shards are TLB-miss bound
+    for random rows (~45 GB/s per peer measured), these are not (link rate)."""
 
     def __init__(self, cuda_stream, rows_of_this_rank, n_rows_total, feature_size, pitch=None):
+        import os
         from . import FeatureTable
         rank, world = dist.get_rank(), dist.get_world_size()
         pitch = pitch or feature_size
-        n_local = (n_rows_total - rank + world - 1) // world
+        rows_of = lambda r: (n_rows_total - r + world - 1) // world
+        n_local = rows_of(rank)
         assert rows_of_this_rank.shape == (n_local, feature_size), (rows_of_this_rank.shape, n_local)
-        self._local = C.c_void_p()
-        check(lib().nb_malloc_device(max(n_local, 1) * pitch * 4, C.byref(self._local)))
-        check(lib().nb_memset_async(cuda_stream._h, self._local, 0, max(n_local, 1) * pitch * 4))
-        src = rows_of_this_rank.contiguous()
-        # strided upload into the pitched shard
+        self._local, fd = C.c_void_p(), C.c_int(-1)
+        check(lib().nb_vmm_alloc(cuda_stream._h, n_local * pitch * 4, C.byref(self._local), C.byref(fd)))
         torch.cuda.current_stream().synchronize()
         cuda_stream.CUDA_DEVICE_SYNCHRONIZE()
-        shard = torch.as_tensor(_Raw(self._local.value, n_local * pitch), device=cuda_stream.device).view(n_local, pitch)
-        shard[:, :feature_size] = src
+        if n_local:
+            # strided upload into the pitched shard
+            shard = torch.as_tensor(_Raw(self._local.value, n_local * pitch), device=cuda_stream.device).view(n_local, pitch)
+            if pitch != feature_size:
+                shard.zero_()
+            shard[:, :feature_size] = rows_of_this_rank
         torch.cuda.synchronize()
-        handle = (C.c_char * 64)()
-        check(lib().nb_ipc_get_handle(self._local, handle))
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle.raw))
+        peer_fds = exchange_fds(fd.value)
         self._peers, ptrs = [], []
         for r in range(world):
             if r == rank:
                 ptrs.append(self._local.value)
             else:
                 p = C.c_void_p()
-                check(lib().nb_ipc_open_handle(handles[r], C.byref(p)))
+                check(lib().nb_vmm_import(cuda_stream._h, peer_fds[r], rows_of(r) * pitch * 4, C.byref(p)))
+                os.close(peer_fds[r])     # the mapping keeps the allocation alive
                 self._peers.append(p)
                 ptrs.append(p.value)
         self.table = FeatureTable(cuda_stream, ptrs, feature_size, pitch, n_rows_total, keepalive=self)
@@ -98,11 +139,15 @@ class ShardedTable:
         return self.table.gather(out, ids, n_rows)
 
     def close(self):
+        torch.cuda.synchronize()
         dist.barrier()
         for p in self._peers:
-            lib().nb_ipc_close_handle(p)
+            check(lib().nb_vmm_free(p))
         self._peers = []
-        lib().nb_free_device(self._local)
+        dist.barrier()
+        if self._local:
+            check(lib().nb_vmm_free(self._local))
+            self._local = None
 
 
 class _Raw:

@@ -57,6 +57,46 @@ def test_seed_sharding_and_gradient_bucket_world2():
     assert torch.equal(g2, torch.arange(4, dtype=torch.float32) * 3)
 
 
+def _fd_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tempfile
+    import __graft_entry__ as ge
+    ge.load_package()
+    from sample_based_gnn_b200 import dist as nd
+    with tempfile.TemporaryFile() as f:           # stands in for the exported shard descriptor
+        f.write(f"shard-of-rank-{rank}".encode())
+        f.flush()
+        got = nd.exchange_fds(f.fileno())
+        seen = {}
+        for r, fd in got.items():
+            seen[r] = os.pread(fd, 64, 0).decode()
+            os.close(fd)
+    ok = sorted(seen) == [r for r in range(world) if r != rank] and all(v == f"shard-of-rank-{r}" for r, v in seen.items())
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if rank == 0:
+        q.put(oks)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_descriptor_exchange_world3():
+    """The sharded table hands each shard's POSIX descriptor to every other rank (SCM_RIGHTS over unix sockets)."""
+    world, port = 3, 29613
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fd_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    oks = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert oks == [True] * world
+
+
 def test_bench_sharding_matches_package():
     sys.path.insert(0, ROOT)
     import bench

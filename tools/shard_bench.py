@@ -19,7 +19,7 @@ def main():
     nts = ge.load_package()
     from sample_based_gnn_b200 import dist as nd
     cs = nts.Cuda_Stream.on_torch_stream(local)
-    V, F, N = 111_059_956 // 4, 128, 400_000          # quarter of papers100M's vertices: 14.2 GB of rows in total
+    V, F, N = int(os.environ.get("SHARD_V", 111_059_956 // 4)), 128, 400_000          # quarter of papers100M's vertices: 14.2 GB of rows in total
     n_local = (V - rank + world - 1) // world
     mine = torch.rand((n_local, F), device="cuda")
     st = nd.ShardedTable(cs, mine, V, F)
@@ -37,6 +37,23 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    # per-peer probe: ids that all live on one shard
+    probe = []
+    for peer in range(world):
+        pid = (torch.randint(0, V // world - 1, (N,), device="cuda", dtype=torch.int32, generator=g) * world + peer).to(torch.int32)
+        st.gather(out, pid, N)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(5):
+            st.gather(out, pid, N)
+        p1.record(); torch.cuda.synchronize()
+        probe.append(N * F * 4 / (p0.elapsed_time(p1) / 5) / 1e6)
+    allms = [None] * world
+    dist.all_gather_object(allms, (round(ms, 4), [round(x) for x in probe]))
+    if rank == 0:
+        for r, x in enumerate(allms):
+            print(f"SHARD_RANK {r}: all-peers {x[0]} ms; per-peer GB/s {x[1]}")
     # correctness of one remote row
     v = int(ids[(reps - 1) % 8][0])
     owner, row = v % world, v // world
