@@ -227,15 +227,23 @@ def main_b200(args):
     P = max(1, args.pipeline)
     PITCH = args.pitch if args.pitch else F0          # row pitch of the 602-wide tensors, in floats
 
-    st_sample, st_train = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for kv in args.opt:
+        name, value = kv.split("=")
+        check(lib.nb_set_option(name.encode(), int(value)))
+    st_sample, st_train = torch.cuda.Stream(dev, priority=args.sample_priority), torch.cuda.Stream(dev)
     cs_sample, cs_train = nts.Cuda_Stream(local, st_sample), nts.Cuda_Stream(local, st_train)
+    # e2e path: the host waits for every batch's sampled sizes, so sampling is on its critical path and gets a high-priority
+    # stream (its small kernels are scheduled ahead of the resident gather / aggregation blocks of the previous batch). In the
+    # device-resident path nothing waits for the sampler, and a normal-priority stream leaves the aggregation undisturbed.
+    st_sample_api = torch.cuda.Stream(dev, priority=-1)
+    cs_sample_api = nts.Cuda_Stream(local, st_sample_api)
     with torch.cuda.stream(st_train):
         graph = nts.FullyRepGraph(cs_sample, v, column_offset=col_off, row_indices=src)
         # one sampler (arena) per pipeline slot, all on the sampling stream (the reference's PIPELINE_NUM SampledSubgraphs)
         # bottom_csr=False: the bottom hop's backward never runs in the GCN toolkits (core/ntsContext.hpp:443), so its CSR is not built
         sampler = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=P, cuda_stream=[cs_sample] * P, build_csr=True,
                                   bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
-        fast = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=2, cuda_stream=[cs_sample] * 2, build_csr=True,
+        fast = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=2, cuda_stream=[cs_sample_api] * 2, build_csr=True,
                                bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
         api_ev = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
         gen = torch.Generator(device=dev).manual_seed(0x5EED0002)
@@ -328,11 +336,11 @@ def main_b200(args):
     def api_issue(i):
         """sample batch i asynchronously on the sampling stream into slot i % 2 (FastSampler pipeline slot, as PIPELINE_NUM=2)"""
         k = i % 2
-        st_sample.wait_event(api_ev[k]["consumed"])
+        st_sample_api.wait_event(api_ev[k]["consumed"])
         fast.work_offset = i * BATCH
-        with torch.cuda.stream(st_sample):
+        with torch.cuda.stream(st_sample_api):
             fast.sample_gpu_fast(BATCH, ssg_id=k, sync=False)          # stages + uploads the seeds from host memory
-        api_ev[k]["sampled"].record(st_sample)
+        api_ev[k]["sampled"].record(st_sample_api)
         api_state["issued"] = i
 
     def step_api(i, timed):
@@ -383,7 +391,7 @@ def main_b200(args):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            launches0 = cs_sample.launch_count() + cs_train.launch_count()
+            launches0 = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count()
             clocks = ClockSampler(local) if sample_clocks else None
             if clocks:
                 clocks.start()
@@ -404,7 +412,7 @@ def main_b200(args):
         sp, st_ = sizes_pin[args.warmup:n_steps].numpy().astype(np.int64), sizes_top[args.warmup:n_steps].numpy().astype(np.int64)
         work = {"edges": int(sp[:, 1].sum() + st_[:, 1].sum()), "V1": int(sp[:, 0].sum()), "E1": int(sp[:, 1].sum()),
                 "S1": int(sp[:, 2].sum())}
-        launches = cs_sample.launch_count() + cs_train.launch_count() - launches0
+        launches = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() - launches0
         return ms, launches, work, {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in kern_ev.items()}
 
     ms, launches, work, kms = run("async", sample_clocks=True)
@@ -478,7 +486,7 @@ def main_b200(args):
                     "epoch_ms_est": (ms_max / args.steps) * (all_seeds.size / BATCH / world)}),
                 "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": BATCH * 4 + 64,
                         "d2h_bytes_per_step": BATCH * F1 * 4 + 3 * 32, "ms_per_step": ms_e2e_max / args.steps,
-                        "path": "FastSampler.sample_gpu_fast(slot i+1, async) || wait(slot i) -> load_feature_gpu -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
+                        "path": "FastSampler.sample_gpu_fast(slot i+1, async, high-priority stream) || wait(slot i) -> load_feature_gpu -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
                 "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "fused_gather_aggregate": {"value": edges_fused_all / (ms_fused_max * 1e-3), "unit": "edges/s",
                                            "ms_per_step": ms_fused_max / args.steps,
@@ -499,6 +507,8 @@ if __name__ == "__main__":
     ap.add_argument("--pipeline", type=int, default=2, help="PIPELINE_NUM: sampler arenas in flight (sampling overlaps training)")
     ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
+    ap.add_argument("--sample-priority", type=int, default=0, help="CUDA stream priority of the sampling stream (-1 = high)")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to nb_set_option (tuning experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

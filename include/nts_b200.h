@@ -99,8 +99,14 @@ int nb_device_count(int *count);
  *       table, core/ntsDataloador.hpp:187) is copied to HBM once, on the first gather that sees it, and read from HBM afterwards
  *       (the buffer must not change after that); 0 (default) = gather over PCIe like the reference
  *   "mirror_host_adjacency" / NB_MIRROR_HOST_ADJACENCY : 1 (default) = the same for the adjacency array that the stage-shaped
- *       sampling calls receive as a mapped host pointer (core/ntsFastSampler.hpp:159-166); the topology never changes after load */
+ *       sampling calls receive as a mapped host pointer (core/ntsFastSampler.hpp:159-166); the topology never changes after load
+ *   "trace" / NB_TRACE : 1 = wall-clock time spent inside every entry point is accumulated (host side); 2 = the call's stream is
+ *       synchronised before the clock stops (host + GPU time per call; serialises, diagnostic only). The table goes to stderr at
+ *       exit or through nb_trace_dump(). Replaces the reference's get_time() accumulators (core/ntsFastSampler.hpp:30-37) and
+ *       Cuda_Stream::cpu_inclusiveTime / inclusiveTime (cuda/ntsCUDA.hpp:180-198). */
 int nb_set_option(const char *name, int value);
+int nb_trace_dump(void);
+int nb_trace_reset(void);
 
 /* ---- context: class Cuda_Stream (cuda/ntsCUDA.hpp:177-199; cuda/ntsCUDAGraphOP.cu:203-262) ----
  * nb_ctx_create      <- Cuda_Stream::Cuda_Stream()     (adopt_stream == 0: creates a non-blocking stream;
@@ -238,6 +244,12 @@ int nb_set_cache_index(nb_ctx *ctx, uint32_t *cache_map_dev, uint32_t *cache_loc
  * nb_gather_rows        <- Cuda_Stream::zero_copy_feature_move_gpu (cuda/ntsCUDA.hpp:370-374): out[i,:] = table[ids[i],:].
  *                          `table` may be device memory or mapped pinned host memory; table_pitch
  *                          is the row pitch in floats (>= feature_size; the reference is always dense).
+ *                          A pitch larger than feature_size declares ROW PADDING (here and in the *_dyn aggregation calls):
+ *                          columns [feature_size, min(pitch, feature_size rounded up to 8)) of every output row may be
+ *                          written (pad columns of the input flow into pad columns of the output), so that rows move as
+ *                          128-bit vectors / whole 32-byte sectors. Dense tensors (the reference's only layout) pass
+ *                          pitch == feature_size; a column slice of a wider tensor whose neighbouring columns hold data must
+ *                          be made contiguous by the caller first.
  * nb_gather_rows_cached <- FastSampler::load_feature_gpu_cache (core/ntsFastSampler.hpp:263-317) =
  *                          zero_copy_feature_move_gpu_cache + gather_feature_from_gpu_cache (:378-383) with
  *                          the hot/cold split done on the device in the same kernel:
@@ -275,6 +287,11 @@ int nb_stage_destroy(nb_stage *s);
 int nb_stage_submit(nb_stage *s, int slot, const uint32_t *ids_dev, uint32_t n_rows, const uint32_t *cache_node_hashmap_dev);
 int nb_stage_gather(nb_stage *s, int slot, float *out, uint32_t out_pitch, const float *cache_table, uint32_t cache_pitch,
                     const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out);
+/* The same with the hot cache partitioned over the GPUs of the node (nb_table below; cache slot k lives on shard k % n at row
+ * k / n and is read over NVLink inside the kernel): GS_SAMPLE_PC_MULTI's replicated cache (toolkits/GS_SAMPLE_PC_MULTI.hpp:916-1015)
+ * turned into one N-times larger cache. */
+int nb_stage_gather_table(nb_stage *s, int slot, float *out, uint32_t out_pitch, nb_table *hot_table,
+                          const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out);
 
 /* Sharded HBM feature table (multi-GPU): row v lives on shard v % n_shards at local row
  * v / n_shards. shard_ptrs[k] is a device pointer valid on THIS device (local allocation or a

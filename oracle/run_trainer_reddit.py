@@ -61,8 +61,13 @@ GPU_NUM:1
     out = r.stdout + r.stderr
     times = [float(m.group(1)) for m in re.finditer(r"Epoch\[\d+\]:Times\[([0-9.eE+-]+)\(s\)\]", out)]
     print("rc", r.returncode, "wall %.1fs" % wall, "epoch times (s):", times)
+    tracing = False
     for l in out.splitlines():
-        if re.search(r"sample_time|transfer_feature_time|training_time|average epoch|run_time|exec_time|rror", l):
+        tracing = tracing or l.startswith("[nts_b200 trace")
+        if tracing and (l.startswith("[nts_b200 trace") or l.startswith("nb_") or l.startswith("entry point")):
+            print(l)
+            continue
+        if re.search(r"sample[_ ]time|transfer[_a-z ]*time|train(ing)?[_ ]time|average epoch|run[_ ]time|exec_time|rror", l):
             print(l[-160:])
 
 

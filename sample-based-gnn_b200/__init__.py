@@ -491,6 +491,13 @@ class ColdStage:
                                     ptr(cache_node_hashmap_dev), ptr(ids_dev), C.byref(n_cold)))
         return n_cold.value
 
+    def gather_table(self, slot, out, hot_table, cache_node_hashmap_dev, ids_dev):
+        """hot rows from a (GPU-sharded) FeatureTable indexed by cache slot, cold rows from the staged block"""
+        n_cold = C.c_uint32()
+        check(lib().nb_stage_gather_table(self._h, slot, ptr(out), _pitch(out, self.F), hot_table._h, ptr(cache_node_hashmap_dev),
+                                          ptr(ids_dev), C.byref(n_cold)))
+        return n_cold.value
+
     def __del__(self):
         try:
             lib().nb_stage_destroy(self._h)

@@ -84,6 +84,9 @@ _SIGS = {
     "nb_stage_destroy": (I32, [P]),
     "nb_stage_submit": (I32, [P, I32, P, U32, P]),
     "nb_stage_gather": (I32, [P, I32, P, U32, P, U32, P, P, C.POINTER(U32)]),
+    "nb_stage_gather_table": (I32, [P, I32, P, U32, P, P, P, C.POINTER(U32)]),
+    "nb_trace_dump": (I32, []),
+    "nb_trace_reset": (I32, []),
     "nb_table_create": (I32, [P, U32, C.POINTER(P), U32, U32, U64, C.POINTER(P)]),
     "nb_table_destroy": (I32, [P]),
     "nb_table_gather": (I32, [P, P, P, P, U32, U32]),

@@ -19,6 +19,11 @@
 #include "common.cuh"
 
 constexpr int AGG_THREADS = 256;
+static int g_agg_blocks_per_sm = 8, g_agg_persistent = 1;
+void nb_agg_set_option(int which, int value) {
+  if (which == 0) g_agg_blocks_per_sm = value < 1 ? 1 : value > 8 ? 8 : value;
+  else g_agg_persistent = value;
+}
 
 // UNR = segment entries whose row loads are issued before the first accumulate (UNR*CHUNK independent vector loads per
 // lane in flight); narrow rows (CHUNK 1-2, e.g. F=128) take 4 entries at a time, wide rows 2. Accumulation stays in
@@ -153,7 +158,10 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
                           const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
                           uint64_t out_pitch, SegEpilogue epi) {
   const uint32_t nvec = F / VEC;
-  const unsigned grid = nb_grid(n_rows, AGG_THREADS / 32, 8);
+  // persistent grid (blocks loop over rows) by default; "agg_persistent"=0 launches one warp per row so that blocks retire
+  // every few microseconds and a concurrent higher-priority stream (the sampler of the next batch) gets SM slots in between
+  const unsigned grid = g_agg_persistent ? nb_grid(n_rows, AGG_THREADS / 32, g_agg_blocks_per_sm)
+                                         : (unsigned)((n_rows + AGG_THREADS / 32 - 1) / (AGG_THREADS / 32));
   const uint32_t per_lane = (nvec + 31) / 32;
 #define NB_SEG(C)                                                                                              \
   do {                                                                                                         \

@@ -50,6 +50,16 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *offsets,
                    uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch, uint64_t out_pitch, const float *e1,
                    const float *e2, const float *va, const float *vb);
+// (optionally sharded) HBM feature table; gather.cu
+struct nb_table {
+  nb_ctx *ctx;
+  uint32_t n_shards, feature_size, pitch;
+  uint64_t n_rows;
+  const float **shards_dev;  // device array of n_shards row-base pointers
+};
+int nb_launch_gather_tiered(nb_ctx *ctx, float *out, uint64_t out_pitch, const float *cache, uint64_t cache_pitch, const nb_table *hot,
+                            const uint32_t *cache_map, const uint32_t *ids, uint32_t n_rows, const float *staged, uint64_t staged_pitch,
+                            const uint32_t *cold_slot, uint32_t F);
 const void *nb_mirror_host(nb_ctx *ctx, const void *p, int is_adjacency = 0);  // HBM copy of a mapped-host allocation (or p itself)
 void nb_mirror_host_enable(int on, int adjacency);  // stream-ordered reuse; grows with cudaMalloc
 
@@ -62,9 +72,23 @@ struct DeviceGuard {
   }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+// Per-entry-point wall-clock accounting (NB_TRACE=1: host time inside each nb_* call; NB_TRACE=2: the call's stream is
+// synchronised before the clock stops, so the time includes the GPU work -- serialising, diagnostic only). A table is printed
+// to stderr at exit, or on demand by nb_trace_dump(). Replaces the reference's manual get_time() accumulators
+// (core/ntsFastSampler.hpp:30-37, cuda/ntsCUDA.hpp:180-198 cpu_inclusiveTime / inclusiveTime).
+struct NbTraceScope {
+  const char *name;
+  const nb_ctx *ctx;   // the stream is read when the scope closes: nb_ctx_set_stream replaces (and destroys) it inside the call
+  uint64_t t0;
+  NbTraceScope(const char *fn, const nb_ctx *c);
+  ~NbTraceScope();
+};
+void nb_trace_set_level(int level);
+void nb_agg_set_option(int which, int value);  // 0: resident blocks per SM of the segment reduction (1..8), 1: persistent grid on/off
 #define NB_GUARD(ctx)                                                                              \
   DeviceGuard guard__((ctx)->device);                                                              \
-  NB_REQUIRE(guard__.ok, NB_ERR_CUDA, "cudaSetDevice(%d) failed (no CUDA device?)", (ctx)->device)
+  NB_REQUIRE(guard__.ok, NB_ERR_CUDA, "cudaSetDevice(%d) failed (no CUDA device?)", (ctx)->device); \
+  NbTraceScope trace__(__func__, (ctx))
 
 static inline unsigned nb_grid(uint64_t work_items, unsigned items_per_block, unsigned max_blocks_per_sm = 8) {
   uint64_t need = (work_items + items_per_block - 1) / items_per_block;
@@ -184,8 +208,12 @@ static inline int nb_pick_vec(uint32_t feature_size, const void *a, uint64_t pit
   for (int vec = 4; vec >= 2; vec >>= 1) {
     const uint32_t up = (feature_size + vec - 1) / vec * vec;
     if (pitch_a % vec == 0 && pitch_b % vec == 0 && pitch_a >= up && pitch_b >= up && pa % (4 * vec) == 0 && pb % (4 * vec) == 0) {
-      if (f_eff) *f_eff = up;
-      else if (up != feature_size) continue;
+      if (f_eff) {
+        // whole 32-byte sectors when the padding allows: a row that stops 16 bytes short of a sector boundary costs a partial-sector
+        // write per row (602 floats at pitch 608: copying 604 runs 8 % slower than copying 608)
+        const uint32_t up8 = (feature_size + 7) / 8 * 8;
+        *f_eff = (pitch_a >= up8 && pitch_b >= up8) ? up8 : up;
+      } else if (up != feature_size) continue;
       return vec;
     }
   }

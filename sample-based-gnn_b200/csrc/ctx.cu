@@ -2,6 +2,7 @@
 // Replaces class Cuda_Stream's stream ownership (cuda/ntsCUDAGraphOP.cu:203-262 of the reference)
 // and the free allocation/copy helpers (cuda/ntsCUDA.hpp:30-71).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -12,6 +13,58 @@ void nb_set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- tracing ------------------------------------------------------------------------------------------
+#include <time.h>
+#include <map>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+static int g_trace = -1;  // -1: read NB_TRACE on first use
+struct TraceStat { uint64_t calls, ns; };
+static std::map<const char *, TraceStat> g_trace_stats;  // keyed by the address of __func__ (one per entry point)
+static std::mutex g_trace_mutex;
+static uint64_t now_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + ts.tv_nsec;
+}
+static void trace_print() {
+  std::lock_guard<std::mutex> lock(g_trace_mutex);
+  if (g_trace_stats.empty()) return;
+  std::vector<std::pair<const char *, TraceStat>> rows(g_trace_stats.begin(), g_trace_stats.end());
+  std::sort(rows.begin(), rows.end(), [](const std::pair<const char *, TraceStat> &a, const std::pair<const char *, TraceStat> &b) { return a.second.ns > b.second.ns; });
+  fprintf(stderr, "[nts_b200 trace, NB_TRACE=%d: %s]\n%-36s %10s %12s %10s\n", g_trace,
+          g_trace >= 2 ? "host + GPU time per call (stream synchronised)" : "host time inside each call", "entry point", "calls", "total ms", "mean us");
+  for (auto &r : rows)
+    fprintf(stderr, "%-36s %10llu %12.3f %10.2f\n", r.first, (unsigned long long)r.second.calls, r.second.ns / 1e6, r.second.ns / 1e3 / r.second.calls);
+}
+static int trace_level() {
+  if (g_trace < 0) {
+    const char *e = getenv("NB_TRACE");
+    g_trace = e ? atoi(e) : 0;
+    if (g_trace > 0) atexit(trace_print);
+  }
+  return g_trace;
+}
+void nb_trace_set_level(int level) {
+  const bool first = trace_level() <= 0 && level > 0;
+  static bool registered = false;
+  if (first && !registered && !getenv("NB_TRACE")) { atexit(trace_print); registered = true; }
+  g_trace = level;
+}
+NbTraceScope::NbTraceScope(const char *fn, const nb_ctx *c) : name(nullptr), ctx(c), t0(0) {
+  if (trace_level() > 0) { name = fn; t0 = now_ns(); }
+}
+NbTraceScope::~NbTraceScope() {
+  if (!name) return;
+  if (g_trace >= 2 && ctx) cudaStreamSynchronize(ctx->stream);
+  const uint64_t dt = now_ns() - t0;
+  std::lock_guard<std::mutex> lock(g_trace_mutex);
+  TraceStat &s = g_trace_stats[name];
+  s.calls++;
+  s.ns += dt;
 }
 
 int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out) {
@@ -29,7 +82,6 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out) {
   return NB_OK;
 }
 
-#include <stdlib.h>
 // ---- HBM mirror of host-resident tables (features, adjacency) --------------------------------------
 // The reference keeps the feature table and the adjacency (row_indices) in mapped pinned host memory and reads them over
 // PCIe (zero copy: core/ntsDataloador.hpp:187,483; core/FullyRepGraph.hpp:727 + core/ntsFastSampler.hpp:159-166). On a 180 GB part the table fits in HBM, so the first
@@ -170,6 +222,9 @@ extern "C" {
 
 int nb_abi_version(void) { return NB_ABI_VERSION; }
 const char *nb_last_error(void) { return g_err; }
+
+int nb_trace_dump(void) { trace_print(); return NB_OK; }
+int nb_trace_reset(void) { std::lock_guard<std::mutex> lock(g_trace_mutex); g_trace_stats.clear(); return NB_OK; }
 
 int nb_device_count(int *count) {
   NB_REQUIRE(count, NB_ERR_ARG, "count is NULL");

@@ -14,16 +14,13 @@
 
 #include "common.cuh"
 
-struct nb_table {
-  nb_ctx *ctx;
-  uint32_t n_shards, feature_size, pitch;
-  uint64_t n_rows;
-  const float **shards_dev;  // device array of n_shards row-base pointers
-};
-
 constexpr int GATHER_THREADS = 256;
+static int g_gather_narrow_rows = 4;  // "gather_narrow_rows": rows per warp iteration for rows of <= 32 vectors (1 = one row at a time)
 
 // MODE 0: plain table. MODE 1: hot/cold (cache_map slot != -1 -> cache table). MODE 2: sharded table (v % n, v / n).
+// MODE 3: three tiers -- hot rows (cache_map slot != -1) from a cache table that is either local (shards == NULL) or sharded over
+// the GPUs (slot % n, slot / n), cold rows from the staged block of stage.cu (table = staged rows, cold_slot[i] = row of batch
+// position i in that block).
 // CHUNK = vectors per lane held in registers: a row of up to 32*CHUNK vectors is fetched with CHUNK independent
 // requests per lane before the first store (602 floats = 301 float2 -> CHUNK 10, 2.4 KB in flight per warp);
 // the next row's id is fetched one iteration ahead so the id -> row dependency is off the critical path.
@@ -32,7 +29,7 @@ __global__ void __launch_bounds__(GATHER_THREADS)
 k_gather_rows(float *__restrict__ out, const float *__restrict__ table, uint64_t table_pitch, const float *__restrict__ cache,
               uint64_t cache_pitch, const uint32_t *__restrict__ cache_map, const float *const *__restrict__ shards,
               uint32_t n_shards, const uint32_t *__restrict__ ids, uint32_t n_rows, const uint32_t *__restrict__ n_rows_dev,
-              uint32_t nvec, uint64_t out_pitch, uint32_t *hit_count) {
+              uint32_t nvec, uint64_t out_pitch, uint32_t *hit_count, const uint32_t *__restrict__ cold_slot = nullptr) {
   const unsigned lane = lane_id();
   const unsigned warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
   const unsigned warps = (gridDim.x * GATHER_THREADS) >> 5;
@@ -48,7 +45,13 @@ k_gather_rows(float *__restrict__ out, const float *__restrict__ table, uint64_t
       const uint32_t slot = cache_map[v];
       if (slot != 0xffffffffu) { src = cache + (uint64_t)slot * cache_pitch; hits++; }
       else src = table + (uint64_t)v * table_pitch;
-    } else src = shards[v % n_shards] + (uint64_t)(v / n_shards) * table_pitch;
+    } else if (MODE == 2) src = shards[v % n_shards] + (uint64_t)(v / n_shards) * table_pitch;
+    else {
+      const uint32_t slot = cache_map[v];
+      if (slot == 0xffffffffu) src = table + (uint64_t)cold_slot[i] * table_pitch;
+      else if (shards) src = shards[slot % n_shards] + (uint64_t)(slot / n_shards) * cache_pitch;
+      else src = cache + (uint64_t)slot * cache_pitch;
+    }
     float *dst = out + (uint64_t)i * out_pitch;
     for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {
       Vec<VEC> x[CHUNK];
@@ -63,6 +66,53 @@ k_gather_rows(float *__restrict__ out, const float *__restrict__ table, uint64_t
         if (k < nvec) x[c].store(dst + (uint64_t)k * VEC);
       }
     }
+  }
+  if (MODE == 1 && hit_count && lane == 0 && hits) atomicAdd(hit_count, hits);
+}
+
+// Narrow rows (<= 32 vectors, e.g. F = 100 or 128): one vector per lane per row, so a warp that moves one row at a time has a
+// single 16-byte request per lane in flight and the kernel is latency bound (~2.6 TB/s algorithmic at F = 100). Here a warp owns
+// ROWS consecutive rows per iteration: ROWS ids in one broadcast load, ROWS independent row loads, then ROWS stores.
+template <int VEC, int ROWS, int MODE>
+__global__ void __launch_bounds__(GATHER_THREADS)
+k_gather_rows_narrow(float *__restrict__ out, const float *__restrict__ table, uint64_t table_pitch, const float *__restrict__ cache,
+                     uint64_t cache_pitch, const uint32_t *__restrict__ cache_map, const float *const *__restrict__ shards,
+                     uint32_t n_shards, const uint32_t *__restrict__ ids, uint32_t n_rows, const uint32_t *__restrict__ n_rows_dev,
+                     uint32_t nvec, uint64_t out_pitch, uint32_t *hit_count, const uint32_t *__restrict__ cold_slot) {
+  const unsigned lane = lane_id();
+  const unsigned warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * GATHER_THREADS) >> 5;
+  if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
+  unsigned hits = 0;
+  for (unsigned i0 = warp * ROWS; i0 < n_rows; i0 += warps * ROWS) {
+    const float *src[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      const unsigned i = i0 + r;
+      src[r] = nullptr;
+      if (i < n_rows) {
+        const uint32_t v = ids[i];
+        if (MODE == 0) src[r] = table + (uint64_t)v * table_pitch;
+        else if (MODE == 1) {
+          const uint32_t slot = cache_map[v];
+          if (slot != 0xffffffffu) { src[r] = cache + (uint64_t)slot * cache_pitch; hits++; }
+          else src[r] = table + (uint64_t)v * table_pitch;
+        } else if (MODE == 2) src[r] = shards[v % n_shards] + (uint64_t)(v / n_shards) * table_pitch;
+        else {
+          const uint32_t slot = cache_map[v];
+          if (slot == 0xffffffffu) src[r] = table + (uint64_t)cold_slot[i] * table_pitch;
+          else if (shards) src[r] = shards[slot % n_shards] + (uint64_t)(slot / n_shards) * cache_pitch;
+          else src[r] = cache + (uint64_t)slot * cache_pitch;
+        }
+      }
+    }
+    Vec<VEC> x[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+      if (src[r] && lane < nvec) x[r].load(src[r] + (uint64_t)lane * VEC);
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+      if (src[r] && lane < nvec) x[r].store(out + (uint64_t)(i0 + r) * out_pitch + (uint64_t)lane * VEC);
   }
   if (MODE == 1 && hit_count && lane == 0 && hits) atomicAdd(hit_count, hits);
 }
@@ -125,7 +175,8 @@ k_gather_rows_tma(float *__restrict__ out, const float *__restrict__ table, uint
 
 // returns the number of bytes a bulk row copy may move (0 = layout not eligible)
 static uint32_t tma_row_bytes(uint32_t F, const void *a, uint64_t pitch_a, const void *b, uint64_t pitch_b, const void *c = nullptr, uint64_t pitch_c = 4) {
-  const uint32_t bytes = (F * 4 + 15) & ~15u;
+  uint32_t bytes = (F * 4 + 31) & ~31u;   // whole 32-byte sectors when every pitch has the room (no partial-sector write per row)
+  if (pitch_a * 4 < bytes || pitch_b * 4 < bytes || (c && pitch_c * 4 < bytes)) bytes = (F * 4 + 15) & ~15u;
   if (pitch_a % 4 || pitch_b % 4 || pitch_c % 4) return 0;
   if (pitch_a * 4 < bytes || pitch_b * 4 < bytes || (c && pitch_c * 4 < bytes)) return 0;
   if ((uintptr_t)a % 16 || (uintptr_t)b % 16 || (uintptr_t)c % 16) return 0;
@@ -200,11 +251,20 @@ k_row_override(float *__restrict__ out_a, const float *__restrict__ share_a, uin
 template <int VEC, int MODE>
 static int launch_gather_v(nb_ctx *ctx, float *out, const float *table, uint64_t table_pitch, const float *cache, uint64_t cache_pitch,
                            const uint32_t *cache_map, const float *const *shards, uint32_t n_shards, const uint32_t *ids,
-                           uint32_t n_rows, const uint32_t *n_rows_dev, uint32_t F, uint64_t out_pitch, uint32_t *hit_count) {
+                           uint32_t n_rows, const uint32_t *n_rows_dev, uint32_t F, uint64_t out_pitch, uint32_t *hit_count,
+                           const uint32_t *cold_slot = nullptr) {
   const uint32_t nvec = F / VEC, per_lane = (nvec + 31) / 32;
+  if (per_lane <= 1 && g_gather_narrow_rows > 1) {
+    constexpr int ROWS = 4;
+    const unsigned grid = nb_grid(n_rows, GATHER_THREADS / 32 * ROWS, 8);
+    k_gather_rows_narrow<VEC, ROWS, MODE><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, table, table_pitch, cache, cache_pitch, cache_map,
+        shards, n_shards, ids, n_rows, n_rows_dev, nvec, out_pitch, hit_count, cold_slot);
+    NB_LAUNCH_CHECK(ctx);
+    return NB_OK;
+  }
   const unsigned grid = nb_grid(n_rows, GATHER_THREADS / 32, 8);
 #define NB_G(C) k_gather_rows<VEC, C, MODE><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, table, table_pitch, cache, cache_pitch, \
-      cache_map, shards, n_shards, ids, n_rows, n_rows_dev, nvec, out_pitch, hit_count)
+      cache_map, shards, n_shards, ids, n_rows, n_rows_dev, nvec, out_pitch, hit_count, cold_slot)
   if (per_lane <= 1) NB_G(1); else if (per_lane <= 2) NB_G(2); else if (per_lane <= 4) NB_G(4);
   else if (per_lane <= 5) NB_G(5); else if (per_lane <= 8) NB_G(8); else NB_G(10);
 #undef NB_G
@@ -216,11 +276,23 @@ template <int MODE>
 static int launch_gather(nb_ctx *ctx, float *out, const float *table, uint64_t table_pitch, const float *cache, uint64_t cache_pitch,
                          const uint32_t *cache_map, const float *const *shards, uint32_t n_shards, const uint32_t *ids,
                          uint32_t n_rows, uint32_t F, uint64_t out_pitch, uint32_t *hit_count, int vec,
-                         const uint32_t *n_rows_dev = nullptr) {
+                         const uint32_t *n_rows_dev = nullptr, const uint32_t *cold_slot = nullptr) {
   if (n_rows == 0) return NB_OK;
-  if (vec == 4) return launch_gather_v<4, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count);
-  if (vec == 2) return launch_gather_v<2, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count);
-  return launch_gather_v<1, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count);
+  if (vec == 4) return launch_gather_v<4, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count, cold_slot);
+  if (vec == 2) return launch_gather_v<2, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count, cold_slot);
+  return launch_gather_v<1, MODE>(ctx, out, table, table_pitch, cache, cache_pitch, cache_map, shards, n_shards, ids, n_rows, n_rows_dev, F, out_pitch, hit_count, cold_slot);
+}
+
+// stage.cu's merge: hot rows from the (local or sharded) cache table, cold rows from the staged block
+int nb_launch_gather_tiered(nb_ctx *ctx, float *out, uint64_t out_pitch, const float *cache, uint64_t cache_pitch, const nb_table *hot,
+                            const uint32_t *cache_map, const uint32_t *ids, uint32_t n_rows, const float *staged, uint64_t staged_pitch,
+                            const uint32_t *cold_slot, uint32_t F) {
+  if (hot) cache_pitch = hot->pitch;
+  int vec = nb_pick_vec(F, staged, staged_pitch, out, out_pitch);
+  const int v2 = nb_pick_vec(F, hot ? nullptr : cache, cache_pitch, out, out_pitch);
+  if (v2 < vec) vec = v2;
+  return launch_gather<3>(ctx, out, staged, staged_pitch, cache, cache_pitch, cache_map, hot ? hot->shards_dev : nullptr,
+                          hot ? hot->n_shards : 0, ids, n_rows, F, out_pitch, nullptr, vec, nullptr, cold_slot);
 }
 
 extern "C" {
@@ -228,6 +300,10 @@ extern "C" {
 int nb_set_option(const char *name, int value) {
   NB_REQUIRE(name, NB_ERR_ARG, "nb_set_option: NULL name");
   if (!strcmp(name, "gather_variant")) { g_gather_variant = value; return NB_OK; }
+  if (!strcmp(name, "gather_narrow_rows")) { g_gather_narrow_rows = value; return NB_OK; }
+  if (!strcmp(name, "agg_blocks_per_sm")) { nb_agg_set_option(0, value); return NB_OK; }
+  if (!strcmp(name, "agg_persistent")) { nb_agg_set_option(1, value); return NB_OK; }
+  if (!strcmp(name, "trace")) { nb_trace_set_level(value); return NB_OK; }
   if (!strcmp(name, "mirror_host_tables")) { nb_mirror_host_enable(value, 0); return NB_OK; }
   if (!strcmp(name, "mirror_host_adjacency")) { nb_mirror_host_enable(value, 1); return NB_OK; }
   nb_set_error("nb_set_option: unknown option %s", name);
@@ -241,7 +317,8 @@ int nb_gather_rows(nb_ctx *ctx, float *out, const float *table, const uint32_t *
   NB_GUARD(ctx);
   if (n_rows == 0) return NB_OK;
   table = (const float *)nb_mirror_host(ctx, table);
-  const uint32_t tb = gather_variant() == 1 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
+  // rows of <= 128 floats: the register path with 4 rows per warp beats bulk copies of 400-512 byte rows (tools/gather_bench.py)
+  const uint32_t tb = gather_variant() == 1 && feature_size > 128 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
   if (tb) return launch_gather_tma<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, n_rows, nullptr, tb, out_pitch);
   uint32_t fe = feature_size;
   int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch, &fe);
@@ -255,7 +332,7 @@ int nb_gather_rows_dyn(nb_ctx *ctx, float *out, const float *table, const uint32
   NB_GUARD(ctx);
   if (max_rows == 0) return NB_OK;
   table = (const float *)nb_mirror_host(ctx, table);
-  const uint32_t tb = gather_variant() == 1 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
+  const uint32_t tb = gather_variant() == 1 && feature_size > 128 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
   if (tb) return launch_gather_tma<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, max_rows, n_rows_dev, tb, out_pitch);
   uint32_t fe = feature_size;
   int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch, &fe);

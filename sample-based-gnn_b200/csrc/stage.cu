@@ -5,18 +5,21 @@
 // after a synchronous D2H and then reads cold rows over PCIe 4 bytes at a time from a zero-copy mapping
 // (core/ntsFastSampler.hpp:263-317). Here the split happens on the device, only the cold ids travel to the host, a worker
 // thread packs those rows into a pinned staging buffer and ships them with one cudaMemcpyAsync on a side stream, and the merge
-// kernel (hot rows from the cache, cold rows from the staged block) waits on that copy's event. submit() returns immediately,
-// so the staging of batch i+1 overlaps the training of batch i (2 slots).
+// (the gather kernel in its three-tier mode, gather.cu: hot rows from the cache, cold rows from the staged block) waits on that
+// copy's event. submit() returns immediately, so the staging of batch i+1 overlaps the training of batch i (2 slots).
+// The cache table may itself be sharded over the GPUs of the node and read over NVLink (nb_stage_gather_table): that is the
+// papers100M-shaped configuration -- partitioned hot cache + host-streamed cold rows.
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 constexpr int STAGE_SLOTS = 2;
 
 struct StageSlot {
-  uint32_t *cold_pos_dev, *cold_ids_dev, *count_dev;  // compacted cold rows: position in the batch, global id
+  uint32_t *cold_slot_dev, *cold_ids_dev, *count_dev;  // cold rows: batch position -> row of the staged block; compacted global ids
   uint32_t *cold_ids_host, *count_host;               // pinned
   float *rows_host, *rows_dev;                        // pinned staging block and its device copy
   cudaEvent_t ids_ready, rows_ready, consumed;
@@ -40,9 +43,9 @@ struct nb_stage {
 };
 
 // rows whose cache slot is -1: warp-ballot compaction, one atomic per warp. The order of the list does not matter to the
-// merge (each cold id travels with its position in the batch), so no scan is needed
+// merge (each batch position remembers which staged row is its own), so no scan is needed
 __global__ void __launch_bounds__(256)
-k_cold_split(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ cache_map, uint32_t n, uint32_t *__restrict__ cold_pos,
+k_cold_split(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ cache_map, uint32_t n, uint32_t *__restrict__ cold_slot,
              uint32_t *__restrict__ cold_ids, uint32_t *count) {
   const unsigned lane = lane_id();
   for (unsigned i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
@@ -57,38 +60,28 @@ k_cold_split(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ cach
     base = __shfl_sync(FULL_MASK, base, 0);
     if (cold) {
       const uint32_t k = base + __popc(mask & ((1u << lane) - 1u));
-      cold_pos[k] = i;
+      cold_slot[i] = k;
       cold_ids[k] = v;
     }
   }
 }
 
-// hot rows: out[i,:] = cache[slot,:]; cold rows: out[cold_pos[k],:] = staged[k,:]
-__global__ void __launch_bounds__(256)
-k_stage_merge(float *__restrict__ out, uint64_t out_pitch, const float *__restrict__ cache, uint64_t cache_pitch,
-              const uint32_t *__restrict__ cache_map, const uint32_t *__restrict__ ids, uint32_t n, const float *__restrict__ staged,
-              const uint32_t *__restrict__ cold_pos, const uint32_t *__restrict__ n_cold_dev, uint32_t F) {
-  const unsigned lane = lane_id(), warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n_cold = *n_cold_dev;
-  for (unsigned w = warp; w < n + n_cold; w += warps) {
-    const float *src;
-    float *dst;
-    if (w < n) {
-      const uint32_t slot = cache_map[ids[w]];
-      if (slot == 0xffffffffu) continue;
-      src = cache + (uint64_t)slot * cache_pitch;
-      dst = out + (uint64_t)w * out_pitch;
-    } else {
-      const uint32_t k = w - n;
-      src = staged + (uint64_t)k * F;
-      dst = out + (uint64_t)cold_pos[k] * out_pitch;
-    }
-    for (unsigned j = lane; j < F; j += 32) dst[j] = src[j];
+// threads packing cold rows: NB_STAGE_THREADS, else up to 16 of the host's cores. Explicit, because launchers such as torchrun
+// export OMP_NUM_THREADS=1 and a serial pack (random 400-2400 byte rows out of a multi-GB table) would cap the cold tier at ~3 GB/s
+static int stage_threads() {
+  static int n = 0;
+  if (!n) {
+    const char *e = getenv("NB_STAGE_THREADS");
+    n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    if (!e && n > 16) n = 16;
+    if (n < 1) n = 1;
   }
+  return n;
 }
 
 static void stage_worker(nb_stage *s) {
   cudaSetDevice(s->ctx->device);
+  const int n_threads = stage_threads();
   while (true) {
     int k;
     {
@@ -104,7 +97,7 @@ static void stage_worker(nb_stage *s) {
     const uint32_t nc = e == cudaSuccess ? *sl.count_host : 0;
     if (e == cudaSuccess) {
       const size_t row_bytes = (size_t)s->F * sizeof(float);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(n_threads)
       for (long r = 0; r < (long)nc; r++)
         memcpy(sl.rows_host + (size_t)r * s->F, s->host_table + (uint64_t)sl.cold_ids_host[r] * s->host_pitch, row_bytes);
       if (nc) e = cudaMemcpyAsync(sl.rows_dev, sl.rows_host, (size_t)nc * row_bytes, cudaMemcpyHostToDevice, s->side);
@@ -131,7 +124,7 @@ int nb_stage_create(nb_ctx *ctx, const float *host_table, uint32_t host_pitch, u
   NB_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   for (int k = 0; k < STAGE_SLOTS; k++) {
     StageSlot &sl = s->slot[k];
-    NB_CUDA(cudaMalloc(&sl.cold_pos_dev, (size_t)max_rows * 4));
+    NB_CUDA(cudaMalloc(&sl.cold_slot_dev, (size_t)max_rows * 4));
     NB_CUDA(cudaMalloc(&sl.cold_ids_dev, (size_t)max_rows * 4));
     NB_CUDA(cudaMalloc(&sl.count_dev, 64));
     NB_CUDA(cudaMalloc(&sl.rows_dev, (size_t)max_rows * feature_size * 4));
@@ -157,7 +150,7 @@ int nb_stage_destroy(nb_stage *s) {
   cudaStreamSynchronize(s->side);
   for (int k = 0; k < STAGE_SLOTS; k++) {
     StageSlot &sl = s->slot[k];
-    cudaFree(sl.cold_pos_dev); cudaFree(sl.cold_ids_dev); cudaFree(sl.count_dev); cudaFree(sl.rows_dev);
+    cudaFree(sl.cold_slot_dev); cudaFree(sl.cold_ids_dev); cudaFree(sl.count_dev); cudaFree(sl.rows_dev);
     cudaFreeHost(sl.cold_ids_host); cudaFreeHost(sl.count_host); cudaFreeHost(sl.rows_host);
     cudaEventDestroy(sl.ids_ready); cudaEventDestroy(sl.rows_ready); cudaEventDestroy(sl.consumed);
   }
@@ -181,7 +174,7 @@ int nb_stage_submit(nb_stage *s, int slot, const uint32_t *ids_dev, uint32_t n_r
   NB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.consumed, 0));  // the merge that last read this slot's buffers has run
   NB_CUDA(cudaMemsetAsync(sl.count_dev, 0, 4, ctx->stream));
   if (n_rows) {
-    k_cold_split<<<nb_grid(n_rows, 256, 4), 256, 0, ctx->stream>>>(ids_dev, cache_node_hashmap_dev, n_rows, sl.cold_pos_dev, sl.cold_ids_dev, sl.count_dev);
+    k_cold_split<<<nb_grid(n_rows, 256, 4), 256, 0, ctx->stream>>>(ids_dev, cache_node_hashmap_dev, n_rows, sl.cold_slot_dev, sl.cold_ids_dev, sl.count_dev);
     NB_LAUNCH_CHECK(ctx);
     NB_CUDA(cudaMemcpyAsync(sl.cold_ids_host, sl.cold_ids_dev, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -198,9 +191,8 @@ int nb_stage_submit(nb_stage *s, int slot, const uint32_t *ids_dev, uint32_t n_r
 
 // out[i,:] for the id list given to submit(): waits (host side) until the worker has issued the copy, then orders the merge
 // kernel behind it on the ctx stream. n_cold_out (may be NULL) receives the number of rows that came from the host.
-int nb_stage_gather(nb_stage *s, int slot, float *out, uint32_t out_pitch, const float *cache_table, uint32_t cache_pitch,
-                    const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out) {
-  NB_REQUIRE(s && slot >= 0 && slot < STAGE_SLOTS && out && out_pitch >= s->F, NB_ERR_ARG, "nb_stage_gather: bad argument");
+static int stage_gather(nb_stage *s, int slot, float *out, uint32_t out_pitch, const float *cache_table, uint32_t cache_pitch,
+                        const nb_table *hot, const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out) {
   nb_ctx *ctx = s->ctx;
   NB_GUARD(ctx);
   StageSlot &sl = s->slot[slot];
@@ -214,12 +206,27 @@ int nb_stage_gather(nb_stage *s, int slot, float *out, uint32_t out_pitch, const
   if (n_cold_out) *n_cold_out = sl.n_cold;
   NB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.rows_ready, 0));
   if (sl.n_rows) {
-    k_stage_merge<<<nb_grid((uint64_t)sl.n_rows + sl.n_cold, 8, 8), 256, 0, ctx->stream>>>(out, out_pitch, cache_table, cache_pitch,
-        cache_node_hashmap_dev, ids_dev, sl.n_rows, sl.rows_dev, sl.cold_pos_dev, sl.count_dev, s->F);
-    NB_LAUNCH_CHECK(ctx);
+    int rc = nb_launch_gather_tiered(ctx, out, out_pitch, cache_table, cache_pitch, hot, cache_node_hashmap_dev, ids_dev, sl.n_rows,
+                                     sl.rows_dev, s->F, sl.cold_slot_dev, s->F);
+    if (rc != NB_OK) return rc;
   }
   NB_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
   return NB_OK;
+}
+
+int nb_stage_gather(nb_stage *s, int slot, float *out, uint32_t out_pitch, const float *cache_table, uint32_t cache_pitch,
+                    const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out) {
+  NB_REQUIRE(s && slot >= 0 && slot < STAGE_SLOTS && out && out_pitch >= s->F, NB_ERR_ARG, "nb_stage_gather: bad argument");
+  NB_REQUIRE(cache_pitch >= s->F, NB_ERR_ARG, "nb_stage_gather: bad cache pitch");
+  return stage_gather(s, slot, out, out_pitch, cache_table, cache_pitch, nullptr, cache_node_hashmap_dev, ids_dev, n_cold_out);
+}
+
+int nb_stage_gather_table(nb_stage *s, int slot, float *out, uint32_t out_pitch, nb_table *hot_table,
+                          const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev, uint32_t *n_cold_out) {
+  NB_REQUIRE(s && slot >= 0 && slot < STAGE_SLOTS && out && out_pitch >= s->F && hot_table, NB_ERR_ARG, "nb_stage_gather_table: bad argument");
+  NB_REQUIRE(hot_table->feature_size == s->F, NB_ERR_ARG, "nb_stage_gather_table: the hot table holds rows of %u floats, the stage of %u",
+             hot_table->feature_size, s->F);
+  return stage_gather(s, slot, out, out_pitch, nullptr, 0, hot_table, cache_node_hashmap_dev, ids_dev, n_cold_out);
 }
 
 }  // extern "C"

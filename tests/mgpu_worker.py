@@ -30,6 +30,27 @@ def main():
         torch.cuda.synchronize()
         assert torch.equal(out.cpu(), full[ids.cpu().long()]), f"rank {rank}: sharded gather mismatch (pitch {pitch})"
         st.close()
+    # papers100M-shaped tiering: the hot cache (every 3rd vertex) is partitioned over the ranks and read over NVLink, the cold
+    # rows are staged from this rank's host table on a side stream
+    hot = np.arange(0, V, 3, dtype=np.uint32)
+    hashmap = np.full(V, 0xFFFFFFFF, np.uint32)
+    hashmap[hot] = np.arange(hot.size, dtype=np.uint32)
+    cache = full[torch.from_numpy(hot.astype(np.int64))] + 100.0       # distinguishable from the cold copy
+    st = nd.ShardedTable(cs, cache[rank::world].cuda(), hot.size, F)
+    stage = nts.ColdStage(cs, full, max_rows=20000)
+    d_hash = torch.from_numpy(hashmap.view(np.int32)).cuda()
+    ids_np = np.random.default_rng(9 + rank).integers(0, V, 20000).astype(np.uint32)
+    ids = torch.from_numpy(ids_np.view(np.int32)).cuda()
+    out = torch.empty((20000, F), device="cuda")
+    stage.submit(0, ids, 20000, d_hash)
+    n_cold = stage.gather_table(0, out, st.table, d_hash, ids)
+    torch.cuda.synchronize()
+    want = full[torch.from_numpy(ids_np.astype(np.int64))].clone()
+    is_hot = hashmap[ids_np] != 0xFFFFFFFF
+    want[torch.from_numpy(is_hot)] += 100.0
+    assert n_cold == int((~is_hot).sum()) and torch.equal(out.cpu(), want), f"rank {rank}: tiered gather mismatch"
+    del stage
+    st.close()
     w = torch.nn.Parameter(torch.zeros(602, 128, device="cuda"))
     w.grad = torch.full_like(w, float(rank + 1))
     nd.GradBucket([w]).all_reduce()

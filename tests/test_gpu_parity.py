@@ -765,3 +765,21 @@ def test_cold_row_staging_overlapped_slots(nts, cs):
             assert np.array_equal(bits(f32(o)[:b.size]), bits(oracle.gather_rows_cached(table_np, cache_np, hashmap, b)))
     with pytest.raises(nts.NtsError):
         stage.submit(0, d_ids[0], 30001, d_hash)
+    # the same with the hot cache partitioned over three shards (cache slot k -> shard k % 3, row k // 3), pitched rows
+    pitch = F + 4
+    shards = []
+    for r in range(3):
+        t = torch.zeros((len(range(r, hot.size, 3)), pitch), device="cuda")
+        t[:, :F] = torch.from_numpy(cache_np[r::3]).cuda()
+        shards.append(t)
+    hot_table = nts.FeatureTable(cs, shards, F, pitch, hot.size, keepalive=shards)
+    outs2 = [torch.full((max(b.size, 1), F), 7.0, device="cuda") for b in batches]
+    stage.submit(0, d_ids[0], batches[0].size, d_hash)
+    for i, b in enumerate(batches):
+        if i + 1 < len(batches):
+            stage.submit((i + 1) % 2, d_ids[i + 1], batches[i + 1].size, d_hash)
+        assert stage.gather_table(i % 2, outs2[i], hot_table, d_hash, d_ids[i]) == int((hashmap[b] == 0xFFFFFFFF).sum())
+    cs.CUDA_DEVICE_SYNCHRONIZE()
+    for b, o in zip(batches, outs2):
+        if b.size:
+            assert np.array_equal(bits(f32(o)[:b.size]), bits(oracle.gather_rows_cached(table_np, cache_np, hashmap, b)))

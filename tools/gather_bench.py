@@ -37,6 +37,18 @@ with torch.cuda.stream(stream):
     F=128
     bench("LSU F=128", t128, o128, 128, 128, 0, 128)
     bench("TMA F=128", t128, o128, 128, 128, 1, 128)
+    # narrow rows (products F=100, papers F=128) on a table larger than L2: TMA bulk rows vs one row per warp vs 4 rows per warp
+    V = 2449029
+    for Fn in (100, 128, 64, 256):
+        F = Fn
+        tn = torch.rand((V, Fn), device='cuda'); on = torch.empty((N, Fn), device='cuda')
+        bench(f"TMA F={Fn} (V=2.4M)", tn, on, Fn, Fn, 1, Fn)
+        check(lib.nb_set_option(b"gather_narrow_rows", 1))
+        bench(f"LSU F={Fn} 1 row/warp", tn, on, Fn, Fn, 0, Fn)
+        check(lib.nb_set_option(b"gather_narrow_rows", 4))
+        bench(f"LSU F={Fn} 4 rows/warp", tn, on, Fn, Fn, 0, Fn)
+        del tn, on
+    V, F = 232965, 602
     # copy peak for context
     a = torch.empty(N*608, device='cuda'); b = torch.empty_like(a)
     for _ in range(3): b.copy_(a)
