@@ -5,7 +5,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnts_b200.so")
+LIB_PATH = os.environ.get("NB_LIB_PATH") or os.path.join(_HERE, "lib", "libnts_b200.so")   # NB_LIB_PATH: A/B runs of two builds
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "nts_b200.h")
 
 NB_WEIGHT_SUM, NB_WEIGHT_MEAN, NB_WEIGHT_NONE, NB_WEIGHT_MEAN_SAMPLED = 0, 1, 2, 3

@@ -19,10 +19,12 @@
 #include "common.cuh"
 
 constexpr int AGG_THREADS = 256;
-static int g_agg_blocks_per_sm = 8, g_agg_persistent = 1;
+static int g_agg_blocks_per_sm = 8, g_agg_persistent = 1, g_agg_long_rows = 0, g_agg_pipe_wide = 1;  // pipe: 0 never, 1 rows of <= 64 vectors, 2 always
 void nb_agg_set_option(int which, int value) {
   if (which == 0) g_agg_blocks_per_sm = value < 1 ? 1 : value > 8 ? 8 : value;
-  else g_agg_persistent = value;
+  else if (which == 1) g_agg_persistent = value;
+  else if (which == 2) g_agg_long_rows = value;
+  else g_agg_pipe_wide = value;
 }
 
 // UNR = segment entries whose row loads are issued before the first accumulate (UNR*CHUNK independent vector loads per
@@ -95,9 +97,11 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
           const unsigned k = c0 + c * 32 + lane;
           if (k < nvec) {
             Vec<VEC> a, b;
-            a.load(epi.va + (uint64_t)k * VEC);
+            // va / vb are the same few lines for every row of the launch: read them through L1. As streaming (L1-bypassing)
+            // loads they all land on the same L2 slices and serialise there (150K rows x 1 KB: ~35 us of the GAT backward)
+            a.load_cached(epi.va + (uint64_t)k * VEC);
             acc[c].axpy(a, s1);
-            if (epi.e2) { b.load(epi.vb + (uint64_t)k * VEC); acc[c].axpy(b, s2); }
+            if (epi.e2) { b.load_cached(epi.vb + (uint64_t)k * VEC); acc[c].axpy(b, s2); }
           }
         }
       }
@@ -108,6 +112,220 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
         if (k < nvec) acc[c].store(o + (uint64_t)k * VEC);
       }
     }
+  }
+}
+
+// ---- load-balanced variant (opt-in: nb_set_option("agg_long_rows", 1)) --------------------------------------------------------
+// Measured side by side on the B200 (same box, same call) this variant costs ~2 us per launch over the plain kernel above on the
+// headline workload, whose sampled segments never exceed the fanout -- so it is not the default. It is the kernel to switch on
+// for take-all layers or hub-heavy CSR backwards.
+// Load balance. A warp walks its segment sequentially (that is what keeps the CPU summation order), so one hub row -- a source
+// that thousands of sampled columns point at in the CSR backward, or a take-all column of a hub in the forward -- would keep a
+// single warp busy long after the rest of the grid has finished (4 row loads in flight: ~3 GB/s per warp, ~0.15 us per entry).
+// Segments longer than SEG_LONG are therefore only *recorded* (per block, in shared memory) by the warp that meets them and are
+// reduced after the warp loop by the whole block: all 256 threads stage a batch of input rows in shared memory (up to 256
+// independent vector loads in flight instead of 4), then every thread adds its own feature columns entry by entry -- the same
+// order, the same rounding, the same bits as the warp path. No second launch, no global work list.
+//
+// Latency. Short segments (CSR backward: ~1.6 entries per row; top hops) are bound by the dependent chain
+// offsets -> (idx, w) -> input rows -> store (~3.3 us per row measured), not by bandwidth. The warp loop is software pipelined:
+// the offsets of the row two iterations ahead and the first 32 (idx, w) of the next row are requested before the current row
+// is reduced, which leaves rows -> store on the critical path.
+constexpr uint32_t SEG_LONG = 96;          // entries
+constexpr uint32_t SEG_LOCAL_CAP = 32;     // long rows a block can queue; further ones are reduced by their warp (slow, correct)
+constexpr uint32_t SEG_LONG_MAX_F = 2048;  // 8 accumulators per thread
+constexpr uint32_t SEG_STAGE_BYTES = 16 * 1024;
+
+template <int VEC>
+__device__ __noinline__ void segment_block_reduce(uint32_t r, const float *__restrict__ in, float *__restrict__ out,
+                                                     const float *__restrict__ weight, const uint32_t *__restrict__ idx,
+                                                     const uint32_t *__restrict__ offsets, uint32_t nvec, uint64_t pitch, uint64_t out_pitch,
+                                                     const SegEpilogue &epi, float *s_rows, uint32_t batch) {
+  const uint32_t Fp = nvec * VEC, t = threadIdx.x;
+  uint32_t *s_idx = (uint32_t *)(s_rows + (size_t)batch * Fp);
+  float *s_w = (float *)(s_idx + batch);
+  const uint32_t beg = offsets[r], end = offsets[r + 1];
+  float acc[SEG_LONG_MAX_F / AGG_THREADS];
+#pragma unroll
+  for (int q = 0; q < (int)(SEG_LONG_MAX_F / AGG_THREADS); q++) acc[q] = 0.f;
+  for (uint32_t j0 = beg; j0 < end; j0 += batch) {
+    const uint32_t cnt = min(batch, end - j0);
+    if (t < cnt) {
+      s_idx[t] = idx[j0 + t];
+      s_w[t] = weight ? weight[j0 + t] : 1.0f;
+    }
+    __syncthreads();
+    for (uint32_t k = t; k < cnt * nvec; k += AGG_THREADS) {
+      const uint32_t e = k / nvec, c = k - e * nvec;
+      Vec<VEC> x;
+      x.load(in + (uint64_t)s_idx[e] * pitch + (uint64_t)c * VEC);
+      *reinterpret_cast<decltype(x.v) *>(s_rows + (size_t)e * Fp + (size_t)c * VEC) = x.v;
+    }
+    __syncthreads();
+    for (uint32_t e = 0; e < cnt; e++) {
+      const float w = s_w[e];
+#pragma unroll
+      for (int q = 0; q < (int)(SEG_LONG_MAX_F / AGG_THREADS); q++) {
+        const uint32_t f = t + q * AGG_THREADS;
+        if (f < Fp) acc[q] = __fadd_rn(acc[q], __fmul_rn(s_rows[(size_t)e * Fp + f], w));
+      }
+    }
+    __syncthreads();
+  }
+  float s1 = 0.f, s2 = 0.f;
+  if (epi.e1) { s1 = epi.e1[r]; s2 = epi.e2 ? epi.e2[r] : 0.f; }
+#pragma unroll
+  for (int q = 0; q < (int)(SEG_LONG_MAX_F / AGG_THREADS); q++) {
+    const uint32_t f = t + q * AGG_THREADS;
+    if (f < Fp) {
+      float a = acc[q];
+      if (epi.e1) {
+        a = __fadd_rn(a, __fmul_rn(epi.va[f], s1));
+        if (epi.e2) a = __fadd_rn(a, __fmul_rn(epi.vb[f], s2));
+      }
+      out[(uint64_t)r * out_pitch + f] = a;
+    }
+  }
+}
+
+template <int VEC, int CHUNK, int UNR, bool PIPE>
+__global__ void __launch_bounds__(AGG_THREADS)
+k_segment_reduce_lb(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
+                 const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
+                 const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch,
+                 SegEpilogue epi = SegEpilogue{nullptr, nullptr, nullptr, nullptr}, uint32_t long_batch = 0) {
+  extern __shared__ __align__(16) float s_stage[];  // long_batch staged rows + their (idx, w); empty when long_batch == 0
+  __shared__ uint32_t s_long[SEG_LOCAL_CAP];
+  __shared__ uint32_t s_nlong;
+  if (long_batch) {
+    if (threadIdx.x == 0) s_nlong = 0;
+    __syncthreads();
+  }
+  const unsigned lane = lane_id();
+  const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
+  if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
+  // pipeline registers: current row (beg, end, first 32 entries), next row's offsets
+  uint32_t beg = 0, end = 0, nbeg = 0, nend = 0, cur_idx = 0;
+  float cur_w = 1.0f, cur_s1 = 0.f, cur_s2 = 0.f;
+  if (PIPE && epi.e1 && warp < n_rows) { cur_s1 = epi.e1[warp]; cur_s2 = epi.e2 ? epi.e2[warp] : 0.f; }
+  if (PIPE) {
+    if (warp < n_rows) { beg = offsets[warp]; end = offsets[warp + 1]; }
+    if (warp + warps < n_rows) { nbeg = offsets[warp + warps]; nend = offsets[warp + warps + 1]; }
+    if (lane < end - beg) {
+      cur_idx = idx[beg + lane];
+      if (weight) cur_w = weight[beg + lane];
+    }
+  }
+  for (unsigned r = warp; r < n_rows; r += warps) {
+    uint32_t nnbeg = 0, nnend = 0, nxt_idx = 0;
+    float nxt_w = 1.0f, nxt_s1 = 0.f, nxt_s2 = 0.f;
+    if (PIPE) {
+      if (epi.e1 && r + warps < n_rows) { nxt_s1 = epi.e1[r + warps]; nxt_s2 = epi.e2 ? epi.e2[r + warps] : 0.f; }
+      if (r + 2 * warps < n_rows) { nnbeg = offsets[r + 2 * warps]; nnend = offsets[r + 2 * warps + 1]; }
+      if (lane < nend - nbeg) {
+        nxt_idx = idx[nbeg + lane];
+        if (weight) nxt_w = weight[nbeg + lane];
+      }
+    } else {
+      // wide rows are bandwidth bound: the extra requests and registers of the pipeline cost more than the latency they hide
+      beg = offsets[r];
+      end = offsets[r + 1];
+      cur_idx = 0;
+      cur_w = 1.0f;
+      if (lane < end - beg) {
+        cur_idx = idx[beg + lane];
+        if (weight) cur_w = weight[beg + lane];
+      }
+      if (epi.e1) { cur_s1 = epi.e1[r]; cur_s2 = epi.e2 ? epi.e2[r] : 0.f; }
+    }
+    bool queued = false;
+    if (long_batch && end - beg > SEG_LONG) {
+      uint32_t k = 0;
+      if (lane == 0) k = atomicAdd(&s_nlong, 1u);
+      k = __shfl_sync(FULL_MASK, k, 0);
+      if (k < SEG_LOCAL_CAP) {
+        if (lane == 0) s_long[k] = r;
+        queued = true;
+      }
+    }
+    if (!queued) {
+      for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {  // one pass unless the row is wider than 32*CHUNK vectors
+        Vec<VEC> acc[CHUNK];
+#pragma unroll
+        for (int c = 0; c < CHUNK; c++) acc[c].zero();
+        for (uint32_t j0 = beg; j0 < end; j0 += 32) {
+          const uint32_t cnt = min(32u, end - j0);
+          uint32_t my_idx = cur_idx;
+          float my_w = cur_w;
+          if (j0 != beg) {
+            my_idx = 0;
+            my_w = 1.0f;
+            if (lane < cnt) {
+              my_idx = idx[j0 + lane];
+              if (weight) my_w = weight[j0 + lane];
+            }
+          }
+          for (uint32_t t = 0; t < cnt; t += UNR) {
+            Vec<VEC> x[UNR][CHUNK];
+            float w[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+              // entries past the end of the batch re-read entry t (cheap, cached) and are not accumulated
+              const uint32_t tt = t + u < cnt ? t + u : t;
+              const uint32_t s = __shfl_sync(FULL_MASK, my_idx, tt);
+              w[u] = __shfl_sync(FULL_MASK, my_w, tt);
+              const float *p = in + (uint64_t)s * pitch;
+              if (t + u < cnt) {
+#pragma unroll
+                for (int c = 0; c < CHUNK; c++) {
+                  const unsigned k = c0 + c * 32 + lane;
+                  if (k < nvec) x[u][c].load(p + (uint64_t)k * VEC);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+              if (t + u < cnt) {
+#pragma unroll
+                for (int c = 0; c < CHUNK; c++) {
+                  const unsigned k = c0 + c * 32 + lane;
+                  if (k < nvec) acc[c].axpy(x[u][c], w[u]);
+                }
+              }
+            }
+          }
+        }
+        if (epi.e1) {
+          const float s1 = cur_s1, s2 = cur_s2;
+#pragma unroll
+          for (int c = 0; c < CHUNK; c++) {
+            const unsigned k = c0 + c * 32 + lane;
+            if (k < nvec) {
+              // va / vb are the same few lines for every row of the launch: read them through L1. As streaming (L1-bypassing)
+              // loads they all land on the same L2 slices and serialise there (150K rows x 1 KB: ~100 us of the GAT backward)
+              Vec<VEC> a, b;
+              a.load_cached(epi.va + (uint64_t)k * VEC);
+              acc[c].axpy(a, s1);
+              if (epi.e2) { b.load_cached(epi.vb + (uint64_t)k * VEC); acc[c].axpy(b, s2); }
+            }
+          }
+        }
+        float *o = out + (uint64_t)r * out_pitch;
+#pragma unroll
+        for (int c = 0; c < CHUNK; c++) {
+          const unsigned k = c0 + c * 32 + lane;
+          if (k < nvec) acc[c].store(o + (uint64_t)k * VEC);
+        }
+      }
+    }
+    if (PIPE) { beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend; cur_idx = nxt_idx; cur_w = nxt_w; cur_s1 = nxt_s1; cur_s2 = nxt_s2; }
+  }
+  if (long_batch) {
+    __syncthreads();
+    const uint32_t nl = min(s_nlong, SEG_LOCAL_CAP);
+    for (uint32_t i = 0; i < nl; i++)
+      segment_block_reduce<VEC>(s_long[i], in, out, weight, idx, offsets, nvec, pitch, out_pitch, epi, s_stage, long_batch);
   }
 }
 
@@ -158,6 +376,15 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
                           const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
                           uint64_t out_pitch, SegEpilogue epi) {
   const uint32_t nvec = F / VEC;
+  // block path for long segments: staging batch sized to SEG_STAGE_BYTES of dynamic shared memory
+  uint32_t long_batch = 0;
+  size_t smem = 0;
+  if (!push && g_agg_long_rows && F <= SEG_LONG_MAX_F) {
+    long_batch = SEG_STAGE_BYTES / (F * 4u);
+    if (long_batch > 64) long_batch = 64;
+    if (long_batch < 2) long_batch = 2;
+    smem = (size_t)long_batch * F * 4 + (size_t)long_batch * 8;
+  }
   // persistent grid (blocks loop over rows) by default; "agg_persistent"=0 launches one warp per row so that blocks retire
   // every few microseconds and a concurrent higher-priority stream (the sampler of the next batch) gets SM slots in between
   const unsigned grid = g_agg_persistent ? nb_grid(n_rows, AGG_THREADS / 32, g_agg_blocks_per_sm)
@@ -166,6 +393,8 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
 #define NB_SEG(C)                                                                                              \
   do {                                                                                                         \
     if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
+    else if (long_batch && (g_agg_pipe_wide == 2 || (C <= 2 && g_agg_pipe_wide == 1))) k_segment_reduce_lb<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), true><<<grid, AGG_THREADS, smem, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, long_batch); \
+    else if (long_batch) k_segment_reduce_lb<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), false><<<grid, AGG_THREADS, smem, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, long_batch); \
     else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2)><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
   } while (0)
   if (per_lane <= 1) NB_SEG(1);

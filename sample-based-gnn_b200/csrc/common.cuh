@@ -84,7 +84,10 @@ struct NbTraceScope {
   ~NbTraceScope();
 };
 void nb_trace_set_level(int level);
-void nb_agg_set_option(int which, int value);  // 0: resident blocks per SM of the segment reduction (1..8), 1: persistent grid on/off
+bool nb_trace_on();
+uint64_t nb_trace_now_ns();
+void nb_trace_add(const char *name, uint64_t ns);  // name must be a string literal (the table is keyed by its address)
+void nb_agg_set_option(int which, int value);  // 0: resident blocks per SM of the segment reduction (1..8), 1: persistent grid on/off, 2: block-per-row path for long segments on/off
 #define NB_GUARD(ctx)                                                                              \
   DeviceGuard guard__((ctx)->device);                                                              \
   NB_REQUIRE(guard__.ok, NB_ERR_CUDA, "cudaSetDevice(%d) failed (no CUDA device?)", (ctx)->device); \
@@ -135,6 +138,7 @@ template <int VEC> struct Vec;
 template <> struct Vec<4> {
   float4 v;
   __device__ __forceinline__ void load(const float *p) { v = ldg_stream4(p); }
+  __device__ __forceinline__ void load_cached(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }  // L1-allocating: data every warp re-reads
   __device__ __forceinline__ void store(float *p) const { stg_stream4(p, v); }
   __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
   // out = out + in*w : multiply, then add, each rounded (core/ntsBaseOp.hpp:546-562 spells it mul+add)
@@ -147,6 +151,7 @@ template <> struct Vec<4> {
 template <> struct Vec<2> {
   float2 v;
   __device__ __forceinline__ void load(const float *p) { v = ldg_stream2(p); }
+  __device__ __forceinline__ void load_cached(const float *p) { v = __ldg(reinterpret_cast<const float2 *>(p)); }
   __device__ __forceinline__ void store(float *p) const { stg_stream2(p, v); }
   __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
   __device__ __forceinline__ void axpy(const Vec<2> &in, float w) {
@@ -157,6 +162,7 @@ template <> struct Vec<2> {
 template <> struct Vec<1> {
   float v;
   __device__ __forceinline__ void load(const float *p) { v = ldg_stream1(p); }
+  __device__ __forceinline__ void load_cached(const float *p) { v = __ldg(p); }
   __device__ __forceinline__ void store(float *p) const { stg_stream1(p, v); }
   __device__ __forceinline__ void zero() { v = 0.f; }
   __device__ __forceinline__ void axpy(const Vec<1> &in, float w) { v = __fadd_rn(v, __fmul_rn(in.v, w)); }

@@ -48,6 +48,14 @@ static int trace_level() {
   }
   return g_trace;
 }
+bool nb_trace_on() { return trace_level() > 0; }
+uint64_t nb_trace_now_ns() { return now_ns(); }
+void nb_trace_add(const char *name, uint64_t ns) {
+  std::lock_guard<std::mutex> lock(g_trace_mutex);
+  TraceStat &s = g_trace_stats[name];
+  s.calls++;
+  s.ns += ns;
+}
 void nb_trace_set_level(int level) {
   const bool first = trace_level() <= 0 && level > 0;
   static bool registered = false;

@@ -240,16 +240,50 @@ __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_rows(const float *__restrict__ alpha, const float *__restrict__ ds, const float *__restrict__ dsum,
                const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ src_to_dst,
                uint32_t n_src, float *__restrict__ wcsr, float *__restrict__ rs, float *__restrict__ dd) {
-  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n_src; s += gridDim.x * blockDim.x) {
-    float r = 0.f;
-    for (uint32_t j = row_offset[s]; j < row_offset[s + 1]; j++) {
-      const uint32_t e = csr_to_csc[j];
-      wcsr[j] = alpha[e];
-      r += ds[e];
+  // thread per src for rows of up to four entries (the common case: ~1.6 entries per row); longer rows are walked by the whole
+  // warp afterwards instead of serialising one thread on a chain of dependent loads
+  const unsigned lane = lane_id();
+  const unsigned n_round = (n_src + 31u) & ~31u;
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += gridDim.x * blockDim.x) {
+    uint32_t beg = 0, end = 0;
+    if (s < n_src) { beg = row_offset[s]; end = row_offset[s + 1]; }
+    const bool is_long = end - beg > 4u;
+    if (s < n_src && !is_long) {
+      // up to four entries: all the index loads, then all the value loads, in flight together (a dependent per-entry loop
+      // costs two memory round trips per entry)
+      uint32_t e[4];
+      float a[4], d[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) e[k] = beg + k < end ? csr_to_csc[beg + k] : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        a[k] = beg + k < end ? alpha[e[k]] : 0.f;
+        d[k] = beg + k < end ? ds[e[k]] : 0.f;
+      }
+      float r = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (beg + k < end) { wcsr[beg + k] = a[k]; r += d[k]; }
+      rs[s] = r;
     }
-    rs[s] = r;
-    const uint32_t d = src_to_dst[s];
-    dd[s] = d != 0xffffffffu ? dsum[d] : 0.f;
+    if (s < n_src) {
+      const uint32_t d = src_to_dst[s];
+      dd[s] = d != 0xffffffffu ? dsum[d] : 0.f;
+    }
+    unsigned pending = __ballot_sync(FULL_MASK, is_long);
+    while (pending) {
+      const int owner = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const uint32_t b = __shfl_sync(FULL_MASK, beg, owner), e_end = __shfl_sync(FULL_MASK, end, owner);
+      float r = 0.f;
+      for (uint32_t j = b + lane; j < e_end; j += 32) {
+        const uint32_t e = csr_to_csc[j];
+        wcsr[j] = alpha[e];
+        r += ds[e];
+      }
+      r = warp_sum(r);
+      if ((int)lane == owner) rs[s] = r;
+    }
   }
 }
 

@@ -303,6 +303,8 @@ int nb_set_option(const char *name, int value) {
   if (!strcmp(name, "gather_narrow_rows")) { g_gather_narrow_rows = value; return NB_OK; }
   if (!strcmp(name, "agg_blocks_per_sm")) { nb_agg_set_option(0, value); return NB_OK; }
   if (!strcmp(name, "agg_persistent")) { nb_agg_set_option(1, value); return NB_OK; }
+  if (!strcmp(name, "agg_long_rows")) { nb_agg_set_option(2, value); return NB_OK; }
+  if (!strcmp(name, "agg_pipe_wide")) { nb_agg_set_option(3, value); return NB_OK; }
   if (!strcmp(name, "trace")) { nb_trace_set_level(value); return NB_OK; }
   if (!strcmp(name, "mirror_host_tables")) { nb_mirror_host_enable(value, 0); return NB_OK; }
   if (!strcmp(name, "mirror_host_adjacency")) { nb_mirror_host_enable(value, 1); return NB_OK; }

@@ -305,6 +305,42 @@ def test_gather_and_aggregate_match_oracle(nts, cs, F):
     np.testing.assert_allclose(f32(xg.grad), DX, rtol=RTOL, atol=1e-6)
 
 
+@pytest.mark.parametrize("F,pitch", [(7, 7), (128, 128), (602, 608), (1433, 1433)])
+def test_long_segments_take_the_block_path_with_identical_bits(nts, cs, F, pitch):
+    """With nb_set_option("agg_long_rows", 1), hub rows (segments longer than 96 entries) are reduced by a whole block: same
+    order, same bits as the oracle and as the default warp-per-row kernel, for every length around the threshold, with and
+    without weights, padded or dense rows."""
+    lib, check, ptr = nts._capi.lib(), nts._capi.check, nts._capi.ptr
+    rng = np.random.default_rng(F)
+    lens = np.array([0, 1, 95, 96, 97, 130, 0, 500, 3, 5000, 64, 257, 96, 2], np.uint32)
+    off = np.zeros(lens.size + 1, np.uint32)
+    off[1:] = np.cumsum(lens)
+    E, R, S = int(off[-1]), lens.size, 900
+    idx = rng.integers(0, S, E).astype(np.uint32)
+    w = rng.standard_normal(E).astype(np.float32)
+    X = rng.standard_normal((S, F)).astype(np.float32)
+    xp = torch.zeros((S, pitch), device="cuda")
+    xp[:, :F] = torch.from_numpy(X).cuda()
+    d_off, d_idx, d_w = (torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda() for a in (off, idx, w))
+    for weight, W in ((d_w, w), (None, np.ones(E, np.float32))):
+        Y = oracle.aggregate_fwd(X, off, idx, W)
+        outs = []
+        for long_rows in (1, 0):
+            check(lib.nb_set_option(b"agg_long_rows", long_rows))
+            y = torch.full((R, pitch), 3.0, device="cuda")
+            for _ in range(2):       # twice: the long-row list must re-arm itself between launches
+                cs.aggregate_fwd_pitched(xp, y, weight, d_idx, d_off, R, F, pitch, pitch)
+            outs.append(f32(y)[:, :F])
+        check(lib.nb_set_option(b"agg_long_rows", 0))          # the default: plain warp-per-row kernel
+        assert np.array_equal(bits(outs[0]), bits(Y)) and np.array_equal(bits(outs[1]), bits(Y))
+    # the CSR backward entry point shares the kernels: rows = sources, entries = (dst, w_b)
+    for long_rows in (1, 0):
+        check(lib.nb_set_option(b"agg_long_rows", long_rows))
+        dx = torch.empty((R, pitch), device="cuda")
+        cs.aggregate_bwd_pitched(xp, dx, d_w, d_off, d_idx, R, F, pitch, pitch)
+        assert np.array_equal(bits(f32(dx)[:, :F]), bits(oracle.aggregate_bwd_csr(X, off, idx, w)))
+
+
 def test_unaligned_views_fall_back_to_narrower_vectors(nts, cs):
     V, F = 500, 64
     pairs, graph = make_graph(nts, cs, V, 10, seed=1)
@@ -415,6 +451,37 @@ def test_gat_legacy_ops_and_fused_layer(nts, cs, F):
         hg, ag = h.clone().requires_grad_(True), a.clone().requires_grad_(True)
         (op(hg, ag) * torch.from_numpy(dout).cuda()).sum().backward()
         np.testing.assert_allclose(f32(hg.grad), DH, rtol=1e-3, atol=1e-4)
+
+
+def test_gat_fused_layer_with_hub_sources(nts, cs):
+    """Skewed sources: CSR rows of hundreds of entries (block-per-row segment reduction, warp-cooperative row pass in the backward)."""
+    V, F = 600, 128
+    rng = np.random.default_rng(77)
+    p = 1.0 / np.arange(1, V + 1) ** 1.2
+    p /= p.sum()
+    pairs = np.concatenate([np.stack([rng.choice(V, 60, replace=False, p=p), np.full(60, v)], 1) for v in range(V)]).astype(np.uint32)
+    graph = nts.FullyRepGraph(cs, V, edge_pairs=pairs)
+    seeds = rng.permutation(V)[:400].astype(np.uint32)
+    sampler = nts.FastSampler(graph, seeds, 2, 400, [12, 40], cuda_stream=cs, merge_src_dst=True, build_csr=True)
+    sg = sampler.sample_gpu_fast(400, weightType=nts.WeightType.None_)
+    for hop, long_rows in ((0, 0), (1, 0), (1, 1)):
+        nts._capi.check(nts._capi.lib().nb_set_option(b"agg_long_rows", long_rows))
+        lay = sg.sampled_sgs[hop]
+        co, ri, dl = u32(lay.dev_column_offset), u32(lay.dev_row_indices), u32(lay.dev_dst_local_id)
+        assert np.diff(u32(lay.dev_row_offset).astype(np.int64)).max() > (96 if hop == 1 else 32)
+        H = rng.standard_normal((lay.src_size, F)).astype(np.float32)
+        att = (rng.standard_normal(2 * F) * 0.3).astype(np.float32)
+        h, a = torch.from_numpy(H).cuda(), torch.from_numpy(att).cuda()
+        op = nts.GATFusedOp(sg, hop, cs)
+        out = op.forward(h, a)
+        OUT, ALPHA, PRE = oracle.gat_layer_fwd(H, att, co, ri, dl)
+        np.testing.assert_allclose(f32(out), OUT, rtol=1e-4, atol=1e-5)
+        dout = rng.standard_normal(OUT.shape).astype(np.float32)
+        dh, datt = op.backward(h, a, torch.from_numpy(dout).cuda())
+        DH, DATT = oracle.gat_layer_bwd(H, att, dout, f32(op.score_pre), f32(op.alpha), co, ri, dl)
+        np.testing.assert_allclose(f32(dh), DH, rtol=1e-3, atol=2e-4)
+        np.testing.assert_allclose(f32(datt), DATT, rtol=1e-3, atol=2e-3)
+    nts._capi.check(nts._capi.lib().nb_set_option(b"agg_long_rows", 0))
 
 
 # ---------------------------------------------------------------------------------------------
