@@ -38,7 +38,9 @@ def test_reference_trainer_runs_on_libnts_b200(alg):
     assert r.returncode == 0, out[-3000:]
     accs = [float(m.group(1)) for m in re.finditer(r"Train Acc: ([0-9.]+)", out)]
     losses = [float(m.group(1)) for m in re.finditer(r"Epoch\[\d+\]:Times\[[^\]]*\]:loss\s+([0-9.eE+-]+)", out)]
-    assert len(accs) >= 4 and len(losses) >= 4, out[-2000:]
+    assert len(accs) >= 4, out[-2000:]
+    if alg not in MULTI_GPU_TOOLKITS:                 # the *_MULTI toolkits print the epoch time without the loss
+        assert len(losses) >= 4, out[-2000:]
     assert max(accs[-2:]) >= 0.70, accs               # cora, 5 epochs (the reference's own log reaches 0.93 after 10;
                                                       # the *CACHE toolkits train on bounded-stale hot embeddings and start slower)
-    assert losses[-1] < losses[0], losses
+    assert not losses or losses[-1] < losses[0], losses
