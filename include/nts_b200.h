@@ -150,6 +150,13 @@ int nb_memset_async(nb_ctx *ctx, void *dst_dev, int value, size_t bytes); /* cud
 int nb_graph_create(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *column_offset_host,
                     const uint32_t *row_indices_host, const uint32_t *in_degree_host, const uint32_t *out_degree_host,
                     nb_graph **out);
+/* The same from the raw edge list (EDGE_FILE format: little-endian (u32 src, u32 dst) pairs, core/FullyRepGraph.hpp:738-795),
+ * built ON THE DEVICE: replaces FullyRepGraph::GenerateAll's host counting sort (core/FullyRepGraph.hpp:724-798). Column = dst,
+ * entries of a column in file order (a stable LSD radix sort by dst, hand-written: csrc/ingest.cu), degrees clamped >= 1.
+ * `pairs` is host memory (pageable or pinned) or, with pairs_on_device, 8-byte aligned device memory; ids >= n_vertices are
+ * rejected (NB_ERR_ARG). Bit-identical to nb_graph_create on the host-built arrays. */
+int nb_graph_create_from_pairs(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *pairs, int pairs_on_device,
+                               nb_graph **out);
 int nb_graph_destroy(nb_graph *g);
 int nb_graph_info(nb_graph *g, uint32_t *n_vertices, uint64_t *n_edges, const uint32_t **column_offset_dev,
                   const uint32_t **row_indices_dev, const uint32_t **in_degree_dev, const uint32_t **out_degree_dev);

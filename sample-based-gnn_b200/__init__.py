@@ -213,14 +213,27 @@ class Cuda_Stream:
 
 
 class FullyRepGraph:
-    """core/FullyRepGraph.hpp:682-799: the global in-edge CSC. `GenerateAll`'s two-pass counting sort
-    (column = dst, entries in file order) is restated with a stable argsort on the host (one-time
-    ingestion, as in the reference); the arrays are then made resident in HBM (nb_graph)."""
+    """core/FullyRepGraph.hpp:682-799: the global in-edge CSC, resident in HBM (nb_graph). From an edge list it is built on
+    the device (`GenerateAll`'s two-pass counting sort -- column = dst, entries in file order -- as a stable radix sort by
+    dst, csrc/ingest.cu); `build_on_host=True` keeps the host restatement (stable argsort), which the tests use as the
+    second opinion."""
 
     def __init__(self, cuda_stream, global_vertices, edge_pairs=None, column_offset=None, row_indices=None,
-                 in_degree=None, out_degree=None):
+                 in_degree=None, out_degree=None, build_on_host=False):
         self.cs = cuda_stream
         self.global_vertices = int(global_vertices)
+        if edge_pairs is not None and not build_on_host:
+            # the CSC is built on the device (stable radix sort by dst, csrc/ingest.cu); edge_pairs: numpy [E,2] / flat, or a
+            # CUDA int32 tensor of the same layout
+            on_dev = hasattr(edge_pairs, "is_cuda") and edge_pairs.is_cuda
+            pairs = edge_pairs.contiguous() if on_dev else np.ascontiguousarray(edge_pairs, dtype=np.uint32).reshape(-1, 2)
+            n_edges = int(pairs.numel() // 2) if on_dev else int(pairs.shape[0])
+            h = C.c_void_p()
+            check(lib().nb_graph_create_from_pairs(self.cs._h, self.global_vertices, n_edges, ptr(pairs), 1 if on_dev else 0, C.byref(h)))
+            self._h = h
+            self.global_edges = n_edges
+            self.column_offset = self.row_indices = self.in_degree = self.out_degree = None   # device resident: device_arrays()
+            return
         if edge_pairs is not None:
             column_offset, row_indices, ind, outd = self.build_csc_host(edge_pairs, self.global_vertices)
             if in_degree is None:

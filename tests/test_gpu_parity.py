@@ -341,6 +341,33 @@ def test_long_segments_take_the_block_path_with_identical_bits(nts, cs, F, pitch
         assert np.array_equal(bits(f32(dx)[:, :F]), bits(oracle.aggregate_bwd_csr(X, off, idx, w)))
 
 
+@pytest.mark.parametrize("V,E,seed", [(1, 5, 0), (7, 0, 1), (2708, 13566, 2), (300, 70000, 3), (70000, 300000, 4), (20_000_000, 3_000_000, 5),
+                                      (232965, 12_000_000, 6)])
+def test_graph_built_on_device_matches_reference_ordering(nts, cs, V, E, seed):
+    """nb_graph_create_from_pairs (stable radix sort by dst on the device) == FullyRepGraph::GenerateAll's ordering as restated
+    by the oracle: column = dst, entries in FILE order, degrees clamped >= 1. Multi-edges, hubs, empty columns, 1..4 digit passes."""
+    rng = np.random.default_rng(seed)
+    src = (rng.random(E) ** 3 * V).astype(np.uint32)            # skewed: hubs and many duplicates
+    dst = (rng.random(E) ** 2 * V).astype(np.uint32)
+    pairs = np.stack([src, dst], 1).astype(np.uint32)
+    co, ri = oracle.build_csc(pairs, V)
+    ind, outd = oracle.degrees(pairs, V)
+    for on_device in (False, True):
+        ep = torch.from_numpy(pairs.view(np.int32)).cuda() if on_device else pairs
+        g = nts.FullyRepGraph(cs, V, edge_pairs=ep)
+        d_co, d_ri, d_in, d_out = g.device_arrays()
+        assert np.array_equal(u32(d_co), co) and (E == 0 or np.array_equal(u32(d_ri)[:E], ri))
+        assert np.array_equal(u32(d_in), ind) and np.array_equal(u32(d_out), outd)
+    if E:
+        h = nts.FullyRepGraph(cs, V, edge_pairs=pairs, build_on_host=True)
+        assert np.array_equal(u32(h.device_arrays()[1])[:E], ri)
+    if V > 1 and E:
+        bad = pairs.copy()
+        bad[E // 2, 0] = V
+        with pytest.raises(nts.NtsError):
+            nts.FullyRepGraph(cs, V, edge_pairs=bad)
+
+
 def test_unaligned_views_fall_back_to_narrower_vectors(nts, cs):
     V, F = 500, 64
     pairs, graph = make_graph(nts, cs, V, 10, seed=1)
