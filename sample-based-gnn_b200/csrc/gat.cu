@@ -240,15 +240,24 @@ __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_rows(const float *__restrict__ alpha, const float *__restrict__ ds, const float *__restrict__ dsum,
                const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ src_to_dst,
                uint32_t n_src, float *__restrict__ wcsr, float *__restrict__ rs, float *__restrict__ dd) {
-  // thread per src for rows of up to four entries (the common case: ~1.6 entries per row); longer rows are walked by the whole
-  // warp afterwards instead of serialising one thread on a chain of dependent loads
+  // thread per src: rows of up to four entries (the common case: ~1.6 entries per row) with all their loads in flight at once,
+  // rows of up to 32 in a plain loop; a hub row is walked by the whole warp afterwards instead of serialising one thread on
+  // hundreds of dependent loads
   const unsigned lane = lane_id();
   const unsigned n_round = (n_src + 31u) & ~31u;
   for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += gridDim.x * blockDim.x) {
     uint32_t beg = 0, end = 0;
     if (s < n_src) { beg = row_offset[s]; end = row_offset[s + 1]; }
-    const bool is_long = end - beg > 4u;
-    if (s < n_src && !is_long) {
+    const bool is_long = end - beg > 32u;
+    if (s < n_src && !is_long && end - beg > 4u) {
+      float r = 0.f;
+      for (uint32_t j = beg; j < end; j++) {
+        const uint32_t e = csr_to_csc[j];
+        wcsr[j] = alpha[e];
+        r += ds[e];
+      }
+      rs[s] = r;
+    } else if (s < n_src && !is_long) {
       // up to four entries: all the index loads, then all the value loads, in flight together (a dependent per-entry loop
       // costs two memory round trips per entry)
       uint32_t e[4];
