@@ -282,6 +282,30 @@ def main_b200(args):
     kern_ev = {"gather": [], "agg_fwd_602": []}
     st_comm = torch.cuda.Stream(dev)
     comm_box = [None]
+    cs_comm = nts.Cuda_Stream(local, st_comm)
+    peer_ar = None
+    if world > 1 and not args.nccl_allreduce:
+        from sample_based_gnn_b200 import dist as nbdist
+        peer_ar = nbdist.PeerAllReduce(cs_comm, grads.numel())   # the dense-gradient exchange as one kernel over peer memory
+
+    pending_box = [None]
+
+    def issue_allreduce():
+        if pending_box[0] is None:
+            return
+        st_comm.wait_event(pending_box[0])          # the backward that produced the gradients
+        if not args.comm_early:
+            after_gather = torch.cuda.Event()
+            after_gather.record(st_train)
+            st_comm.wait_event(after_gather)
+        if peer_ar is not None:
+            peer_ar.all_reduce(grads)               # one kernel over NVLink peer memory, enqueued on st_comm
+        else:
+            with torch.cuda.stream(st_comm):
+                dist.all_reduce(grads)
+        comm_box[0] = torch.cuda.Event()
+        comm_box[0].record(st_comm)
+        pending_box[0] = None
 
     def step_async(i, timed, fused=False):
         """value: inputs resident in HBM, no host synchronisation anywhere (sizes stay on the device). Batch i is sampled on
@@ -300,6 +324,9 @@ def main_b200(args):
             check(lib.nb_gather_rows_dyn(cs_train._h, ptr(x0), ptr(table), bot.source, ns[1], caps[1][2], F0, PITCH, PITCH))
             if timed:
                 b.record(st_train)
+            issue_allreduce()   # the previous step's gradient exchange starts here: it overlaps the aggregation below, not the gather
+                                # (the gather is one 200 KB-shared-memory CTA per SM with a fixed share of the rows: an SM that NCCL's
+                                # CTAs hold back delays the whole kernel, while the aggregation's 1184 blocks rebalance by themselves)
             check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(x0), ptr(y1), bot.edge_weight_forward, bot.row_indices,
                                                bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
             if timed:
@@ -307,6 +334,7 @@ def main_b200(args):
                 kern_ev["gather"].append((a, b))
                 kern_ev["agg_fwd_602"].append((b, c))
         else:  # bottom hop aggregated straight from the feature table through the global ids: X0 is never materialised
+            issue_allreduce()
             check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
                                                bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
         if comm_box[0] is not None:
@@ -319,15 +347,11 @@ def main_b200(args):
         check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_top[i]), nd[0].value, 32, 0))
         sl["consumed"].record(st_train)
         if world > 1:
-            # the dense-gradient exchange runs on its own stream behind this step's backward and overlaps the next step's
-            # gather / bottom aggregation; the next step's top hop (the first consumer of updated weights) waits for it
-            bwd_done = torch.cuda.Event()
-            bwd_done.record(st_train)
-            st_comm.wait_event(bwd_done)
-            with torch.cuda.stream(st_comm):
-                dist.all_reduce(grads)
-            comm_box[0] = torch.cuda.Event()
-            comm_box[0].record(st_comm)
+            # the dense-gradient exchange of this step runs on its own stream behind this step's backward; it is issued by the
+            # NEXT step right after its gather launch (issue_allreduce) and the next step's top hop -- the first consumer of the
+            # updated weights -- waits for it
+            pending_box[0] = torch.cuda.Event()
+            pending_box[0].record(st_train)
 
     api_state = {"issued": -1, "checksum": 0.0}
     y0_ring = [torch.empty((BATCH, F1)).pin_memory() for _ in range(2)]
@@ -354,13 +378,17 @@ def main_b200(args):
         t, bt = sg.sampled_sgs
         xx = x0[:bt.src_size, :F0]
         fast.load_feature_gpu(cs_train, sg, xx, table[:, :F0])
+        issue_allreduce()                                           # the previous step's gradient exchange, behind this gather
         yy1 = nts.SingleGPUAllSampleGraphOp(sg, 1, cs_train).forward(xx)
         op_top = nts.SingleGPUAllSampleGraphOp(sg, 0, cs_train)
+        if comm_box[0] is not None:
+            st_train.wait_event(comm_box[0])                        # updated weights before the top hop
         yy0 = op_top.forward(h1[:t.src_size])
         op_top.backward(dy0)
         api_ev[k]["consumed"].record(st_train)
         if world > 1:
-            dist.all_reduce(grads)
+            pending_box[0] = torch.cuda.Event()
+            pending_box[0].record(st_train)
         if i + 1 < n_steps:
             api_issue(i + 1)                                        # next batch samples while this one gathers / aggregates
         # the step's result goes to one of two pinned host buffers; the host consumes step i-1's while step i runs
@@ -382,6 +410,7 @@ def main_b200(args):
         step = {"async": step_async, "fused": lambda i, t: step_async(i, t, True), "api": step_api}[mode]
         api_state["issued"] = -1
         comm_box[0] = None
+        pending_box[0] = None
         for k in kern_ev.values():
             k.clear()
         with torch.cuda.stream(st_train):
@@ -391,7 +420,7 @@ def main_b200(args):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            launches0 = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count()
+            launches0 = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count()
             clocks = ClockSampler(local) if sample_clocks else None
             if clocks:
                 clocks.start()
@@ -399,6 +428,7 @@ def main_b200(args):
             t0.record(st_train)
             for i in range(args.warmup, n_steps):
                 step(i, True)
+            issue_allreduce()                      # the last step's exchange
             if comm_box[0] is not None:
                 st_train.wait_event(comm_box[0])
             t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes all streams
@@ -412,7 +442,7 @@ def main_b200(args):
         sp, st_ = sizes_pin[args.warmup:n_steps].numpy().astype(np.int64), sizes_top[args.warmup:n_steps].numpy().astype(np.int64)
         work = {"edges": int(sp[:, 1].sum() + st_[:, 1].sum()), "V1": int(sp[:, 0].sum()), "E1": int(sp[:, 1].sum()),
                 "S1": int(sp[:, 2].sum())}
-        launches = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() - launches0
+        launches = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count() - launches0
         return ms, launches, work, {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in kern_ev.items()}
 
     ms, launches, work, kms = run("async", sample_clocks=True)
@@ -480,7 +510,8 @@ def main_b200(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(v, e_total, {
                     "per_gpu_batch": BATCH, "pipeline_num": P, "row_pitch_floats": PITCH,
-                    "parallelism": (f"dp{world}: seeds sharded contiguously, one bucketed NCCL allreduce of the dense grads per step"
+                    "parallelism": (f"dp{world}: seeds sharded contiguously, one bucketed sum all-reduce of the dense grads per step ("
+                                    + ("NCCL" if args.nccl_allreduce else "one kernel over NVLink peer memory, nb_peer_allreduce_sum") + ")"
                                     if world > 1 else "single GPU"),
                     "avg_E_per_step": work["edges"] / n, "avg_S1": S1, "avg_E1": E1, "avg_V1": V1,
                     "epoch_ms_est": (ms_max / args.steps) * (all_seeds.size / BATCH / world)}),
@@ -492,6 +523,9 @@ def main_b200(args):
                                            "ms_per_step": ms_fused_max / args.steps,
                                            "note": "same results; the bottom hop aggregates straight from the feature table, X0 is never written"}}
         print(json.dumps(line))
+    if peer_ar is not None:
+        assert not peer_ar.timed_out(), "peer all-reduce: a rank never arrived"
+        peer_ar.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -508,6 +542,8 @@ if __name__ == "__main__":
     ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
     ap.add_argument("--sample-priority", type=int, default=0, help="CUDA stream priority of the sampling stream (-1 = high)")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="exchange the dense gradients with NCCL instead of the peer-memory kernel")
+    ap.add_argument("--comm-early", action="store_true", help="issue the gradient all-reduce right behind the backward (overlaps the next gather)")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to nb_set_option (tuning experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

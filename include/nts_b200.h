@@ -326,6 +326,22 @@ int nb_vmm_import(nb_ctx *ctx, int fd, size_t bytes, void **dev_ptr_out);
 int nb_vmm_grant(void *dev_ptr, int device);
 int nb_vmm_free(void *dev_ptr);
 
+/* ---- dense-gradient exchange over NVLink peer memory -----------------------------------------------
+ * nb_peer_allreduce_sum <- Parameter::reduce_multi_gpu_gradient -> NCCL_Communicator::AllReduce (core/NtsScheduler.hpp:830-836,
+ *                          cuda/ntsCUDAGraphOP.cu:173-200): in-place SUM over the ranks of one node of a small fp32 buffer (the
+ *                          dense weight gradients, ~330 KB per step), as ONE kernel over peer-mapped memory: every rank's block
+ *                          (nb_peer_comm_block_bytes, allocated with nb_vmm_alloc and mapped by every other rank with
+ *                          nb_vmm_import) holds arrival flags and two data slots; ranks sum the slots in rank order, so the
+ *                          result is bit-identical on every rank. blocks[r] = rank r's block as mapped on ctx's device
+ *                          (blocks[rank] = the local allocation). Every rank calls it with the same n, in the same order; a peer
+ *                          that never arrives makes the kernel give up after ~20 s (nb_peer_comm_check) instead of hanging. */
+typedef struct nb_peer_comm nb_peer_comm;
+size_t nb_peer_comm_block_bytes(uint64_t max_floats);
+int nb_peer_comm_create(nb_ctx *ctx, uint32_t rank, uint32_t world, uint64_t max_floats, void *const *blocks, nb_peer_comm **out);
+int nb_peer_comm_destroy(nb_peer_comm *c);
+int nb_peer_allreduce_sum(nb_peer_comm *c, float *inout, uint64_t n);
+int nb_peer_comm_check(nb_peer_comm *c, int *timed_out);
+
 /* ---- sparse aggregation ----------------------------------------------------------------------
  * nb_aggregate_csc_fwd <- Cuda_Stream::Gather_By_Dst_From_Src_Spmm (cuSPARSE, cuda/ntsCUDAGraphOP.cu:425-587) and
  *                         Gather_By_Dst_From_Src / _Optim (cuda/ntsCUDA.hpp:223-267):

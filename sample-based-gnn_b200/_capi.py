@@ -86,6 +86,11 @@ _SIGS = {
     "nb_stage_submit": (I32, [P, I32, P, U32, P]),
     "nb_stage_gather": (I32, [P, I32, P, U32, P, U32, P, P, C.POINTER(U32)]),
     "nb_stage_gather_table": (I32, [P, I32, P, U32, P, P, P, C.POINTER(U32)]),
+    "nb_peer_comm_block_bytes": (SZ, [U64]),
+    "nb_peer_comm_create": (I32, [P, U32, U32, U64, C.POINTER(P), C.POINTER(P)]),
+    "nb_peer_comm_destroy": (I32, [P]),
+    "nb_peer_allreduce_sum": (I32, [P, P, U64]),
+    "nb_peer_comm_check": (I32, [P, C.POINTER(I32)]),
     "nb_trace_dump": (I32, []),
     "nb_trace_reset": (I32, []),
     "nb_table_create": (I32, [P, U32, C.POINTER(P), U32, U32, U64, C.POINTER(P)]),

@@ -35,11 +35,65 @@ def interleave_seeds(ids, rank, world, global_batch):
     return np.concatenate(out) if out else ids[:0]
 
 
-class GradBucket:
-    """All dense gradients of a step in one flat buffer -> one sum-allreduce (latency-bound: ~330 KB for 602-128-41)."""
+class PeerAllReduce:
+    """In-place SUM all-reduce of a small fp32 CUDA tensor over the ranks of one node as ONE kernel over NVLink peer memory
+    (nb_peer_allreduce_sum, csrc/peer.cu) -- no NCCL call on the step's critical path. Each rank's block (arrival flags + two
+    data slots) is a cuMemCreate allocation shared by POSIX descriptor, like the sharded table's shards. Ranks are summed in
+    rank order: bit-identical results on every rank. Enqueued on `cuda_stream`'s stream."""
 
-    def __init__(self, params):
+    def __init__(self, cuda_stream, max_floats):
+        import os
+        self.cs, self.max_floats = cuda_stream, int(max_floats)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        nbytes = int(lib().nb_peer_comm_block_bytes(self.max_floats))
+        self._local, fd = C.c_void_p(), C.c_int(-1)
+        check(lib().nb_vmm_alloc(cuda_stream._h, nbytes, C.byref(self._local), C.byref(fd)))
+        peer_fds = exchange_fds(fd.value)
+        self._peers, blocks = [], []
+        for r in range(world):
+            if r == rank:
+                blocks.append(self._local.value)
+            else:
+                p = C.c_void_p()
+                check(lib().nb_vmm_import(cuda_stream._h, peer_fds[r], nbytes, C.byref(p)))
+                os.close(peer_fds[r])
+                self._peers.append(p)
+                blocks.append(p.value)
+        arr = (C.c_void_p * world)(*blocks)
+        self._h = C.c_void_p()
+        check(lib().nb_peer_comm_create(cuda_stream._h, rank, world, self.max_floats, arr, C.byref(self._h)))   # zeroes this rank's flags
+        dist.barrier()                     # every rank's flags are zero before anyone signals
+
+    def all_reduce(self, t):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_floats
+        check(lib().nb_peer_allreduce_sum(self._h, t.data_ptr(), t.numel()))
+        return t
+
+    def timed_out(self):
+        e = C.c_int(0)
+        check(lib().nb_peer_comm_check(self._h, C.byref(e)))
+        return bool(e.value)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier()
+        lib().nb_peer_comm_destroy(self._h)
+        for p in self._peers:
+            check(lib().nb_vmm_free(p))
+        self._peers = []
+        dist.barrier()
+        if self._local:
+            check(lib().nb_vmm_free(self._local))
+            self._local = None
+
+
+class GradBucket:
+    """All dense gradients of a step in one flat buffer -> one sum-allreduce (latency-bound: ~330 KB for 602-128-41):
+    `peer` (a PeerAllReduce) does it as one kernel over NVLink peer memory, otherwise one NCCL / gloo all_reduce."""
+
+    def __init__(self, params, peer=None):
         self.params = list(params)
+        self.peer = peer
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
 
@@ -49,7 +103,9 @@ class GradBucket:
             g = p.grad if p.grad is not None else torch.zeros_like(p)
             self.flat[off:off + p.numel()].copy_(g.reshape(-1))
             off += p.numel()
-        if dist.is_initialized() and dist.get_world_size() > 1:
+        if self.peer is not None:
+            self.peer.all_reduce(self.flat)
+        elif dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         off = 0
         for p in self.params:

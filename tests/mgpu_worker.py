@@ -51,6 +51,26 @@ def main():
     assert n_cold == int((~is_hot).sum()) and torch.equal(out.cpu(), want), f"rank {rank}: tiered gather mismatch"
     del stage
     st.close()
+    # one-kernel all-reduce over peer memory: bit-identical to the rank-ordered fp32 sum, on every rank, for ragged sizes, many
+    # back-to-back exchanges (slot / flag reuse) and ranks that arrive at different times
+    par = nd.PeerAllReduce(cs, 602 * 128 + 128 * 41)
+    for it, n in enumerate([1, 3, 4, 5, 1000, 602 * 128 + 128 * 41, 77, 82304] * 6):
+        gens = [torch.Generator().manual_seed(1000 * it + r) for r in range(world)]
+        parts = [torch.randn(n, generator=g) for g in gens]
+        want = parts[0].clone()
+        for q in parts[1:]:
+            want += q
+        mine_t = parts[rank].cuda()
+        if it % 5 == rank % 5:
+            torch.cuda._sleep(2_000_000)          # this rank arrives ~1 ms late
+        par.all_reduce(mine_t)
+        assert torch.equal(mine_t.cpu(), want), f"rank {rank}: peer all-reduce mismatch at exchange {it} (n={n})"
+    assert not par.timed_out()
+    wp = torch.nn.Parameter(torch.zeros(64, 3, device="cuda"))
+    wp.grad = torch.full_like(wp, float(rank + 1))
+    nd.GradBucket([wp], peer=par).all_reduce()
+    assert torch.equal(wp.grad, torch.full_like(wp, float(world * (world + 1) // 2)))
+    par.close()
     w = torch.nn.Parameter(torch.zeros(602, 128, device="cuda"))
     w.grad = torch.full_like(w, float(rank + 1))
     nd.GradBucket([w]).all_reduce()
