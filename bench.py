@@ -324,9 +324,11 @@ def main_b200(args):
             check(lib.nb_gather_rows_dyn(cs_train._h, ptr(x0), ptr(table), bot.source, ns[1], caps[1][2], F0, PITCH, PITCH))
             if timed:
                 b.record(st_train)
-            issue_allreduce()   # the previous step's gradient exchange starts here: it overlaps the aggregation below, not the gather
-                                # (the gather is one 200 KB-shared-memory CTA per SM with a fixed share of the rows: an SM that NCCL's
-                                # CTAs hold back delays the whole kernel, while the aggregation's 1184 blocks rebalance by themselves)
+            issue_allreduce()   # the previous step's gradient exchange is enqueued here, on its own stream, behind that step's backward:
+                                # it overlaps this gather and the aggregation below and has both (~0.23 ms) to absorb rank skew.
+                                # --comm-late holds it back until the gather is done: the gather keeps its full bandwidth
+                                # (0.82 vs 0.78 of peak at N=2) but at N=8 the exchange then has only the aggregation (~0.1 ms)
+                                # to hide in and the step stalls on the slowest rank (0.325 vs 0.295 ms measured).
             check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(x0), ptr(y1), bot.edge_weight_forward, bot.row_indices,
                                                bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
             if timed:
@@ -543,7 +545,9 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-batches", type=int, default=20)
     ap.add_argument("--sample-priority", type=int, default=0, help="CUDA stream priority of the sampling stream (-1 = high)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="exchange the dense gradients with NCCL instead of the peer-memory kernel")
-    ap.add_argument("--comm-early", action="store_true", help="issue the gradient all-reduce right behind the backward (overlaps the next gather)")
+    ap.add_argument("--comm-late", dest="comm_early", action="store_false",
+                    help="hold the gradient all-reduce back until the next step's gather has finished (it then overlaps only the aggregation)")
+    ap.set_defaults(comm_early=True)
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to nb_set_option (tuning experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
