@@ -1,0 +1,21 @@
+"""The benchmark driver and the measurement tools under tools/ must at least parse (they only run on a GPU box)."""
+import ast
+import glob
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_and_tools_parse():
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(ROOT, "tools", "*.py")))
+    assert len(files) >= 8
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
+
+
+def test_bench_cli_contract():
+    """bench.py keeps the driver's flags (--gpus/--steps/--warmup/--impl) and defaults to one GPU."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for flag in ('"--gpus"', '"--steps"', '"--warmup"', '"--impl"'):
+        assert flag in src
+    assert 'ap.add_argument("--gpus", type=int, default=1)' in src
