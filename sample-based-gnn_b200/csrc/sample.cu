@@ -445,7 +445,6 @@ __global__ void k_degrees_from_csc(const uint32_t *col_off, const uint32_t *row_
 }
 
 // =============================================================================================
-static uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
 extern "C" {
 
