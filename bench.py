@@ -9,9 +9,12 @@ between the dense layers:
     aggregate forward bottom hop (F=602) and top hop (F=128)   SingleGPUAllSampleGraphOp::forward
     aggregate backward top hop (F=128)                         ::backward  (the bottom hop's backward into
                                                                X0 never runs: core/ntsContext.hpp:443)
-    N > 1: one bucketed NCCL sum-allreduce of the dense weight gradients (602x128 + 128x41 floats)
+    N > 1: one bucketed sum of the dense weight gradients (602x128 + 128x41 floats) over NVLink peer memory
 The dense layers themselves are libtorch and outside the path; the top hop aggregates a resident
-synthetic [S_0,128] activation instead.
+synthetic [S_0,128] activation instead. Headline step: the bottom hop reads its input rows straight from
+the feature table (lazy load_feature_gpu); "materialized_x0" is the same step with the gather kernel first.
+Timing: W warm-up steps, then --windows windows of exactly K steps each (CUDA events on the training
+stream, ranks aligned on the device before every window, max over ranks); the median window is reported.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo, one JSON line
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's own OpenMP CPU path
@@ -68,11 +71,13 @@ def shard_seeds(ids, rank, world):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled DURING the timed region (NVML in-process, ~2 ms period)."""
+    """SM clock and throttle reasons sampled from the first warm-up step to the end of the last timed window of the headline mode
+    (NVML in-process, ~0.5 ms period); samples that fall inside a timed window are counted separately."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.sm, self.mask, self.stop_flag, self.max_sm = index, [], 0, False, None
+        self.sm_timed, self.in_window = [], False
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -88,11 +93,17 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         while not self.stop_flag:
             try:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                self.sm.append(mhz)
+                if self.in_window:
+                    self.sm_timed.append(mhz)
                 self.mask |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
+
+    def mark(self, inside):
+        self.in_window = inside
 
     def summary(self):
         self.stop_flag = True
@@ -103,8 +114,11 @@ class ClockSampler(threading.Thread):
                               ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
                 if self.mask & bit:
                     reasons.append(name)
-        return {"sm_mhz": int(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
-                "samples": len(self.sm)}
+        if self.is_alive():
+            self.join(timeout=1.0)
+        use = self.sm_timed or self.sm     # samples taken inside the timed windows; the whole run (warm-up on) if a window was too short
+        return {"sm_mhz": int(np.median(use)) if use else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.sm), "samples_in_timed_windows": len(self.sm_timed)}
 
 
 def write_reference_inputs(td, v, col_off, src, seeds):
@@ -171,14 +185,12 @@ def cpu_metric(r):
     return r["edges"] / t, t / max(r["batches"], 1) * 1e3
 
 
-def config_dict(v, e, extra=None):
-    c = {"workload": f"Reddit-shaped synthetic graph ({v} vertices, {e} edges, power-law in-degree), GCN_SAMPLE hot path: "
-                     f"sample fanout 25-10 + reindex/CSC/CSR/weights + gather F=602 + aggregate fwd 602/128 + bwd 128",
-         "batch": BATCH, "fanout": "25-10", "layers": "602-128-41",
-         "l2": "inputs larger than L2: each batch gathers ~130K random rows (~313 MB) of a 561 MB HBM-resident table"}
-    if extra:
-        c.update(extra)
-    return c
+def config_dict(v, e):
+    """identical in both arms (the driver compares the two lines' config); run-specific detail goes under "run" """
+    return {"workload": f"Reddit-shaped synthetic graph ({v} vertices, {e} edges, power-law in-degree), GCN_SAMPLE hot path: "
+                        f"sample fanout 25-10 + reindex/CSC/CSR/weights + gather F=602 + aggregate fwd 602/128 + bwd 128",
+            "batch": BATCH, "fanout": "25-10", "layers": "602-128-41",
+            "l2": "inputs larger than L2: each batch reads ~130K distinct random rows (~313 MB) of a 561 MB HBM-resident table"}
 
 
 def main_reference(args):
@@ -217,13 +229,16 @@ def main_b200(args):
     if world > 1:
         os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
+    strong = args.scaling == "strong"
+    B = BATCH // world if strong else BATCH          # strong: fixed global batch, local batch = BATCH / N (GAT_SAMPLE_ALL_MULTI.hpp:322)
     v, col_off, src = reddit_shaped_graph(args.scale)
     e_total = int(src.size)
     all_seeds = train_seeds(v)
     my_seeds = shard_seeds(all_seeds, rank, world)
-    n_steps = args.warmup + args.steps
-    reps = -(-n_steps * BATCH // my_seeds.size)
-    my_seeds = np.tile(my_seeds, reps)[: n_steps * BATCH]
+    K, W, R = args.steps, args.warmup, max(1, args.windows)
+    n_steps = W + R * K                              # per mode: W warm-up steps, then R timed windows of exactly K steps
+    reps = -(-n_steps * B // my_seeds.size)
+    my_seeds = np.tile(my_seeds, reps)[: n_steps * B]
     P = max(1, args.pipeline)
     PITCH = args.pitch if args.pitch else F0          # row pitch of the 602-wide tensors, in floats
 
@@ -241,24 +256,25 @@ def main_b200(args):
         graph = nts.FullyRepGraph(cs_sample, v, column_offset=col_off, row_indices=src)
         # one sampler (arena) per pipeline slot, all on the sampling stream (the reference's PIPELINE_NUM SampledSubgraphs)
         # bottom_csr=False: the bottom hop's backward never runs in the GCN toolkits (core/ntsContext.hpp:443), so its CSR is not built
-        sampler = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=P, cuda_stream=[cs_sample] * P, build_csr=True,
+        sampler = nts.FastSampler(graph, my_seeds, 2, B, FANOUT, pipeline_num=P, cuda_stream=[cs_sample] * P, build_csr=True,
                                   bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
-        fast = nts.FastSampler(graph, my_seeds, 2, BATCH, FANOUT, pipeline_num=2, cuda_stream=[cs_sample_api] * 2, build_csr=True,
+        fast = nts.FastSampler(graph, my_seeds, 2, B, FANOUT, pipeline_num=2, cuda_stream=[cs_sample_api] * 2, build_csr=True,
                                bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
         api_ev = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
         gen = torch.Generator(device=dev).manual_seed(0x5EED0002)
         table = torch.zeros((v, PITCH), device=dev)                               # HBM-resident feature table
         table[:, :F0] = torch.rand((v, F0), generator=gen, device=dev) * 2 - 1
-        cap_s1, cap_s0 = min(BATCH * 25 * 10, v), min(BATCH * 25, v)
+        cap_s1, cap_s0 = min(B * 25 * 10, v), min(B * 25, v)
         x0 = torch.zeros((cap_s1, PITCH), device=dev)
         y1 = torch.zeros((cap_s0, PITCH), device=dev)
         h1 = torch.rand((cap_s0, F1), generator=gen, device=dev)                 # stands in for relu(Y1 W1)
-        y0 = torch.empty((BATCH, F1), device=dev)
-        dy0 = torch.rand((BATCH, F1), generator=gen, device=dev)
+        y0 = torch.empty((B, F1), device=dev)
+        dy0 = torch.rand((B, F1), generator=gen, device=dev)
         dh1 = torch.empty((cap_s0, F1), device=dev)
-        grads = torch.zeros(F0 * F1 + F1 * NCLS, device=dev)                      # dense W gradients, one bucket
+        n_grad = F0 * F1 + F1 * NCLS
+        grads_src = torch.rand(n_grad, generator=torch.Generator(device=dev).manual_seed(77 + rank), device=dev) - 0.5
+        grads = grads_src.clone()                                                 # dense W gradients, one bucket
         seeds_dev = torch.from_numpy(my_seeds.view(np.int32)).to(dev)
-        y0_host = torch.empty((BATCH, F1)).pin_memory()
         sizes_pin = torch.zeros((n_steps, 8), dtype=torch.int32).pin_memory()     # LayerMeta of the bottom layer per step
         sizes_top = torch.zeros((n_steps, 8), dtype=torch.int32).pin_memory()
     torch.cuda.synchronize()
@@ -268,7 +284,7 @@ def main_b200(args):
     with torch.cuda.stream(st_sample):
         for k in range(P):
             views = (nts._capi.LayerView * 2)()
-            check(lib.nb_sampler_sample(sampler._samplers[k], ptr(my_seeds[:BATCH]), BATCH, 0, SEED_SAMPLER + rank, 0,
+            check(lib.nb_sampler_sample(sampler._samplers[k], ptr(my_seeds[:B]), B, 0, SEED_SAMPLER + rank, 0,
                                         nts.WeightType.Sum, None, 0xFFFFFFFF, views, 1))
             nd, ns, caps = [C.c_void_p(), C.c_void_p()], [C.c_void_p(), C.c_void_p()], [[C.c_uint32() for _ in range(3)] for _ in range(2)]
             for l in range(2):
@@ -279,18 +295,22 @@ def main_b200(args):
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    kern_ev = {"gather": [], "agg_fwd_602": []}
-    st_comm = torch.cuda.Stream(dev)
-    comm_box = [None]
+    kern_ev = {"gather": [], "agg_fwd_602": [], "agg_fwd_602_from_table": []}
+    # ---- dense-gradient exchange (N > 1) ------------------------------------------------------------------------------------
+    # split (default): nb_peer_allreduce_begin right behind the backward IN the training stream (push over NVLink, waits for
+    #   nobody), nb_peer_allreduce_end right before the next step's top hop, the first consumer of the updated weights: the next
+    #   gather + bottom aggregation (~0.2 ms) absorb rank skew and no second stream competes for SM slots.
+    # one / nccl: round 1's placement -- one launch (peer kernel or NCCL) on a communication stream, early or late (--comm-late).
+    st_comm = torch.cuda.Stream(dev, priority=-1)
     cs_comm = nts.Cuda_Stream(local, st_comm)
+    exchange = args.exchange if world > 1 else "none"
     peer_ar = None
-    if world > 1 and not args.nccl_allreduce:
+    if exchange in ("split", "one"):
         from sample_based_gnn_b200 import dist as nbdist
-        peer_ar = nbdist.PeerAllReduce(cs_comm, grads.numel())   # the dense-gradient exchange as one kernel over peer memory
+        peer_ar = nbdist.PeerAllReduce(cs_train if exchange == "split" else cs_comm, n_grad)
+    comm_box, pending_box, open_box = [None], [None], [False]
 
-    pending_box = [None]
-
-    def issue_allreduce():
+    def issue_allreduce():      # exchange in ("one", "nccl"): the previous step's exchange, on the communication stream
         if pending_box[0] is None:
             return
         st_comm.wait_event(pending_box[0])          # the backward that produced the gradients
@@ -298,8 +318,8 @@ def main_b200(args):
             after_gather = torch.cuda.Event()
             after_gather.record(st_train)
             st_comm.wait_event(after_gather)
-        if peer_ar is not None:
-            peer_ar.all_reduce(grads)               # one kernel over NVLink peer memory, enqueued on st_comm
+        if exchange == "one":
+            peer_ar.all_reduce(grads)
         else:
             with torch.cuda.stream(st_comm):
                 dist.all_reduce(grads)
@@ -307,40 +327,64 @@ def main_b200(args):
         comm_box[0].record(st_comm)
         pending_box[0] = None
 
-    def step_async(i, timed, fused=False):
+    def exchange_before_consumer():
+        if exchange == "split":
+            if open_box[0]:
+                peer_ar.end(grads)
+                open_box[0] = False
+        elif comm_box[0] is not None:
+            st_train.wait_event(comm_box[0])
+            comm_box[0] = None
+
+    def exchange_after_backward():
+        if exchange == "split":
+            peer_ar.begin(grads)
+            open_box[0] = True
+        elif exchange in ("one", "nccl"):
+            pending_box[0] = torch.cuda.Event()
+            pending_box[0].record(st_train)
+
+    def exchange_flush():       # closes the last step's exchange inside the timed region
+        if exchange in ("one", "nccl"):
+            issue_allreduce()
+        exchange_before_consumer()
+
+    def step_async(i, timed, fused=True):
         """value: inputs resident in HBM, no host synchronisation anywhere (sizes stay on the device). Batch i is sampled on
-        the sampling stream into arena i % P while the training stream gathers / aggregates batch i-1."""
+        the sampling stream into arena i % P while the training stream works on batch i-1. fused: the bottom hop aggregates
+        straight from the feature table through the layer's global ids (what load_feature_gpu(lazy=True) + the op do): X0 is
+        never written. fused=False materialises X0 first (gather kernel + aggregation over X0), as the reference does."""
         sl = slots[i % P]
         top, bot, nd, ns, caps = sl["top"], sl["bot"], sl["nd"], sl["ns"], sl["caps"]
         st_sample.wait_event(sl["consumed"])
-        check(lib.nb_sampler_sample(sampler._samplers[i % P], ptr(seeds_dev[i * BATCH:(i + 1) * BATCH]), BATCH, 1,
+        check(lib.nb_sampler_sample(sampler._samplers[i % P], ptr(seeds_dev[i * B:(i + 1) * B]), B, 1,
                                     SEED_SAMPLER + rank, i, nts.WeightType.Sum, None, 0xFFFFFFFF, None, 0))
         sl["sampled"].record(st_sample)
         st_train.wait_event(sl["sampled"])
-        if timed and not fused:
+        if timed:
             a, b, c = ev(), ev(), ev()
             a.record(st_train)
         if not fused:
             check(lib.nb_gather_rows_dyn(cs_train._h, ptr(x0), ptr(table), bot.source, ns[1], caps[1][2], F0, PITCH, PITCH))
             if timed:
                 b.record(st_train)
-            issue_allreduce()   # the previous step's gradient exchange is enqueued here, on its own stream, behind that step's backward:
-                                # it overlaps this gather and the aggregation below and has both (~0.23 ms) to absorb rank skew.
-                                # --comm-late holds it back until the gather is done: the gather keeps its full bandwidth
-                                # (0.82 vs 0.78 of peak at N=2) but at N=8 the exchange then has only the aggregation (~0.1 ms)
-                                # to hide in and the step stalls on the slowest rank (0.325 vs 0.295 ms measured).
+            if exchange in ("one", "nccl"):
+                issue_allreduce()
             check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(x0), ptr(y1), bot.edge_weight_forward, bot.row_indices,
                                                bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
             if timed:
                 c.record(st_train)
                 kern_ev["gather"].append((a, b))
                 kern_ev["agg_fwd_602"].append((b, c))
-        else:  # bottom hop aggregated straight from the feature table through the global ids: X0 is never materialised
-            issue_allreduce()
+        else:
+            if exchange in ("one", "nccl"):
+                issue_allreduce()
             check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
                                                bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
-        if comm_box[0] is not None:
-            st_train.wait_event(comm_box[0])
+            if timed:
+                b.record(st_train)
+                kern_ev["agg_fwd_602_from_table"].append((a, b))
+        exchange_before_consumer()
         check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(h1), ptr(y0), top.edge_weight_forward, top.row_indices,
                                            top.column_offset, nd[0], caps[0][0], F1, F1, F1))
         check(lib.nb_aggregate_csr_bwd_dyn(cs_train._h, ptr(dy0), ptr(dh1), top.edge_weight_backward, top.row_offset,
@@ -348,24 +392,19 @@ def main_b200(args):
         check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_pin[i]), nd[1].value, 32, 0))
         check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_top[i]), nd[0].value, 32, 0))
         sl["consumed"].record(st_train)
-        if world > 1:
-            # the dense-gradient exchange of this step runs on its own stream behind this step's backward; it is issued by the
-            # NEXT step right after its gather launch (issue_allreduce) and the next step's top hop -- the first consumer of the
-            # updated weights -- waits for it
-            pending_box[0] = torch.cuda.Event()
-            pending_box[0].record(st_train)
+        exchange_after_backward()
 
     api_state = {"issued": -1, "checksum": 0.0}
-    y0_ring = [torch.empty((BATCH, F1)).pin_memory() for _ in range(2)]
+    y0_ring = [torch.empty((B, F1)).pin_memory() for _ in range(2)]
     y0_done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def api_issue(i):
         """sample batch i asynchronously on the sampling stream into slot i % 2 (FastSampler pipeline slot, as PIPELINE_NUM=2)"""
         k = i % 2
         st_sample_api.wait_event(api_ev[k]["consumed"])
-        fast.work_offset = i * BATCH
+        fast.work_offset = i * B
         with torch.cuda.stream(st_sample_api):
-            fast.sample_gpu_fast(BATCH, ssg_id=k, sync=False)          # stages + uploads the seeds from host memory
+            fast.sample_gpu_fast(B, ssg_id=k, sync=False)          # stages + uploads the seeds from host memory
         api_ev[k]["sampled"].record(st_sample_api)
         api_state["issued"] = i
 
@@ -378,19 +417,19 @@ def main_b200(args):
         sg = fast.wait(k)                                           # host waits for the sizes of batch i only
         st_train.wait_event(api_ev[k]["sampled"])
         t, bt = sg.sampled_sgs
-        xx = x0[:bt.src_size, :F0]
-        fast.load_feature_gpu(cs_train, sg, xx, table[:, :F0])
-        issue_allreduce()                                           # the previous step's gradient exchange, behind this gather
-        yy1 = nts.SingleGPUAllSampleGraphOp(sg, 1, cs_train).forward(xx)
+        if args.materialize_x0:
+            xx = fast.load_feature_gpu(cs_train, sg, x0[:bt.src_size, :F0], table[:, :F0])
+        else:
+            xx = fast.load_feature_gpu(cs_train, sg, x0[:, :F0], table[:, :F0], lazy=True)   # a promise: nothing is copied
+        if exchange in ("one", "nccl"):
+            issue_allreduce()
+        yy1 = nts.SingleGPUAllSampleGraphOp(sg, 1, cs_train).forward(xx)   # lazy: aggregates straight from the table
         op_top = nts.SingleGPUAllSampleGraphOp(sg, 0, cs_train)
-        if comm_box[0] is not None:
-            st_train.wait_event(comm_box[0])                        # updated weights before the top hop
+        exchange_before_consumer()                                  # updated weights before the top hop
         yy0 = op_top.forward(h1[:t.src_size])
         op_top.backward(dy0)
         api_ev[k]["consumed"].record(st_train)
-        if world > 1:
-            pending_box[0] = torch.cuda.Event()
-            pending_box[0].record(st_train)
+        exchange_after_backward()
         if i + 1 < n_steps:
             api_issue(i + 1)                                        # next batch samples while this one gathers / aggregates
         # the step's result goes to one of two pinned host buffers; the host consumes step i-1's while step i runs
@@ -399,72 +438,137 @@ def main_b200(args):
         if i > 0:
             y0_done[(i - 1) % 2].synchronize()
             api_state["checksum"] += float(y0_ring[(i - 1) % 2][0, 0])
-        if i + 1 == n_steps:
-            y0_done[i % 2].synchronize()
-            api_state["checksum"] += float(y0_ring[i % 2][0, 0])
         sizes_pin[i, 0], sizes_pin[i, 1], sizes_pin[i, 2] = bt.v_size, bt.e_size, bt.src_size
         sizes_top[i, 1] = t.e_size
         del yy1
 
-    clock_box = [None]
+    barrier_buf = torch.zeros(4, device=dev)
 
-    def run(mode, sample_clocks=False):
-        step = {"async": step_async, "fused": lambda i, t: step_async(i, t, True), "api": step_api}[mode]
+    def align_ranks():
+        """host barrier, then every rank meets ON THE DEVICE in the training stream immediately before the window's first event
+        (an exchange of four floats through the peer kernels): host skew after the NCCL barrier cannot leak into the window"""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+            if exchange == "split":
+                peer_ar.all_reduce(barrier_buf)
+
+    def run(mode, clocks=None):
+        step = {"fused": lambda i, t: step_async(i, t, True), "materialized": lambda i, t: step_async(i, t, False), "api": step_api}[mode]
         api_state["issued"] = -1
-        comm_box[0] = None
-        pending_box[0] = None
+        comm_box[0], pending_box[0], open_box[0] = None, None, False
         for k in kern_ev.values():
             k.clear()
+        wins, issue_ms = [], []
+        launches = 0
         with torch.cuda.stream(st_train):
-            for i in range(args.warmup):
-                step(i, False)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            launches0 = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count()
-            clocks = ClockSampler(local) if sample_clocks else None
             if clocks:
                 clocks.start()
-            t0, t1 = ev(), ev()
-            t0.record(st_train)
-            for i in range(args.warmup, n_steps):
-                step(i, True)
-            issue_allreduce()                      # the last step's exchange
-            if comm_box[0] is not None:
-                st_train.wait_event(comm_box[0])
-            t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes all streams
-            torch.cuda.synchronize()
-            if clocks:
-                clock_box[0] = clocks.summary()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-        ms = t0.elapsed_time(t1)
-        sp, st_ = sizes_pin[args.warmup:n_steps].numpy().astype(np.int64), sizes_top[args.warmup:n_steps].numpy().astype(np.int64)
-        work = {"edges": int(sp[:, 1].sum() + st_[:, 1].sum()), "V1": int(sp[:, 0].sum()), "E1": int(sp[:, 1].sum()),
-                "S1": int(sp[:, 2].sum())}
-        launches = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count() - launches0
-        return ms, launches, work, {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in kern_ev.items()}
+            for i in range(W):
+                step(i, False)
+            exchange_flush()
+            if peer_ar is not None:
+                torch.cuda.synchronize()
+                peer_ar.stats(reset=True)
+            for w in range(R):
+                align_ranks()
+                launches0 = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count()
+                t0, t1 = ev(), ev()
+                if clocks:
+                    clocks.mark(True)
+                h0 = time.perf_counter()
+                t0.record(st_train)
+                for i in range(W + w * K, W + (w + 1) * K):
+                    step(i, True)
+                exchange_flush()                   # the last step's exchange
+                if mode == "api":                  # the host consumes the last step's output inside the window
+                    last = W + (w + 1) * K - 1
+                    y0_done[last % 2].synchronize()
+                    api_state["checksum"] += float(y0_ring[last % 2][0, 0])
+                t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes all streams
+                h1_ = time.perf_counter()
+                torch.cuda.synchronize()
+                if clocks:
+                    clocks.mark(False)
+                launches += cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count() - launches0
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                wins.append(t0.elapsed_time(t1))
+                issue_ms.append((h1_ - h0) * 1e3)
+        a, b_ = W, n_steps
+        sp, st_ = sizes_pin[a:b_].numpy().astype(np.int64), sizes_top[a:b_].numpy().astype(np.int64)
+        per_win = lambda x: [int(x[w * K:(w + 1) * K].sum()) for w in range(R)]
+        work = {"edges": per_win(sp[:, 1] + st_[:, 1]), "V1": int(sp[:, 0].sum()) / R, "E1": int(sp[:, 1].sum()) / R, "S1": int(sp[:, 2].sum()) / R}
+        kms = {k: sum(x.elapsed_time(y) for x, y in lst) / max(len(lst), 1) for k, lst in kern_ev.items()}
+        wait = peer_ar.stats(reset=True) if peer_ar is not None else None
+        return dict(ms=wins, issue_ms=issue_ms, launches=launches / R, work=work, kms=kms, wait=wait)
 
-    ms, launches, work, kms = run("async", sample_clocks=True)
-    clk = clock_box[0]
-    ms_e2e, _, work_e2e, _ = run("api")
-    ms_fused, _, work_fused, _ = run("fused")
+    clocks = ClockSampler(local)
+    res = {"fused": run("fused", clocks)}
+    clk = clocks.summary()
+    res["api"] = run("api")
+    res["materialized"] = run("materialized")
+
+    # ---- exchange correctness, on the exact path the timed region used: bit-identical to the rank-ordered fp32 sum ------------
+    exchange_check = None
+    if world > 1:
+        parts = [torch.rand(n_grad, generator=torch.Generator(device=dev).manual_seed(77 + r), device=dev) - 0.5 for r in range(world)]
+        want = parts[0].clone()
+        for q in parts[1:]:
+            want += q                                   # rank order, fp32: what the peer kernel computes
+        with torch.cuda.stream(st_train):
+            grads.copy_(grads_src)
+            if exchange == "split":
+                peer_ar.begin(grads)
+                peer_ar.end(grads)
+            elif exchange == "one":
+                st_comm.wait_stream(st_train)
+                peer_ar.all_reduce(grads)
+                st_train.wait_stream(st_comm)
+            else:
+                dist.all_reduce(grads)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(grads, want))
+        close = bool(torch.allclose(grads, want, rtol=1e-5, atol=1e-6))
+        flag = torch.tensor([1.0 if same else 0.0, 1.0 if close else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        digest = torch.tensor([float(grads.double().sum().item())], dtype=torch.float64, device=dev)
+        dmax, dmin = digest.clone(), digest.clone()
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dmin, op=dist.ReduceOp.MIN)
+        exchange_check = ("bit-identical to the rank-ordered fp32 sum on every rank" if flag[0].item() == 1.0 else
+                          "within 1e-5 of the rank-ordered sum (summation order differs)" if flag[1].item() == 1.0 else "MISMATCH")
+        if dmax.item() != dmin.item():
+            exchange_check += "; RANKS DISAGREE"
 
     def reduce(x, op):
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
+            return list(x)
+        t = torch.tensor(x, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=op)
-        return float(t.item())
+        return [float(y) for y in t.tolist()]
 
     MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
-    ms_max, ms_e2e_max, ms_fused_max = reduce(ms, MAX), reduce(ms_e2e, MAX), reduce(ms_fused, MAX)
-    edges_all, edges_e2e_all, edges_fused_all = reduce(work["edges"], SUM), reduce(work_e2e["edges"], SUM), reduce(work_fused["edges"], SUM)
-    launches_all = reduce(launches, SUM)
-    value = edges_all / (ms_max * 1e-3)
-    e2e_value = edges_e2e_all / (ms_e2e_max * 1e-3)
+
+    def summarize(r):
+        """per window: time = max over ranks, edges = sum over ranks; the reported window is the median one"""
+        ms = reduce(r["ms"], MAX)
+        edges = reduce(r["work"]["edges"], SUM)
+        order = sorted(range(R), key=lambda w: ms[w])
+        mid = order[R // 2]
+        return {"ms": ms[mid], "edges": edges[mid], "value": edges[mid] / (ms[mid] * 1e-3), "ms_per_step": ms[mid] / K,
+                "windows_ms_per_step": [round(x / K, 5) for x in ms],
+                "host_issue_ms_per_step": round(float(np.median(reduce(r["issue_ms"], MAX))) / K, 5)}
+
+    sm = {k: summarize(r) for k, r in res.items()}
+    launches_all = reduce([res["fused"]["launches"]], SUM)[0]
+    wait_all = None
+    if peer_ar is not None:
+        w_ = res["fused"]["wait"]
+        wait_all = {"mean_us_max_over_ranks": round(reduce([w_[1]], MAX)[0], 2), "max_us_over_ranks": round(reduce([w_[2]], MAX)[0], 2),
+                    "exchanges_per_rank": w_[0]}
 
     if rank == 0:
         peaks = {}
@@ -474,15 +578,19 @@ def main_b200(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        n = args.steps
-        S1, E1, V1 = work["S1"] / n, work["E1"] / n, work["V1"] / n
-        bytes_gather = S1 * (4 + 8 * F0)
-        bytes_agg = E1 * (8 + 4 * F0) + 4 * (V1 + 1) + 4 * V1 * F0
-        kernels = {"gather_rows(F=602)": {"ms": kms["gather"], "algorithmic_bytes": bytes_gather,
-                                          "gbs": bytes_gather / (kms["gather"] * 1e-3) / 1e9},
-                   "segment_reduce_fwd(F=602)": {"ms": kms["agg_fwd_602"], "algorithmic_bytes": bytes_agg,
-                                                 "gbs": bytes_agg / (kms["agg_fwd_602"] * 1e-3) / 1e9}}
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        wk = res["fused"]["work"]
+        S1, E1, V1 = wk["S1"] / K, wk["E1"] / K, wk["V1"] / K
+        wm = res["materialized"]["work"]
+        S1m, E1m, V1m = wm["S1"] / K, wm["E1"] / K, wm["V1"] / K
+        bytes_gather = S1m * (4 + 8 * F0)
+        bytes_agg = lambda e1, v1: e1 * (8 + 4 * F0) + 4 * (v1 + 1) + 4 * v1 * F0
+        kf, km = res["fused"]["kms"], res["materialized"]["kms"]
+        kernels = {"segment_reduce_fwd(F=602, rows from the feature table)": {"ms": kf["agg_fwd_602_from_table"], "algorithmic_bytes": bytes_agg(E1, V1)},
+                   "gather_rows(F=602)": {"ms": km["gather"], "algorithmic_bytes": bytes_gather},
+                   "segment_reduce_fwd(F=602, rows from X0)": {"ms": km["agg_fwd_602"], "algorithmic_bytes": bytes_agg(E1m, V1m)}}
+        for x in kernels.values():
+            x["gbs"] = x["algorithmic_bytes"] / (x["ms"] * 1e-3) / 1e9 if x["ms"] else 0.0
+        dom = "segment_reduce_fwd(F=602, rows from the feature table)"          # the dominant kernel of the headline (fused) step
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
                 "kernels": {k: {"gbs": round(x["gbs"], 1), "frac": round(x["gbs"] / peak, 3), "ms": round(x["ms"], 4),
@@ -492,7 +600,9 @@ def main_b200(args):
             try:
                 tr = json.load(open(traffic_file))
                 roof["traffic"] = tr.get(dom)
-                roof["traffic_note"] = tr.get("note")
+                roof["traffic_note"] = ("NOT measured in this run: " + str(tr.get("note")))
+                if roof["traffic"]:
+                    roof["dram_side_frac"] = roof["traffic"] / (kernels[dom]["ms"] * 1e-3) / 1e9 / peak
             except Exception:
                 pass
         cpu = None
@@ -507,35 +617,43 @@ def main_b200(args):
                                  + f"sample/gather/fwd/bwd s = {r['sample_s']:.3f}/{r['gather_s']:.3f}/{r['fwd_s']:.3f}/{r['bwd_s']:.3f}"}
             except Exception as ex:  # the checker must never take the bench down
                 cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-        line = {"metric": "sampled_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        f_, a_, m_ = sm["fused"], sm["api"], sm["materialized"]
+        ex_name = {"split": "own kernels over NVLink peer memory: nb_peer_allreduce_begin behind the backward / _end before the next top hop, in the training stream",
+                   "one": "one kernel over NVLink peer memory (nb_peer_allreduce_sum) on a communication stream", "nccl": "NCCL all_reduce on a communication stream",
+                   "none": "none (single GPU)"}[exchange]
+        line = {"metric": "sampled_edges_per_s", "value": f_["value"], "unit": "edges/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": f_["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(v, e_total, {
-                    "per_gpu_batch": BATCH, "pipeline_num": P, "row_pitch_floats": PITCH,
-                    "parallelism": (f"dp{world}: seeds sharded contiguously, one bucketed sum all-reduce of the dense grads per step ("
-                                    + ("NCCL" if args.nccl_allreduce else "one kernel over NVLink peer memory, nb_peer_allreduce_sum") + ")"
-                                    if world > 1 else "single GPU"),
-                    "avg_E_per_step": work["edges"] / n, "avg_S1": S1, "avg_E1": E1, "avg_V1": V1,
-                    "epoch_ms_est": (ms_max / args.steps) * (all_seeds.size / BATCH / world)}),
-                "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": BATCH * 4 + 64,
-                        "d2h_bytes_per_step": BATCH * F1 * 4 + 3 * 32, "ms_per_step": ms_e2e_max / args.steps,
-                        "path": "FastSampler.sample_gpu_fast(slot i+1, async, high-priority stream) || wait(slot i) -> load_feature_gpu -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
-                "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-                "fused_gather_aggregate": {"value": edges_fused_all / (ms_fused_max * 1e-3), "unit": "edges/s",
-                                           "ms_per_step": ms_fused_max / args.steps,
-                                           "note": "same results; the bottom hop aggregates straight from the feature table, X0 is never written"}}
+                "config": config_dict(v, e_total),
+                "run": {"per_gpu_batch": B, "global_batch": B * world, "pipeline_num": P, "row_pitch_floats": PITCH,
+                        "parallelism": f"dp{world}: seeds sharded contiguously; dense-gradient sum per step = {ex_name}" if world > 1 else "single GPU",
+                        "windows": R, "window_rule": "each window times exactly `steps` steps between device-aligned events; the median window is reported",
+                        "windows_ms_per_step": f_["windows_ms_per_step"], "host_issue_ms_per_step": f_["host_issue_ms_per_step"],
+                        "avg_E_per_step": f_["edges"] / K / world, "avg_S1": S1, "avg_E1": E1, "avg_V1": V1,
+                        "epoch_ms_est": f_["ms_per_step"] * (all_seeds.size / (B * world)),
+                        "bottom_hop": "aggregated straight from the feature table through the layer's global ids (load_feature_gpu(lazy) + SingleGPUAllSampleGraphOp.forward); bit-identical to gather + aggregate, X0 never written"},
+                "collective": ex_name, "exchange_check": exchange_check, "exchange_wait_us": wait_all,
+                "e2e": {"value": a_["value"], "unit": "edges/s", "h2d_bytes_per_step": B * 4 + 64,
+                        "d2h_bytes_per_step": B * F1 * 4 + 3 * 32, "ms_per_step": a_["ms_per_step"],
+                        "windows_ms_per_step": a_["windows_ms_per_step"], "host_issue_ms_per_step": a_["host_issue_ms_per_step"],
+                        "path": "FastSampler.sample_gpu_fast(slot i+1, async, high-priority stream) || wait(slot i) -> load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
+                "gpu_launches": int(round(launches_all)), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "materialized_x0": {"value": m_["value"], "unit": "edges/s", "ms_per_step": m_["ms_per_step"],
+                                    "windows_ms_per_step": m_["windows_ms_per_step"],
+                                    "note": "same step with X0 materialised first (gather kernel, then aggregation over X0), as the reference's load_feature_gpu does"}}
         print(json.dumps(line))
     if peer_ar is not None:
         assert not peer_ar.timed_out(), "peer all-reduce: a rank never arrived"
         peer_ar.close()
     if world > 1:
+        assert exchange_check is None or "MISMATCH" not in exchange_check and "DISAGREE" not in exchange_check, exchange_check
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only; the metric is quoted at 1.0)")
@@ -544,9 +662,14 @@ if __name__ == "__main__":
     ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
     ap.add_argument("--sample-priority", type=int, default=0, help="CUDA stream priority of the sampling stream (-1 = high)")
-    ap.add_argument("--nccl-allreduce", action="store_true", help="exchange the dense gradients with NCCL instead of the peer-memory kernel")
+    ap.add_argument("--exchange", default="split", choices=["split", "one", "nccl"],
+                    help="dense-gradient sum at N>1: split = peer-memory push behind the backward + reduce before the next top hop, in the "
+                         "training stream (default); one = one peer-memory kernel on a communication stream; nccl = NCCL all_reduce")
+    ap.add_argument("--windows", type=int, default=5, help="timed windows of exactly --steps steps each; the median window is reported")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: fixed global batch 1024, local batch 1024/N")
+    ap.add_argument("--materialize-x0", action="store_true", help="e2e path: gather X0 first instead of the lazy feature handle")
     ap.add_argument("--comm-late", dest="comm_early", action="store_false",
-                    help="hold the gradient all-reduce back until the next step's gather has finished (it then overlaps only the aggregation)")
+                    help="--exchange one|nccl: hold the all-reduce back until the next step's gather has finished")
     ap.set_defaults(comm_early=True)
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to nb_set_option (tuning experiments)")
     args = ap.parse_args()

@@ -103,8 +103,13 @@ int nb_device_count(int *count);
  *   "trace" / NB_TRACE : 1 = wall-clock time spent inside every entry point is accumulated (host side); 2 = the call's stream is
  *       synchronised before the clock stops (host + GPU time per call; serialises, diagnostic only). The table goes to stderr at
  *       exit or through nb_trace_dump(). Replaces the reference's get_time() accumulators (core/ntsFastSampler.hpp:30-37) and
- *       Cuda_Stream::cpu_inclusiveTime / inclusiveTime (cuda/ntsCUDA.hpp:180-198). */
+ *       Cuda_Stream::cpu_inclusiveTime / inclusiveTime (cuda/ntsCUDA.hpp:180-198).
+ *   A mirror is keyed by the host allocation it copies and lives until that allocation is released with nb_free_host (ntsFreeHost)
+ *   or nb_mirror_invalidate(ptr) is called; a lookup that finds another allocation (a different size) at the same base drops the
+ *   stale copy and mirrors again. The mirrored buffer must not be WRITTEN while its mirror is alive (call nb_mirror_invalidate
+ *   after changing it); memory released with cudaFreeHost directly, bypassing this library, must be invalidated by the caller. */
 int nb_set_option(const char *name, int value);
+int nb_mirror_invalidate(const void *host_ptr);
 int nb_trace_dump(void);
 int nb_trace_reset(void);
 
@@ -261,6 +266,14 @@ int nb_set_cache_index(nb_ctx *ctx, uint32_t *cache_map_dev, uint32_t *cache_loc
  *                          zero_copy_feature_move_gpu_cache + gather_feature_from_gpu_cache (:378-383) with
  *                          the hot/cold split done on the device in the same kernel:
  *                          slot = cache_node_hashmap[ids[i]]; slot != -1 ? cache_table[slot,:] : cold_table[ids[i],:].
+ * nb_gather_rows_indexed<- Cuda_Stream::zero_copy_feature_move_gpu_cache (slot_map == NULL) and
+ *                          Cuda_Stream::gather_feature_from_gpu_cache (slot_map = cache_node_hashmap) (cuda/ntsCUDA.hpp:378-383;
+ *                          kernels cuda/ntsCUDATransferKernel.cuh:154-183), the pair FastSampler::load_feature_gpu_cache issues after
+ *                          its CPU hot/cold split (core/ntsFastSampler.hpp:284-312): for i in [0, n):
+ *                              lid = local_idx[i]; v = ids[lid]; out[lid,:] = table[slot_map ? slot_map[v] : v, :]
+ *                          local_idx and slot_map may be mapped pinned host memory (the toolkits fill both on the CPU,
+ *                          GS_SAMPLE_PC_MULTI.hpp:955-1013). Asynchronous; the adaptor synchronises like the reference does, because
+ *                          the caller rewrites local_idx for the next batch.
  * nb_gather_labels      <- Cuda_Stream::global_copy_label_move_gpu (:384-387).
  * nb_row_override       <- Cuda_Stream::dev_load_share_embedding (:534-537), dev_load_share_aggregate (:495-497):
  *                          rows i with cache_map[destination[i]] == super_batch_id (or != -1 when
@@ -273,6 +286,9 @@ int nb_gather_rows_dyn(nb_ctx *ctx, float *out, const float *table, const uint32
 int nb_gather_rows_cached(nb_ctx *ctx, float *out, const float *cold_table, uint32_t cold_pitch, const float *cache_table,
                           uint32_t cache_pitch, const uint32_t *cache_node_hashmap_dev, const uint32_t *ids_dev,
                           uint32_t n_rows, uint32_t feature_size, uint32_t out_pitch, uint32_t *hit_count_dev_or_null);
+int nb_gather_rows_indexed(nb_ctx *ctx, float *out, uint32_t out_pitch, const float *table, uint32_t table_pitch,
+                           const uint32_t *ids_dev, const uint32_t *local_idx, const uint32_t *slot_map_or_null, uint32_t n,
+                           uint32_t feature_size);
 int nb_gather_labels(nb_ctx *ctx, int64_t *out, const int64_t *labels_dev, const uint32_t *ids_dev, uint32_t n);
 int nb_row_override(nb_ctx *ctx, float *out, const float *share, const uint32_t *cache_map_dev,
                     const uint32_t *cache_location_dev, const uint32_t *destination_dev, uint32_t n_dst,
@@ -327,20 +343,31 @@ int nb_vmm_grant(void *dev_ptr, int device);
 int nb_vmm_free(void *dev_ptr);
 
 /* ---- dense-gradient exchange over NVLink peer memory -----------------------------------------------
- * nb_peer_allreduce_sum <- Parameter::reduce_multi_gpu_gradient -> NCCL_Communicator::AllReduce (core/NtsScheduler.hpp:830-836,
- *                          cuda/ntsCUDAGraphOP.cu:173-200): in-place SUM over the ranks of one node of a small fp32 buffer (the
- *                          dense weight gradients, ~330 KB per step), as ONE kernel over peer-mapped memory: every rank's block
- *                          (nb_peer_comm_block_bytes, allocated with nb_vmm_alloc and mapped by every other rank with
- *                          nb_vmm_import) holds arrival flags and two data slots; ranks sum the slots in rank order, so the
- *                          result is bit-identical on every rank. blocks[r] = rank r's block as mapped on ctx's device
- *                          (blocks[rank] = the local allocation). Every rank calls it with the same n, in the same order; a peer
- *                          that never arrives makes the kernel give up after ~20 s (nb_peer_comm_check) instead of hanging. */
+ * Replaces Parameter::reduce_multi_gpu_gradient -> NCCL_Communicator::AllReduce (core/NtsScheduler.hpp:830-836,
+ * cuda/ntsCUDAGraphOP.cu:173-200): in-place SUM over the ranks of one node of a small fp32 buffer (the dense weight gradients,
+ * ~330 KB per step) by this library's own kernels over peer-mapped memory. Every rank's block (nb_peer_comm_block_bytes,
+ * allocated with nb_vmm_alloc and mapped by every other rank with nb_vmm_import) holds arrival flags and two slots of `world`
+ * regions. blocks[r] = rank r's block as mapped on ctx's device (blocks[rank] = the local allocation).
+ * nb_peer_allreduce_begin : PUSH -- this rank's buffer is written into its region of every rank's slot (remote stores over
+ *                           NVLink), then a flag per chunk; waits for nobody.
+ * nb_peer_allreduce_end   : REDUCE -- waits (bounded, ~20 s, then nb_peer_comm_check reports it) for every rank's flags and
+ *                           sums the regions of the LOCAL slot in rank order: bit-identical on every rank, deterministic.
+ *                           Whatever the caller enqueues between begin and end (the next batch's gather + aggregation)
+ *                           absorbs rank skew; both kernels run in ctx's stream, so they never wait for SM slots behind a
+ *                           persistent kernel of another stream. One exchange in flight per communicator.
+ * nb_peer_allreduce_sum   : both phases in ONE launch.
+ * Every rank issues the same sequence of calls with the same n.
+ * nb_peer_comm_stats      : exchanges ended, and the time their reduce phases spent polling for the slowest peer (sum / max, ns)
+ *                           since the last reset -- the rank-skew the exchange could not hide, as a number. */
 typedef struct nb_peer_comm nb_peer_comm;
-size_t nb_peer_comm_block_bytes(uint64_t max_floats);
+size_t nb_peer_comm_block_bytes(uint64_t max_floats, uint32_t world);
 int nb_peer_comm_create(nb_ctx *ctx, uint32_t rank, uint32_t world, uint64_t max_floats, void *const *blocks, nb_peer_comm **out);
 int nb_peer_comm_destroy(nb_peer_comm *c);
 int nb_peer_allreduce_sum(nb_peer_comm *c, float *inout, uint64_t n);
+int nb_peer_allreduce_begin(nb_peer_comm *c, const float *in, uint64_t n);
+int nb_peer_allreduce_end(nb_peer_comm *c, float *out, uint64_t n);
 int nb_peer_comm_check(nb_peer_comm *c, int *timed_out);
+int nb_peer_comm_stats(nb_peer_comm *c, uint64_t *exchanges, uint64_t *wait_ns_sum, uint64_t *wait_ns_max, int reset);
 
 /* ---- sparse aggregation ----------------------------------------------------------------------
  * nb_aggregate_csc_fwd <- Cuda_Stream::Gather_By_Dst_From_Src_Spmm (cuSPARSE, cuda/ntsCUDAGraphOP.cu:425-587) and

@@ -12,8 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("NTS_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
 
+# every toolkit toolkits/main.cpp dispatches to (:67-186)
 ALGORITHMS = ["GCNSAMPLEALLGPU", "GCNSAMPLEGPU", "GSSAMPLEALLGPU", "GATSAMPLEALLGPU", "GSSAMPLECACHE", "GCNSAMPLEPDCACHE",
-              "GCNSAMPLEALLMULTI", "GATSAMPLEALLMULTI", "GCNSAMPLESINGLE"]
+              "GSSAMPLEPDCACHE", "GATSAMPLEPDCACHE", "GCNSAMPLEALLMULTI", "GATSAMPLEALLMULTI", "GCNSAMPLEPCMULTI", "GSSAMPLEPCMULTI",
+              "GATSAMPLEPCMULTI", "GCNSAMPLESINGLE"]
+# toolkits whose feature load goes through FastSampler::load_feature_gpu_cache when the cfg says CACHE:1 (graph->config->cacheflag,
+# e.g. toolkits/GCN_SAMPLE_PD_CACHE.hpp:535-545): staged a second time with CACHE:1, the setting of the shipped gcn_reddit_sample.cfg
+CACHED_FEATURE_TOOLKITS = ["GCNSAMPLEPDCACHE", "GSSAMPLEPDCACHE", "GATSAMPLEPDCACHE", "GCNSAMPLEPCMULTI", "GSSAMPLEPCMULTI", "GATSAMPLEPCMULTI"]
 
 CFG = """ALGORITHM:{alg}
 VERTICES:2708
@@ -40,7 +45,7 @@ PROC_CUDA:0
 PROC_REP:0
 LOCK_FREE:1
 PUSHDOWN:0
-CACHE:0
+CACHE:{cache}
 GPU_NUM:{gpus}
 """
 
@@ -52,11 +57,17 @@ def main():
         shutil.copyfile(os.path.join(REF, "data", f), os.path.join(data, f))
     with zipfile.ZipFile(os.path.join(REF, "data", "cora.featuretable.zip")) as z:
         z.extractall(data)
+    n = 0
     for alg in ALGORITHMS:
         multi = "MULTI" in alg
-        with open(os.path.join(OUT, f"cfg_{alg}.cfg"), "w") as f:
-            f.write(CFG.format(alg=alg, batch=1024, epochs=5, pipeline=2 if "CACHE" in alg else 1, gpus=2 if multi else 1))
-    print("staged", len(ALGORITHMS), "cfgs under", OUT)
+        pipeline = 2 if ("CACHE" in alg or "PCMULTI" in alg) else 1
+        for cache in ([0, 1] if alg in CACHED_FEATURE_TOOLKITS else [0]):
+            for gpus in ([1, 2] if multi else [1]):       # the *_MULTI toolkits also run on one device (GPU_NUM:1)
+                name = f"cfg_{alg}" + ("_cache1" if cache else "") + (f"_g{gpus}" if multi else "") + ".cfg"
+                with open(os.path.join(OUT, name), "w") as f:
+                    f.write(CFG.format(alg=alg, batch=1024, epochs=5, pipeline=pipeline, gpus=gpus, cache=cache))
+                n += 1
+    print("staged", n, "cfgs under", OUT)
 
 
 if __name__ == "__main__":

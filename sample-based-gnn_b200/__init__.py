@@ -24,7 +24,7 @@ from . import _capi
 from ._capi import (NB_SAMPLER_BUILD_CSR, NB_SAMPLER_MERGE_SRC_DST, NB_SAMPLER_NO_BOTTOM_CSR, NB_SAMPLER_UP_DEGREE, NB_WEIGHT_MEAN,
                     NB_WEIGHT_MEAN_SAMPLED, NB_WEIGHT_NONE, NB_WEIGHT_SUM, LayerView, NtsError, check, lib, ptr)
 
-__all__ = ["ColdStage", "preSample", "write_pre_sample_file", "read_pre_sample_file", "set_cache_index", "Cuda_Stream", "FullyRepGraph", "FastSampler", "SampledSubgraph", "sampCSC", "WeightType",
+__all__ = ["ColdStage", "LazyFeature", "preSample", "write_pre_sample_file", "read_pre_sample_file", "set_cache_index", "Cuda_Stream", "FullyRepGraph", "FastSampler", "SampledSubgraph", "sampCSC", "WeightType",
            "SingleGPUAllSampleGraphOp", "SingleGPUSampleGraphOp", "GATFusedOp", "BatchGPUSrcDstScatterOp",
            "BatchGPUEdgeSoftMax", "BatchGPUAggregateDst", "FeatureTable", "NtsError"]
 
@@ -156,6 +156,22 @@ class Cuda_Stream:
         check(lib().nb_gather_rows_cached(self._h, ptr(dev_feature), ptr(cold_feature), feature_size,
                                           ptr(dev_cache_feature), feature_size, ptr(cache_node_hashmap), ptr(src_vertex),
                                           vertex_size, feature_size, feature_size, ptr(hit_count)))
+
+    def zero_copy_feature_move_gpu_cache(self, dev_feature, host_pinned_feature, src_vertex, feature_size, vertex_size, local_idx):
+        """:378-380 -- row local_idx[i] of dev_feature <- table row src_vertex[local_idx[i]] (the cold list of
+        FastSampler::load_feature_gpu_cache); synchronises like the reference (cuda/ntsCUDAGraphOP.cu:1744-1756)."""
+        check(lib().nb_gather_rows_indexed(self._h, ptr(dev_feature), _pitch(dev_feature, feature_size), ptr(host_pinned_feature),
+                                           _pitch(host_pinned_feature, feature_size), ptr(src_vertex), ptr(local_idx), None,
+                                           vertex_size, feature_size))
+        self.CUDA_DEVICE_SYNCHRONIZE()
+
+    def gather_feature_from_gpu_cache(self, dev_feature, dev_cache_feature, src_vertex, feature_size, vertex_size, local_idx,
+                                      cache_node_hashmap):
+        """:381-383 -- row local_idx[i] of dev_feature <- cache row cache_node_hashmap[src_vertex[local_idx[i]]] (the hot list)."""
+        check(lib().nb_gather_rows_indexed(self._h, ptr(dev_feature), _pitch(dev_feature, feature_size), ptr(dev_cache_feature),
+                                           _pitch(dev_cache_feature, feature_size), ptr(src_vertex), ptr(local_idx),
+                                           ptr(cache_node_hashmap), vertex_size, feature_size))
+        self.CUDA_DEVICE_SYNCHRONIZE()
 
     def global_copy_label_move_gpu(self, dev_label, global_dev_label, dst_vertex, vertex_size):
         check(lib().nb_gather_labels(self._h, ptr(dev_label), ptr(global_dev_label), ptr(dst_vertex), vertex_size))
@@ -410,8 +426,13 @@ class FastSampler:
         return self._finish(ssg_id, views)
 
     # -- loaders (ntsFastSampler.hpp:227-317, 400-426, 472-529)
-    def load_feature_gpu(self, cuda_stream, subgraph, local_feature, global_feature_buffer):
+    def load_feature_gpu(self, cuda_stream, subgraph, local_feature, global_feature_buffer, lazy=False):
+        """X0[i,:] = table[source_bottom[i],:] (core/ntsFastSampler.hpp:244-261). lazy=True returns a LazyFeature instead of
+        copying: the bottom hop's SingleGPU[All]SampleGraphOp.forward then aggregates straight from the table through the global
+        ids (identical bits), and X0 is written only if somebody asks for it (LazyFeature.materialize())."""
         l = subgraph.sampled_sgs[self.layer - 1]
+        if lazy:
+            return LazyFeature(cuda_stream, l, local_feature, global_feature_buffer)
         F = local_feature.shape[1]
         if local_feature.shape[0] != l.src_size:
             local_feature.resize_(l.src_size, F)
@@ -441,6 +462,28 @@ class FastSampler:
         l = subgraph.sampled_sgs[self.layer - 1]
         cuda_stream.dev_load_share_embedding(dev_embedding, share_embedding, dev_cache_map, dev_cache_location,
                                              dev_embedding.shape[1], l.dev_destination, l.v_size, super_batch_id)
+
+
+class LazyFeature:
+    """The gathered bottom-layer input X0 = table[source,:] as a promise. The only consumer in the GCN toolkits is the bottom
+    hop's aggregation (toolkits/GCN_SAMPLE_GPU.hpp:360-374), which can read the table rows through the layer's global ids
+    (sample_ans) directly: same rows, same order, same bits, and the [S,F] copy (write S*4F + read E*4F) never happens.
+    `materialize()` performs the ordinary gather for any other reader (GraphSAGE's self term, debugging)."""
+
+    def __init__(self, cuda_stream, layer, local_feature, table):
+        self.cs, self.layer_csc, self.buffer, self.table = cuda_stream, layer, local_feature, table
+        self.shape = (layer.src_size, table.shape[1])
+        self._x0 = None
+
+    def materialize(self):
+        if self._x0 is None:
+            l, F = self.layer_csc, self.shape[1]
+            buf = self.buffer
+            if buf.shape[0] != l.src_size:
+                buf = buf[:l.src_size] if buf.shape[0] > l.src_size else buf.resize_(l.src_size, F)
+            self.cs.zero_copy_feature_move_gpu(buf, self.table, l.dev_source, F, l.src_size, _pitch(self.table, F), _pitch(buf, F))
+            self._x0 = buf
+        return self._x0
 
 
 def preSample(train_ids, batch_size, pipeline_num, layers, whole_graph, cache_rate=0.8, cuda_stream=None):
@@ -566,6 +609,15 @@ class SingleGPUAllSampleGraphOp:
 
     def forward(self, f_input):
         l = self.subgraphs.sampled_sgs[self.layer]
+        if isinstance(f_input, LazyFeature):
+            if f_input.layer_csc is not l:
+                f_input = f_input.materialize()
+            else:   # bottom hop straight from the feature table: input row of edge e = table[sample_ans[e]]
+                table, F = f_input.table, f_input.shape[1]
+                out = _alloc_like_rows(l.v_size, F, table)
+                self.cuda_stream.aggregate_fwd_pitched(table, out, l.dev_e_w() if self.with_weight else None, l.dev_sample_ans,
+                                                       l.dev_c_o(), l.v_size, F, _pitch(table, F), _pitch(out, F))
+                return out
         F = f_input.shape[1]
         assert f_input.shape[0] == l.src_size
         out = _alloc_like_rows(l.v_size, F, f_input)
@@ -595,6 +647,8 @@ class SingleGPUAllSampleGraphOp:
         return grad
 
     def __call__(self, x):
+        if isinstance(x, LazyFeature):     # the gathered features are a leaf without a gradient (core/ntsContext.hpp:443)
+            return self.forward(x)
         return _AggFn.apply(x, self)
 
 

@@ -39,6 +39,7 @@ _SIGS = {
     "nb_last_error": (C.c_char_p, []),
     "nb_device_count": (I32, [C.POINTER(I32)]),
     "nb_set_option": (I32, [C.c_char_p, I32]),
+    "nb_mirror_invalidate": (I32, [P]),
     "nb_ctx_create": (I32, [I32, P, I32, C.POINTER(P)]),
     "nb_ctx_destroy": (I32, [P]),
     "nb_ctx_set_stream": (I32, [P, P]),
@@ -78,6 +79,7 @@ _SIGS = {
     "nb_aggregate_csc_fwd_dyn": (I32, [P, P, P, P, P, P, P, U32, U32, U32, U32]),
     "nb_aggregate_csr_bwd_dyn": (I32, [P, P, P, P, P, P, P, U32, U32, U32, U32]),
     "nb_gather_rows_cached": (I32, [P, P, P, U32, P, U32, P, P, U32, U32, U32, P]),
+    "nb_gather_rows_indexed": (I32, [P, P, U32, P, U32, P, P, P, U32, U32]),
     "nb_gather_labels": (I32, [P, P, P, P, U32]),
     "nb_row_override": (I32, [P, P, P, P, P, P, U32, U32, U32]),
     "nb_row_override2": (I32, [P, P, P, P, P, P, P, P, U32, U32, U32, U32]),
@@ -86,11 +88,14 @@ _SIGS = {
     "nb_stage_submit": (I32, [P, I32, P, U32, P]),
     "nb_stage_gather": (I32, [P, I32, P, U32, P, U32, P, P, C.POINTER(U32)]),
     "nb_stage_gather_table": (I32, [P, I32, P, U32, P, P, P, C.POINTER(U32)]),
-    "nb_peer_comm_block_bytes": (SZ, [U64]),
+    "nb_peer_comm_block_bytes": (SZ, [U64, U32]),
     "nb_peer_comm_create": (I32, [P, U32, U32, U64, C.POINTER(P), C.POINTER(P)]),
     "nb_peer_comm_destroy": (I32, [P]),
     "nb_peer_allreduce_sum": (I32, [P, P, U64]),
     "nb_peer_comm_check": (I32, [P, C.POINTER(I32)]),
+    "nb_peer_allreduce_begin": (I32, [P, P, U64]),
+    "nb_peer_allreduce_end": (I32, [P, P, U64]),
+    "nb_peer_comm_stats": (I32, [P, C.POINTER(U64), C.POINTER(U64), C.POINTER(U64), I32]),
     "nb_trace_dump": (I32, []),
     "nb_trace_reset": (I32, []),
     "nb_table_create": (I32, [P, U32, C.POINTER(P), U32, U32, U64, C.POINTER(P)]),

@@ -132,20 +132,43 @@ const void *nb_mirror_host(nb_ctx *ctx, const void *table, int is_adjacency) {
   std::lock_guard<std::mutex> lock(g_mirror_mutex);
   auto key = std::make_pair(ctx->device, (uintptr_t)base);
   auto it = g_mirrors.find(key);
+  if (it != g_mirrors.end() && it->second.size != size) {
+    // another allocation now lives at this base (the old one was freed behind our back): the copy is stale
+    if (it->second.mirror) { cudaStreamSynchronize(ctx->stream); cudaFree(it->second.mirror); }
+    g_mirrors.erase(it);
+    it = g_mirrors.end();
+  }
   if (it == g_mirrors.end()) {
     void *m = nullptr;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || size > free_b / 2 || cudaMalloc(&m, size) != cudaSuccess) {
       cudaGetLastError();
-      g_mirrors[key] = MirrorEntry{(uintptr_t)base, size, nullptr};  // remember the refusal, stay zero-copy
-      return table;
+      return table;   // no room right now: stay zero-copy for this call and try again on the next one
     }
     if (cudaMemcpyAsync(m, (const void *)(uintptr_t)base, size, cudaMemcpyDefault, ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(m); return table; }
     it = g_mirrors.insert(std::make_pair(key, MirrorEntry{(uintptr_t)base, size, m})).first;
   }
-  if (!it->second.mirror) return table;
   return (const void *)((const char *)it->second.mirror + ((uintptr_t)attr.devicePointer - it->second.dev_base));
+}
+// drops (and frees) every device's mirror of the host allocation that contains p; called by nb_free_host and nb_mirror_invalidate
+static void mirror_drop(const void *p) {
+  if (!p) return;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return; }
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return;
+  const uintptr_t dp = (uintptr_t)attr.devicePointer;
+  std::lock_guard<std::mutex> lock(g_mirror_mutex);
+  for (auto it = g_mirrors.begin(); it != g_mirrors.end();) {
+    if (dp >= it->second.dev_base && dp < it->second.dev_base + it->second.size) {
+      if (it->second.mirror) {
+        DeviceGuard g(it->first.first);
+        cudaDeviceSynchronize();   // kernels reading the mirror have finished
+        cudaFree(it->second.mirror);
+      }
+      it = g_mirrors.erase(it);
+    } else ++it;
+  }
 }
 void nb_mirror_host_enable(int on, int adjacency) { if (adjacency) g_mirror_adjacency = on; else g_mirror_tables = on; }
 
@@ -309,7 +332,8 @@ int nb_malloc_pinned(size_t bytes, void **out) {
   NB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable));
   return NB_OK;
 }
-int nb_free_host(void *p) { if (p) NB_CUDA(cudaFreeHost(p)); return NB_OK; }
+int nb_free_host(void *p) { if (p) { mirror_drop(p); NB_CUDA(cudaFreeHost(p)); } return NB_OK; }
+int nb_mirror_invalidate(const void *host_ptr) { mirror_drop(host_ptr); return NB_OK; }
 int nb_device_pointer(void *host_mapped, void **out) {
   NB_REQUIRE(out, NB_ERR_ARG, "out is NULL");
   NB_CUDA(cudaHostGetDevicePointer(out, host_mapped, 0));

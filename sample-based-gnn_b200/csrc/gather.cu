@@ -117,6 +117,42 @@ k_gather_rows_narrow(float *__restrict__ out, const float *__restrict__ table, u
   if (MODE == 1 && hit_count && lane == 0 && hits) atomicAdd(hit_count, hits);
 }
 
+// List-indirected gather, the reference's cached-load pair (zero_copy_feature_move_gpu_cache_kernel /
+// gather_feature_from_gpu_cache_kernel, cuda/ntsCUDATransferKernel.cuh:154-183): for i in [0, n)
+//   lid = local_idx[i];  v = ids[lid];  row = slot_map ? slot_map[v] : v;  out[lid,:] = table[row,:]
+// local_idx / slot_map may live in mapped pinned host memory (the toolkits build both on the CPU). A warp owns ROWS list
+// entries per iteration so that the three dependent index loads of ROWS rows overlap; rows move as VEC-wide vectors.
+template <int VEC, int ROWS>
+__global__ void __launch_bounds__(GATHER_THREADS)
+k_gather_rows_indexed(float *__restrict__ out, uint64_t out_pitch, const float *__restrict__ table, uint64_t table_pitch,
+                      const uint32_t *__restrict__ ids, const uint32_t *__restrict__ local_idx, const uint32_t *__restrict__ slot_map,
+                      uint32_t n, uint32_t nvec) {
+  const unsigned lane = lane_id();
+  const unsigned warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * GATHER_THREADS) >> 5;
+  for (unsigned i0 = warp * ROWS; i0 < n; i0 += warps * ROWS) {
+    uint32_t lid[ROWS], row[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) lid[r] = i0 + r < n ? local_idx[i0 + r] : 0u;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) row[r] = i0 + r < n ? ids[lid[r]] : 0u;
+    if (slot_map) {
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) row[r] = i0 + r < n ? slot_map[row[r]] : 0u;
+    }
+    for (unsigned k0 = 0; k0 < nvec; k0 += 32) {
+      const unsigned k = k0 + lane;
+      Vec<VEC> x[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++)
+        if (i0 + r < n && k < nvec) x[r].load(table + (uint64_t)row[r] * table_pitch + (uint64_t)k * VEC);
+#pragma unroll
+      for (int r = 0; r < ROWS; r++)
+        if (i0 + r < n && k < nvec) x[r].store(out + (uint64_t)lid[r] * out_pitch + (uint64_t)k * VEC);
+    }
+  }
+}
+
 // ---- TMA variant -------------------------------------------------------------------------------
 // Rows whose byte length and addresses are 16-byte aligned (row pitches that are multiples of 4 floats, e.g. the
 // 602-float Reddit row stored at pitch 608 = 19 x 128 B) move global -> shared -> global with bulk async copies
@@ -353,6 +389,24 @@ int nb_gather_rows_cached(nb_ctx *ctx, float *out, const float *cold_table, uint
   int v2 = nb_pick_vec(feature_size, cache_table, cache_pitch, out, out_pitch);
   return launch_gather<1>(ctx, out, cold_table, cold_pitch, cache_table, cache_pitch, cache_node_hashmap_dev, nullptr, 0, ids_dev,
                           n_rows, feature_size, out_pitch, hit_count_dev_or_null, v1 < v2 ? v1 : v2);
+}
+
+int nb_gather_rows_indexed(nb_ctx *ctx, float *out, uint32_t out_pitch, const float *table, uint32_t table_pitch,
+                           const uint32_t *ids_dev, const uint32_t *local_idx, const uint32_t *slot_map_or_null, uint32_t n,
+                           uint32_t feature_size) {
+  NB_REQUIRE(ctx && (n == 0 || (out && table && ids_dev && local_idx)), NB_ERR_ARG, "nb_gather_rows_indexed: NULL argument");
+  NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && out_pitch >= feature_size, NB_ERR_ARG, "nb_gather_rows_indexed: bad pitch");
+  NB_GUARD(ctx);
+  if (n == 0) return NB_OK;
+  table = (const float *)nb_mirror_host(ctx, table);
+  uint32_t fe = feature_size;
+  const int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch, &fe);
+  const unsigned grid = nb_grid(n, GATHER_THREADS / 32 * 4, 8);
+  if (vec == 4) k_gather_rows_indexed<4, 4><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, out_pitch, table, table_pitch, ids_dev, local_idx, slot_map_or_null, n, fe / 4);
+  else if (vec == 2) k_gather_rows_indexed<2, 4><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, out_pitch, table, table_pitch, ids_dev, local_idx, slot_map_or_null, n, fe / 2);
+  else k_gather_rows_indexed<1, 4><<<grid, GATHER_THREADS, 0, ctx->stream>>>(out, out_pitch, table, table_pitch, ids_dev, local_idx, slot_map_or_null, n, fe);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
 }
 
 int nb_gather_labels(nb_ctx *ctx, int64_t *out, const int64_t *labels_dev, const uint32_t *ids_dev, uint32_t n) {

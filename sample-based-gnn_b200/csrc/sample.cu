@@ -44,7 +44,10 @@ struct nb_sampler {
   uint32_t flags, max_batch;
   LayerBuf lay[NB_MAX_LAYERS];
   LayerMeta *meta_dev;   // [L+1]
-  LayerMeta *meta_host;  // pinned [L+1]
+  LayerMeta *meta_host;  // the sizes of the batch that nb_sampler_wait / a synchronous sample last completed (points into meta_ring)
+  LayerMeta *meta_ring;  // pinned [RING][NB_MAX_LAYERS+1]: every batch in flight copies its sizes into its own slot, so a second
+                         // asynchronous nb_sampler_sample before nb_sampler_wait cannot tear the sizes the host reads
+  int meta_slot;         // slot of the batch enqueued last
   uint32_t *bitmap[2], *word_rank;  // layer i marks bitmap[i & 1]; its relabel pass clears the other one for layer i + 1
   uint32_t n_words;
   unsigned long long *tile_states;  // [3 * L][max_tiles]
@@ -55,7 +58,7 @@ struct nb_sampler {
   static const int RING = 8;
   uint8_t *stage[RING];
   cudaEvent_t stage_done[RING];
-  cudaEvent_t meta_ready;  // recorded after the sizes of the latest batch reached meta_host
+  cudaEvent_t meta_ready[RING];  // recorded after the sizes of that slot's batch reached meta_ring
   int stage_next;
   uint32_t epoch;
   cudaGraphExec_t graph_exec;
@@ -587,13 +590,15 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   s->tile_states = (unsigned long long *)(base + o_state);
   s->meta_dev = (LayerMeta *)(base + o_meta);
   s->params_dev = (BatchParams *)(base + o_params);
-  NB_CUDA(cudaHostAlloc(&s->meta_host, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1), cudaHostAllocDefault));
-  memset(s->meta_host, 0, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1));
+  NB_CUDA(cudaHostAlloc(&s->meta_ring, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1) * nb_sampler::RING, cudaHostAllocDefault));
+  memset(s->meta_ring, 0, sizeof(LayerMeta) * (NB_MAX_LAYERS + 1) * nb_sampler::RING);
+  s->meta_host = s->meta_ring;
+  s->meta_slot = 0;
   for (int r = 0; r < nb_sampler::RING; r++) {
     NB_CUDA(cudaHostAlloc(&s->stage[r], sizeof(BatchParams) + (size_t)max_batch * 4, cudaHostAllocDefault));
     NB_CUDA(cudaEventCreateWithFlags(&s->stage_done[r], cudaEventDisableTiming));
+    NB_CUDA(cudaEventCreateWithFlags(&s->meta_ready[r], cudaEventDisableTiming));
   }
-  NB_CUDA(cudaEventCreateWithFlags(&s->meta_ready, cudaEventDisableTiming));
   const char *ng = getenv("NB_NO_GRAPH");
   s->use_graph = !(ng && ng[0] == '1');
   NB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -606,10 +611,9 @@ int nb_sampler_destroy(nb_sampler *s) {
   DeviceGuard guard(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-  for (int r = 0; r < nb_sampler::RING; r++) { cudaFreeHost(s->stage[r]); cudaEventDestroy(s->stage_done[r]); }
-  cudaEventDestroy(s->meta_ready);
+  for (int r = 0; r < nb_sampler::RING; r++) { cudaFreeHost(s->stage[r]); cudaEventDestroy(s->stage_done[r]); cudaEventDestroy(s->meta_ready[r]); }
   cudaFree(s->arena);
-  cudaFreeHost(s->meta_host);
+  cudaFreeHost(s->meta_ring);
   delete s;
   return NB_OK;
 }
@@ -690,6 +694,7 @@ static int run_batch(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int
   const int slot = s->stage_next;
   s->stage_next = (slot + 1) % nb_sampler::RING;
   NB_CUDA(cudaEventSynchronize(s->stage_done[slot]));  // the upload that last used this slot has completed
+  NB_CUDA(cudaEventSynchronize(s->meta_ready[slot]));  // ... and so has the copy of that batch's sizes into this slot of meta_ring
   BatchParams *hp = (BatchParams *)s->stage[slot];
   memset(hp, 0, sizeof(*hp));
   hp->rng_seed = rng_seed; hp->rng_offset = rng_offset; hp->omit = omit; hp->n_seeds = n_seeds;
@@ -731,13 +736,17 @@ static int run_batch(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int
     int rc = enqueue_kernels(s, st);
     if (rc != NB_OK) return rc;
   }
-  NB_CUDA(cudaMemcpyAsync(s->meta_host, s->meta_dev, sizeof(LayerMeta) * (s->L + 1), cudaMemcpyDeviceToHost, st));
-  NB_CUDA(cudaEventRecord(s->meta_ready, st));
+  NB_CUDA(cudaMemcpyAsync(s->meta_ring + (size_t)slot * (NB_MAX_LAYERS + 1), s->meta_dev, sizeof(LayerMeta) * (s->L + 1), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaEventRecord(s->meta_ready[slot], st));
+  s->meta_slot = slot;
   return NB_OK;
 }
 
 static int finish_batch(nb_sampler *s, nb_layer_view *views_out) {
-  NB_CUDA(cudaEventSynchronize(s->meta_ready));  // waits for this sampler's batch only, not for later work on the stream
+  // the batch enqueued last (an earlier one's arena contents are already being overwritten by it, so its sizes are the only
+  // meaningful ones); waits for that batch only, not for later work on the stream
+  NB_CUDA(cudaEventSynchronize(s->meta_ready[s->meta_slot]));
+  s->meta_host = s->meta_ring + (size_t)s->meta_slot * (NB_MAX_LAYERS + 1);
   for (int i = 0; i < s->L; i++) {
     if (s->meta_host[i].err) {
       nb_set_error("sampler layer %d: %s capacity exceeded (E=%u cap %u, S=%u cap %u)", i,

@@ -193,15 +193,26 @@ int nb_stage_submit(nb_stage *s, int slot, const uint32_t *ids_dev, uint32_t n_r
     NB_REQUIRE(sl.state != 1, NB_ERR_ARG, "nb_stage_submit: slot %d is still being staged", slot);
     sl.state = 1;
   }
-  NB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.consumed, 0));  // the merge that last read this slot's buffers has run
-  NB_CUDA(cudaMemsetAsync(sl.count_dev, 0, 4, ctx->stream));
-  if (n_rows) {
-    k_cold_split<<<nb_grid(n_rows, 256, 4), 256, 0, ctx->stream>>>(ids_dev, cache_node_hashmap_dev, n_rows, sl.cold_slot_dev, sl.cold_ids_dev, sl.count_dev);
-    NB_LAUNCH_CHECK(ctx);
-    NB_CUDA(cudaMemcpyAsync(sl.cold_ids_host, sl.cold_ids_dev, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // any failure below must leave the slot free again: a slot stuck in state 1 that was never queued would make the next
+  // nb_stage_gather wait for ever
+  auto enqueue = [&]() -> int {
+    NB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.consumed, 0));  // the merge that last read this slot's buffers has run
+    NB_CUDA(cudaMemsetAsync(sl.count_dev, 0, 4, ctx->stream));
+    if (n_rows) {
+      k_cold_split<<<nb_grid(n_rows, 256, 4), 256, 0, ctx->stream>>>(ids_dev, cache_node_hashmap_dev, n_rows, sl.cold_slot_dev, sl.cold_ids_dev, sl.count_dev);
+      NB_LAUNCH_CHECK(ctx);
+      NB_CUDA(cudaMemcpyAsync(sl.cold_ids_host, sl.cold_ids_dev, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    NB_CUDA(cudaMemcpyAsync(sl.count_host, sl.count_dev, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaEventRecord(sl.ids_ready, ctx->stream));
+    return NB_OK;
+  };
+  const int rc = enqueue();
+  if (rc != NB_OK) {
+    std::lock_guard<std::mutex> g(s->m);
+    sl.state = 0;
+    return rc;
   }
-  NB_CUDA(cudaMemcpyAsync(sl.count_host, sl.count_dev, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  NB_CUDA(cudaEventRecord(sl.ids_ready, ctx->stream));
   sl.n_rows = n_rows;
   {
     std::lock_guard<std::mutex> g(s->m);

@@ -36,16 +36,17 @@ def interleave_seeds(ids, rank, world, global_batch):
 
 
 class PeerAllReduce:
-    """In-place SUM all-reduce of a small fp32 CUDA tensor over the ranks of one node as ONE kernel over NVLink peer memory
-    (nb_peer_allreduce_sum, csrc/peer.cu) -- no NCCL call on the step's critical path. Each rank's block (arrival flags + two
-    data slots) is a cuMemCreate allocation shared by POSIX descriptor, like the sharded table's shards. Ranks are summed in
-    rank order: bit-identical results on every rank. Enqueued on `cuda_stream`'s stream."""
+    """In-place SUM all-reduce of a small fp32 CUDA tensor over the ranks of one node by this library's own kernels over NVLink
+    peer memory (csrc/peer.cu) -- no NCCL call on the step's critical path. Each rank's block (arrival flags + two slots of
+    `world` regions) is a cuMemCreate allocation shared by POSIX descriptor, like the sharded table's shards. Push based:
+    begin() writes this rank's buffer into every rank's slot and signals, end() waits for every rank's flags and sums the local
+    slot in rank order (bit-identical on every rank); all_reduce() does both in one launch. Enqueued on `cuda_stream`'s stream."""
 
     def __init__(self, cuda_stream, max_floats):
         import os
         self.cs, self.max_floats = cuda_stream, int(max_floats)
         rank, world = dist.get_rank(), dist.get_world_size()
-        nbytes = int(lib().nb_peer_comm_block_bytes(self.max_floats))
+        nbytes = int(lib().nb_peer_comm_block_bytes(self.max_floats, world))
         self._local, fd = C.c_void_p(), C.c_int(-1)
         check(lib().nb_vmm_alloc(cuda_stream._h, nbytes, C.byref(self._local), C.byref(fd)))
         peer_fds = exchange_fds(fd.value)
@@ -68,6 +69,21 @@ class PeerAllReduce:
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_floats
         check(lib().nb_peer_allreduce_sum(self._h, t.data_ptr(), t.numel()))
         return t
+
+    def begin(self, t):
+        """push phase: nothing waits; enqueue the work that should hide the rank skew, then end()"""
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_floats
+        check(lib().nb_peer_allreduce_begin(self._h, t.data_ptr(), t.numel()))
+
+    def end(self, t):
+        check(lib().nb_peer_allreduce_end(self._h, t.data_ptr(), t.numel()))
+        return t
+
+    def stats(self, reset=True):
+        """(exchanges ended, mean us, max us) the reduce phases spent waiting for the slowest rank since the last reset"""
+        n, s, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().nb_peer_comm_stats(self._h, C.byref(n), C.byref(s), C.byref(m), 1 if reset else 0))
+        return n.value, (s.value / n.value / 1e3 if n.value else 0.0), m.value / 1e3
 
     def timed_out(self):
         e = C.c_int(0)
@@ -104,7 +120,14 @@ class GradBucket:
             self.flat[off:off + p.numel()].copy_(g.reshape(-1))
             off += p.numel()
         if self.peer is not None:
+            # the pack / unpack copies run on torch's current stream, the exchange on the peer's own: order them both ways
+            cur = torch.cuda.current_stream(self.flat.device)
+            peer_stream = torch.cuda.ExternalStream(self.peer.cs.stream or 0, device=self.flat.device)
+            if peer_stream.cuda_stream != cur.cuda_stream:
+                peer_stream.wait_stream(cur)
             self.peer.all_reduce(self.flat)
+            if peer_stream.cuda_stream != cur.cuda_stream:
+                cur.wait_stream(peer_stream)
         elif dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         off = 0

@@ -347,12 +347,21 @@ public:
   void zero_copy_feature_move_gpu(float *dev_feature, float *pinned_host_feature, VertexId_CUDA *src_vertex, VertexId_CUDA feature_size, VertexId_CUDA vertex_size) {
     NTS_B200_CHECK(nb_gather_rows(ctx, dev_feature, pinned_host_feature, src_vertex, vertex_size, feature_size, feature_size, feature_size));
     total_transfer_node += vertex_size; }
-  /* the reference splits hot/cold rows on the CPU into local_idx lists and runs one kernel per list; both lists index the same
-   * output rows, so each call gathers its list through an id indirection */
-  void zero_copy_feature_move_gpu_cache(float *, float *, VertexId_CUDA *, VertexId_CUDA, VertexId_CUDA, VertexId_CUDA *) {
-    NTS_B200_UNSUPPORTED("zero_copy_feature_move_gpu_cache (use gather_feature_cached: the hot/cold split happens on the device)"); }
-  void gather_feature_from_gpu_cache(float *, float *, VertexId_CUDA *, VertexId_CUDA, VertexId_CUDA, VertexId_CUDA *, VertexId_CUDA *) {
-    NTS_B200_UNSUPPORTED("gather_feature_from_gpu_cache (use gather_feature_cached: the hot/cold split happens on the device)"); }
+  /* FastSampler::load_feature_gpu_cache (core/ntsFastSampler.hpp:263-317) splits the bottom layer's sources into a cold and a hot
+   * list on the CPU (positions into dev_source, written to mapped pinned arrays) and issues one call per list: row local_idx[i] of
+   * dev_feature <- host table row src_vertex[local_idx[i]] / cache row cache_node_hashmap[src_vertex[local_idx[i]]]. Both synchronise
+   * (cuda/ntsCUDAGraphOP.cu:1744-1770): the caller refills the lists for the next batch right away. */
+  void zero_copy_feature_move_gpu_cache(float *dev_feature, float *host_pinned_feature, VertexId_CUDA *src_vertex, VertexId_CUDA feature_size,
+                                        VertexId_CUDA vertex_size, VertexId_CUDA *local_idx) {
+    total_transfer_node += vertex_size;
+    NTS_B200_CHECK(nb_gather_rows_indexed(ctx, dev_feature, feature_size, host_pinned_feature, feature_size, src_vertex, local_idx, NULL,
+                                          vertex_size, feature_size));
+    CUDA_DEVICE_SYNCHRONIZE(); }
+  void gather_feature_from_gpu_cache(float *dev_feature, float *dev_cache_feature, VertexId_CUDA *src_vertex, VertexId_CUDA feature_size,
+                                     VertexId_CUDA vertex_size, VertexId_CUDA *local_idx, VertexId_CUDA *cache_node_hashmap) {
+    NTS_B200_CHECK(nb_gather_rows_indexed(ctx, dev_feature, feature_size, dev_cache_feature, feature_size, src_vertex, local_idx,
+                                          cache_node_hashmap, vertex_size, feature_size));
+    CUDA_DEVICE_SYNCHRONIZE(); }
   /* new: FastSampler::load_feature_gpu_cache in one call (core/ntsFastSampler.hpp:263-317) */
   void gather_feature_cached(float *dev_feature, float *cold_feature, float *dev_cache_feature, VertexId_CUDA *dev_cache_node_hashmap, VertexId_CUDA *src_vertex,
                              VertexId_CUDA feature_size, VertexId_CUDA vertex_size, VertexId_CUDA *dev_hit_count = NULL) {

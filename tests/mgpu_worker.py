@@ -65,6 +65,34 @@ def main():
             torch.cuda._sleep(2_000_000)          # this rank arrives ~1 ms late
         par.all_reduce(mine_t)
         assert torch.equal(mine_t.cpu(), want), f"rank {rank}: peer all-reduce mismatch at exchange {it} (n={n})"
+    # split form: push, unrelated work in the same stream, then reduce; late ranks; stats; begin/end misuse is rejected
+    filler = torch.empty(1 << 22, device="cuda")
+    for it in range(24):
+        n = [82304, 5, 4096][it % 3]
+        parts = [torch.randn(n, generator=torch.Generator().manual_seed(5000 + 10 * it + r)) for r in range(world)]
+        want = parts[0].clone()
+        for q in parts[1:]:
+            want += q
+        mine_t = parts[rank].cuda()
+        if it % 4 == rank % 4:
+            torch.cuda._sleep(1_000_000)
+        par.begin(mine_t)
+        filler.fill_(float(it))                    # the work that hides the skew
+        out_t = torch.empty_like(mine_t)
+        par.end(out_t)
+        assert torch.equal(out_t.cpu(), want), f"rank {rank}: split exchange mismatch at {it} (n={n})"
+        assert torch.equal(mine_t.cpu(), parts[rank]), "begin() must not modify its input"
+    n_ex, mean_us, max_us = par.stats()
+    assert n_ex >= 24 and max_us < 5e6, (n_ex, mean_us, max_us)
+    t4 = torch.ones(4, device="cuda")
+    par.begin(t4)
+    try:
+        par.begin(t4)
+        raise AssertionError("a second begin() before end() must be rejected")
+    except nts.NtsError:
+        pass
+    par.end(t4)
+    assert torch.equal(t4.cpu(), torch.full((4,), float(world)))
     assert not par.timed_out()
     wp = torch.nn.Parameter(torch.zeros(64, 3, device="cuda"))
     wp.grad = torch.full_like(wp, float(rank + 1))

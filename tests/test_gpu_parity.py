@@ -425,6 +425,31 @@ def test_cached_gather_labels_and_row_override(nts, cs):
     assert np.array_equal(f32(tf_), oracle.row_override(feat, share_f, cache_map, cache_loc, dst, 2))
 
 
+@pytest.mark.parametrize("F,hot_frac", [(100, 0.25), (602, 0.1), (1433, 0.2), (7, 0.0), (128, 1.0)])
+def test_cached_load_pair_in_the_reference_call_shape(nts, cs, F, hot_frac):
+    """FastSampler::load_feature_gpu_cache as the reference issues it (core/ntsFastSampler.hpp:284-312): a CPU split of the bottom
+    layer's sources into a cold and a hot position list held in MAPPED PINNED host arrays, then one indexed gather per list. The two
+    calls together must equal the oracle's cached gather, bit for bit (and the fused nb_gather_rows_cached)."""
+    V, S = 5000, 3000
+    rng = np.random.default_rng(11)
+    table_np = rng.standard_normal((V, F)).astype(np.float32)
+    hot = np.sort(rng.permutation(V)[:int(V * hot_frac)]).astype(np.uint32)
+    cache_np = table_np[hot] + np.float32(1000.0) if hot.size else np.zeros((1, F), np.float32)
+    hashmap = np.full(V, 0xFFFFFFFF, np.uint32)
+    hashmap[hot] = np.arange(hot.size, dtype=np.uint32)
+    src_np = np.sort(rng.permutation(V)[:S]).astype(np.uint32)          # dev_source: distinct, ascending
+    ref = oracle.gather_rows_cached(table_np, cache_np, hashmap, src_np)
+    is_hot = hashmap[src_np] != 0xFFFFFFFF
+    pin = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory()
+    local_idx, local_idx_cache = pin(np.flatnonzero(~is_hot).astype(np.uint32)), pin(np.flatnonzero(is_hot).astype(np.uint32))
+    h_hashmap, cold = pin(hashmap), pin(table_np)
+    out = torch.full((S, F), float("nan"), device="cuda")
+    src = torch.from_numpy(src_np.view(np.int32)).cuda()
+    cs.zero_copy_feature_move_gpu_cache(out, cold, src, F, int(local_idx.numel()), local_idx)
+    cs.gather_feature_from_gpu_cache(out, torch.from_numpy(cache_np).cuda(), src, F, int(local_idx_cache.numel()), local_idx_cache, h_hashmap)
+    assert np.array_equal(bits(f32(out)), bits(ref))
+
+
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("F", [8, 41, 128])
 def test_gat_legacy_ops_and_fused_layer(nts, cs, F):
@@ -669,6 +694,17 @@ def test_padded_rows_and_tma_gather_match_dense(nts, cs):
     y_f = torch.empty((lay.v_size, P), device="cuda")
     cs.aggregate_fwd_pitched(padded, y_f, lay.dev_e_w(), lay.dev_sample_ans, lay.dev_c_o(), lay.v_size, F, P, P)
     assert torch.equal(y_f[:, :F], y_d)
+    # the same through the operator surface: load_feature_gpu(lazy=True) hands the op a promise instead of X0
+    for tab in (dense, padded[:, :F]):
+        buf = torch.full((lay.src_size + 3, tab.stride(0)), 5.0, device="cuda")[:, :F]
+        lz = sampler.load_feature_gpu(cs, sg, buf, tab, lazy=True)
+        assert isinstance(lz, nts.LazyFeature) and lz.shape == (lay.src_size, F)
+        y_l = op.forward(lz)
+        assert torch.equal(y_l, y_d) and bool((buf == 5.0).all())          # nothing was copied
+        assert torch.equal(op(lz), y_d)                                     # autograd wrapper accepts the promise too
+        assert torch.equal(lz.materialize(), x_d)                           # any other reader gets the ordinary gather
+        top = nts.SingleGPUAllSampleGraphOp(sg, 0, cs)                      # a promise handed to the wrong hop is materialised first
+        assert top.forward(torch.ones((sg.sampled_sgs[0].src_size, 4), device="cuda")).shape[0] == sg.sampled_sgs[0].v_size
 
 
 def test_async_sampling_pipeline_slots_and_no_bottom_csr(nts, cs):

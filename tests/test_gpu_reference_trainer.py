@@ -13,8 +13,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 BIN = os.path.join(REFDIR, "nts_b200")
 
-TOOLKITS = ["GCNSAMPLEALLGPU", "GCNSAMPLEGPU", "GSSAMPLEALLGPU", "GATSAMPLEALLGPU", "GSSAMPLECACHE", "GCNSAMPLEPDCACHE"]
-MULTI_GPU_TOOLKITS = ["GCNSAMPLEALLMULTI", "GATSAMPLEALLMULTI"]   # GPU_NUM:2 -- one thread per GPU + NCCL_Communicator of the adaptor
+TOOLKITS = ["GCNSAMPLEALLGPU", "GCNSAMPLEGPU", "GSSAMPLEALLGPU", "GATSAMPLEALLGPU", "GSSAMPLECACHE", "GCNSAMPLEPDCACHE", "GSSAMPLEPDCACHE",
+            "GATSAMPLEPDCACHE"]
+# CACHE:1 (the shipped gcn_reddit_sample.cfg's setting): the feature load goes through FastSampler::load_feature_gpu_cache ->
+# zero_copy_feature_move_gpu_cache + gather_feature_from_gpu_cache (core/ntsFastSampler.hpp:263-317)
+CACHED = ["GCNSAMPLEPDCACHE_cache1", "GSSAMPLEPDCACHE_cache1", "GATSAMPLEPDCACHE_cache1"]
+# one thread per GPU + the adaptor's NCCL_Communicator; GPU_NUM:1 runs everywhere, GPU_NUM:2 where the box has two GPUs
+MULTI = ["GCNSAMPLEALLMULTI", "GATSAMPLEALLMULTI", "GCNSAMPLEPCMULTI", "GSSAMPLEPCMULTI", "GATSAMPLEPCMULTI",
+         "GCNSAMPLEPCMULTI_cache1", "GSSAMPLEPCMULTI_cache1", "GATSAMPLEPCMULTI_cache1"]
+CASES = TOOLKITS + CACHED + [f"{m}_g{g}" for m in MULTI for g in (1, 2)]
 
 
 def _gpus():
@@ -26,20 +33,21 @@ def _gpus():
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/nts_b200 not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("alg", TOOLKITS + MULTI_GPU_TOOLKITS)
-def test_reference_trainer_runs_on_libnts_b200(alg):
-    if alg in MULTI_GPU_TOOLKITS and _gpus() < 2:
+@pytest.mark.parametrize("case", CASES)
+def test_reference_trainer_runs_on_libnts_b200(case):
+    if case.endswith("_g2") and _gpus() < 2:
         pytest.skip("needs 2 GPUs")
     import glob
     for f in glob.glob(os.path.join(REFDIR, "data", "*pre_sample*.bin")):   # hot-vertex lists a previous toolkit left behind
         os.remove(f)
-    r = subprocess.run([BIN, f"cfg_{alg}.cfg"], cwd=REFDIR, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([BIN, f"cfg_{case}.cfg"], cwd=REFDIR, capture_output=True, text=True, timeout=300)
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
+    assert "is not provided by libnts_b200" not in out, out[-2000:]
     accs = [float(m.group(1)) for m in re.finditer(r"Train Acc: ([0-9.]+)", out)]
     losses = [float(m.group(1)) for m in re.finditer(r"Epoch\[\d+\]:Times\[[^\]]*\]:loss\s+([0-9.eE+-]+)", out)]
     assert len(accs) >= 4, out[-2000:]
-    if alg not in MULTI_GPU_TOOLKITS:                 # the *_MULTI toolkits print the epoch time without the loss
+    if "MULTI" not in case:                           # the *_MULTI toolkits print the epoch time without the loss
         assert len(losses) >= 4, out[-2000:]
     assert max(accs[-2:]) >= 0.70, accs               # cora, 5 epochs (the reference's own log reaches 0.93 after 10;
                                                       # the *CACHE toolkits train on bounded-stale hot embeddings and start slower)
