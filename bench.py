@@ -38,6 +38,7 @@ FANOUT, BATCH = [25, 10], 1024
 TRAIN_FRAC = 0.66
 SEED_GRAPH, SEED_SHUFFLE, SEED_SAMPLER = 0x5EED0001, 0x5EED0003, 0x5EED0004
 REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+REF_GPU_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_driver")
 
 
 def reddit_shaped_graph(scale=1.0):
@@ -133,12 +134,20 @@ def write_reference_inputs(td, v, col_off, src, seeds):
     return ef, sf
 
 
-def run_reference_driver(v, col_off, src, seeds, batches, warmup, threads):
+def run_reference_driver(v, col_off, src, seeds, batches, warmup, threads, gpu_box=None):
+    """the reference's own CPU path (oracle/_ref/ref_driver); gpu_box (a list) additionally receives the reference's own GPU
+    path on the same inputs (oracle/_ref/ref_gpu_driver: its CUDA kernels + cuSPARSE compiled for sm_100) when that binary exists"""
     with tempfile.TemporaryDirectory() as td:
         ef, sf = write_reference_inputs(td, v, col_off, src, seeds)
         env = dict(os.environ, NTS_ORACLE_CPUS=str(threads + 1), OMP_NUM_THREADS=str(threads))
-        out = subprocess.run([REF_DRIVER, "bench", ef, str(v), sf, str(BATCH), ",".join(map(str, FANOUT)), str(F0), str(F1),
-                              str(batches), str(warmup)], capture_output=True, text=True, env=env, check=True).stdout
+        argv = ["bench", ef, str(v), sf, str(BATCH), ",".join(map(str, FANOUT)), str(F0), str(F1)]
+        out = subprocess.run([REF_DRIVER] + argv + [str(batches), str(warmup)], capture_output=True, text=True, env=env, check=True).stdout
+        if gpu_box is not None and os.path.exists(REF_GPU_DRIVER):
+            try:
+                g = subprocess.run([REF_GPU_DRIVER] + argv + ["30", "5"], capture_output=True, text=True, env=env, timeout=600)
+                gpu_box.append(json.loads([l for l in g.stdout.splitlines() if l.startswith("{")][-1]))
+            except Exception as ex:  # a reported extra, never fatal
+                gpu_box.append({"failed": str(ex)[:300]})
     return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
 
 
@@ -172,11 +181,11 @@ def run_oracle_port(v, col_off, src, seeds, batches, warmup):
     return acc
 
 
-def cpu_baseline_run(v, col_off, src, seeds, batches, warmup):
+def cpu_baseline_run(v, col_off, src, seeds, batches, warmup, gpu_box=None):
     """(result dict, kind, cores): the reference's own OpenMP path when its driver is present, else the C port"""
     if os.path.exists(REF_DRIVER):
         threads = os.cpu_count() or 1
-        return run_reference_driver(v, col_off, src, seeds, batches, warmup, threads), "reference", threads
+        return run_reference_driver(v, col_off, src, seeds, batches, warmup, threads, gpu_box), "reference", threads
     return run_oracle_port(v, col_off, src, seeds, min(batches, 5), min(warmup, 1)), "port", 1
 
 
@@ -508,8 +517,9 @@ def main_b200(args):
     clocks = ClockSampler(local)
     res = {"fused": run("fused", clocks)}
     clk = clocks.summary()
-    res["api"] = run("api")
-    res["materialized"] = run("materialized")
+    modes = args.modes.split(",")
+    res["api"] = run("api") if "api" in modes else res["fused"]                     # --modes: tuning sweeps skip the other arms
+    res["materialized"] = run("materialized") if "materialized" in modes else res["fused"]
 
     # ---- exchange correctness, on the exact path the timed region used: bit-identical to the rank-ordered fp32 sum ------------
     exchange_check = None
@@ -584,7 +594,9 @@ def main_b200(args):
         S1m, E1m, V1m = wm["S1"] / K, wm["E1"] / K, wm["V1"] / K
         bytes_gather = S1m * (4 + 8 * F0)
         bytes_agg = lambda e1, v1: e1 * (8 + 4 * F0) + 4 * (v1 + 1) + 4 * v1 * F0
-        kf, km = res["fused"]["kms"], res["materialized"]["kms"]
+        kf, km = res["fused"]["kms"], dict(res["materialized"]["kms"])
+        if "materialized" not in modes:
+            km["gather"] = km["agg_fwd_602"] = 0.0
         kernels = {"segment_reduce_fwd(F=602, rows from the feature table)": {"ms": kf["agg_fwd_602_from_table"], "algorithmic_bytes": bytes_agg(E1, V1)},
                    "gather_rows(F=602)": {"ms": km["gather"], "algorithmic_bytes": bytes_gather},
                    "segment_reduce_fwd(F=602, rows from X0)": {"ms": km["agg_fwd_602"], "algorithmic_bytes": bytes_agg(E1m, V1m)}}
@@ -606,9 +618,10 @@ def main_b200(args):
             except Exception:
                 pass
         cpu = None
+        ref_gpu_box = []
         if world == 1 and not args.no_cpu_baseline:
             try:
-                r, kind, threads = cpu_baseline_run(v, col_off, src, all_seeds, args.cpu_batches, 2)
+                r, kind, threads = cpu_baseline_run(v, col_off, src, all_seeds, args.cpu_batches, 2, ref_gpu_box)
                 val, _ = cpu_metric(r)
                 cpu = {"value": val, "unit": "edges/s", "cores": threads, "kind": kind,
                        "sample": f"{r['batches']} mini-batches of {BATCH} seeds of the same workload through "
@@ -617,6 +630,26 @@ def main_b200(args):
                                  + f"sample/gather/fwd/bwd s = {r['sample_s']:.3f}/{r['gather_s']:.3f}/{r['fwd_s']:.3f}/{r['bwd_s']:.3f}"}
             except Exception as ex:  # the checker must never take the bench down
                 cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        ref_gpu = None
+        if ref_gpu_box:
+            g = ref_gpu_box[0]
+            ref_gpu = dict(g)
+            if "failed" not in g and g.get("batches"):
+                nbg = g["batches"]
+                ref_gpu["what"] = ("the reference's own GPU path on this box, same graph / seeds / batch (oracle/_ref/ref_gpu_driver = /root/reference/cuda/"
+                                   "ntsCUDAGraphOP.cu built for sm_100 + its FastSampler): sample_gpu_fast (host wall clock, it round-trips through the "
+                                   "host), zero_copy_feature_move_gpu from its pinned-host table and from an HBM copy, cuSPARSE SpMM fwd F=602 / F=128, "
+                                   "bwd F=128; CUDA events, mean ms per batch")
+                ref_step = g["sample_ms"] + g["gather_host_table_ms"] + g["spmm_fwd_F0_ms"] + g["spmm_fwd_F1_ms"] + g["spmm_bwd_F1_ms"]
+                ref_step_hbm = ref_step - g["gather_host_table_ms"] + g["gather_hbm_table_ms"]
+                ref_gpu["serial_step_ms"] = ref_step
+                ref_gpu["serial_step_ms_with_hbm_table"] = ref_step_hbm
+                ref_gpu["edges_per_s"] = g["edges"] / nbg / (ref_step * 1e-3)
+                ref_gpu["edges_per_s_with_hbm_table"] = g["edges"] / nbg / (ref_step_hbm * 1e-3)
+                ref_gpu["ours_over_reference_gpu"] = {
+                    "step (value / reference with HBM table)": round(sm["fused"]["value"] / ref_gpu["edges_per_s_with_hbm_table"], 2),
+                    "gather kernel (HBM table)": round(g["gather_hbm_table_ms"] / km["gather"], 2) if km["gather"] else None,
+                    "aggregate fwd F=602 (vs cuSPARSE)": round(g["spmm_fwd_F0_ms"] / km["agg_fwd_602"], 2) if km["agg_fwd_602"] else None}
         f_, a_, m_ = sm["fused"], sm["api"], sm["materialized"]
         ex_name = {"split": "own kernels over NVLink peer memory: nb_peer_allreduce_begin behind the backward / _end before the next top hop, in the training stream",
                    "one": "one kernel over NVLink peer memory (nb_peer_allreduce_sum) on a communication stream", "nccl": "NCCL all_reduce on a communication stream",
@@ -637,7 +670,7 @@ def main_b200(args):
                         "d2h_bytes_per_step": B * F1 * 4 + 3 * 32, "ms_per_step": a_["ms_per_step"],
                         "windows_ms_per_step": a_["windows_ms_per_step"], "host_issue_ms_per_step": a_["host_issue_ms_per_step"],
                         "path": "FastSampler.sample_gpu_fast(slot i+1, async, high-priority stream) || wait(slot i) -> load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
-                "gpu_launches": int(round(launches_all)), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": int(round(launches_all)), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
                 "materialized_x0": {"value": m_["value"], "unit": "edges/s", "ms_per_step": m_["ms_per_step"],
                                     "windows_ms_per_step": m_["windows_ms_per_step"],
                                     "note": "same step with X0 materialised first (gather kernel, then aggregation over X0), as the reference's load_feature_gpu does"}}
@@ -665,6 +698,7 @@ if __name__ == "__main__":
     ap.add_argument("--exchange", default="split", choices=["split", "one", "nccl"],
                     help="dense-gradient sum at N>1: split = peer-memory push behind the backward + reduce before the next top hop, in the "
                          "training stream (default); one = one peer-memory kernel on a communication stream; nccl = NCCL all_reduce")
+    ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of exactly --steps steps each; the median window is reported")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: fixed global batch 1024, local batch 1024/N")
     ap.add_argument("--materialize-x0", action="store_true", help="e2e path: gather X0 first instead of the lazy feature handle")

@@ -42,6 +42,9 @@ def test_reference_trainer_runs_on_libnts_b200(case):
         os.remove(f)
     r = subprocess.run([BIN, f"cfg_{case}.cfg"], cwd=REFDIR, capture_output=True, text=True, timeout=300)
     out = r.stdout + r.stderr
+    if os.environ.get("NB_TRAINER_LOGS"):              # keep every case's full output (diagnostics on the GPU box)
+        os.makedirs(os.environ["NB_TRAINER_LOGS"], exist_ok=True)
+        open(os.path.join(os.environ["NB_TRAINER_LOGS"], f"trainer_{case}.log"), "w").write(f"rc={r.returncode}\n" + out)
     assert r.returncode == 0, out[-3000:]
     assert "is not provided by libnts_b200" not in out, out[-2000:]
     accs = [float(m.group(1)) for m in re.finditer(r"Train Acc: ([0-9.]+)", out)]
