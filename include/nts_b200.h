@@ -100,6 +100,9 @@ int nb_device_count(int *count);
  *       (the buffer must not change after that); 0 (default) = gather over PCIe like the reference
  *   "mirror_host_adjacency" / NB_MIRROR_HOST_ADJACENCY : 1 (default) = the same for the adjacency array that the stage-shaped
  *       sampling calls receive as a mapped host pointer (core/ntsFastSampler.hpp:159-166); the topology never changes after load
+ *   "sampler_fused" / NB_SAMPLER_FUSED : 1 (default) = samplers created afterwards use the small-shape kernels (a layer's prefix
+ *       sums recomputed per block in shared memory: 2 launches per layer instead of 4) wherever the layer fits; 0 = general path only.
+ *       Both give identical results.
  *   "trace" / NB_TRACE : 1 = wall-clock time spent inside every entry point is accumulated (host side); 2 = the call's stream is
  *       synchronised before the clock stops (host + GPU time per call; serialises, diagnostic only). The table goes to stderr at
  *       exit or through nb_trace_dump(). Replaces the reference's get_time() accumulators (core/ntsFastSampler.hpp:30-37) and

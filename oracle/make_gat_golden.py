@@ -26,7 +26,10 @@ from refio import read_record  # noqa: E402
 DRIVER = os.path.join(HERE, "_ref", "ref_gpu_driver")
 # name: (n_dst, n_src_extra, max_fanout, F, seed, hub)  -- hub: one source that most columns point at (long CSR row)
 CASES = {"f8": (200, 300, 12, 8, 1, False), "f41_ragged": (333, 500, 25, 41, 2, False), "f128_hub": (500, 2500, 10, 128, 3, True),
-         "f128_reddit_hop": (1024, 22000, 25, 128, 4, False)}
+         "f128_top_hop": (1024, 3000, 25, 128, 4, False)}
+# per-edge [E,2F] / [E,F] intermediates are kept only for the small cases (they are pure copies / products of kept arrays)
+KEEP_EDGE_TENSORS = {"f8"}
+EDGE_TENSORS = ["e_msg", "d_e_msg", "e_msg_out", "d_e_msg_out", "cached"]
 
 
 def layer(n_dst, n_extra, max_f, seed, hub):
@@ -70,6 +73,9 @@ def main(out_dir):
                                                     "att": att, "dout": dout.ravel()})
             subprocess.run([DRIVER, "gat", fin, fout], check=True)
             rec = read_record(fout)["graph"]
+        if name not in KEEP_EDGE_TENSORS:
+            for k in EDGE_TENSORS:
+                rec.pop(k, None)
         np.savez_compressed(os.path.join(out_dir, f"gat_{name}.npz"), column_offset=co, row_indices=ri, dst_local_id=dl, n_src=np.uint32(S),
                             F=np.uint32(F), h=h, att=att, dout=dout, **rec)
         print(name, "E =", ri.size, {k: v.shape for k, v in rec.items()})

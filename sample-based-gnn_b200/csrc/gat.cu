@@ -125,7 +125,11 @@ k_gat_node_scores(const float *__restrict__ h, const float *__restrict__ att, fl
 
 __device__ __forceinline__ float lrelu(float s, float slope) { return s > 0.f ? s : slope * s; }
 
-template <int VEC, int CHUNK>
+// One warp per dst column. Columns of <= 32 edges (every sampled column: fanout <= 32) keep the edge's source id and score in
+// the lane that owns the edge: ONE gather of al[src] per edge, max / sum by shuffles, weights straight from registers
+// (the general path below re-reads al[row_indices[e]] in three passes). UNR input rows are in flight before the first
+// accumulate, as in k_segment_reduce; accumulation order is the column's stored order either way.
+template <int VEC, int CHUNK, int UNR>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_fwd(const float *__restrict__ h, const float *__restrict__ al, const float *__restrict__ ar, float slope,
           const uint32_t *__restrict__ col_off, const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ dl,
@@ -134,34 +138,58 @@ k_gat_fwd(const float *__restrict__ h, const float *__restrict__ al, const float
   for (unsigned d = warp; d < n_dst; d += warps) {
     const uint32_t beg = col_off[d], end = col_off[d + 1];
     const float ard = (beg < end) ? ar[dl[d]] : 0.f;
-    float mx = -INFINITY;
-    for (uint32_t e = beg + lane; e < end; e += 32) mx = fmaxf(mx, lrelu(al[row_indices[e]] + ard, slope));
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (uint32_t e = beg + lane; e < end; e += 32) sum += expf(lrelu(al[row_indices[e]] + ard, slope) - mx);
-    sum = warp_sum(sum);
+    const bool short_col = end - beg <= 32u;
+    uint32_t my_idx = 0;
+    float my_s = 0.f, mx = -INFINITY, sum = 0.f;
+    if (short_col) {
+      const bool mine = beg + lane < end;
+      if (mine) { my_idx = row_indices[beg + lane]; my_s = al[my_idx] + ard; }
+      mx = warp_max(mine ? lrelu(my_s, slope) : -INFINITY);
+      sum = warp_sum(mine ? expf(lrelu(my_s, slope) - mx) : 0.f);
+    } else {
+      for (uint32_t e = beg + lane; e < end; e += 32) mx = fmaxf(mx, lrelu(al[row_indices[e]] + ard, slope));
+      mx = warp_max(mx);
+      for (uint32_t e = beg + lane; e < end; e += 32) sum += expf(lrelu(al[row_indices[e]] + ard, slope) - mx);
+      sum = warp_sum(sum);
+    }
     for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {
       Vec<VEC> acc[CHUNK];
 #pragma unroll
       for (int c = 0; c < CHUNK; c++) acc[c].zero();
       for (uint32_t j0 = beg; j0 < end; j0 += 32) {
         const uint32_t cnt = min(32u, end - j0);
-        uint32_t my_idx = 0;
         float my_w = 0.f;
         if (lane < cnt) {
-          my_idx = row_indices[j0 + lane];
-          const float s = al[my_idx] + ard;
-          my_w = expf(lrelu(s, slope) - mx) / sum;
-          if (c0 == 0) { score_pre[j0 + lane] = s; alpha[j0 + lane] = my_w; }
+          if (!short_col) { my_idx = row_indices[j0 + lane]; my_s = al[my_idx] + ard; }
+          my_w = expf(lrelu(my_s, slope) - mx) / sum;
+          if (c0 == 0) { score_pre[j0 + lane] = my_s; alpha[j0 + lane] = my_w; }
         }
-        for (uint32_t t = 0; t < cnt; t++) {
-          const uint32_t s0 = __shfl_sync(FULL_MASK, my_idx, t);
-          const float w0 = __shfl_sync(FULL_MASK, my_w, t);
-          const float *p0 = h + (uint64_t)s0 * pitch;
+        for (uint32_t t = 0; t < cnt; t += UNR) {
+          Vec<VEC> x[UNR][CHUNK];
+          float w[UNR];
 #pragma unroll
-          for (int c = 0; c < CHUNK; c++) {
-            const unsigned k = c0 + c * 32 + lane;
-            if (k < nvec) { Vec<VEC> x; x.load(p0 + (uint64_t)k * VEC); acc[c].axpy(x, w0); }
+          for (int u = 0; u < UNR; u++) {
+            const uint32_t tt = t + u < cnt ? t + u : t;
+            const uint32_t s0 = __shfl_sync(FULL_MASK, my_idx, tt);
+            w[u] = __shfl_sync(FULL_MASK, my_w, tt);
+            const float *p0 = h + (uint64_t)s0 * pitch;
+            if (t + u < cnt) {
+#pragma unroll
+              for (int c = 0; c < CHUNK; c++) {
+                const unsigned k = c0 + c * 32 + lane;
+                if (k < nvec) x[u][c].load(p0 + (uint64_t)k * VEC);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; u++) {
+            if (t + u < cnt) {
+#pragma unroll
+              for (int c = 0; c < CHUNK; c++) {
+                const unsigned k = c0 + c * 32 + lane;
+                if (k < nvec) acc[c].axpy(x[u][c], w[u]);
+              }
+            }
           }
         }
       }
@@ -299,14 +327,13 @@ k_gat_bwd_rows(const float *__restrict__ alpha, const float *__restrict__ ds, co
 // datt[0:F] += sum_s rs[s] h[s,:];  datt[F:2F] += sum_d dsum[d] h[dl[d],:]
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_att(const float *__restrict__ h, const float *__restrict__ rs, const float *__restrict__ dd, uint32_t n_src, uint32_t F,
-              float *__restrict__ datt) {
+              float *__restrict__ partial) {
   // one pass over H. A block owns a contiguous slice of rows; thread (g, k) sums feature column k over the rows g, g+G, ... of the
   // slice (G = blockDim / F row groups when F <= blockDim), four rows in flight; the groups are combined in shared memory and
-  // the block adds its 2F partial sums to datt. dd[s] is the column total of the dst that equals src s (0 if s is not a dst).
+  // the block writes its 2F partial sums for stage 2. dd[s] is the column total of the dst that equals src s (0 if s is not a dst).
   __shared__ float s_a[GAT_THREADS], s_b[GAT_THREADS];
   const unsigned rows_per_block = (n_src + gridDim.x - 1) / gridDim.x;
-  const unsigned r0 = blockIdx.x * rows_per_block, r1 = min(n_src, r0 + rows_per_block);
-  if (r0 >= r1) return;
+  const unsigned r0 = min(n_src, blockIdx.x * rows_per_block), r1 = min(n_src, r0 + rows_per_block);   // an empty slice writes zeros
   const unsigned G = F <= GAT_THREADS ? GAT_THREADS / F : 1;
   const unsigned g = threadIdx.x / (F <= GAT_THREADS ? F : GAT_THREADS), lanes = F <= GAT_THREADS ? F : GAT_THREADS;
   for (unsigned k0 = 0; k0 < F; k0 += lanes) {
@@ -331,11 +358,20 @@ k_gat_bwd_att(const float *__restrict__ h, const float *__restrict__ rs, const f
     __syncthreads();
     if (g == 0 && k < F) {
       for (unsigned gg = 1; gg < G; gg++) { a += s_a[gg * lanes + threadIdx.x]; b += s_b[gg * lanes + threadIdx.x]; }
-      atomicAdd(&datt[k], a);
-      atomicAdd(&datt[F + k], b);
+      partial[(uint64_t)blockIdx.x * 2 * F + k] = a;       // no float atomics: stage 2 sums the block partials in block order
+      partial[(uint64_t)blockIdx.x * 2 * F + F + k] = b;
     }
     __syncthreads();
   }
+}
+// stage 2: datt[k] = sum over blocks, in block order (deterministic run to run)
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_att_reduce(const float *__restrict__ partial, uint32_t n_blocks, uint32_t n2f, float *__restrict__ datt) {
+  const unsigned k = blockIdx.x * GAT_THREADS + threadIdx.x;
+  if (k >= n2f) return;
+  float acc = 0.f;
+  for (uint32_t b = 0; b < n_blocks; b++) acc += partial[(uint64_t)b * n2f + k];
+  datt[k] = acc;
 }
 
 template <int VEC>
@@ -343,7 +379,7 @@ static int launch_gat_fwd(nb_ctx *ctx, const float *h, const float *al, const fl
                           const uint32_t *ri, const uint32_t *dl, uint32_t n_dst, uint32_t F, float *pre, float *alpha, float *out) {
   const uint32_t nvec = F / VEC, per_lane = (nvec + 31) / 32;
   const unsigned grid = nb_grid(n_dst, GAT_THREADS / 32, 8);
-#define NB_GAT(C) k_gat_fwd<VEC, C><<<grid, GAT_THREADS, 0, ctx->stream>>>(h, al, ar, slope, co, ri, dl, n_dst, nvec, F, pre, alpha, out)
+#define NB_GAT(C) k_gat_fwd<VEC, C, (C <= 2 ? 4 : 2)><<<grid, GAT_THREADS, 0, ctx->stream>>>(h, al, ar, slope, co, ri, dl, n_dst, nvec, F, pre, alpha, out)
   if (per_lane <= 1) NB_GAT(1); else if (per_lane <= 2) NB_GAT(2); else if (per_lane <= 4) NB_GAT(4);
   else if (per_lane <= 8) NB_GAT(8); else NB_GAT(12);
 #undef NB_GAT
@@ -442,9 +478,10 @@ int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
   NB_CUDA(cudaMemsetAsync(datt, 0, (size_t)2 * F * 4, ctx->stream));
   if (n_src == 0) return NB_OK;
   float *scratch;
-  int rc = nb_ctx_scratch(ctx, ((size_t)2 * n_edges + n_dst + 2 * (size_t)n_src + 64) * sizeof(float), (void **)&scratch);
+  const unsigned att_blocks = (unsigned)min((uint64_t)ctx->sm_count * 8, ((uint64_t)n_src + 15) / 16);   // >= 16 rows of H per block
+  int rc = nb_ctx_scratch(ctx, ((size_t)2 * n_edges + n_dst + 2 * (size_t)n_src + 64 + (size_t)att_blocks * 2 * F) * sizeof(float), (void **)&scratch);
   if (rc) return rc;
-  float *ds = scratch, *wcsr = ds + n_edges, *dsum = wcsr + n_edges, *rs = dsum + n_dst + 8, *dd = rs + n_src + 8;
+  float *ds = scratch, *wcsr = ds + n_edges, *dsum = wcsr + n_edges, *rs = dsum + n_dst + 8, *dd = rs + n_src + 8, *partial = dd + n_src + 8;
   if (n_dst) {
     const int vec = nb_pick_vec(F, h, F, dout, F);
     const uint32_t nvec = F / vec, per_lane = (nvec + 31) / 32;
@@ -468,7 +505,9 @@ int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
   // dh[s,:] = sum_j alpha[e_j] dout[dst_j,:] + rs[s] att[0:F] + dd[s] att[F:2F]: the tuned CSR segment reduction with a rank-2 epilogue
   rc = nb_run_segment(ctx, false, dout, dh, wcsr, column_indices, row_offset, n_src, F, nullptr, F, F, rs, dd, att, att + F);
   if (rc) return rc;
-  k_gat_bwd_att<<<NB_SM_COUNT * 8, GAT_THREADS, 0, ctx->stream>>>(h, rs, dd, n_src, F, datt);
+  k_gat_bwd_att<<<att_blocks, GAT_THREADS, 0, ctx->stream>>>(h, rs, dd, n_src, F, partial);
+  NB_LAUNCH_CHECK(ctx);
+  k_gat_att_reduce<<<(2 * F + GAT_THREADS - 1) / GAT_THREADS, GAT_THREADS, 0, ctx->stream>>>(partial, att_blocks, 2 * F, datt);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
 }

@@ -163,7 +163,7 @@ int nb_hotness(nb_ctx *ctx, nb_graph *g, const uint32_t *seeds, uint32_t n_seeds
     NB_LAUNCH_CHECK(ctx);
   }
   HotOp op{cnt, cache_ids_dev, st, V, capacity};
-  ScanWs ws{tiles, params};
+  ScanWs ws = nb_scan_ws(tiles, n_tiles, params);
   k_scan<HotOp><<<nb_grid(V, SCAN_TILE, 4), SCAN_THREADS, 0, s>>>(op, ws);
   NB_LAUNCH_CHECK(ctx);
   if (counts_dev_or_null) NB_CUDA(cudaMemcpyAsync(counts_dev_or_null, cnt, (size_t)V * 4, cudaMemcpyDeviceToDevice, s));

@@ -197,7 +197,7 @@ extern "C" int nb_graph_create_from_pairs(nb_ctx *ctx, uint32_t n_vertices, uint
       k_rs_hist<<<nb_grid(n_tiles, 1, 8), RS_THREADS, 0, st>>>(t.keys[a], E, shift, n_tiles, t.tile_hist);
       NB_LAUNCH_CHECK(ctx);
       FlatScanOp op{t.tile_hist, t.tile_hist, nullptr, (uint32_t)n_hist};
-      ScanWs ws{t.tile_state, t.params + p};
+      ScanWs ws = nb_scan_ws(t.tile_state, scan_tiles, t.params + p);
       k_scan<FlatScanOp><<<nb_grid(n_hist, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(op, ws);
       NB_LAUNCH_CHECK(ctx);
       k_rs_scatter<<<nb_grid(n_tiles, 1, 4), RS_THREADS, 0, st>>>(t.keys[a], vbuf[a], E, shift, n_tiles, t.tile_hist, t.keys[b], vbuf[b]);
@@ -206,7 +206,7 @@ extern "C" int nb_graph_create_from_pairs(nb_ctx *ctx, uint32_t n_vertices, uint
   }
   {  // column_offset = exclusive scan of the in-degree histogram (before the clamp)
     FlatScanOp op{g->in_deg, g->col_off, g->col_off + V, V};
-    ScanWs ws{t.tile_state, t.params + 6};
+    ScanWs ws = nb_scan_ws(t.tile_state, scan_tiles, t.params + 6);
     k_scan<FlatScanOp><<<nb_grid(V, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(op, ws);
     NB_LAUNCH_CHECK(ctx);
   }

@@ -32,10 +32,14 @@ struct LayerBuf {
   uint32_t *destination, *column_offset, *sample_ans, *row_indices, *edge_dst, *source;
   uint32_t *row_offset, *row_count, *row_cursor, *column_indices, *csr_tmp, *csr_to_csc, *long_rows;
   uint32_t *dst_local_id, *src_to_dst;
+  uint32_t *dst_base, *dst_deg;   // [cap_dst] g_col_off[d] and the in-degree of every dst, written by whoever produced `destination`
+                                  // (the previous layer's source emission; layer 0: the sampling kernel itself)
   float *ewf, *ewb;
 };
 
 #define NB_MAX_LAYERS 8
+static int g_sampler_fused = -1;   // "sampler_fused" / NB_SAMPLER_FUSED: 1 (default) = small-shape path where it fits, 0 = general path only
+void nb_sampler_set_fused(int on) { g_sampler_fused = on; }
 struct nb_sampler {
   nb_ctx *ctx;
   nb_graph *g;
@@ -64,6 +68,7 @@ struct nb_sampler {
   cudaGraphExec_t graph_exec;
   uint64_t graph_kernels;
   bool use_graph;
+  int fused;   // small-shape path: 2 kernels per layer (+2 for a CSR) instead of 4 (+4); see k_sample_fused
 };
 
 // counts = min(deg, fanout) (fanout -1: deg), 0 for omitted dst; scan -> column_offset; total -> E.
@@ -315,7 +320,9 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
           uint32_t *__restrict__ dst_local_id, uint32_t *__restrict__ src_to_dst, const LayerMeta *meta, int histogram,
           int fuse_weights, float *__restrict__ ewf, const uint32_t *__restrict__ edge_dst, const uint32_t *__restrict__ col_off,
           const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg, const BatchParams *params,
-          uint32_t *__restrict__ source, uint32_t n_words, uint32_t *__restrict__ other_bitmap) {
+          uint32_t *__restrict__ source, uint32_t n_words, uint32_t *__restrict__ other_bitmap,
+          const uint32_t *__restrict__ g_col_off = nullptr, uint32_t *__restrict__ next_base = nullptr,
+          uint32_t *__restrict__ next_deg = nullptr) {
   const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
   // the next layer marks the other bitmap: clear it here, off the critical path (no memset node per layer)
   if (other_bitmap)
@@ -328,7 +335,15 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
     const unsigned lane = lane_id();
     for (unsigned w = tid >> 5; w < n_words; w += stride >> 5) {
       const uint32_t bits = bitmap[w];
-      if (bits & (1u << lane)) source[word_rank[w] + __popc(bits & ((1u << lane) - 1u))] = w * 32u + lane;
+      if (bits & (1u << lane)) {
+        const uint32_t k = word_rank[w] + __popc(bits & ((1u << lane) - 1u)), v = w * 32u + lane;
+        source[k] = v;
+        if (next_base) {   // the next layer's dst list is this `source`: its sampler finds base / degree without touching g_col_off
+          const uint32_t b = g_col_off[v];
+          next_base[k] = b;
+          next_deg[k] = g_col_off[v + 1] - b;
+        }
+      }
     }
   }
   for (unsigned e = tid; e < E; e += stride) {
@@ -391,23 +406,44 @@ __device__ __forceinline__ void csr_emit(uint32_t pos, uint32_t e, uint32_t *col
 __global__ void __launch_bounds__(256)
 k_csr_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restrict__ csr_tmp, uint32_t *__restrict__ column_indices,
            uint32_t *__restrict__ csr_to_csc, const uint32_t *__restrict__ edge_dst, float *__restrict__ ewb,
-           const float *__restrict__ ewf, uint32_t *__restrict__ long_rows, LayerMeta *meta, const BatchParams *params) {
+           const float *__restrict__ ewf, uint32_t *__restrict__ long_rows, LayerMeta *meta, const BatchParams *params,
+           int inline_long = 0) {
   if (meta->err) return;
   if (params->weight_type == NB_WEIGHT_NONE) ewb = nullptr;
   const unsigned S = meta->n_src;
-  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-    const uint32_t a = row_offset[s], n = row_offset[s + 1] - a;
-    if (n > CSR_SHORT) { long_rows[atomicAdd(&meta->long_rows, 1u)] = s; continue; }  // hub source: queued for a whole warp
-    uint32_t ev[CSR_SHORT];
+  const unsigned lane = lane_id();
+  const unsigned S_round = (S + 31u) & ~31u;   // whole warps stay together for the cooperative long-row pass
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < S_round; s += gridDim.x * blockDim.x) {
+    uint32_t a = 0, n = 0;
+    if (s < S) { a = row_offset[s]; n = row_offset[s + 1] - a; }
+    const bool is_long = n > CSR_SHORT;
+    if (is_long && !inline_long) long_rows[atomicAdd(&meta->long_rows, 1u)] = s;  // hub source: queued for k_csr_long_rows
+    if (!is_long && n) {
+      uint32_t ev[CSR_SHORT];
 #pragma unroll
-    for (uint32_t i = 0; i < CSR_SHORT; i++) ev[i] = i < n ? csr_tmp[a + i] : 0xffffffffu;
+      for (uint32_t i = 0; i < CSR_SHORT; i++) ev[i] = i < n ? csr_tmp[a + i] : 0xffffffffu;
 #pragma unroll
-    for (uint32_t i = 0; i < CSR_SHORT; i++) {
-      if (i < n) {
-        uint32_t rank = 0;
+      for (uint32_t i = 0; i < CSR_SHORT; i++) {
+        if (i < n) {
+          uint32_t rank = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < CSR_SHORT; k++) rank += (ev[k] < ev[i]);
-        csr_emit(a + rank, ev[i], column_indices, csr_to_csc, edge_dst, ewb, ewf);
+          for (uint32_t k = 0; k < CSR_SHORT; k++) rank += (ev[k] < ev[i]);
+          csr_emit(a + rank, ev[i], column_indices, csr_to_csc, edge_dst, ewb, ewf);
+        }
+      }
+    }
+    if (inline_long) {   // a hub source is ordered by the whole warp (rank counting, O(n^2/32)), not by one thread
+      unsigned pending = __ballot_sync(FULL_MASK, is_long);
+      while (pending) {
+        const int owner = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const uint32_t ra = __shfl_sync(FULL_MASK, a, owner), rn = __shfl_sync(FULL_MASK, n, owner);
+        for (uint32_t i = lane; i < rn; i += 32) {
+          const uint32_t e = csr_tmp[ra + i];
+          uint32_t rank = 0;
+          for (uint32_t k = 0; k < rn; k++) rank += (__ldg(&csr_tmp[ra + k]) < e);
+          csr_emit(ra + rank, e, column_indices, csr_to_csc, edge_dst, ewb, ewf);
+        }
       }
     }
   }
@@ -431,6 +467,290 @@ k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restr
       for (uint32_t k = 0; k < n; k++) rank += (__ldg(&csr_tmp[a + k]) < e);
       csr_emit(a + rank, e, column_indices, csr_to_csc, edge_dst, ewb, ewf);
     }
+  }
+}
+
+// =============================================================================================
+// Small-shape path. A 1024-seed mini-batch is latency bound, not bandwidth bound: a layer has 1K-25K dst and 25K-250K
+// edges, and the general pipeline above spends most of its time in launch gaps and in chains of dependent loads
+// (11 launches, ~8 us each). When the per-layer arrays fit in shared memory every block recomputes the layer's prefix
+// sums for itself (a few tens of KB from L2) instead of waiting for a separate scan kernel:
+//   k_sample_fused   = count + exclusive scan (in smem, per block) + neighbour selection + bitmap marks
+//   k_relabel_fused  = popcount scan of the dedup bitmap (in smem, per block) + `source` emission + relabel + histogram +
+//                      weights (+ the next layer's per-dst adjacency base / degree, so its sampler skips one dependent load)
+//   k_csr_fill_fused = row_offset scan (in smem, per block) + stable-fill step 1;  k_csr_rows handles long rows itself
+// i.e. 2 launches per layer (+2 for a layer whose CSR is built): 6 instead of 11 for the benchmark's two layers.
+// Results are bit-identical to the general path (same arithmetic, same ordering rules); tests run both.
+constexpr int FS_THREADS = 512;   // two such blocks fit an SM: they find room next to a training-stream kernel sooner than one 1024-thread block
+constexpr size_t FS_SMEM_MAX = 200 * 1024;
+
+// exclusive prefix of one value per thread over the block; *total = block sum. s_warp: 33 words of shared memory.
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *s_warp, unsigned *total) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();   // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < nwarps ? s_warp[lane] : 0u, wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(FULL_MASK, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[warp] + incl - v;
+}
+
+// in place: s_v[0..n) values -> exclusive prefix sums, s_v[n] = total (returned). Every thread of the block calls it.
+__device__ __forceinline__ unsigned block_scan_array(unsigned *s_v, unsigned n, unsigned *s_warp) {
+  const unsigned ipt = (n + blockDim.x - 1) / blockDim.x;
+  const unsigned a = min(n, threadIdx.x * ipt), b = min(n, a + ipt);
+  unsigned sum = 0;
+  for (unsigned i = a; i < b; i++) sum += s_v[i];
+  unsigned total;
+  unsigned run = block_excl_scan(sum, s_warp, &total);
+  for (unsigned i = a; i < b; i++) { const unsigned c = s_v[i]; s_v[i] = run; run += c; }
+  if (threadIdx.x == 0) s_v[n] = total;
+  __syncthreads();
+  return total;
+}
+
+// One sampling layer's count + scan + neighbour selection. Selection code and RNG counters are those of k_sample: same draws.
+template <int GROUP>
+__global__ void __launch_bounds__(FS_THREADS)
+k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_row_idx, const uint32_t *__restrict__ dst,
+               uint32_t *__restrict__ dst_base, uint32_t *__restrict__ dst_deg, int dense, uint32_t *__restrict__ col_off,
+               uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst, uint32_t *__restrict__ bitmap, LayerMeta *meta,
+               const LayerMeta *prev, int fanout, const BatchParams *params, uint32_t layer, int merge, int bottom, int hash_slots,
+               uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor, uint32_t *__restrict__ src_to_dst,
+               uint32_t cap_src, uint32_t cap_edges, uint32_t cap_dst) {
+  extern __shared__ uint32_t s_dyn[];   // [cap_dst + 1] counts -> offsets, then the per-warp hash sets (fanout > 32)
+  __shared__ unsigned s_warp[33];
+  uint32_t *s_off = s_dyn;
+  uint32_t *s_hash = s_dyn + ((cap_dst + 1 + 31) & ~31u);
+  const unsigned n_dst = prev ? (prev->err ? 0u : meta->n_dst) : params->n_seeds;
+  const uint32_t *omit = bottom ? params->omit : nullptr;
+  const uint32_t omit_value = params->omit_value;
+  const int replay = params->replay;
+  // 1. counts (every block, redundantly: n_dst words from L2), exactly CountOp::load
+  for (unsigned i = threadIdx.x; i < n_dst; i += FS_THREADS) {
+    uint32_t deg;
+    if (dense) deg = dst_deg[i];
+    else {
+      const uint32_t d = dst[i], b = g_col_off[d];
+      deg = g_col_off[d + 1] - b;
+      if (blockIdx.x == 0) { dst_base[i] = b; dst_deg[i] = deg; }
+    }
+    uint32_t c = (fanout < 0 || deg < (uint32_t)fanout) ? deg : (uint32_t)fanout;
+    if (omit) {
+      const uint32_t f = omit[dst[i]];
+      if (omit_value == 0xffffffffu ? (f != 0xffffffffu) : (f == omit_value)) c = 0;
+    }
+    s_off[i] = c;
+  }
+  __syncthreads();
+  // 2. exclusive scan -> column offsets
+  const unsigned E = block_scan_array(s_off, n_dst, s_warp);
+  const unsigned err = (prev && prev->err) ? prev->err : (E > cap_edges ? 1u : 0u);
+  if (blockIdx.x == 0) {
+    for (unsigned i = threadIdx.x; i <= n_dst; i += FS_THREADS) col_off[i] = s_off[i];
+    if (threadIdx.x == 0) { meta->n_dst = n_dst; meta->n_edges = E; meta->n_src = 0; meta->long_rows = 0; meta->err = err; }
+  }
+  if (err) return;
+  if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
+    const unsigned bound = min(cap_src, E + (merge ? n_dst : 0u));
+    for (unsigned k = blockIdx.x * FS_THREADS + threadIdx.x; k < bound; k += gridDim.x * FS_THREADS) {
+      row_count[k] = 0;
+      row_cursor[k] = 0;
+      if (src_to_dst) src_to_dst[k] = 0xffffffffu;
+    }
+  }
+  // 3. neighbour selection (see k_sample for the rule and the RNG counter layout)
+  const uint64_t key = params->rng_seed ^ (params->rng_offset >> 32 << 32);
+  const uint32_t rng_offset = (uint32_t)params->rng_offset;
+  const unsigned lane = lane_id();
+  constexpr unsigned GPW = 32 / GROUP;
+  const unsigned gl = lane % GROUP, gid = lane / GROUP;
+  const unsigned gmask = GROUP == 32 ? FULL_MASK : (((1u << GROUP) - 1u) << (gid * GROUP));
+  const unsigned groups = gridDim.x * (FS_THREADS / 32) * GPW;
+  uint32_t *my_hash = s_hash + (threadIdx.x >> 5) * hash_slots;
+  const Philox rng(key);
+  for (unsigned j = (blockIdx.x * (FS_THREADS / 32) + (threadIdx.x >> 5)) * GPW + gid; j < n_dst; j += groups) {
+    const uint32_t off = s_off[j];
+    const uint32_t num = s_off[j + 1] - off;
+    uint32_t base, deg;
+    if (dense) { base = dst_base[j]; deg = dst_deg[j]; }
+    else { const uint32_t d = dst[j]; base = g_col_off[d]; deg = g_col_off[d + 1] - base; }
+    if (merge && gl == 0) { const uint32_t d = dst[j]; atomicOr(&bitmap[d >> 5], 1u << (d & 31)); }
+    if (num == 0) continue;
+    if (replay) {
+      for (uint32_t t = gl; t < num; t += GROUP) {
+        uint32_t v = sample_ans[off + t];
+        edge_dst[off + t] = j;
+        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+      }
+    } else if (num == deg) {  // take all, stored order
+      for (uint32_t t = gl; t < num; t += GROUP) {
+        uint32_t v = g_row_idx[base + t];
+        sample_ans[off + t] = v;
+        edge_dst[off + t] = j;
+        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+      }
+    } else if (num <= GROUP) {
+      const bool holder = gl < num;
+      const unsigned holders = __ballot_sync(gmask, holder) & gmask;
+      bool need = holder;
+      uint32_t pos = 0xffffffffu;
+      uint4 r = make_uint4(0, 0, 0, 0);
+      for (unsigned round = 0;; round++) {
+        if (need) {
+          if ((round & 3) == 0) r = rng(j, gl + 32u * (round >> 2), layer, rng_offset);
+          uint32_t x = (round & 3) == 0 ? r.x : (round & 3) == 1 ? r.y : (round & 3) == 2 ? r.z : r.w;
+          pos = __umulhi(x, deg);
+        }
+        bool keep = true;
+        if (holder) {
+          unsigned grp = __match_any_sync(holders, pos);
+          unsigned settled = __ballot_sync(holders, !need);
+          keep = !need || ((grp & settled) == 0 && lane == (unsigned)(__ffs(grp) - 1));
+        }
+        need = !keep;
+        if (!__any_sync(gmask, need)) break;
+      }
+      if (holder) {
+        uint32_t v = g_row_idx[base + pos];
+        sample_ans[off + gl] = v;
+        edge_dst[off + gl] = j;
+        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+      }
+    } else if (GROUP == 32) {  // fanout > 32: shared-memory set, 32 draws per round
+      for (int t = lane; t < hash_slots; t += 32) my_hash[t] = 0xffffffffu;
+      __syncwarp();
+      uint32_t have = 0;
+      for (unsigned round = 0; have < num; round++) {
+        const uint32_t want = num - have;
+        const bool active = lane < want;
+        bool won = false;
+        uint32_t pos = 0;
+        if (active) {
+          uint4 r = rng(j, lane + 32u * round, layer, rng_offset);
+          pos = __umulhi(r.x, deg);
+          uint32_t h = (pos * 2654435761u) & (hash_slots - 1);
+          while (true) {
+            uint32_t old = atomicCAS(&my_hash[h], 0xffffffffu, pos);
+            if (old == 0xffffffffu) { won = true; break; }
+            if (old == pos) break;
+            h = (h + 1) & (hash_slots - 1);
+          }
+        }
+        unsigned wins = __ballot_sync(FULL_MASK, won);
+        if (won) {
+          uint32_t slot = have + __popc(wins & ((1u << lane) - 1));
+          uint32_t v = g_row_idx[base + pos];
+          sample_ans[off + slot] = v;
+          edge_dst[off + slot] = j;
+          atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        }
+        have += __popc(wins);
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// dedup + relabel of one layer: bitmap ranks in shared memory, `source` ascending, local ids, CSR histogram, weights, and the next
+// layer's per-dst adjacency base / degree (its dst list IS this `source`). Same results as k_scan<BitmapOp> + k_relabel.
+__global__ void __launch_bounds__(FS_THREADS)
+k_relabel_fused(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ bitmap,
+                uint32_t *__restrict__ row_count, const uint32_t *__restrict__ dst, uint32_t *__restrict__ dst_local_id,
+                uint32_t *__restrict__ src_to_dst, LayerMeta *meta, LayerMeta *next_meta, int histogram, int fuse_weights,
+                float *__restrict__ ewf, const uint32_t *__restrict__ edge_dst, const uint32_t *__restrict__ col_off,
+                const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg, const BatchParams *params,
+                uint32_t *__restrict__ source, uint32_t n_words, uint32_t *__restrict__ other_bitmap, uint32_t cap_src,
+                const uint32_t *__restrict__ g_col_off, uint32_t *__restrict__ next_base, uint32_t *__restrict__ next_deg) {
+  extern __shared__ uint32_t s_dyn[];   // [n_words] bits, [n_words + 1] ranks
+  __shared__ unsigned s_warp[33];
+  uint32_t *s_bits = s_dyn, *s_rank = s_dyn + ((n_words + 31) & ~31u);
+  const unsigned stride = gridDim.x * FS_THREADS, tid = blockIdx.x * FS_THREADS + threadIdx.x;
+  if (other_bitmap)
+    for (unsigned w = tid; w <= n_words; w += stride) other_bitmap[w] = 0u;
+  if (meta->err) return;
+  for (unsigned w = threadIdx.x; w < n_words; w += FS_THREADS) {
+    const uint32_t b = bitmap[w];
+    s_bits[w] = b;
+    s_rank[w] = __popc(b);
+  }
+  __syncthreads();
+  const unsigned S = block_scan_array(s_rank, n_words, s_warp);
+  if (tid == 0) {
+    meta->n_src = S;
+    if (S > cap_src) meta->err = 2;
+    next_meta->n_dst = S;
+  }
+  if (S > cap_src) return;
+  const unsigned E = meta->n_edges, nd = meta->n_dst;
+  const int weight_type = params->weight_type;
+  {
+    const unsigned lane = lane_id();
+    for (unsigned w = tid >> 5; w < n_words; w += stride >> 5) {
+      const uint32_t bits = s_bits[w];
+      if (bits & (1u << lane)) {
+        const uint32_t k = s_rank[w] + __popc(bits & ((1u << lane) - 1u)), v = w * 32u + lane;
+        source[k] = v;
+        if (next_base) {   // consecutive lanes hold consecutive vertices: coalesced
+          const uint32_t b = g_col_off[v];
+          next_base[k] = b;
+          next_deg[k] = g_col_off[v + 1] - b;
+        }
+      }
+    }
+  }
+  for (unsigned e = tid; e < E; e += stride) {
+    const uint32_t v = sample_ans[e];
+    const uint32_t local = s_rank[v >> 5] + __popc(s_bits[v >> 5] & ((1u << (v & 31)) - 1u));
+    row_indices[e] = local;
+    if (histogram) atomicAdd(&row_count[local], 1u);
+    if (fuse_weights && weight_type != NB_WEIGHT_NONE) {
+      const uint32_t j = edge_dst[e];
+      ewf[e] = edge_weight_fn(out_deg[v], in_deg[dst[j]], col_off[j + 1] - col_off[j], weight_type);
+    }
+  }
+  if (dst_local_id)
+    for (unsigned j = tid; j < nd; j += stride) {
+      const uint32_t v = dst[j];
+      const uint32_t local = s_rank[v >> 5] + __popc(s_bits[v >> 5] & ((1u << (v & 31)) - 1u));
+      dst_local_id[j] = local;
+      src_to_dst[local] = j;
+    }
+}
+
+// CSR build step 1 with the row-offset scan done per block in shared memory (same results as k_scan<RowOp> + k_csr_fill)
+__global__ void __launch_bounds__(FS_THREADS)
+k_csr_fill_fused(const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_offset,
+                 uint32_t *__restrict__ row_cursor, uint32_t *__restrict__ csr_tmp, const LayerMeta *meta) {
+  extern __shared__ uint32_t s_dyn[];   // [n_src + 1]
+  __shared__ unsigned s_warp[33];
+  const unsigned S = meta->err ? 0u : meta->n_src;
+  for (unsigned i = threadIdx.x; i < S; i += FS_THREADS) s_dyn[i] = row_count[i];
+  __syncthreads();
+  block_scan_array(s_dyn, S, s_warp);
+  if (blockIdx.x == 0)
+    for (unsigned i = threadIdx.x; i <= S; i += FS_THREADS) row_offset[i] = s_dyn[i];
+  if (meta->err) return;
+  const unsigned E = meta->n_edges;
+  for (unsigned e = blockIdx.x * FS_THREADS + threadIdx.x; e < E; e += gridDim.x * FS_THREADS) {
+    const uint32_t s = row_indices[e];
+    csr_tmp[s_dyn[s] + atomicAdd(&row_cursor[s], 1u)] = e;
   }
 }
 
@@ -526,7 +846,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   size_t words = 0;              // arena size in 4-byte words
   auto take = [&](size_t n) { size_t at = words; words += (n + 31) & ~(size_t)31; return at; };
   struct Off { size_t destination, column_offset, sample_ans, row_indices, edge_dst, source, row_offset, row_count, row_cursor,
-               column_indices, csr_tmp, csr_to_csc, long_rows, dst_local_id, src_to_dst, ewf, ewb; } off[NB_MAX_LAYERS];
+               column_indices, csr_tmp, csr_to_csc, long_rows, dst_local_id, src_to_dst, ewf, ewb, dst_base, dst_deg; } off[NB_MAX_LAYERS];
   uint64_t max_items = 0;
   for (int i = 0; i < n_layers; i++) {
     s->fanout[i] = fanout[i];
@@ -552,6 +872,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     o.column_indices = take(cap_e); o.csr_tmp = take(cap_e); o.csr_to_csc = take(cap_e); o.long_rows = take(cap_s);
     o.dst_local_id = take(cap_dst); o.src_to_dst = take(cap_s);
     o.ewf = take(cap_e); o.ewb = take(cap_e);
+    o.dst_base = take(cap_dst); o.dst_deg = take(cap_dst);
     if (cap_dst > max_items) max_items = cap_dst;
     if (cap_s > max_items) max_items = cap_s;
     cap_dst = cap_s;
@@ -584,6 +905,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     b.csr_tmp = base + o.csr_tmp; b.csr_to_csc = base + o.csr_to_csc; b.long_rows = base + o.long_rows;
     b.dst_local_id = base + o.dst_local_id; b.src_to_dst = base + o.src_to_dst;
     b.ewf = (float *)(base + o.ewf); b.ewb = (float *)(base + o.ewb);
+    b.dst_base = base + o.dst_base; b.dst_deg = base + o.dst_deg;
   }
   for (int i = 1; i < n_layers; i++) s->lay[i].destination = s->lay[i - 1].source;  // layer chaining (FullyRepGraph.hpp:309)
   s->bitmap[0] = base + o_bitmap; s->bitmap[1] = base + o_bitmap1; s->word_rank = base + o_rank;
@@ -601,6 +923,8 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   }
   const char *ng = getenv("NB_NO_GRAPH");
   s->use_graph = !(ng && ng[0] == '1');
+  if (g_sampler_fused < 0) { const char *e = getenv("NB_SAMPLER_FUSED"); g_sampler_fused = e ? atoi(e) : 1; }
+  s->fused = g_sampler_fused;
   NB_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = s;
   return NB_OK;
@@ -646,41 +970,96 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
     LayerBuf &b = s->lay[i];
     LayerMeta *m = s->meta_dev + i;
     uint32_t *bm = s->bitmap[i & 1], *bm_other = (s->L > 1) ? s->bitmap[(i + 1) & 1] : nullptr;
-    ScanWs ws0{s->tile_states + (size_t)(3 * i + 0) * s->max_tiles, pp}, ws1{s->tile_states + (size_t)(3 * i + 1) * s->max_tiles, pp},
-        ws2{s->tile_states + (size_t)(3 * i + 2) * s->max_tiles, pp};
+    ScanWs ws0 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 0) * s->max_tiles, s->max_tiles, pp),
+           ws1 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 1) * s->max_tiles, s->max_tiles, pp),
+           ws2 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 2) * s->max_tiles, s->max_tiles, pp);
     const bool layer_csr = csr && !(i == s->L - 1 && s->L > 1 && (s->flags & NB_SAMPLER_NO_BOTTOM_CSR));
     const int histogram = (layer_csr || up) ? 1 : 0;
-    CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, i ? m - 1 : nullptr, b.cap_edges, s->fanout[i], i == s->L - 1 ? 1 : 0};
-    k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
-    NB_LAUNCH_CHECK(ctx);
-    launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
-                  pp, (uint32_t)i, merge ? 1 : 0, (histogram || merge) ? b.row_count : nullptr, b.row_cursor,
-                  merge ? b.src_to_dst : nullptr, b.cap_src);
-    NB_LAUNCH_CHECK(ctx);
-    BitmapOp bop{bm, s->word_rank, m, m + 1, s->n_words, b.cap_src};
-    k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
-    NB_LAUNCH_CHECK(ctx);
-    k_relabel<<<nb_grid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
-        b.sample_ans, b.row_indices, bm, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
-        merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp,
-        b.source, s->n_words, bm_other);
-    NB_LAUNCH_CHECK(ctx);
+    const int bottom = i == s->L - 1 ? 1 : 0;
+    uint32_t *next_base = i + 1 < s->L ? s->lay[i + 1].dst_base : nullptr, *next_deg = i + 1 < s->L ? s->lay[i + 1].dst_deg : nullptr;
+    uint32_t *rc_ptr = (histogram || merge) ? b.row_count : nullptr;
+    // ---- count + scan + neighbour selection
+    uint32_t hs = 1; while (s->fanout[i] > 32 && hs < 2u * (uint32_t)s->fanout[i]) hs <<= 1;
+    const int hash_slots = s->fanout[i] > 32 ? (int)hs : 0;
+    const size_t smem_sample = ((size_t)((b.cap_dst + 1 + 31) & ~31u) + (size_t)hash_slots * (FS_THREADS / 32)) * 4;
+    if (s->fused && smem_sample <= FS_SMEM_MAX) {
+      const int group = (s->fanout[i] < 0 || s->fanout[i] > 16) ? 32 : (s->fanout[i] > 8 ? 16 : 8);
+      const unsigned per_block = (FS_THREADS / 32) * (32 / group);
+      unsigned grid = (b.cap_dst + per_block - 1) / per_block;
+      const unsigned max_grid = (unsigned)ctx->sm_count * (smem_sample <= 96 * 1024 ? 2u : 1u);
+      if (grid > max_grid) grid = max_grid;
+      if (grid < 1) grid = 1;
+#define NB_FS(G)                                                                                                                   \
+      do {                                                                                                                         \
+        static bool attr = false;                                                                                                  \
+        if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_sample_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; } \
+        k_sample_fused<G><<<grid, FS_THREADS, smem_sample, st>>>(g->col_off, g->row_idx, b.destination, b.dst_base, b.dst_deg, i > 0 ? 1 : 0,  \
+            b.column_offset, b.sample_ans, b.edge_dst, bm, m, i ? m - 1 : nullptr, s->fanout[i], pp, (uint32_t)i, merge ? 1 : 0, bottom,   \
+            hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, b.cap_dst);                       \
+      } while (0)
+      if (group == 32) NB_FS(32); else if (group == 16) NB_FS(16); else NB_FS(8);
+#undef NB_FS
+      NB_LAUNCH_CHECK(ctx);
+    } else {
+      CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, i ? m - 1 : nullptr, b.cap_edges, s->fanout[i], bottom};
+      k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
+      NB_LAUNCH_CHECK(ctx);
+      launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
+                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src);
+      NB_LAUNCH_CHECK(ctx);
+    }
+    // ---- dedup ranks + source emission + relabel (+ histogram, weights)
+    const size_t smem_relabel = ((size_t)((s->n_words + 31) & ~31u) + s->n_words + 1) * 4;
+    if (s->fused && smem_relabel <= FS_SMEM_MAX) {
+      static bool attr = false;
+      if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_relabel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
+      const uint64_t work = (uint64_t)b.cap_edges + b.cap_dst + (uint64_t)s->n_words * 32;
+      unsigned grid = (unsigned)((work + FS_THREADS - 1) / FS_THREADS);
+      const unsigned max_grid = (unsigned)ctx->sm_count * (smem_relabel <= 96 * 1024 ? 2u : 1u);
+      if (grid > max_grid) grid = max_grid;
+      k_relabel_fused<<<grid, FS_THREADS, smem_relabel, st>>>(
+          b.sample_ans, b.row_indices, bm, b.row_count, b.destination, merge ? b.dst_local_id : nullptr, merge ? b.src_to_dst : nullptr,
+          m, m + 1, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp, b.source, s->n_words, bm_other,
+          b.cap_src, g->col_off, next_base, next_deg);
+      NB_LAUNCH_CHECK(ctx);
+    } else {
+      BitmapOp bop{bm, s->word_rank, m, m + 1, s->n_words, b.cap_src};
+      k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+      NB_LAUNCH_CHECK(ctx);
+      k_relabel<<<nb_grid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
+          b.sample_ans, b.row_indices, bm, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
+          merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp,
+          b.source, s->n_words, bm_other, g->col_off, next_base, next_deg);
+      NB_LAUNCH_CHECK(ctx);
+    }
     if (up) {
       k_weights_sampled<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
     if (layer_csr) {
-      RowOp rop{b.row_count, b.row_offset, m};
-      k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, ws2);
-      NB_LAUNCH_CHECK(ctx);
-      k_csr_fill<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
-      NB_LAUNCH_CHECK(ctx);
-      k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
-                                                               b.ewb, b.ewf, b.long_rows, m, pp);
-      NB_LAUNCH_CHECK(ctx);
-      k_csr_long_rows<<<nb_grid(b.cap_src, 8, 2), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc,
-                                                                  b.edge_dst, b.ewb, b.ewf, b.long_rows, m, pp);
-      NB_LAUNCH_CHECK(ctx);
+      const size_t smem_csr = ((size_t)b.cap_src + 1) * 4;
+      if (s->fused && smem_csr <= FS_SMEM_MAX) {
+        static bool attr = false;
+        if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_csr_fill_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
+        unsigned grid = (b.cap_edges + FS_THREADS - 1) / FS_THREADS;
+        const unsigned max_grid = (unsigned)ctx->sm_count * (smem_csr <= 96 * 1024 ? 2u : 1u);
+        if (grid > max_grid) grid = max_grid;
+        if (grid < 1) grid = 1;
+        k_csr_fill_fused<<<grid, FS_THREADS, smem_csr, st>>>(b.row_indices, b.row_count, b.row_offset, b.row_cursor, b.csr_tmp, m);
+        NB_LAUNCH_CHECK(ctx);
+        k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
+                                                                 b.ewb, b.ewf, b.long_rows, m, pp, 1);
+        NB_LAUNCH_CHECK(ctx);
+      } else {
+        RowOp rop{b.row_count, b.row_offset, m};
+        k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, ws2);
+        NB_LAUNCH_CHECK(ctx);
+        k_csr_fill<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
+        NB_LAUNCH_CHECK(ctx);
+        k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
+                                                                 b.ewb, b.ewf, b.long_rows, m, pp, 1);
+        NB_LAUNCH_CHECK(ctx);
+      }
     }
   }
   return NB_OK;
@@ -866,7 +1245,7 @@ __global__ void k_legacy_weight(float *edge_weight, const uint32_t *__restrict__
 }
 
 static int legacy_state(nb_ctx *ctx, uint32_t n_items_for_scan, uint32_t n_vertices, uint64_t n_edges, LegacyState **st,
-                        unsigned long long **tiles, uint32_t **bitmap, uint32_t **word_rank, uint32_t **edge_dst) {
+                        unsigned long long **tiles, uint32_t **bitmap, uint32_t **word_rank, uint32_t **edge_dst, size_t *n_tiles_out) {
   const uint32_t n_words = (n_vertices + 31) / 32;
   uint32_t items = n_items_for_scan > n_words ? n_items_for_scan : n_words;
   const size_t n_tiles = (items + SCAN_TILE - 1) / SCAN_TILE + 1;
@@ -880,6 +1259,7 @@ static int legacy_state(nb_ctx *ctx, uint32_t n_items_for_scan, uint32_t n_verti
   *word_rank = *bitmap + n_words + 32;
   *edge_dst = *word_rank + n_words + 32;
   NB_CUDA(cudaMemsetAsync(*tiles, 0, n_tiles * 8, ctx->stream));
+  *n_tiles_out = n_tiles;
   return NB_OK;
 }
 
@@ -889,7 +1269,8 @@ int nb_sample_count(nb_ctx *ctx, const uint32_t *dst_dev, uint32_t *local_column
              "nb_sample_count: NULL argument");
   NB_GUARD(ctx);
   LegacyState *st; unsigned long long *tiles; uint32_t *bitmap, *rank, *edge_dst;
-  int rc = legacy_state(ctx, dst_size, 32, 0, &st, &tiles, &bitmap, &rank, &edge_dst);
+  size_t n_tiles_ws = 0;
+  int rc = legacy_state(ctx, dst_size, 32, 0, &st, &tiles, &bitmap, &rank, &edge_dst, &n_tiles_ws);
   if (rc) return rc;
   LegacyState h;
   memset(&h, 0, sizeof(h));
@@ -897,7 +1278,7 @@ int nb_sample_count(nb_ctx *ctx, const uint32_t *dst_dev, uint32_t *local_column
   h.params.omit = omit_flag_dev; h.params.omit_value = omit_value; h.params.epoch = 1;
   NB_CUDA(cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
   CountOp cop{global_column_offset_dev, dst_dev, &st->params, local_column_offset_dev, &st->meta[0], nullptr, 0xffffffffu, (int)fanout, 1};
-  ScanWs ws{tiles, &st->params};
+  ScanWs ws = nb_scan_ws(tiles, n_tiles_ws, &st->params);
   k_scan<CountOp><<<nb_grid(dst_size, SCAN_TILE, 4), SCAN_THREADS, 0, ctx->stream>>>(cop, ws);
   NB_LAUNCH_CHECK(ctx);
   NB_CUDA(cudaMemcpyAsync(edge_size_out, &st->meta[0].n_edges, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -915,7 +1296,8 @@ int nb_sample_traverse(nb_ctx *ctx, const uint32_t *destination_dev, const uint3
   NB_GUARD(ctx);
   global_row_indices_dev = (const uint32_t *)nb_mirror_host(ctx, global_row_indices_dev, 1);  // adjacency left in pinned host memory by the caller
   LegacyState *st; unsigned long long *tiles; uint32_t *bitmap, *rank, *edge_dst;
-  int rc = legacy_state(ctx, vtx_size, n_vertices, edge_size, &st, &tiles, &bitmap, &rank, &edge_dst);
+  size_t n_tiles_ws = 0;
+  int rc = legacy_state(ctx, vtx_size, n_vertices, edge_size, &st, &tiles, &bitmap, &rank, &edge_dst, &n_tiles_ws);
   if (rc) return rc;
   const uint32_t n_words = (n_vertices + 31) / 32;
   LegacyState h;
@@ -928,7 +1310,7 @@ int nb_sample_traverse(nb_ctx *ctx, const uint32_t *destination_dev, const uint3
                 r_i_dev, edge_dst, bitmap, &st->meta[0], &st->params, layer, add_dst_to_src ? 1 : 0);
   NB_LAUNCH_CHECK(ctx);
   BitmapOp bop{bitmap, rank, &st->meta[0], &st->meta[1], n_words, 0xffffffffu};
-  ScanWs ws{tiles, &st->params};
+  ScanWs ws = nb_scan_ws(tiles, n_tiles_ws, &st->params);
   k_scan<BitmapOp><<<nb_grid(n_words, SCAN_TILE, 4), SCAN_THREADS, 0, ctx->stream>>>(bop, ws);
   NB_LAUNCH_CHECK(ctx);
   k_emit_sources<<<nb_grid(n_words, 8, 8), 256, 0, ctx->stream>>>(bitmap, rank, src_dev, nullptr, nullptr, nullptr, &st->meta[0], n_words, src_index_dev);

@@ -29,13 +29,20 @@ struct BatchParams {
 struct ScanWs {
   unsigned long long *tile_state;  // one array per scan launch of a batch; entries are tagged with the batch epoch
   const BatchParams *params;
+  unsigned *ticket;                // [2], zero between launches: next tile to hand out, blocks that have left
 };
+// every caller sizes its tile_state array one entry larger than the largest tile count; that spare entry holds the ticket words
+static inline ScanWs nb_scan_ws(unsigned long long *tile_state, size_t entries, const BatchParams *params) {
+  return ScanWs{tile_state, params, reinterpret_cast<unsigned *>(tile_state + entries - 1)};
+}
 
 
 // ---------------------------------------------------------------------------------------------
 // Single-pass exclusive scan (decoupled look-back, Merrill & Garland) over n items, n read from
-// device memory through Op. Tiles are handed out by an atomic ticket so a tile's predecessors are
-// always resident or finished; the last block to leave resets the workspace for the next launch.
+// device memory through Op. Tiles are handed out by an atomic ticket, so the block that owns a tile's
+// predecessor is always running or finished whatever the grid size and whoever else occupies the SMs
+// (a static blockIdx -> tile map can deadlock when the grid is not fully resident); the last block to
+// leave zeroes the ticket for the next launch (graph replays included).
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -49,9 +56,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
   if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) op.total(0);
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // tile state word: [63:34] batch epoch, [33:32] 1 = aggregate, 2 = inclusive prefix, [31:0] value.
-  // The grid never exceeds the number of co-resident blocks, so waiting on a lower tile cannot deadlock.
   const unsigned long long tag = ((unsigned long long)(ws.params->epoch & 0x3fffffffu)) << 34;
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  __shared__ unsigned s_tile;
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ws.ticket[0], 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= ntiles) break;
     // items are produced with coalesced (striped) indices and handed to their owner thread (blocked layout) through
     // shared memory; the +i/32 padding keeps both access patterns nearly conflict free
     unsigned v[SCAN_ITEMS], sum = 0;
@@ -121,6 +132,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Op op, ScanWs ws) {
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) op.total(s_prefix + block_total);
     __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ws.ticket[1], 1u) == gridDim.x - 1) { ws.ticket[0] = 0u; ws.ticket[1] = 0u; }
   }
 }
 

@@ -30,6 +30,14 @@ def cs(nts):
     return nts.Cuda_Stream.on_torch_stream(0)  # same stream as torch's ops, like the toolkits
 
 
+@pytest.fixture(params=["fused", "general"])
+def sampler_path(nts, request):
+    """both sampler pipelines: the small-shape kernels (default where a layer fits in shared memory) and the general one"""
+    nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_fused", 1 if request.param == "fused" else 0))
+    yield request.param
+    nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_fused", 1))
+
+
 def make_graph(nts, cs, V, avg_deg, seed, unique=True, max_deg=None):
     rng = np.random.default_rng(seed)
     deg = np.minimum((rng.pareto(1.5, V) * avg_deg * 0.5).astype(np.int64), max_deg or V - 1)
@@ -46,7 +54,7 @@ def make_graph(nts, cs, V, avg_deg, seed, unique=True, max_deg=None):
 
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", names())
-def test_replay_reference_records_bit_exact(nts, cs, name):
+def test_replay_reference_records_bit_exact(nts, cs, name, sampler_path):
     """north star check 1: replaying the reference's recorded neighbour sets gives bit-exact
     subgraph indices, CSC, CSR and weights; gather / aggregate / gradients follow."""
     g = load(name)
@@ -103,7 +111,7 @@ def test_replay_reference_records_bit_exact(nts, cs, name):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("fanout,build_csr,merge,up", [([25, 10], True, False, False), ([5, 5, 5], True, True, False),
                                                         ([40, 3], True, False, True), ([-1, 4], False, False, False)])
-def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, build_csr, merge, up):
+def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, build_csr, merge, up, sampler_path):
     V = 20000
     pairs, graph = make_graph(nts, cs, V, 30, seed=7)
     co, ri = oracle.build_csc(pairs, V)
@@ -142,6 +150,36 @@ def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, b
                 assert np.array_equal(got, nb)
             else:
                 assert got.size == f and np.unique(got).size == f and np.isin(got, nb).all()
+
+
+def test_sampler_paths_agree_bit_for_bit(nts, cs):
+    """the small-shape kernels and the general pipeline: same RNG counters -> same draws -> every array identical; hub rows in the CSR"""
+    lib, check = nts._capi.lib(), nts._capi.check
+    V = 30000
+    pairs, graph = make_graph(nts, cs, V, 35, seed=11)
+    hub = np.stack([np.full(6000, 17, np.uint32), np.random.default_rng(5).permutation(V)[:6000].astype(np.uint32)], 1)
+    graph = nts.FullyRepGraph(cs, V, edge_pairs=np.concatenate([pairs, hub]))        # vertex 17 is a source of 6000 columns
+    seeds = np.random.default_rng(2).permutation(V)[:1024].astype(np.uint32)
+    out = {}
+    for fused in (1, 0):
+        check(lib.nb_set_option(b"sampler_fused", fused))
+        for fanout, merge, up in (([25, 10], False, False), ([40, 4, 3], True, False), ([6, 6], False, True)):
+            sm = nts.FastSampler(graph, seeds, len(fanout), 1024, fanout, cuda_stream=cs, merge_src_dst=merge, up_degree=up, build_csr=True)
+            sg = sm.sample_gpu_fast(1024)
+            arrs = []
+            for l in sg.sampled_sgs:
+                arrs += [u32(l.dev_column_offset), u32(l.dev_sample_ans), u32(l.dev_source), u32(l.dev_row_indices), u32(l.dev_row_offset),
+                         u32(l.dev_column_indices), u32(l.dev_csr_to_csc), u32(l.dev_edge_weight_forward), u32(l.dev_edge_weight_backward)]
+                if merge:
+                    arrs += [u32(l.dev_dst_local_id), u32(l.dev_src_to_dst)]
+            out[(fused, tuple(fanout))] = arrs
+    check(lib.nb_set_option(b"sampler_fused", 1))
+    for (fused, fan), arrs in out.items():
+        if fused:
+            other = out[(0, fan)]
+            assert len(arrs) == len(other)
+            for k, (a, b) in enumerate(zip(arrs, other)):
+                assert np.array_equal(a, b), (fan, k)
 
 
 def test_gpu_sampler_is_reproducible_and_counter_based(nts, cs):
@@ -503,6 +541,81 @@ def test_gat_legacy_ops_and_fused_layer(nts, cs, F):
         hg, ag = h.clone().requires_grad_(True), a.clone().requires_grad_(True)
         (op(hg, ag) * torch.from_numpy(dout).cuda()).sum().backward()
         np.testing.assert_allclose(f32(hg.grad), DH, rtol=1e-3, atol=1e-4)
+
+
+def _gat_goldens():
+    import glob
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(os.path.basename(f)[4:-4] for f in glob.glob(os.path.join(d, "gat_*.npz")))
+
+
+@pytest.mark.parametrize("name", _gat_goldens())
+def test_gat_against_reference_kernel_records(nts, cs, name):
+    """a14 pinned: tests/golden/gat_*.npz hold the outputs of the reference's OWN CUDA kernels (cuda/ntsCUDADistKernel.cuh, run on a
+    B200 by oracle/_ref/ref_gpu_driver <- oracle/make_gat_golden.py) for the op chain of toolkits/GAT_SAMPLE_ALL_MULTI.hpp:383-464.
+    Legacy-shaped ops and the fused layer, forward and backward, against those records. Tolerance: 1e-5 relative (north star) plus an
+    absolute floor of 1e-5 x the tensor's largest magnitude -- the reference sums in a different order (cuBLAS dot over [E,2F] for the
+    score, float atomics for the source gradient), so elements that cancel to near zero cannot agree to 1e-5 of themselves."""
+    import os
+    lib, check, ptr = nts._capi.lib(), nts._capi.check, nts._capi.ptr
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"gat_{name}.npz")))
+    F, S = int(g["F"]), int(g["n_src"])
+    co, ri, dl = g["column_offset"], g["row_indices"], g["dst_local_id"]
+    V, E = co.size - 1, ri.size
+    d32 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32) if a.dtype == np.uint32 else np.ascontiguousarray(a)).cuda()
+    t_co, t_ri, t_dl = d32(co), d32(ri), d32(dl)
+    h, att, dout = d32(g["h"].reshape(S, F)), d32(g["att"]), d32(g["dout"].reshape(V, F))
+
+    def close(mine, ref, what, rtol=1e-5, floor=1e-5):
+        ref = np.asarray(ref, np.float32).reshape(mine.shape)
+        np.testing.assert_allclose(mine, ref, rtol=rtol, atol=floor * float(np.abs(ref).max() + 1e-30), err_msg=f"{name}: {what}")
+
+    # ---- legacy-shaped ops, one reference kernel each
+    alpha = torch.empty(E, device="cuda"); cached = torch.empty(E, device="cuda")
+    cs.Edge_Softmax_Forward_Norm_Block(alpha, d32(g["m"]), cached, t_ri, t_co, V, 1)
+    close(f32(alpha), g["alpha"], "Edge_Softmax_Forward_Norm_Block")
+    assert torch.equal(alpha, cached)
+    d_m = torch.empty(E, device="cuda")
+    cs.Edge_Softmax_Backward_Block(d_m, d32(g["d_a"]), d32(g["alpha"]), t_ri, t_co, V, 1)
+    close(f32(d_m), g["d_m"], "Edge_Softmax_Backward_Block")
+    e_src = g["h"].reshape(S, F)[ri.astype(np.int64)]
+    emo = (e_src * g["alpha"][:, None]).astype(np.float32)               # e_msg.slice(0:F) * a, one rounding per element
+    nbr = torch.empty((V, F), device="cuda")
+    cs.Gather_Msg_to_Dst(nbr, d32(emo), t_ri, t_co, V, F)
+    close(f32(nbr), g["out"], "Gather_Msg_to_Dst")
+    if "e_msg" in g:                                                     # small cases carry the per-edge tensors
+        msg = torch.empty((E, 2 * F), device="cuda")
+        cs.Scatter_Src_Dst_to_Msg(msg, h, t_ri, t_co, V, F, t_dl)
+        assert np.array_equal(f32(msg), g["e_msg"].reshape(E, 2 * F)), "Scatter_Src_Dst_to_Msg is a copy: bit-exact"
+        assert np.array_equal(emo, g["e_msg_out"].reshape(E, F))
+        back = torch.empty((E, F), device="cuda")
+        cs.Scatter_Dst_to_Msg(back, dout, t_ri, t_co, V, F)
+        assert np.array_equal(f32(back), g["d_e_msg_out"].reshape(E, F)), "Scatter_Dst_to_Msg is a copy: bit-exact"
+        gsrc = torch.zeros((S, F), device="cuda")
+        cs.Gather_Msg_To_Src_Dst(gsrc, d32(g["d_e_msg"].reshape(E, 2 * F)), t_ri, t_co, V, F, t_dl, S)
+        close(f32(gsrc), g["dh"], "Gather_Msg_To_Src_Dst")
+    # ---- fused layer (nb_gat_fwd / nb_gat_bwd) against the same records
+    pre, al, out = torch.empty(E, device="cuda"), torch.empty(E, device="cuda"), torch.empty((V, F), device="cuda")
+    check(lib.nb_gat_fwd(cs._h, ptr(h), ptr(att), 0.2, ptr(t_co), ptr(t_ri), ptr(t_dl), V, S, F, ptr(pre), ptr(al), ptr(out)))
+    close(f32(pre), g["score_pre"], "fused score")
+    close(f32(al), g["alpha"], "fused alpha")
+    close(f32(out), g["out"], "fused forward output")
+    order = np.argsort(ri, kind="stable").astype(np.uint32)              # stable CSR of the layer (sampCSC::csc_to_csr order)
+    row_offset = np.zeros(S + 1, np.uint32)
+    np.cumsum(np.bincount(ri, minlength=S), out=row_offset[1:])
+    edge_dst = np.repeat(np.arange(V, dtype=np.uint32), np.diff(co.astype(np.int64)))
+    src_to_dst = np.full(S, 0xFFFFFFFF, np.uint32)
+    src_to_dst[dl] = np.arange(V, dtype=np.uint32)
+    dh, datt = torch.empty((S, F), device="cuda"), torch.empty(2 * F, device="cuda")
+    args = (cs._h, ptr(h), ptr(att), 0.2, ptr(dout), ptr(pre), ptr(al), ptr(t_co), ptr(t_ri), ptr(t_dl), ptr(d32(row_offset)),
+            ptr(d32(edge_dst[order])), ptr(d32(order)), ptr(d32(src_to_dst)), V, S, E, F)
+    check(lib.nb_gat_bwd(*args, ptr(dh), ptr(datt)))
+    close(f32(dh), g["dh"], "fused dH")
+    close(f32(datt), g["datt"], "fused d(att)", floor=2e-5)
+    dh2, datt2 = torch.empty_like(dh), torch.empty_like(datt)
+    check(lib.nb_gat_bwd(*args, ptr(dh2), ptr(datt2)))                   # no float atomics anywhere: run-to-run identical
+    assert torch.equal(dh, dh2) and torch.equal(datt, datt2)
 
 
 def test_gat_fused_layer_with_hub_sources(nts, cs):
