@@ -388,8 +388,11 @@ def main_b200(args):
         else:
             if exchange in ("one", "nccl"):
                 issue_allreduce()
-            check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
-                                               bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
+            # load_feature_gpu + the bottom hop's forward as one kernel: rows come straight from the table through the layer's
+            # source ids; the per-source use counts steer L2 (rows the batch reads again are kept, single-use rows are not)
+            check(lib.nb_aggregate_gathered_fwd_dyn(cs_train._h, ptr(table), PITCH, bot.source, ptr(y1), bot.edge_weight_forward,
+                                                    bot.row_indices, bot.column_offset, None if args.no_l2_hints else bot.source_use_count,
+                                                    nd[1], caps[1][0], F0, PITCH))
             if timed:
                 b.record(st_train)
                 kern_ev["agg_fwd_602_from_table"].append((a, b))
@@ -694,13 +697,14 @@ if __name__ == "__main__":
     ap.add_argument("--pipeline", type=int, default=2, help="PIPELINE_NUM: sampler arenas in flight (sampling overlaps training)")
     ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
-    ap.add_argument("--sample-priority", type=int, default=0, help="CUDA stream priority of the sampling stream (-1 = high)")
+    ap.add_argument("--sample-priority", type=int, default=-1, help="CUDA stream priority of the sampling stream (-1 = high: its small kernels get SM slots ahead of the queued aggregation blocks; 0.184 -> 0.158 ms per step, profiles/r2_sweep_pipeline.txt)")
     ap.add_argument("--exchange", default="split", choices=["split", "one", "nccl"],
                     help="dense-gradient sum at N>1: split = peer-memory push behind the backward + reduce before the next top hop, in the "
                          "training stream (default); one = one peer-memory kernel on a communication stream; nccl = NCCL all_reduce")
     ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of exactly --steps steps each; the median window is reported")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: fixed global batch 1024, local batch 1024/N")
+    ap.add_argument("--no-l2-hints", action="store_true", help="A/B: gather-fused aggregation without the per-source L2 eviction hints")
     ap.add_argument("--materialize-x0", action="store_true", help="e2e path: gather X0 first instead of the lazy feature handle")
     ap.add_argument("--comm-late", dest="comm_early", action="store_false",
                     help="--exchange one|nccl: hold the all-reduce back until the next step's gather has finished")

@@ -6,17 +6,20 @@
  * ntsCUDAFuseKernel.cuh, ntsCUDADistKernel.cuh) and the aggregation is the reference's cuSPARSE SpMM wrapper. It needs a GPU.
  *
  * Modes
- *   bench <edge_file> <V> <seed_file> <batch> <fanout a,b> <F0> <F1> <batches> <warmup>
- *       the reference's GPU mini-batch path on the same graph / seeds as bench.py, stage by stage, in the toolkit's own call
- *       order (toolkits/GCN_SAMPLE_ALLGPU.hpp:289-397):
- *         FastSampler::sample_gpu_fast                    core/ntsFastSampler.hpp:648-709 (kernels cuda/ntsCUDAGraphOP.cu:1246-1659)
+ *   bench <edge_file> <V> <seed_file> <batch> <fanout a,b> <F0> <F1> <batches> <warmup> [gpu_sampler]
+ *       the reference's mini-batch path of BASELINE config 2 (toolkits/GCN_SAMPLE_GPU.hpp:289-397: CPU sampling, GPU gather and
+ *       aggregation) on the same graph / seeds as bench.py, stage by stage, in the toolkit's own call order:
+ *         FastSampler::sample_fast(to_gpu)                core/ntsFastSampler.hpp:962-1140 (+ sampCSC::copy_data_to_device_async)
  *         Cuda_Stream::zero_copy_feature_move_gpu         cuda/ntsCUDAGraphOP.cu:1711-1729  (table in pinned host memory = the
  *                                                         reference layout, and the same kernel on an HBM-resident copy)
  *         Cuda_Stream::Gather_By_Dst_From_Src_Spmm        :425-587  (cuSPARSE SpMM, bottom hop F0 and top hop F1)
- *         Cuda_Stream::Push_From_Dst_To_Src_Spmm          :621-770  (cuSPARSE SpMM, top hop backward, what
- *                                                         SingleGPUAllSampleGraphOp::backward calls, core/ntsSingleGPUSampleGraphOp.hpp:283)
+ *         Cuda_Stream::Gather_By_Src_From_Dst_Spmm        :901-1042 (cuSPARSE SpMM over the CSR, top hop backward:
+ *                                                         SingleGPUSampleGraphOp::backward, core/ntsSingleGPUSampleGraphOp.hpp:126-176)
  *       each timed with CUDA events on the Cuda_Stream's stream (sampling: host wall clock around the call + stream
- *       synchronise, because the reference's sampler round-trips through the host). Prints one JSON line.
+ *       synchronise). With a trailing `gpu_sampler` argument the batch is sampled by FastSampler::sample_gpu_fast instead
+ *       (GCN_SAMPLE_ALLGPU's path; on the B200 box that kernel chain dies with an illegal memory access -- its |V|-sized mark
+ *       array is cudaMalloc'd and never cleared, SURVEY.md section 8 quirks -- which is why it is not the default).
+ *       Prints one JSON line.
  *   gat <in.bin> <out.bin>
  *       the reference's GAT edge kernels on a given sampled layer (record format of oracle/refio.py; arrays column_offset,
  *       row_indices, dst_local_id, h [S,F], att [2F], dout [V,F]; header word 1 = F, word 2 = S):
@@ -85,8 +88,10 @@ static int run_bench(int argc, char **argv) {
   }
   FullyRepGraph *full = new FullyRepGraph(g);
   full->ReadRepGraphFromRawFile();     /* adjacency in mapped pinned host memory, core/FullyRepGraph.hpp:727 */
+  const bool gpu_sampler = argc > 11 && std::string(argv[11]) == "gpu_sampler";
   Cuda_Stream *cs = new Cuda_Stream[1];
-  FastSampler *sampler = new FastSampler(full, seeds, L, batch, fanout, 1, cs);   /* GPU ctor, core/ntsFastSampler.hpp:125-176 */
+  FastSampler *sampler = gpu_sampler ? new FastSampler(full, seeds, L, batch, fanout, 1, cs)              /* GPU ctor, :125-176 */
+                                     : new FastSampler(g, full, seeds, L, fanout, batch, true, 0, 1, cs); /* CPU sampler, to_gpu (GCN_SAMPLE_GPU.hpp:475) */
   cudaStream_t st = cs[0].stream;
   /* feature table: all ones (FEATURE_FILE:random, core/ntsDataloador.hpp:846-850) in pinned mapped host memory like GNNDatum's
    * (core/ntsDataloador.hpp:187), plus an HBM copy to time the same kernel without PCIe */
@@ -112,7 +117,7 @@ static int run_bench(int argc, char **argv) {
     fflush(stdout); int saved = dup(1); dup2(fileno(devnull), 1);   /* the sampler printf()s */
     CK(cudaStreamSynchronize(st));
     double s0 = get_time();
-    SampledSubgraph *sg = sampler->sample_gpu_fast(batch, 0);
+    SampledSubgraph *sg = gpu_sampler ? sampler->sample_gpu_fast(batch, 0) : sampler->sample_fast(batch, 0);
     CK(cudaStreamSynchronize(st));
     double s1 = get_time();
     fflush(stdout); dup2(saved, 1); close(saved);
@@ -121,13 +126,15 @@ static int run_bench(int argc, char **argv) {
     t_gh.start(); cs[0].zero_copy_feature_move_gpu(x0, host_table_dev, bot->dev_source, F0, bot->src_size); t_gh.stop(timed);
     t_gd.start(); cs[0].zero_copy_feature_move_gpu(x0, hbm_table, bot->dev_source, F0, bot->src_size); t_gd.stop(timed);
     t_f0.start();
-    cs[0].Gather_By_Dst_From_Src_Spmm(x0, y1, bot->dev_e_w(), bot->dev_r_i(), bot->dev_c_o(), bot->src_size, 0, 0, 0, 0, bot->e_size, bot->v_size, F0, true, false);
+    float *bw = gpu_sampler ? bot->dev_e_w() : bot->dev_e_w_f(), *tw = gpu_sampler ? top->dev_e_w() : top->dev_e_w_f();
+    cs[0].Gather_By_Dst_From_Src_Spmm(x0, y1, bw, bot->dev_r_i(), bot->dev_c_o(), bot->src_size, 0, 0, 0, 0, bot->e_size, bot->v_size, F0, true, false);
     t_f0.stop(timed);
     t_f1.start();
-    cs[0].Gather_By_Dst_From_Src_Spmm(h1, y0, top->dev_e_w(), top->dev_r_i(), top->dev_c_o(), top->src_size, 0, 0, 0, 0, top->e_size, top->v_size, F1, true, false);
+    cs[0].Gather_By_Dst_From_Src_Spmm(h1, y0, tw, top->dev_r_i(), top->dev_c_o(), top->src_size, 0, 0, 0, 0, top->e_size, top->v_size, F1, true, false);
     t_f1.stop(timed);
     t_b.start();
-    cs[0].Push_From_Dst_To_Src_Spmm(dy0, dh1, top->dev_e_w(), top->dev_r_i(), top->dev_c_o(), top->src_size, 0, 0, 0, 0, top->e_size, top->v_size, F1, true, false);
+    if (gpu_sampler) cs[0].Push_From_Dst_To_Src_Spmm(dy0, dh1, tw, top->dev_r_i(), top->dev_c_o(), top->src_size, 0, 0, 0, 0, top->e_size, top->v_size, F1, true, false);
+    else cs[0].Gather_By_Src_From_Dst_Spmm(dy0, dh1, top->dev_e_w_b(), top->dev_r_o(), top->dev_c_i(), top->v_size, 0, 0, 0, 0, top->e_size, top->src_size, F1, true, false);
     t_b.stop(timed);
     if (timed) {
       t_sample += s1 - s0; done++;
@@ -135,9 +142,9 @@ static int run_bench(int argc, char **argv) {
       E1 += bot->e_size; S1 += bot->src_size; V1 += bot->v_size;
     }
   }
-  printf("{\"batches\": %d, \"sample_ms\": %.4f, \"gather_host_table_ms\": %.4f, \"gather_hbm_table_ms\": %.4f, \"spmm_fwd_F0_ms\": %.4f, "
+  printf("{\"sampler\": \"%s\", \"batches\": %d, \"sample_ms\": %.4f, \"gather_host_table_ms\": %.4f, \"gather_hbm_table_ms\": %.4f, \"spmm_fwd_F0_ms\": %.4f, "
          "\"spmm_fwd_F1_ms\": %.4f, \"spmm_bwd_F1_ms\": %.4f, \"edges\": %lu, \"E1\": %lu, \"S1\": %lu, \"V1\": %lu}\n",
-         done, done ? t_sample / done * 1e3 : 0.0, t_gh.mean(), t_gd.mean(), t_f0.mean(), t_f1.mean(), t_b.mean(),
+         gpu_sampler ? "sample_gpu_fast" : "sample_fast (CPU, OpenMP) + copy_data_to_device_async", done, done ? t_sample / done * 1e3 : 0.0, t_gh.mean(), t_gd.mean(), t_f0.mean(), t_f1.mean(), t_b.mean(),
          (unsigned long)edges, (unsigned long)E1, (unsigned long)S1, (unsigned long)V1);
   fflush(stdout);
   _exit(0);   /* the reference's destructors double-free device arenas (core/FullyRepGraph.hpp:182-183) */

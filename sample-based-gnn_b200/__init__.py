@@ -133,6 +133,13 @@ class Cuda_Stream:
         check(lib().nb_aggregate_csc_fwd_dyn(self._h, ptr(input), ptr(output), ptr(weight), ptr(row_indices), ptr(column_offset),
                                              ptr(n_dst_dev), n_dst, feature_size, in_pitch, out_pitch))
 
+    def aggregate_gathered_fwd(self, table, source_ids, output, weight, row_indices, column_offset, n_dst, feature_size, table_pitch,
+                               out_pitch, use_count=None, n_dst_dev=None):
+        """load_feature_gpu + the bottom hop's forward in one kernel: output[d] = sum_e w[e] * table[source_ids[row_indices[e]]]"""
+        check(lib().nb_aggregate_gathered_fwd_dyn(self._h, ptr(table), table_pitch, ptr(source_ids), ptr(output), ptr(weight),
+                                                  ptr(row_indices), ptr(column_offset), ptr(use_count), ptr(n_dst_dev), n_dst,
+                                                  feature_size, out_pitch))
+
     def aggregate_bwd_pitched(self, input, output, weight_b, row_offset, column_indices, n_src, feature_size, in_pitch, out_pitch,
                               n_src_dev=None):
         check(lib().nb_aggregate_csr_bwd_dyn(self._h, ptr(input), ptr(output), ptr(weight_b), ptr(row_offset), ptr(column_indices),
@@ -299,25 +306,45 @@ class FullyRepGraph:
 
 
 class sampCSC:
-    """One sampled layer (core/coocsc.hpp:24-462), device members only; tensors are zero-copy views
-    of the sampler's arena and stay valid until the sampler's next batch."""
+    """One sampled layer (core/coocsc.hpp:24-462), device members only; tensors are zero-copy views of the sampler's arena and
+    stay valid until the sampler's next batch. The views are built on first access (a training step touches four or five of the
+    fourteen arrays; building all of them eagerly cost more host time per step than the GPU work of the step)."""
+
+    _ARRAYS = {  # attribute -> (view field, length attribute, +1, kind)
+        "dev_destination": ("destination", "v_size", 0, "u"), "dev_column_offset": ("column_offset", "v_size", 1, "u"),
+        "dev_sample_ans": ("sample_ans", "e_size", 0, "u"), "dev_row_indices": ("row_indices", "e_size", 0, "u"),
+        "dev_source": ("source", "src_size", 0, "u"), "dev_row_offset": ("row_offset", "src_size", 1, "u"),
+        "dev_column_indices": ("column_indices", "e_size", 0, "u"), "dev_csr_to_csc": ("csr_to_csc", "e_size", 0, "u"),
+        "dev_edge_weight_forward": ("edge_weight_forward", "e_size", 0, "f"),
+        "dev_edge_weight_backward": ("edge_weight_backward", "e_size", 0, "f"),
+        "dev_dst_local_id": ("dst_local_id", "v_size", 0, "u"), "dev_src_to_dst": ("src_to_dst", "src_size", 0, "u"),
+        "dev_source_use_count": ("source_use_count", "src_size", 0, "u")}
+    _OPTIONAL = {"dev_row_offset", "dev_column_indices", "dev_csr_to_csc", "dev_edge_weight_backward", "dev_dst_local_id",
+                 "dev_src_to_dst", "dev_source_use_count"}
 
     def __init__(self, view, device, owner):
         self.v_size, self.e_size, self.src_size = view.n_dst, view.n_edges, view.n_src
-        mk = lambda a, n, k="u": _view(a, n, k, device, owner)
-        self.dev_destination = mk(view.destination, self.v_size)
-        self.dev_column_offset = mk(view.column_offset, self.v_size + 1)
-        self.dev_sample_ans = mk(view.sample_ans, self.e_size)
-        self.dev_row_indices = mk(view.row_indices, self.e_size)
-        self.dev_source = mk(view.source, self.src_size)
-        self.dev_row_offset = mk(view.row_offset, self.src_size + 1) if view.row_offset else None
-        self.dev_column_indices = mk(view.column_indices, self.e_size) if view.column_indices else None
-        self.dev_csr_to_csc = mk(view.csr_to_csc, self.e_size) if view.csr_to_csc else None
-        self.dev_edge_weight_forward = mk(view.edge_weight_forward, self.e_size, "f")
-        self.edge_weight = self.dev_edge_weight_forward  # the GPU-sampled path's name (coocsc.hpp:440)
-        self.dev_edge_weight_backward = mk(view.edge_weight_backward, self.e_size, "f") if view.edge_weight_backward else None
-        self.dev_dst_local_id = mk(view.dst_local_id, self.v_size) if view.dst_local_id else None
-        self.dev_src_to_dst = mk(view.src_to_dst, self.src_size) if view.src_to_dst else None
+        self._ptr = {f: getattr(view, f) for f, _, _, _ in self._ARRAYS.values()}
+        self._device, self._owner = device, owner
+
+    def __getattr__(self, name):     # only reached for attributes not set yet
+        spec = sampCSC._ARRAYS.get(name)
+        if spec is None:
+            if name == "edge_weight":   # the GPU-sampled path's name (coocsc.hpp:440)
+                return self.dev_edge_weight_forward
+            raise AttributeError(name)
+        field, n_attr, plus, kind = spec
+        addr = self._ptr[field]
+        if not addr and name in sampCSC._OPTIONAL:
+            t = None
+        else:
+            t = _view(addr, getattr(self, n_attr) + plus, kind, self._device, self._owner)
+        setattr(self, name, t)
+        return t
+
+    def address(self, name):
+        """raw device address of an array (no tensor is built): for callers that only forward pointers to the C ABI"""
+        return self._ptr[sampCSC._ARRAYS[name][0]]
 
     # accessor names of the reference
     def dev_dst(self): return self.dev_destination
@@ -615,8 +642,9 @@ class SingleGPUAllSampleGraphOp:
             else:   # bottom hop straight from the feature table: input row of edge e = table[sample_ans[e]]
                 table, F = f_input.table, f_input.shape[1]
                 out = _alloc_like_rows(l.v_size, F, table)
-                self.cuda_stream.aggregate_fwd_pitched(table, out, l.dev_e_w() if self.with_weight else None, l.dev_sample_ans,
-                                                       l.dev_c_o(), l.v_size, F, _pitch(table, F), _pitch(out, F))
+                self.cuda_stream.aggregate_gathered_fwd(table, l.dev_source, out, l.dev_e_w() if self.with_weight else None, l.dev_r_i(),
+                                                        l.dev_c_o(), l.v_size, F, _pitch(table, F), _pitch(out, F),
+                                                        use_count=l.dev_source_use_count)
                 return out
         F = f_input.shape[1]
         assert f_input.shape[0] == l.src_size

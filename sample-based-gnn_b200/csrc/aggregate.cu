@@ -36,16 +36,24 @@ struct SegEpilogue {
   const float *va, *vb;  // feature-length vectors
 };
 
-template <int VEC, int CHUNK, int UNR>
+// GATHERED (the bottom hop fused with the feature gather): idx[j] is a position in the layer's source list, the input row is
+// in[remap[idx[j]]] (remap = the layer's global source ids, in = the feature table), so X0 = table[source] is never written.
+// use_count[idx[j]] (optional) = how many edges of this batch read that source: rows used more than once are loaded with an L2
+// evict_last hint, rows used once with evict_first, so the re-reads (41 % of the row reads on the Reddit shape) hit L2 instead of
+// being flushed by the single-use rows in between.
+template <int VEC, int CHUNK, int UNR, bool GATHERED>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
                  const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
                  const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch,
-                 SegEpilogue epi = SegEpilogue{nullptr, nullptr, nullptr, nullptr}) {
+                 SegEpilogue epi = SegEpilogue{nullptr, nullptr, nullptr, nullptr}, const uint32_t *__restrict__ remap = nullptr,
+                 const uint32_t *__restrict__ use_count = nullptr) {
   const unsigned lane = lane_id();
   const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
   const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
   if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
+  uint64_t pol_keep = 0, pol_once = 0;
+  if (GATHERED) { pol_keep = l2_policy_evict_last(); pol_once = l2_policy_evict_first(); }
   for (unsigned r = warp; r < n_rows; r += warps) {
     const uint32_t beg = offsets[r], end = offsets[r + 1];
     for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {  // one pass unless the row is wider than 32*CHUNK vectors
@@ -54,11 +62,15 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
       for (int c = 0; c < CHUNK; c++) acc[c].zero();
       for (uint32_t j0 = beg; j0 < end; j0 += 32) {
         const uint32_t cnt = min(32u, end - j0);
-        uint32_t my_idx = 0;
+        uint32_t my_idx = 0, my_keep = 0;
         float my_w = 1.0f;
         if (lane < cnt) {
           my_idx = idx[j0 + lane];
           if (weight) my_w = weight[j0 + lane];
+          if (GATHERED) {
+            if (use_count) my_keep = use_count[my_idx] > 1u ? 1u : 0u;
+            my_idx = remap[my_idx];
+          }
         }
         for (uint32_t t = 0; t < cnt; t += UNR) {
           Vec<VEC> x[UNR][CHUNK];
@@ -70,11 +82,16 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
             const uint32_t s = __shfl_sync(FULL_MASK, my_idx, tt);
             w[u] = __shfl_sync(FULL_MASK, my_w, tt);
             const float *p = in + (uint64_t)s * pitch;
+            uint64_t pol = 0;
+            if (GATHERED) pol = __shfl_sync(FULL_MASK, my_keep, tt) ? pol_keep : pol_once;
             if (t + u < cnt) {
 #pragma unroll
               for (int c = 0; c < CHUNK; c++) {
                 const unsigned k = c0 + c * 32 + lane;
-                if (k < nvec) x[u][c].load(p + (uint64_t)k * VEC);
+                if (k < nvec) {
+                  if (GATHERED) x[u][c].load_hint(p + (uint64_t)k * VEC, pol);
+                  else x[u][c].load(p + (uint64_t)k * VEC);
+                }
               }
             }
           }
@@ -374,12 +391,12 @@ k_push(const float *__restrict__ in, float *__restrict__ out, const float *__res
 template <int VEC>
 static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                           const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
-                          uint64_t out_pitch, SegEpilogue epi) {
+                          uint64_t out_pitch, SegEpilogue epi, const uint32_t *remap, const uint32_t *use_count) {
   const uint32_t nvec = F / VEC;
   // block path for long segments: staging batch sized to SEG_STAGE_BYTES of dynamic shared memory
   uint32_t long_batch = 0;
   size_t smem = 0;
-  if (!push && g_agg_long_rows && F <= SEG_LONG_MAX_F) {
+  if (!push && !remap && g_agg_long_rows && F <= SEG_LONG_MAX_F) {
     long_batch = SEG_STAGE_BYTES / (F * 4u);
     if (long_batch > 64) long_batch = 64;
     if (long_batch < 2) long_batch = 2;
@@ -395,7 +412,8 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
     if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
     else if (long_batch && (g_agg_pipe_wide == 2 || (C <= 2 && g_agg_pipe_wide == 1))) k_segment_reduce_lb<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), true><<<grid, AGG_THREADS, smem, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, long_batch); \
     else if (long_batch) k_segment_reduce_lb<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), false><<<grid, AGG_THREADS, smem, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, long_batch); \
-    else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2)><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
+    else if (remap) k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), true><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, remap, use_count); \
+    else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), false><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
   } while (0)
   if (per_lane <= 1) NB_SEG(1);
   else if (per_lane <= 2) NB_SEG(2);
@@ -412,7 +430,8 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
 
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                    const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
-                   uint64_t out_pitch, const float *e1, const float *e2, const float *va, const float *vb) {
+                   uint64_t out_pitch, const float *e1, const float *e2, const float *va, const float *vb, const uint32_t *remap,
+                   const uint32_t *use_count) {
   SegEpilogue epi{e1, e2, va, vb};
   if (n_rows == 0) return NB_OK;
   if (!in_pitch) in_pitch = F;
@@ -420,9 +439,9 @@ int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const fl
   uint32_t fe = F;
   int vec = (push || e1) ? nb_pick_vec(F, in, in_pitch, out, out_pitch) : nb_pick_vec(F, in, in_pitch, out, out_pitch, &fe);
   if (e1 && vec > 1 && (((uintptr_t)va | (uintptr_t)vb) % (4 * vec))) vec = 1;  // epilogue vectors must allow the same vector loads
-  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi);
-  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi);
-  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi);
+  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, remap, use_count);
+  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, remap, use_count);
+  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, remap, use_count);
 }
 
 static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
@@ -470,6 +489,19 @@ int nb_aggregate_csr_bwd_dyn(nb_ctx *ctx, const float *input, float *output, con
   NB_REQUIRE(feature_size > 0 && input_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
   NB_GUARD(ctx);
   return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, max_src, feature_size, n_src_dev, input_pitch, output_pitch);
+}
+
+// The bottom hop fused with the feature gather (FastSampler::load_feature_gpu + SingleGPU[All]SampleGraphOp::forward in one kernel)
+int nb_aggregate_gathered_fwd_dyn(nb_ctx *ctx, const float *table, uint32_t table_pitch, const uint32_t *source_ids, float *output,
+                                  const float *weight_forward, const uint32_t *row_indices, const uint32_t *column_offset,
+                                  const uint32_t *source_use_count_or_null, const uint32_t *n_dst_dev, uint32_t max_dst,
+                                  uint32_t feature_size, uint32_t output_pitch) {
+  NB_REQUIRE(ctx && (max_dst == 0 || (table && source_ids && output && row_indices && column_offset)), NB_ERR_ARG, "nb_aggregate_gathered_fwd_dyn: NULL argument");
+  NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
+  NB_GUARD(ctx);
+  table = (const float *)nb_mirror_host(ctx, table);
+  return nb_run_segment(ctx, false, table, output, weight_forward, row_indices, column_offset, max_dst, feature_size, n_dst_dev, table_pitch,
+                        output_pitch, nullptr, nullptr, nullptr, nullptr, source_ids, source_use_count_or_null);
 }
 
 int nb_aggregate_push_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight, const uint32_t *row_indices,

@@ -49,7 +49,7 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);
 // segment reduction out[r,:] = sum_j w[j] in[idx[j],:] (+ e1[r] va + e2[r] vb); aggregate.cu
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *offsets,
                    uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch, uint64_t out_pitch, const float *e1,
-                   const float *e2, const float *va, const float *vb);
+                   const float *e2, const float *va, const float *vb, const uint32_t *remap = nullptr, const uint32_t *use_count = nullptr);
 // (optionally sharded) HBM feature table; gather.cu
 struct nb_table {
   nb_ctx *ctx;
@@ -135,10 +135,40 @@ __device__ __forceinline__ void stg_stream1(float *p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// L2 eviction-priority hints (createpolicy): rows that will be read again soon are kept (evict_last), rows read once make room
+// first (evict_first). Used by the gather-fused aggregation, where the sampler knows how often a batch uses every source row.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_hint4(const float *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_hint2(const float *p, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_hint1(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
   float4 v;
   __device__ __forceinline__ void load(const float *p) { v = ldg_stream4(p); }
+  __device__ __forceinline__ void load_hint(const float *p, uint64_t pol) { v = ldg_hint4(p, pol); }
   __device__ __forceinline__ void load_cached(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }  // L1-allocating: data every warp re-reads
   __device__ __forceinline__ void store(float *p) const { stg_stream4(p, v); }
   __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -152,6 +182,7 @@ template <> struct Vec<4> {
 template <> struct Vec<2> {
   float2 v;
   __device__ __forceinline__ void load(const float *p) { v = ldg_stream2(p); }
+  __device__ __forceinline__ void load_hint(const float *p, uint64_t pol) { v = ldg_hint2(p, pol); }
   __device__ __forceinline__ void load_cached(const float *p) { v = __ldg(reinterpret_cast<const float2 *>(p)); }
   __device__ __forceinline__ void store(float *p) const { stg_stream2(p, v); }
   __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
@@ -163,6 +194,7 @@ template <> struct Vec<2> {
 template <> struct Vec<1> {
   float v;
   __device__ __forceinline__ void load(const float *p) { v = ldg_stream1(p); }
+  __device__ __forceinline__ void load_hint(const float *p, uint64_t pol) { v = ldg_hint1(p, pol); }
   __device__ __forceinline__ void load_cached(const float *p) { v = __ldg(p); }
   __device__ __forceinline__ void store(float *p) const { stg_stream1(p, v); }
   __device__ __forceinline__ void zero() { v = 0.f; }

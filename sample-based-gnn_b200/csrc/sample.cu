@@ -954,6 +954,7 @@ static void fill_view(nb_sampler *s, int i, nb_layer_view *v) {
   v->csr_to_csc = csr ? b.csr_to_csc : nullptr;
   v->edge_weight_forward = b.ewf; v->edge_weight_backward = csr ? b.ewb : nullptr;
   v->dst_local_id = merge ? b.dst_local_id : nullptr; v->src_to_dst = merge ? b.src_to_dst : nullptr;
+  v->source_use_count = b.row_count;
 }
 
 // Every kernel of one mini-batch. All arguments are constants of the sampler (per-batch values come from
@@ -974,7 +975,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
            ws1 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 1) * s->max_tiles, s->max_tiles, pp),
            ws2 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 2) * s->max_tiles, s->max_tiles, pp);
     const bool layer_csr = csr && !(i == s->L - 1 && s->L > 1 && (s->flags & NB_SAMPLER_NO_BOTTOM_CSR));
-    const int histogram = (layer_csr || up) ? 1 : 0;
+    const int histogram = 1;   // per-source use counts: the CSR row lengths, UP_DEGREE's out-degrees and the aggregation's L2 hints
     const int bottom = i == s->L - 1 ? 1 : 0;
     uint32_t *next_base = i + 1 < s->L ? s->lay[i + 1].dst_base : nullptr, *next_deg = i + 1 < s->L ? s->lay[i + 1].dst_deg : nullptr;
     uint32_t *rc_ptr = (histogram || merge) ? b.row_count : nullptr;

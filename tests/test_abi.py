@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for n in names:
         assert hasattr(l, n), f"{n} declared in include/nts_b200.h but not exported"
     assert set(names) == set(capi._SIGS), "ctypes signatures out of sync with the header"
-    assert l.nb_abi_version() == 1
+    assert l.nb_abi_version() == 2
 
 
 def test_library_is_sm100a_only(pkg):
@@ -65,4 +65,4 @@ def test_host_csc_build_matches_oracle(pkg):
 
 
 def test_layer_view_struct_layout(pkg):
-    assert ctypes.sizeof(pkg._capi.LayerView) == 16 + 12 * 8
+    assert ctypes.sizeof(pkg._capi.LayerView) == 16 + 13 * 8

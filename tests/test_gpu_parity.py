@@ -573,16 +573,18 @@ def test_gat_against_reference_kernel_records(nts, cs, name):
 
     # ---- legacy-shaped ops, one reference kernel each
     alpha = torch.empty(E, device="cuda"); cached = torch.empty(E, device="cuda")
-    cs.Edge_Softmax_Forward_Norm_Block(alpha, d32(g["m"]), cached, t_ri, t_co, V, 1)
+    t_m, t_da, t_alpha_ref = d32(g["m"]), d32(g["d_a"]), d32(g["alpha"])
+    cs.Edge_Softmax_Forward_Norm_Block(alpha, t_m, cached, t_ri, t_co, V, 1)
     close(f32(alpha), g["alpha"], "Edge_Softmax_Forward_Norm_Block")
     assert torch.equal(alpha, cached)
     d_m = torch.empty(E, device="cuda")
-    cs.Edge_Softmax_Backward_Block(d_m, d32(g["d_a"]), d32(g["alpha"]), t_ri, t_co, V, 1)
+    cs.Edge_Softmax_Backward_Block(d_m, t_da, t_alpha_ref, t_ri, t_co, V, 1)
     close(f32(d_m), g["d_m"], "Edge_Softmax_Backward_Block")
     e_src = g["h"].reshape(S, F)[ri.astype(np.int64)]
     emo = (e_src * g["alpha"][:, None]).astype(np.float32)               # e_msg.slice(0:F) * a, one rounding per element
     nbr = torch.empty((V, F), device="cuda")
-    cs.Gather_Msg_to_Dst(nbr, d32(emo), t_ri, t_co, V, F)
+    t_emo = d32(emo)
+    cs.Gather_Msg_to_Dst(nbr, t_emo, t_ri, t_co, V, F)
     close(f32(nbr), g["out"], "Gather_Msg_to_Dst")
     if "e_msg" in g:                                                     # small cases carry the per-edge tensors
         msg = torch.empty((E, 2 * F), device="cuda")
@@ -593,7 +595,8 @@ def test_gat_against_reference_kernel_records(nts, cs, name):
         cs.Scatter_Dst_to_Msg(back, dout, t_ri, t_co, V, F)
         assert np.array_equal(f32(back), g["d_e_msg_out"].reshape(E, F)), "Scatter_Dst_to_Msg is a copy: bit-exact"
         gsrc = torch.zeros((S, F), device="cuda")
-        cs.Gather_Msg_To_Src_Dst(gsrc, d32(g["d_e_msg"].reshape(E, 2 * F)), t_ri, t_co, V, F, t_dl, S)
+        t_dmsg = d32(g["d_e_msg"].reshape(E, 2 * F))
+        cs.Gather_Msg_To_Src_Dst(gsrc, t_dmsg, t_ri, t_co, V, F, t_dl, S)
         close(f32(gsrc), g["dh"], "Gather_Msg_To_Src_Dst")
     # ---- fused layer (nb_gat_fwd / nb_gat_bwd) against the same records
     pre, al, out = torch.empty(E, device="cuda"), torch.empty(E, device="cuda"), torch.empty((V, F), device="cuda")
@@ -608,8 +611,9 @@ def test_gat_against_reference_kernel_records(nts, cs, name):
     src_to_dst = np.full(S, 0xFFFFFFFF, np.uint32)
     src_to_dst[dl] = np.arange(V, dtype=np.uint32)
     dh, datt = torch.empty((S, F), device="cuda"), torch.empty(2 * F, device="cuda")
-    args = (cs._h, ptr(h), ptr(att), 0.2, ptr(dout), ptr(pre), ptr(al), ptr(t_co), ptr(t_ri), ptr(t_dl), ptr(d32(row_offset)),
-            ptr(d32(edge_dst[order])), ptr(d32(order)), ptr(d32(src_to_dst)), V, S, E, F)
+    t_ro, t_ci, t_c2c, t_s2d = d32(row_offset), d32(edge_dst[order]), d32(order), d32(src_to_dst)   # named: they must outlive the calls
+    args = (cs._h, ptr(h), ptr(att), 0.2, ptr(dout), ptr(pre), ptr(al), ptr(t_co), ptr(t_ri), ptr(t_dl), ptr(t_ro),
+            ptr(t_ci), ptr(t_c2c), ptr(t_s2d), V, S, E, F)
     check(lib.nb_gat_bwd(*args, ptr(dh), ptr(datt)))
     close(f32(dh), g["dh"], "fused dH")
     close(f32(datt), g["datt"], "fused d(att)", floor=2e-5)
