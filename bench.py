@@ -389,10 +389,13 @@ def main_b200(args):
             if exchange in ("one", "nccl"):
                 issue_allreduce()
             # load_feature_gpu + the bottom hop's forward as one kernel: rows come straight from the table through the layer's
-            # source ids; the per-source use counts steer L2 (rows the batch reads again are kept, single-use rows are not)
-            check(lib.nb_aggregate_gathered_fwd_dyn(cs_train._h, ptr(table), PITCH, bot.source, ptr(y1), bot.edge_weight_forward,
-                                                    bot.row_indices, bot.column_offset, None if args.no_l2_hints else bot.source_use_count,
-                                                    nd[1], caps[1][0], F0, PITCH))
+            # packed gather index; its hint bit steers L2 (rows the batch reads again are kept, single-use rows are not)
+            if args.no_l2_hints:   # A/B: the same rows through the plain global ids, no eviction hints
+                check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
+                                                   bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
+            else:
+                check(lib.nb_aggregate_gathered_fwd_dyn(cs_train._h, ptr(table), PITCH, bot.gather_index, ptr(y1), bot.edge_weight_forward,
+                                                        bot.column_offset, nd[1], caps[1][0], F0, PITCH))
             if timed:
                 b.record(st_train)
                 kern_ev["agg_fwd_602_from_table"].append((a, b))

@@ -88,6 +88,9 @@ typedef struct nb_layer_view {
   const uint32_t *dst_local_id;   /* [n_dst] row of each dst inside source (dev_dst_local_id)   */
   const uint32_t *src_to_dst;     /* [n_src] index of the dst equal to this src, or 0xffffffff (new) */
   const uint32_t *source_use_count; /* [n_src] number of this layer's edges that read each source (new; the CSR row lengths) */
+  const uint32_t *gather_index;   /* [n_edges], bottom layer only (NULL elsewhere, and when |V| >= 2^31): sample_ans[e] with bit 31
+                                     set when the batch reads that source more than once -- the index + L2 hint that
+                                     nb_aggregate_gathered_fwd_dyn consumes (new) */
 } nb_layer_view;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -400,14 +403,13 @@ int nb_aggregate_csr_bwd_dyn(nb_ctx *ctx, const float *input, float *output, con
                              uint32_t max_src, uint32_t feature_size, uint32_t input_pitch, uint32_t output_pitch);
 /* nb_aggregate_gathered_fwd_dyn <- FastSampler::load_feature_gpu (core/ntsFastSampler.hpp:244-261) + the bottom hop's
  *                         SingleGPU[All]SampleGraphOp::forward (core/ntsSingleGPUSampleGraphOp.hpp:209-247) as ONE kernel:
- *                         output[d,:] = sum_{e in column d} w[e] * table[source_ids[row_indices[e]],:] -- the same rows in the same
- *                         order as gathering X0 = table[source_ids] first, hence the same bits, without writing or re-reading X0.
- *                         source_use_count (nb_layer_view::source_use_count, may be NULL) steers L2: rows that the batch reads more
+ *                         output[d,:] = sum_{e in column d} w[e] * table[gather_index[e] & 0x7fffffff,:] -- the same rows in the same
+ *                         order as gathering X0 = table[source] first, hence the same bits, without writing or re-reading X0.
+ *                         Bit 31 of a gather_index entry (nb_layer_view::gather_index) steers L2: rows that the batch reads more
  *                         than once are kept (evict_last), single-use rows are not (evict_first). */
-int nb_aggregate_gathered_fwd_dyn(nb_ctx *ctx, const float *table, uint32_t table_pitch, const uint32_t *source_ids, float *output,
-                                  const float *weight_forward, const uint32_t *row_indices, const uint32_t *column_offset,
-                                  const uint32_t *source_use_count_or_null, const uint32_t *n_dst_dev, uint32_t max_dst,
-                                  uint32_t feature_size, uint32_t output_pitch);
+int nb_aggregate_gathered_fwd_dyn(nb_ctx *ctx, const float *table, uint32_t table_pitch, const uint32_t *gather_index, float *output,
+                                  const float *weight_forward, const uint32_t *column_offset, const uint32_t *n_dst_dev,
+                                  uint32_t max_dst, uint32_t feature_size, uint32_t output_pitch);
 int nb_aggregate_push_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight, const uint32_t *row_indices,
                           const uint32_t *column_offset, uint32_t n_dst, uint32_t n_src, uint32_t feature_size);
 

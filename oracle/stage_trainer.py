@@ -61,11 +61,17 @@ def main():
     for alg in ALGORITHMS:
         multi = "MULTI" in alg
         pipeline = 2 if ("CACHE" in alg or "PCMULTI" in alg) else 1
+        if alg == "GATSAMPLEPDCACHE":
+            # its edge-NN lambdas read the shared graph->rtminfo->curr_layer (toolkits/GAT_SAMPLE_PD_CACHE.hpp:428-455) while the other
+            # pipeline thread advances it: with two pipeline threads the reference's own autograd bookkeeping asserts
+            # (core/ntsContext.hpp:491). GAT_SAMPLE_PC_MULTI.hpp fixed this with `int layer = i`. One pipeline slot avoids the race.
+            pipeline = 1
+        epochs = 10 if alg in ("GSSAMPLEPDCACHE", "GATSAMPLEPDCACHE", "GSSAMPLEPCMULTI", "GATSAMPLEPCMULTI") else 5   # stale hot embeddings converge slower
         for cache in ([0, 1] if alg in CACHED_FEATURE_TOOLKITS else [0]):
             for gpus in ([1, 2] if multi else [1]):       # the *_MULTI toolkits also run on one device (GPU_NUM:1)
                 name = f"cfg_{alg}" + ("_cache1" if cache else "") + (f"_g{gpus}" if multi else "") + ".cfg"
                 with open(os.path.join(OUT, name), "w") as f:
-                    f.write(CFG.format(alg=alg, batch=1024, epochs=5, pipeline=pipeline, gpus=gpus, cache=cache))
+                    f.write(CFG.format(alg=alg, batch=1024, epochs=epochs, pipeline=pipeline, gpus=gpus, cache=cache))
                 n += 1
     print("staged", n, "cfgs under", OUT)
 

@@ -133,12 +133,12 @@ class Cuda_Stream:
         check(lib().nb_aggregate_csc_fwd_dyn(self._h, ptr(input), ptr(output), ptr(weight), ptr(row_indices), ptr(column_offset),
                                              ptr(n_dst_dev), n_dst, feature_size, in_pitch, out_pitch))
 
-    def aggregate_gathered_fwd(self, table, source_ids, output, weight, row_indices, column_offset, n_dst, feature_size, table_pitch,
-                               out_pitch, use_count=None, n_dst_dev=None):
-        """load_feature_gpu + the bottom hop's forward in one kernel: output[d] = sum_e w[e] * table[source_ids[row_indices[e]]]"""
-        check(lib().nb_aggregate_gathered_fwd_dyn(self._h, ptr(table), table_pitch, ptr(source_ids), ptr(output), ptr(weight),
-                                                  ptr(row_indices), ptr(column_offset), ptr(use_count), ptr(n_dst_dev), n_dst,
-                                                  feature_size, out_pitch))
+    def aggregate_gathered_fwd(self, table, gather_index, output, weight, column_offset, n_dst, feature_size, table_pitch, out_pitch,
+                               n_dst_dev=None):
+        """load_feature_gpu + the bottom hop's forward in one kernel: output[d] = sum_e w[e] * table[gather_index[e] & 0x7fffffff]
+        (bit 31 of a gather_index entry = the L2 hint; sampCSC.dev_gather_index)"""
+        check(lib().nb_aggregate_gathered_fwd_dyn(self._h, ptr(table), table_pitch, ptr(gather_index), ptr(output), ptr(weight),
+                                                  ptr(column_offset), ptr(n_dst_dev), n_dst, feature_size, out_pitch))
 
     def aggregate_bwd_pitched(self, input, output, weight_b, row_offset, column_indices, n_src, feature_size, in_pitch, out_pitch,
                               n_src_dev=None):
@@ -318,9 +318,9 @@ class sampCSC:
         "dev_edge_weight_forward": ("edge_weight_forward", "e_size", 0, "f"),
         "dev_edge_weight_backward": ("edge_weight_backward", "e_size", 0, "f"),
         "dev_dst_local_id": ("dst_local_id", "v_size", 0, "u"), "dev_src_to_dst": ("src_to_dst", "src_size", 0, "u"),
-        "dev_source_use_count": ("source_use_count", "src_size", 0, "u")}
+        "dev_source_use_count": ("source_use_count", "src_size", 0, "u"), "dev_gather_index": ("gather_index", "e_size", 0, "u")}
     _OPTIONAL = {"dev_row_offset", "dev_column_indices", "dev_csr_to_csc", "dev_edge_weight_backward", "dev_dst_local_id",
-                 "dev_src_to_dst", "dev_source_use_count"}
+                 "dev_src_to_dst", "dev_source_use_count", "dev_gather_index"}
 
     def __init__(self, view, device, owner):
         self.v_size, self.e_size, self.src_size = view.n_dst, view.n_edges, view.n_src
@@ -642,9 +642,13 @@ class SingleGPUAllSampleGraphOp:
             else:   # bottom hop straight from the feature table: input row of edge e = table[sample_ans[e]]
                 table, F = f_input.table, f_input.shape[1]
                 out = _alloc_like_rows(l.v_size, F, table)
-                self.cuda_stream.aggregate_gathered_fwd(table, l.dev_source, out, l.dev_e_w() if self.with_weight else None, l.dev_r_i(),
-                                                        l.dev_c_o(), l.v_size, F, _pitch(table, F), _pitch(out, F),
-                                                        use_count=l.dev_source_use_count)
+                w = l.address("dev_edge_weight_forward") if self.with_weight else None
+                if l.address("dev_gather_index"):
+                    self.cuda_stream.aggregate_gathered_fwd(table, l.address("dev_gather_index"), out, w, l.address("dev_column_offset"),
+                                                            l.v_size, F, _pitch(table, F), _pitch(out, F))
+                else:   # no packed index (|V| >= 2^31): plain aggregation through the global ids
+                    self.cuda_stream.aggregate_fwd_pitched(table, out, w, l.address("dev_sample_ans"), l.address("dev_column_offset"),
+                                                           l.v_size, F, _pitch(table, F), _pitch(out, F))
                 return out
         F = f_input.shape[1]
         assert f_input.shape[0] == l.src_size

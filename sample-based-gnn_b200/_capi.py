@@ -22,7 +22,7 @@ class LayerView(C.Structure):
                 ("row_indices", C.c_void_p), ("source", C.c_void_p), ("row_offset", C.c_void_p),
                 ("column_indices", C.c_void_p), ("csr_to_csc", C.c_void_p), ("edge_weight_forward", C.c_void_p),
                 ("edge_weight_backward", C.c_void_p), ("dst_local_id", C.c_void_p), ("src_to_dst", C.c_void_p),
-                ("source_use_count", C.c_void_p)]
+                ("source_use_count", C.c_void_p), ("gather_index", C.c_void_p)]
 
 
 def header_symbols():
@@ -113,7 +113,7 @@ _SIGS = {
     "nb_aggregate_csc_fwd": (I32, [P, P, P, P, P, P, U32, U32, U32]),
     "nb_aggregate_csr_bwd": (I32, [P, P, P, P, P, P, U32, U32, U32]),
     "nb_aggregate_push_bwd": (I32, [P, P, P, P, P, P, U32, U32, U32]),
-    "nb_aggregate_gathered_fwd_dyn": (I32, [P, P, U32, P, P, P, P, P, P, P, U32, U32, U32]),
+    "nb_aggregate_gathered_fwd_dyn": (I32, [P, P, U32, P, P, P, P, P, U32, U32, U32]),
     "nb_scatter_src_dst_to_msg": (I32, [P, P, P, P, P, U32, U32, P]),
     "nb_gather_msg_to_src_dst": (I32, [P, P, P, P, P, U32, U32, U32, P]),
     "nb_edge_softmax_fwd": (I32, [P, P, P, P, P, U32]),

@@ -36,18 +36,17 @@ struct SegEpilogue {
   const float *va, *vb;  // feature-length vectors
 };
 
-// GATHERED (the bottom hop fused with the feature gather): idx[j] is a position in the layer's source list, the input row is
-// in[remap[idx[j]]] (remap = the layer's global source ids, in = the feature table), so X0 = table[source] is never written.
-// use_count[idx[j]] (optional) = how many edges of this batch read that source: rows used more than once are loaded with an L2
-// evict_last hint, rows used once with evict_first, so the re-reads (41 % of the row reads on the Reddit shape) hit L2 instead of
-// being flushed by the single-use rows in between.
+// GATHERED (the bottom hop fused with the feature gather): `in` is the feature table and idx[j] a PACKED gather index of the
+// sampler (nb_layer_view::gather_index): bits 0-30 = the global id of the edge's source, bit 31 = "this batch reads that row more
+// than once". X0 = table[source] is never written; rows with the bit set are loaded with an L2 evict_last hint, the others with
+// evict_first, so the re-reads (41 % of the row reads on the Reddit shape) hit L2 instead of being flushed by the single-use
+// rows in between. No extra load per edge: the hint travels in the index.
 template <int VEC, int CHUNK, int UNR, bool GATHERED>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
                  const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
                  const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch,
-                 SegEpilogue epi = SegEpilogue{nullptr, nullptr, nullptr, nullptr}, const uint32_t *__restrict__ remap = nullptr,
-                 const uint32_t *__restrict__ use_count = nullptr) {
+                 SegEpilogue epi = SegEpilogue{nullptr, nullptr, nullptr, nullptr}) {
   const unsigned lane = lane_id();
   const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
   const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
@@ -67,10 +66,7 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
         if (lane < cnt) {
           my_idx = idx[j0 + lane];
           if (weight) my_w = weight[j0 + lane];
-          if (GATHERED) {
-            if (use_count) my_keep = use_count[my_idx] > 1u ? 1u : 0u;
-            my_idx = remap[my_idx];
-          }
+          if (GATHERED) { my_keep = my_idx >> 31; my_idx &= 0x7fffffffu; }
         }
         for (uint32_t t = 0; t < cnt; t += UNR) {
           Vec<VEC> x[UNR][CHUNK];
@@ -391,12 +387,12 @@ k_push(const float *__restrict__ in, float *__restrict__ out, const float *__res
 template <int VEC>
 static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                           const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
-                          uint64_t out_pitch, SegEpilogue epi, const uint32_t *remap, const uint32_t *use_count) {
+                          uint64_t out_pitch, SegEpilogue epi, bool packed_index) {
   const uint32_t nvec = F / VEC;
   // block path for long segments: staging batch sized to SEG_STAGE_BYTES of dynamic shared memory
   uint32_t long_batch = 0;
   size_t smem = 0;
-  if (!push && !remap && g_agg_long_rows && F <= SEG_LONG_MAX_F) {
+  if (!push && !packed_index && g_agg_long_rows && F <= SEG_LONG_MAX_F) {
     long_batch = SEG_STAGE_BYTES / (F * 4u);
     if (long_batch > 64) long_batch = 64;
     if (long_batch < 2) long_batch = 2;
@@ -412,7 +408,7 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
     if (push) k_push<VEC, C><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, nvec, F); \
     else if (long_batch && (g_agg_pipe_wide == 2 || (C <= 2 && g_agg_pipe_wide == 1))) k_segment_reduce_lb<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), true><<<grid, AGG_THREADS, smem, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, long_batch); \
     else if (long_batch) k_segment_reduce_lb<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), false><<<grid, AGG_THREADS, smem, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, long_batch); \
-    else if (remap) k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), true><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi, remap, use_count); \
+    else if (packed_index) k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), true><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
     else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), false><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
   } while (0)
   if (per_lane <= 1) NB_SEG(1);
@@ -430,8 +426,7 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
 
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                    const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
-                   uint64_t out_pitch, const float *e1, const float *e2, const float *va, const float *vb, const uint32_t *remap,
-                   const uint32_t *use_count) {
+                   uint64_t out_pitch, const float *e1, const float *e2, const float *va, const float *vb, bool packed_index) {
   SegEpilogue epi{e1, e2, va, vb};
   if (n_rows == 0) return NB_OK;
   if (!in_pitch) in_pitch = F;
@@ -439,9 +434,9 @@ int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const fl
   uint32_t fe = F;
   int vec = (push || e1) ? nb_pick_vec(F, in, in_pitch, out, out_pitch) : nb_pick_vec(F, in, in_pitch, out, out_pitch, &fe);
   if (e1 && vec > 1 && (((uintptr_t)va | (uintptr_t)vb) % (4 * vec))) vec = 1;  // epilogue vectors must allow the same vector loads
-  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, remap, use_count);
-  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, remap, use_count);
-  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, remap, use_count);
+  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index);
+  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index);
+  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index);
 }
 
 static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
@@ -492,16 +487,15 @@ int nb_aggregate_csr_bwd_dyn(nb_ctx *ctx, const float *input, float *output, con
 }
 
 // The bottom hop fused with the feature gather (FastSampler::load_feature_gpu + SingleGPU[All]SampleGraphOp::forward in one kernel)
-int nb_aggregate_gathered_fwd_dyn(nb_ctx *ctx, const float *table, uint32_t table_pitch, const uint32_t *source_ids, float *output,
-                                  const float *weight_forward, const uint32_t *row_indices, const uint32_t *column_offset,
-                                  const uint32_t *source_use_count_or_null, const uint32_t *n_dst_dev, uint32_t max_dst,
-                                  uint32_t feature_size, uint32_t output_pitch) {
-  NB_REQUIRE(ctx && (max_dst == 0 || (table && source_ids && output && row_indices && column_offset)), NB_ERR_ARG, "nb_aggregate_gathered_fwd_dyn: NULL argument");
+int nb_aggregate_gathered_fwd_dyn(nb_ctx *ctx, const float *table, uint32_t table_pitch, const uint32_t *gather_index, float *output,
+                                  const float *weight_forward, const uint32_t *column_offset, const uint32_t *n_dst_dev,
+                                  uint32_t max_dst, uint32_t feature_size, uint32_t output_pitch) {
+  NB_REQUIRE(ctx && (max_dst == 0 || (table && gather_index && output && column_offset)), NB_ERR_ARG, "nb_aggregate_gathered_fwd_dyn: NULL argument");
   NB_REQUIRE(feature_size > 0 && table_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
   NB_GUARD(ctx);
   table = (const float *)nb_mirror_host(ctx, table);
-  return nb_run_segment(ctx, false, table, output, weight_forward, row_indices, column_offset, max_dst, feature_size, n_dst_dev, table_pitch,
-                        output_pitch, nullptr, nullptr, nullptr, nullptr, source_ids, source_use_count_or_null);
+  return nb_run_segment(ctx, false, table, output, weight_forward, gather_index, column_offset, max_dst, feature_size, n_dst_dev, table_pitch,
+                        output_pitch, nullptr, nullptr, nullptr, nullptr, true);
 }
 
 int nb_aggregate_push_bwd(nb_ctx *ctx, const float *input, float *output, const float *weight, const uint32_t *row_indices,

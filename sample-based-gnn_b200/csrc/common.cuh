@@ -49,7 +49,7 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);
 // segment reduction out[r,:] = sum_j w[j] in[idx[j],:] (+ e1[r] va + e2[r] vb); aggregate.cu
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *offsets,
                    uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch, uint64_t out_pitch, const float *e1,
-                   const float *e2, const float *va, const float *vb, const uint32_t *remap = nullptr, const uint32_t *use_count = nullptr);
+                   const float *e2, const float *va, const float *vb, bool packed_index = false);
 // (optionally sharded) HBM feature table; gather.cu
 struct nb_table {
   nb_ctx *ctx;

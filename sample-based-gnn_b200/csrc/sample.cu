@@ -32,6 +32,7 @@ struct LayerBuf {
   uint32_t *destination, *column_offset, *sample_ans, *row_indices, *edge_dst, *source;
   uint32_t *row_offset, *row_count, *row_cursor, *column_indices, *csr_tmp, *csr_to_csc, *long_rows;
   uint32_t *dst_local_id, *src_to_dst;
+  uint32_t *gather_idx;           // [cap_edges], bottom layer only: global src id | (the batch reads that source more than once) << 31
   uint32_t *dst_base, *dst_deg;   // [cap_dst] g_col_off[d] and the in-degree of every dst, written by whoever produced `destination`
                                   // (the previous layer's source emission; layer 0: the sampling kernel itself)
   float *ewf, *ewb;
@@ -754,6 +755,17 @@ k_csr_fill_fused(const uint32_t *__restrict__ row_indices, const uint32_t *__res
   }
 }
 
+// Bottom layer: the packed index the gather-fused aggregation consumes (aggregate.cu, GATHERED): global source id of every edge
+// with bit 31 set when this batch reads that source more than once (row_count = the finished per-source histogram).
+__global__ void __launch_bounds__(256)
+k_pack_gather_index(const uint32_t *__restrict__ sample_ans, const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ row_count,
+                    uint32_t *__restrict__ gather_idx, const LayerMeta *meta) {
+  if (meta->err) return;
+  const unsigned E = meta->n_edges;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
+    gather_idx[e] = sample_ans[e] | (row_count[row_indices[e]] > 1u ? 0x80000000u : 0u);
+}
+
 // degrees from the CSC when the caller has none (clamped >= 1, core/graph.hpp:4525-4530)
 __global__ void k_degrees_from_csc(const uint32_t *col_off, const uint32_t *row_idx, uint32_t *in_deg, uint32_t *out_deg,
                                    uint32_t V, uint64_t E, int phase) {
@@ -846,7 +858,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   size_t words = 0;              // arena size in 4-byte words
   auto take = [&](size_t n) { size_t at = words; words += (n + 31) & ~(size_t)31; return at; };
   struct Off { size_t destination, column_offset, sample_ans, row_indices, edge_dst, source, row_offset, row_count, row_cursor,
-               column_indices, csr_tmp, csr_to_csc, long_rows, dst_local_id, src_to_dst, ewf, ewb, dst_base, dst_deg; } off[NB_MAX_LAYERS];
+               column_indices, csr_tmp, csr_to_csc, long_rows, dst_local_id, src_to_dst, ewf, ewb, dst_base, dst_deg, gather_idx; } off[NB_MAX_LAYERS];
   uint64_t max_items = 0;
   for (int i = 0; i < n_layers; i++) {
     s->fanout[i] = fanout[i];
@@ -873,6 +885,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     o.dst_local_id = take(cap_dst); o.src_to_dst = take(cap_s);
     o.ewf = take(cap_e); o.ewb = take(cap_e);
     o.dst_base = take(cap_dst); o.dst_deg = take(cap_dst);
+    o.gather_idx = (i == n_layers - 1 && g->V < 0x80000000u) ? take(cap_e) : (size_t)-1;
     if (cap_dst > max_items) max_items = cap_dst;
     if (cap_s > max_items) max_items = cap_s;
     cap_dst = cap_s;
@@ -906,6 +919,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     b.dst_local_id = base + o.dst_local_id; b.src_to_dst = base + o.src_to_dst;
     b.ewf = (float *)(base + o.ewf); b.ewb = (float *)(base + o.ewb);
     b.dst_base = base + o.dst_base; b.dst_deg = base + o.dst_deg;
+    b.gather_idx = o.gather_idx == (size_t)-1 ? nullptr : base + o.gather_idx;
   }
   for (int i = 1; i < n_layers; i++) s->lay[i].destination = s->lay[i - 1].source;  // layer chaining (FullyRepGraph.hpp:309)
   s->bitmap[0] = base + o_bitmap; s->bitmap[1] = base + o_bitmap1; s->word_rank = base + o_rank;
@@ -955,6 +969,7 @@ static void fill_view(nb_sampler *s, int i, nb_layer_view *v) {
   v->edge_weight_forward = b.ewf; v->edge_weight_backward = csr ? b.ewb : nullptr;
   v->dst_local_id = merge ? b.dst_local_id : nullptr; v->src_to_dst = merge ? b.src_to_dst : nullptr;
   v->source_use_count = b.row_count;
+  v->gather_index = b.gather_idx;
 }
 
 // Every kernel of one mini-batch. All arguments are constants of the sampler (per-batch values come from
@@ -1035,6 +1050,10 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
     }
     if (up) {
       k_weights_sampled<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
+      NB_LAUNCH_CHECK(ctx);
+    }
+    if (b.gather_idx) {
+      k_pack_gather_index<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.sample_ans, b.row_indices, b.row_count, b.gather_idx, m);
       NB_LAUNCH_CHECK(ctx);
     }
     if (layer_csr) {

@@ -11,7 +11,7 @@ LAYER_KEYS = ["destination", "column_offset", "sample_ans", "source", "row_indic
 
 def names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz"))
-                  if "pre_sample" not in p and "hotness" not in p)
+                  if "pre_sample" not in p and "hotness" not in p and not os.path.basename(p).startswith("gat_"))
 
 
 def load(name):

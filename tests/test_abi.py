@@ -65,4 +65,4 @@ def test_host_csc_build_matches_oracle(pkg):
 
 
 def test_layer_view_struct_layout(pkg):
-    assert ctypes.sizeof(pkg._capi.LayerView) == 16 + 13 * 8
+    assert ctypes.sizeof(pkg._capi.LayerView) == 16 + 14 * 8

@@ -134,6 +134,13 @@ def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, b
             assert np.array_equal(u32(l.dev_edge_weight_backward), bits(r["e_w_b"])), i
             c2c = u32(l.dev_csr_to_csc)
             assert np.array_equal(np.sort(c2c), np.arange(l.e_size, dtype=np.uint32))
+        use = np.bincount(r["row_indices"], minlength=l.src_size).astype(np.uint32)
+        assert np.array_equal(u32(l.dev_source_use_count), use), i            # per-source use counts (the CSR row lengths)
+        if i == len(fanout) - 1:                                               # bottom layer: packed gather index = id | hint bit
+            gi = u32(l.dev_gather_index)
+            assert np.array_equal(gi & 0x7FFFFFFF, ans[i]) and np.array_equal(gi >> 31, (use[r["row_indices"]] > 1).astype(np.uint32)), i
+        else:
+            assert l.dev_gather_index is None
         if merge:
             assert np.array_equal(u32(l.dev_dst_local_id), r["dst_local_id"]), i
             s2d = u32(l.dev_src_to_dst)
