@@ -284,8 +284,9 @@ def main_b200(args):
         grads_src = torch.rand(n_grad, generator=torch.Generator(device=dev).manual_seed(77 + rank), device=dev) - 0.5
         grads = grads_src.clone()                                                 # dense W gradients, one bucket
         seeds_dev = torch.from_numpy(my_seeds.view(np.int32)).to(dev)
-        sizes_pin = torch.zeros((n_steps, 8), dtype=torch.int32).pin_memory()     # LayerMeta of the bottom layer per step
-        sizes_top = torch.zeros((n_steps, 8), dtype=torch.int32).pin_memory()
+        sizes_both = torch.zeros((n_steps, 16), dtype=torch.int32).pin_memory()   # LayerMeta (n_dst, n_edges, n_src, ...) of both layers per step
+        sizes_top, sizes_pin = sizes_both[:, :8], sizes_both[:, 8:]
+        sizes_np = sizes_both.numpy()
     torch.cuda.synchronize()
 
     # fixed arena pointers and device-side size addresses of every pipeline slot
@@ -404,8 +405,7 @@ def main_b200(args):
                                            top.column_offset, nd[0], caps[0][0], F1, F1, F1))
         check(lib.nb_aggregate_csr_bwd_dyn(cs_train._h, ptr(dy0), ptr(dh1), top.edge_weight_backward, top.row_offset,
                                            top.column_indices, ns[0], caps[0][2], F1, F1, F1))
-        check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_pin[i]), nd[1].value, 32, 0))
-        check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_top[i]), nd[0].value, 32, 0))
+        check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_both[i]), nd[0].value, 64, 0))   # LayerMeta of both layers (adjacent), one copy
         sl["consumed"].record(st_train)
         exchange_after_backward()
 
@@ -453,8 +453,8 @@ def main_b200(args):
         if i > 0:
             y0_done[(i - 1) % 2].synchronize()
             api_state["checksum"] += float(y0_ring[(i - 1) % 2][0, 0])
-        sizes_pin[i, 0], sizes_pin[i, 1], sizes_pin[i, 2] = bt.v_size, bt.e_size, bt.src_size
-        sizes_top[i, 1] = t.e_size
+        sizes_np[i, 8:11] = (bt.v_size, bt.e_size, bt.src_size)    # host bookkeeping of the work done (numpy view of the pinned buffer)
+        sizes_np[i, 1] = t.e_size
         del yy1
 
     barrier_buf = torch.zeros(4, device=dev)

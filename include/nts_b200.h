@@ -169,6 +169,9 @@ int nb_graph_create(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const ui
  * rejected (NB_ERR_ARG). Bit-identical to nb_graph_create on the host-built arrays. */
 int nb_graph_create_from_pairs(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *pairs, int pairs_on_device,
                                nb_graph **out);
+/* The same from CSC arrays that already live in device memory (generated or loaded on the GPU); degrees are derived on the device. */
+int nb_graph_create_from_device(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *column_offset_dev,
+                                const uint32_t *row_indices_dev, nb_graph **out);
 int nb_graph_destroy(nb_graph *g);
 int nb_graph_info(nb_graph *g, uint32_t *n_vertices, uint64_t *n_edges, const uint32_t **column_offset_dev,
                   const uint32_t **row_indices_dev, const uint32_t **in_degree_dev, const uint32_t **out_degree_dev);

@@ -257,6 +257,16 @@ class FullyRepGraph:
             self.global_edges = n_edges
             self.column_offset = self.row_indices = self.in_degree = self.out_degree = None   # device resident: device_arrays()
             return
+        if column_offset is not None and hasattr(column_offset, "is_cuda") and column_offset.is_cuda:
+            # CSC arrays already on the device (int32 tensors holding u32 values): adopted without a host round trip
+            co, ri = column_offset.contiguous(), row_indices.contiguous()
+            assert co.dtype == torch.int32 and ri.dtype == torch.int32 and co.numel() == self.global_vertices + 1
+            h = C.c_void_p()
+            check(lib().nb_graph_create_from_device(self.cs._h, self.global_vertices, int(ri.numel()), ptr(co), ptr(ri), C.byref(h)))
+            self._h = h
+            self.global_edges = int(ri.numel())
+            self.column_offset = self.row_indices = self.in_degree = self.out_degree = None
+            return
         if edge_pairs is not None:
             column_offset, row_indices, ind, outd = self.build_csc_host(edge_pairs, self.global_vertices)
             if in_degree is None:
@@ -653,12 +663,11 @@ class SingleGPUAllSampleGraphOp:
         F = f_input.shape[1]
         assert f_input.shape[0] == l.src_size
         out = _alloc_like_rows(l.v_size, F, f_input)
-        if _pitch(f_input, F) == F:
-            self.cuda_stream.Gather_By_Dst_From_Src_Spmm(f_input, out, l.dev_e_w(), l.dev_r_i(), l.dev_c_o(), l.src_size,
-                                                         0, 0, 0, 0, l.e_size, l.v_size, F, self.with_weight, False)
-        else:
-            self.cuda_stream.aggregate_fwd_pitched(f_input, out, l.dev_e_w() if self.with_weight else None, l.dev_r_i(),
-                                                   l.dev_c_o(), l.v_size, F, _pitch(f_input, F), _pitch(out, F))
+        # raw arena addresses (no tensor views are built on the per-step path); the math is Cuda_Stream::Gather_By_Dst_From_Src_Spmm's
+        check(lib().nb_aggregate_csc_fwd_dyn(self.cuda_stream._h, f_input.data_ptr(), out.data_ptr(),
+                                             l.address("dev_edge_weight_forward") if self.with_weight else None,
+                                             l.address("dev_row_indices"), l.address("dev_column_offset"), None, l.v_size, F,
+                                             _pitch(f_input, F), _pitch(out, F)))
         return out
 
     def backward(self, f_output_grad):
@@ -666,14 +675,13 @@ class SingleGPUAllSampleGraphOp:
         F = f_output_grad.shape[1]
         assert f_output_grad.shape[0] == l.v_size
         grad = _alloc_like_rows(l.src_size, F, f_output_grad)
-        if _pitch(f_output_grad, F) != F:
-            assert l.dev_row_offset is not None, "padded tensors need the CSR (build_csr=True)"
-            self.cuda_stream.aggregate_bwd_pitched(f_output_grad, grad, l.dev_e_w_b() if self.with_weight else None, l.dev_r_o(),
-                                                   l.dev_c_i(), l.src_size, F, _pitch(f_output_grad, F), _pitch(grad, F))
-        elif l.dev_row_offset is not None:
-            self.cuda_stream.Gather_By_Src_From_Dst_Spmm(f_output_grad, grad, l.dev_e_w_b(), l.dev_r_o(), l.dev_c_i(),
-                                                         l.v_size, 0, 0, 0, 0, l.e_size, l.src_size, F, self.with_weight, False)
+        if l.address("dev_row_offset"):      # CSR segment reduce: deterministic, every row written once (Gather_By_Src_From_Dst_Spmm)
+            check(lib().nb_aggregate_csr_bwd_dyn(self.cuda_stream._h, f_output_grad.data_ptr(), grad.data_ptr(),
+                                                 l.address("dev_edge_weight_backward") if self.with_weight else None,
+                                                 l.address("dev_row_offset"), l.address("dev_column_indices"), None, l.src_size, F,
+                                                 _pitch(f_output_grad, F), _pitch(grad, F)))
         else:
+            assert _pitch(f_output_grad, F) == F, "padded tensors need the CSR (build_csr=True)"
             self.cuda_stream.Push_From_Dst_To_Src_Spmm(f_output_grad, grad, l.dev_e_w(), l.dev_r_i(), l.dev_c_o(),
                                                        l.src_size, 0, 0, 0, 0, l.e_size, l.v_size, F, self.with_weight, False)
         return grad

@@ -58,6 +58,7 @@ _SIGS = {
     "nb_memset_async": (I32, [P, P, I32, SZ]),
     "nb_graph_create": (I32, [P, U32, U64, P, P, P, P, C.POINTER(P)]),
     "nb_graph_create_from_pairs": (I32, [P, U32, U64, P, I32, C.POINTER(P)]),
+    "nb_graph_create_from_device": (I32, [P, U32, U64, P, P, C.POINTER(P)]),
     "nb_graph_destroy": (I32, [P]),
     "nb_graph_info": (I32, [P, C.POINTER(U32), C.POINTER(U64), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "nb_sampler_create": (I32, [P, P, I32, C.POINTER(I32), U32, U32, U64, C.POINTER(P)]),

@@ -820,6 +820,53 @@ int nb_graph_create(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const ui
   return NB_OK;
 }
 
+__global__ void k_max_degree(const uint32_t *__restrict__ col_off, uint32_t V, uint32_t *out) {
+  uint32_t m = 0;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (uint64_t)gridDim.x * blockDim.x) m = max(m, col_off[v + 1] - col_off[v]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, o));
+  if (lane_id() == 0 && m) atomicMax(out, m);
+}
+
+// The same from arrays that already live in device memory (a graph generated or loaded on the GPU): no host round trip.
+int nb_graph_create_from_device(nb_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *column_offset_dev,
+                                const uint32_t *row_indices_dev, nb_graph **out) {
+  NB_REQUIRE(ctx && out && column_offset_dev && (row_indices_dev || n_edges == 0), NB_ERR_ARG, "nb_graph_create_from_device: NULL argument");
+  NB_REQUIRE(n_vertices > 0 && n_edges < 0xffffffffull, NB_ERR_ARG, "nb_graph_create_from_device: |V| must be > 0 and |E| < 2^32 (u32 offsets)");
+  NB_GUARD(ctx);
+  nb_graph *g = new nb_graph();
+  g->ctx = ctx; g->V = n_vertices; g->E = n_edges;
+  g->col_off = g->row_idx = g->in_deg = g->out_deg = nullptr;
+  auto fail = [&](int rc) { cudaFree(g->col_off); cudaFree(g->row_idx); cudaFree(g->in_deg); cudaFree(g->out_deg); delete g; return rc; };
+#define NB_TRYG(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { nb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(NB_ERR_CUDA); } } while (0)
+  NB_TRYG(cudaMalloc(&g->col_off, ((size_t)n_vertices + 1) * 4));
+  NB_TRYG(cudaMalloc(&g->row_idx, (size_t)(n_edges ? n_edges : 1) * 4));
+  NB_TRYG(cudaMalloc(&g->in_deg, (size_t)n_vertices * 4));
+  NB_TRYG(cudaMalloc(&g->out_deg, (size_t)n_vertices * 4));
+  NB_TRYG(cudaMemcpyAsync(g->col_off, column_offset_dev, ((size_t)n_vertices + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (n_edges) NB_TRYG(cudaMemcpyAsync(g->row_idx, row_indices_dev, (size_t)n_edges * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  uint32_t tail = 0, *mx_dev = nullptr;
+  NB_TRYG(cudaMemcpyAsync(&tail, g->col_off + n_vertices, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  for (int phase = 0; phase < 3; phase++) {
+    k_degrees_from_csc<<<nb_grid(phase == 1 ? n_edges : n_vertices, 256), 256, 0, ctx->stream>>>(g->col_off, g->row_idx, g->in_deg, g->out_deg, n_vertices, n_edges, phase);
+    ctx->launches++;
+  }
+  NB_TRYG(cudaMalloc(&mx_dev, 4));
+  cudaMemsetAsync(mx_dev, 0, 4, ctx->stream);
+  k_max_degree<<<nb_grid(n_vertices, 256), 256, 0, ctx->stream>>>(g->col_off, n_vertices, mx_dev);
+  ctx->launches++;
+  uint32_t mx = 0;
+  cudaMemcpyAsync(&mx, mx_dev, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(mx_dev);
+  if (e != cudaSuccess) { nb_set_error("nb_graph_create_from_device: %s", cudaGetErrorString(e)); return fail(NB_ERR_CUDA); }
+#undef NB_TRYG
+  if (tail != (uint32_t)n_edges) { nb_set_error("column_offset[|V|] != |E|"); return fail(NB_ERR_ARG); }
+  g->max_in_degree = mx;
+  *out = g;
+  return NB_OK;
+}
+
 int nb_graph_destroy(nb_graph *g) {
   if (!g) return NB_OK;
   DeviceGuard guard(g->ctx->device);
