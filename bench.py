@@ -407,7 +407,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         sl["consumed"].record(st_train)
         exchange_after_backward()
 
-    api_state = {"issued": -1, "checksum": 0.0}
+    api_state = {"issued": -1, "checksum": 0.0, "wait_s": 0.0}
     y0_ring = [torch.empty((B, F1)).pin_memory() for _ in range(2)]
     y0_done = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -427,7 +427,9 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         if api_state["issued"] < i:
             api_issue(i)
         k = i % 2
+        tw = time.perf_counter()
         sg = fast.wait(k)                                           # host waits for the sizes of batch i only
+        api_state["wait_s"] += time.perf_counter() - tw
         st_train.wait_event(api_ev[k]["sampled"])
         t, bt = sg.sampled_sgs
         if args.materialize_x0:
@@ -470,6 +472,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
     def run(mode, clocks=None):
         step = {"fused": lambda i, t: step_async(i, t, True), "materialized": lambda i, t: step_async(i, t, False), "api": step_api}[mode]
         api_state["issued"] = -1
+        api_state["wait_s"] = 0.0
         comm_box[0], pending_box[0], open_box[0] = None, None, False
         for k in kern_ev.values():
             k.clear()
@@ -516,7 +519,8 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         work = {"edges": per_win(sp[:, 1] + st_[:, 1]), "V1": int(sp[:, 0].sum()) / R, "E1": int(sp[:, 1].sum()) / R, "S1": int(sp[:, 2].sum()) / R}
         kms = {k: sum(x.elapsed_time(y) for x, y in lst) / max(len(lst), 1) for k, lst in kern_ev.items()}
         wait = peer_ar.stats(reset=True) if peer_ar is not None else None
-        return dict(ms=wins, issue_ms=issue_ms, launches=launches / R, work=work, kms=kms, wait=wait)
+        return dict(ms=wins, issue_ms=issue_ms, launches=launches / R, work=work, kms=kms, wait=wait,
+                    host_wait_ms_per_step=api_state["wait_s"] * 1e3 / (W + R * K))
 
     clocks = ClockSampler(local) if sample_clocks else None
     res = {"fused": run("fused", clocks)}
@@ -1042,6 +1046,7 @@ def main_b200(args):
                 "e2e": {"value": a_["value"], "unit": "edges/s", "h2d_bytes_per_step": B * 4 + 64,
                         "d2h_bytes_per_step": B * F1 * 4 + 3 * 32, "ms_per_step": a_["ms_per_step"],
                         "windows_ms_per_step": a_["windows_ms_per_step"], "host_issue_ms_per_step": a_["host_issue_ms_per_step"],
+                        "host_blocked_in_sampler_wait_ms_per_step": round(res["api"]["host_wait_ms_per_step"], 5),
                         "path": "FastSampler.sample_gpu_fast(slot i+1, async, high-priority stream) || wait(slot i) -> load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
                 "gpu_launches": int(round(launches_all)), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "other_configs": other,
                 "materialized_x0": {"value": m_["value"], "unit": "edges/s", "ms_per_step": m_["ms_per_step"],

@@ -261,6 +261,7 @@ class FullyRepGraph:
             # CSC arrays already on the device (int32 tensors holding u32 values): adopted without a host round trip
             co, ri = column_offset.contiguous(), row_indices.contiguous()
             assert co.dtype == torch.int32 and ri.dtype == torch.int32 and co.numel() == self.global_vertices + 1
+            torch.cuda.synchronize(co.device)     # the arrays may still be being produced on another stream than cuda_stream's
             h = C.c_void_p()
             check(lib().nb_graph_create_from_device(self.cs._h, self.global_vertices, int(ri.numel()), ptr(co), ptr(ri), C.byref(h)))
             self._h = h
