@@ -430,6 +430,9 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         tw = time.perf_counter()
         sg = fast.wait(k)                                           # host waits for the sizes of batch i only
         api_state["wait_s"] += time.perf_counter() - tw
+        if i + 1 < n_steps:
+            api_issue(i + 1)                                        # the next batch samples (other pipeline slot, high-priority stream)
+                                                                    # while this one is gathered / aggregated and the host issues its ops
         st_train.wait_event(api_ev[k]["sampled"])
         t, bt = sg.sampled_sgs
         if args.materialize_x0:
@@ -445,8 +448,6 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         op_top.backward(dy0)
         api_ev[k]["consumed"].record(st_train)
         exchange_after_backward()
-        if i + 1 < n_steps:
-            api_issue(i + 1)                                        # next batch samples while this one gathers / aggregates
         # the step's result goes to one of two pinned host buffers; the host consumes step i-1's while step i runs
         y0_ring[i % 2].copy_(yy0, non_blocking=True)
         y0_done[i % 2].record(st_train)

@@ -36,6 +36,12 @@ void nb_agg_set_option(int which, int value) {
 struct SegEpilogue {
   const float *e1, *e2;  // per output row scalars (e2 may be NULL)
   const float *va, *vb;  // feature-length vectors
+  // fused GAT backward (gat.cu): the row's weights and scalars are derived on the fly from CSC-ordered per-edge arrays instead of
+  // being staged by a separate kernel: for CSR entry j, e = c2c[j]: w = alpha[e]; e1(r) = sum_j ds[e]; e2(r) = dsum[src_to_dst[r]]
+  // (0 when the source is not a dst). e1 / e2 are also written to rs_out / dd_out for the attention-gradient pass.
+  const uint32_t *c2c = nullptr, *src_to_dst = nullptr;
+  const float *alpha = nullptr, *ds = nullptr, *dsum = nullptr;
+  float *rs_out = nullptr, *dd_out = nullptr;
 };
 
 // GATHERED (the bottom hop fused with the feature gather): `in` is the feature table and idx[j] a PACKED gather index of the
@@ -57,6 +63,7 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
   if (GATHERED) { pol_keep = l2_policy_evict_last(); pol_once = l2_policy_evict_first(); }
   for (unsigned r = warp; r < n_rows; r += warps) {
     const uint32_t beg = offsets[r], end = offsets[r + 1];
+    float gat_aux = 0.f, gat_s1 = 0.f, gat_s2 = 0.f;
     for (unsigned c0 = 0; c0 < nvec; c0 += 32 * CHUNK) {  // one pass unless the row is wider than 32*CHUNK vectors
       Vec<VEC> acc[CHUNK];
 #pragma unroll
@@ -67,7 +74,11 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
         float my_w = 1.0f;
         if (lane < cnt) {
           my_idx = idx[j0 + lane];
-          if (weight) my_w = weight[j0 + lane];
+          if (epi.c2c) {
+            const uint32_t e = epi.c2c[j0 + lane];
+            my_w = epi.alpha[e];
+            if (c0 == 0) gat_aux += epi.ds[e];
+          } else if (weight) my_w = weight[j0 + lane];
           if (GATHERED) { my_keep = my_idx >> 31; my_idx &= 0x7fffffffu; }
         }
         for (uint32_t t = 0; t < cnt; t += UNR) {
@@ -105,8 +116,15 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
           }
         }
       }
-      if (epi.e1) {
-        const float s1 = epi.e1[r], s2 = epi.e2 ? epi.e2[r] : 0.f;
+      if (epi.c2c && c0 == 0) {
+        gat_s1 = warp_sum(gat_aux);
+        const uint32_t d = epi.src_to_dst[r];
+        gat_s2 = d != 0xffffffffu ? epi.dsum[d] : 0.f;
+        if (lane == 0) { epi.rs_out[r] = gat_s1; epi.dd_out[r] = gat_s2; }
+      }
+      if (epi.e1 || epi.c2c) {
+        const float s1 = epi.c2c ? gat_s1 : epi.e1[r], s2 = epi.c2c ? gat_s2 : (epi.e2 ? epi.e2[r] : 0.f);
+        const bool two = epi.c2c || epi.e2;
 #pragma unroll
         for (int c = 0; c < CHUNK; c++) {
           const unsigned k = c0 + c * 32 + lane;
@@ -116,7 +134,7 @@ k_segment_reduce(const float *__restrict__ in, float *__restrict__ out, const fl
             // loads they all land on the same L2 slices and serialise there (150K rows x 1 KB: ~35 us of the GAT backward)
             a.load_cached(epi.va + (uint64_t)k * VEC);
             acc[c].axpy(a, s1);
-            if (epi.e2) { b.load_cached(epi.vb + (uint64_t)k * VEC); acc[c].axpy(b, s2); }
+            if (two) { b.load_cached(epi.vb + (uint64_t)k * VEC); acc[c].axpy(b, s2); }
           }
         }
       }
@@ -394,7 +412,7 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
   // block path for long segments: staging batch sized to SEG_STAGE_BYTES of dynamic shared memory
   uint32_t long_batch = 0;
   size_t smem = 0;
-  if (!push && !packed_index && g_agg_long_rows && F <= SEG_LONG_MAX_F) {
+  if (!push && !packed_index && !epi.c2c && g_agg_long_rows && F <= SEG_LONG_MAX_F) {
     long_batch = SEG_STAGE_BYTES / (F * 4u);
     if (long_batch > 64) long_batch = 64;
     if (long_batch < 2) long_batch = 2;
@@ -424,6 +442,20 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
 #undef NB_SEG
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
+}
+
+// CSR segment reduction of the fused GAT backward: dh[s,:] = sum_j alpha[c2c[j]] dout[col[j],:] + (sum_j ds[c2c[j]]) va + dsum[src_to_dst[s]] vb
+int nb_run_segment_gat(nb_ctx *ctx, const float *dout, float *dh, const uint32_t *column_indices, const uint32_t *row_offset, uint32_t n_src,
+                       uint32_t F, const uint32_t *c2c, const float *alpha, const float *ds, const float *dsum, const uint32_t *src_to_dst,
+                       const float *va, const float *vb, float *rs_out, float *dd_out) {
+  if (n_src == 0) return NB_OK;
+  SegEpilogue epi{nullptr, nullptr, va, vb};
+  epi.c2c = c2c; epi.alpha = alpha; epi.ds = ds; epi.dsum = dsum; epi.src_to_dst = src_to_dst; epi.rs_out = rs_out; epi.dd_out = dd_out;
+  int vec = nb_pick_vec(F, dout, F, dh, F);
+  if (vec > 1 && (((uintptr_t)va | (uintptr_t)vb) % (4 * vec))) vec = 1;
+  if (vec == 4) return launch_segment<4>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false);
+  if (vec == 2) return launch_segment<2>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false);
+  return launch_segment<1>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false);
 }
 
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,

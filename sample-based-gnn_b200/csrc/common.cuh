@@ -50,6 +50,9 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *offsets,
                    uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch, uint64_t out_pitch, const float *e1,
                    const float *e2, const float *va, const float *vb, bool packed_index = false);
+int nb_run_segment_gat(nb_ctx *ctx, const float *dout, float *dh, const uint32_t *column_indices, const uint32_t *row_offset, uint32_t n_src,
+                       uint32_t F, const uint32_t *c2c, const float *alpha, const float *ds, const float *dsum, const uint32_t *src_to_dst,
+                       const float *va, const float *vb, float *rs_out, float *dd_out);
 // (optionally sharded) HBM feature table; gather.cu
 struct nb_table {
   nb_ctx *ctx;

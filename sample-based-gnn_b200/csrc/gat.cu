@@ -109,15 +109,43 @@ k_scatter_dst_to_msg(float *__restrict__ msg, const float *__restrict__ y, const
 }
 
 // ---- fused layer ---------------------------------------------------------------------------
-// al[s] = h[s,:].att[0:F], ar[s] = h[s,:].att[F:2F]
+// al[s] = h[s,:].att[0:F], ar[s] = h[s,:].att[F:2F]. One warp per row; rows of 4k floats move as 128-bit vectors with ROWS rows in
+// flight per warp (one 512-byte row is a single vector per lane: latency bound unless several rows overlap), att stays in registers.
+template <int VEC, int ROWS>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_node_scores(const float *__restrict__ h, const float *__restrict__ att, float *__restrict__ al, float *__restrict__ ar,
                   uint32_t n_src, uint32_t F) {
   const unsigned lane = lane_id(), warp = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5, warps = (gridDim.x * GAT_THREADS) >> 5;
+  const unsigned nvec = F / VEC;
+  if (nvec <= 32) {   // the whole row is one vector per lane
+    Vec<VEC> wa, wb;
+    wa.zero(); wb.zero();
+    if (lane < nvec) { wa.load_cached(att + (uint64_t)lane * VEC); wb.load_cached(att + F + (uint64_t)lane * VEC); }
+    for (unsigned s0 = warp * ROWS; s0 < n_src; s0 += warps * ROWS) {
+      Vec<VEC> x[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        x[r].zero();
+        if (s0 + r < n_src && lane < nvec) x[r].load(h + (uint64_t)(s0 + r) * F + (uint64_t)lane * VEC);
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        const float a = warp_sum(x[r].dot(wa)), b = warp_sum(x[r].dot(wb));
+        if (lane == 0 && s0 + r < n_src) { al[s0 + r] = a; ar[s0 + r] = b; }
+      }
+    }
+    return;
+  }
   for (unsigned s = warp; s < n_src; s += warps) {
     const float *p = h + (uint64_t)s * F;
     float a = 0.f, b = 0.f;
-    for (unsigned k = lane; k < F; k += 32) { float x = p[k]; a += x * att[k]; b += x * att[F + k]; }
+    for (unsigned k = lane; k < nvec; k += 32) {
+      Vec<VEC> x, wa, wb;
+      x.load(p + (uint64_t)k * VEC);
+      wa.load_cached(att + (uint64_t)k * VEC);
+      wb.load_cached(att + F + (uint64_t)k * VEC);
+      a += x.dot(wa); b += x.dot(wb);
+    }
     a = warp_sum(a); b = warp_sum(b);
     if (lane == 0) { al[s] = a; ar[s] = b; }
   }
@@ -458,9 +486,15 @@ int nb_gat_fwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
   int rc = nb_ctx_scratch(ctx, (size_t)n_src * 2 * sizeof(float), (void **)&scratch);
   if (rc) return rc;
   float *al = scratch, *ar = scratch + n_src;
-  k_gat_node_scores<<<nb_grid(n_src, GAT_THREADS / 32, 8), GAT_THREADS, 0, ctx->stream>>>(h, att, al, ar, n_src, feature_size);
-  NB_LAUNCH_CHECK(ctx);
   int vec = nb_pick_vec(feature_size, h, feature_size, out, feature_size);
+  {
+    const int av = (((uintptr_t)att | (uintptr_t)(att + feature_size)) % 16 == 0 && vec == 4) ? 4 : (((uintptr_t)att | (uintptr_t)(att + feature_size)) % 8 == 0 && vec >= 2 ? 2 : 1);
+    const unsigned grid = nb_grid(n_src, GAT_THREADS / 32 * 4, 8);
+    if (av == 4) k_gat_node_scores<4, 4><<<grid, GAT_THREADS, 0, ctx->stream>>>(h, att, al, ar, n_src, feature_size);
+    else if (av == 2) k_gat_node_scores<2, 4><<<grid, GAT_THREADS, 0, ctx->stream>>>(h, att, al, ar, n_src, feature_size);
+    else k_gat_node_scores<1, 4><<<grid, GAT_THREADS, 0, ctx->stream>>>(h, att, al, ar, n_src, feature_size);
+    NB_LAUNCH_CHECK(ctx);
+  }
   if (vec == 4) return launch_gat_fwd<4>(ctx, h, al, ar, negative_slope, column_offset, row_indices, dst_local_id, n_dst, feature_size, score_pre, alpha, out);
   if (vec == 2) return launch_gat_fwd<2>(ctx, h, al, ar, negative_slope, column_offset, row_indices, dst_local_id, n_dst, feature_size, score_pre, alpha, out);
   return launch_gat_fwd<1>(ctx, h, al, ar, negative_slope, column_offset, row_indices, dst_local_id, n_dst, feature_size, score_pre, alpha, out);
@@ -500,10 +534,11 @@ int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
   } else {
     NB_CUDA(cudaMemsetAsync(ds, 0, (size_t)n_edges * 4, ctx->stream));
   }
-  k_gat_bwd_rows<<<nb_grid(n_src, GAT_THREADS, 8), GAT_THREADS, 0, ctx->stream>>>(alpha, ds, dsum, row_offset, csr_to_csc, src_to_dst, n_src, wcsr, rs, dd);
-  NB_LAUNCH_CHECK(ctx);
-  // dh[s,:] = sum_j alpha[e_j] dout[dst_j,:] + rs[s] att[0:F] + dd[s] att[F:2F]: the tuned CSR segment reduction with a rank-2 epilogue
-  rc = nb_run_segment(ctx, false, dout, dh, wcsr, column_indices, row_offset, n_src, F, nullptr, F, F, rs, dd, att, att + F);
+  // dh[s,:] = sum_j alpha[e_j] dout[dst_j,:] + rs[s] att[0:F] + dd[s] att[F:2F], rs[s] = sum_j ds[e_j], dd[s] = dsum of the dst equal to s:
+  // the tuned CSR segment reduction derives the row's weights and both scalars on the fly (no staging kernel) and leaves rs / dd
+  // behind for the attention-gradient pass
+  (void)wcsr;
+  rc = nb_run_segment_gat(ctx, dout, dh, column_indices, row_offset, n_src, F, csr_to_csc, alpha, ds, dsum, src_to_dst, att, att + F, rs, dd);
   if (rc) return rc;
   k_gat_bwd_att<<<att_blocks, GAT_THREADS, 0, ctx->stream>>>(h, rs, dd, n_src, F, partial);
   NB_LAUNCH_CHECK(ctx);

@@ -54,6 +54,8 @@ struct nb_sampler {
                          // asynchronous nb_sampler_sample before nb_sampler_wait cannot tear the sizes the host reads
   int meta_slot;         // slot of the batch enqueued last
   uint32_t *bitmap[2], *word_rank;  // layer i marks bitmap[i & 1]; its relabel pass clears the other one for layer i + 1
+  uint32_t *bitmap_l1[2];           // level 1 of the two-level dedup bitmap (NULL: flat bitmap), n_words_l1 words each
+  uint32_t n_words_l1;
   uint32_t n_words;
   unsigned long long *tile_states;  // [3 * L][max_tiles]
   BatchParams *params_dev;
@@ -128,6 +130,30 @@ struct BitmapOp {
   }
 };
 
+// Two-level variant: the items are level-1 words; an item's value is the number of marked vertices under it. The store pass leaves
+// word_rank[w0] for every TOUCHED level-0 word (the only ones anybody looks up).
+struct Bitmap2Op {
+  const uint32_t *bm0, *bm1;
+  uint32_t *word_rank;
+  LayerMeta *meta, *next_meta;
+  uint32_t n_words1, cap_src;
+  __device__ unsigned n() const { return n_words1; }
+  __device__ unsigned load(unsigned w1) const {
+    uint32_t bits = bm1[w1], s = 0;
+    while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; s += __popc(bm0[w1 * 32u + b]); }
+    return s;
+  }
+  __device__ void store(unsigned w1, unsigned excl, unsigned) const {
+    uint32_t bits = bm1[w1], run = excl;
+    while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; word_rank[w1 * 32u + b] = run; run += __popc(bm0[w1 * 32u + b]); }
+  }
+  __device__ void total(unsigned t) const {
+    meta->n_src = t;
+    if (t > cap_src) meta->err = 2;
+    next_meta->n_dst = t;
+  }
+};
+
 // one thread per vertex bit: source[rank] = v for every marked v, rank = word prefix + popcount below.
 // A warp covers one bitmap word, so the writes of a warp are consecutive.
 __global__ void __launch_bounds__(256)
@@ -172,6 +198,15 @@ struct RowOp {
 // mode 1 (replay): sample_ans was supplied; only edge_dst and the bitmap marks are produced.
 constexpr int SAMPLE_WARPS = 8;
 
+// Dedup bitmap, two levels when the graph is large: level 0 has one bit per vertex, level 1 one bit per level-0 word, set by the
+// thread that turns a zero level-0 word non-zero. Everything after sampling (rank scan, source emission, clearing) then walks the
+// |V|/1024 level-1 words and the <= S touched level-0 words instead of all |V|/32 words: O(|V|/1024 + S + E) per layer, which is what
+// keeps a 111M-vertex graph's batch at the cost of a 233K-vertex graph's. bitmap_l1 == NULL: flat bitmap (small graphs).
+__device__ __forceinline__ void mark_vertex(uint32_t *bitmap, uint32_t *bitmap_l1, uint32_t v) {
+  const uint32_t old = atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+  if (bitmap_l1 && old == 0u) atomicOr(&bitmap_l1[v >> 10], 1u << ((v >> 5) & 31));
+}
+
 // GROUP lanes cooperate on one dst (GROUP = 8, 16 or 32 >= fanout for the register path; 32 for the hash path), so a
 // fanout-10 layer keeps two dst per warp busy instead of idling 22 lanes.
 template <int GROUP>
@@ -180,7 +215,7 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
          const uint32_t *__restrict__ col_off, uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst,
          uint32_t *__restrict__ bitmap, const LayerMeta *meta, int fanout, const BatchParams *params, uint32_t layer,
          int merge, int hash_slots, uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor,
-         uint32_t *__restrict__ src_to_dst, uint32_t cap_src) {
+         uint32_t *__restrict__ src_to_dst, uint32_t cap_src, uint32_t *__restrict__ bitmap_l1 = nullptr) {
   extern __shared__ uint32_t s_hash[];
   if (meta->err) return;
   if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
@@ -208,20 +243,20 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
     const uint32_t deg = g_col_off[d + 1] - base;
     const uint32_t off = col_off[j];
     const uint32_t num = col_off[j + 1] - off;
-    if (merge && gl == 0) atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+    if (merge && gl == 0) mark_vertex(bitmap, bitmap_l1, d);
     if (num == 0) continue;
     if (replay) {
       for (uint32_t t = gl; t < num; t += GROUP) {
         uint32_t v = sample_ans[off + t];
         edge_dst[off + t] = j;
-        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        mark_vertex(bitmap, bitmap_l1, v);
       }
     } else if (num == deg) {  // take all, stored order
       for (uint32_t t = gl; t < num; t += GROUP) {
         uint32_t v = g_row_idx[base + t];
         sample_ans[off + t] = v;
         edge_dst[off + t] = j;
-        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        mark_vertex(bitmap, bitmap_l1, v);
       }
     } else if (num <= GROUP) {
       const bool holder = gl < num;
@@ -248,7 +283,7 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
         uint32_t v = g_row_idx[base + pos];
         sample_ans[off + gl] = v;
         edge_dst[off + gl] = j;
-        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        mark_vertex(bitmap, bitmap_l1, v);
       }
     } else if (GROUP == 32) {  // fanout > 32: shared-memory set, 32 draws per round
       for (int t = lane; t < hash_slots; t += 32) my_hash[t] = 0xffffffffu;
@@ -276,7 +311,7 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
           uint32_t v = g_row_idx[base + pos];
           sample_ans[off + slot] = v;
           edge_dst[off + slot] = j;
-          atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+          mark_vertex(bitmap, bitmap_l1, v);
         }
         have += __popc(wins);
         __syncwarp();
@@ -288,7 +323,7 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
 static void launch_sample(cudaStream_t st, unsigned cap_dst, int fanout, const uint32_t *g_col_off, const uint32_t *g_row_idx,
                           const uint32_t *dst, const uint32_t *col_off, uint32_t *sample_ans, uint32_t *edge_dst, uint32_t *bitmap,
                           const LayerMeta *meta, const BatchParams *params, uint32_t layer, int merge, uint32_t *row_count = nullptr,
-                          uint32_t *row_cursor = nullptr, uint32_t *src_to_dst = nullptr, uint32_t cap_src = 0) {
+                          uint32_t *row_cursor = nullptr, uint32_t *src_to_dst = nullptr, uint32_t cap_src = 0, uint32_t *bitmap_l1 = nullptr) {
   uint32_t hs = 1; while (fanout > 32 && hs < 2u * (uint32_t)fanout) hs <<= 1;
   const int hash_slots = fanout > 32 ? (int)hs : 0;
   const int group = (fanout < 0 || fanout > 16) ? 32 : (fanout > 8 ? 16 : 8);
@@ -296,9 +331,9 @@ static void launch_sample(cudaStream_t st, unsigned cap_dst, int fanout, const u
   unsigned grid = nb_grid(cap_dst, per_block, 8);
   if (row_count && grid < NB_SM_COUNT) grid = NB_SM_COUNT;  // enough threads for the scratch clear
   const size_t smem = (size_t)hash_slots * SAMPLE_WARPS * 4;
-  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src);
-  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src);
-  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src);
+  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1);
+  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1);
+  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1);
 }
 
 // global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
@@ -323,14 +358,42 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
           const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg, const BatchParams *params,
           uint32_t *__restrict__ source, uint32_t n_words, uint32_t *__restrict__ other_bitmap,
           const uint32_t *__restrict__ g_col_off = nullptr, uint32_t *__restrict__ next_base = nullptr,
-          uint32_t *__restrict__ next_deg = nullptr) {
+          uint32_t *__restrict__ next_deg = nullptr, const uint32_t *__restrict__ bitmap_l1 = nullptr,
+          uint32_t *__restrict__ other_bitmap_l1 = nullptr, uint32_t n_words_l1 = 0) {
   const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
   // the next layer marks the other bitmap: clear it here, off the critical path (no memset node per layer)
-  if (other_bitmap)
-    for (unsigned w = tid; w <= n_words; w += stride) other_bitmap[w] = 0u;
+  if (other_bitmap) {
+    if (bitmap_l1) {   // two levels: only the touched level-0 words are cleared, found through level 1
+      const unsigned lane = lane_id();
+      for (unsigned w1 = tid >> 5; w1 < n_words_l1; w1 += stride >> 5) {
+        const uint32_t bits1 = other_bitmap_l1[w1];
+        if (bits1 >> lane & 1u) other_bitmap[w1 * 32u + lane] = 0u;
+        __syncwarp();
+        if (lane == 0 && bits1) other_bitmap_l1[w1] = 0u;
+      }
+    } else {
+      for (unsigned w = tid; w <= n_words; w += stride) other_bitmap[w] = 0u;
+    }
+  }
   if (meta->err) return;
   const unsigned E = meta->n_edges, nd = meta->n_dst;
   const int weight_type = params->weight_type;
+  if (bitmap_l1) {   // `source` ascending: warp per level-1 word, lane per touched level-0 word, a short serial walk over its bits
+    const unsigned lane = lane_id();
+    for (unsigned w1 = tid >> 5; w1 < n_words_l1; w1 += stride >> 5) {
+      if (bitmap_l1[w1] >> lane & 1u) {
+        const uint32_t w0 = w1 * 32u + lane;
+        uint32_t bits = bitmap[w0], k = word_rank[w0];
+        while (bits) {
+          const uint32_t v = w0 * 32u + (__ffs(bits) - 1);
+          bits &= bits - 1;
+          source[k] = v;
+          if (next_base) { const uint32_t b = g_col_off[v]; next_base[k] = b; next_deg[k] = g_col_off[v + 1] - b; }
+          k++;
+        }
+      }
+    }
+  } else
   // `source` in ascending global id: one thread per vertex bit, a warp covers one bitmap word (consecutive writes)
   {
     const unsigned lane = lane_id();
@@ -364,6 +427,18 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
       dst_local_id[j] = local;
       src_to_dst[local] = j;
     }
+}
+
+// clears a two-level bitmap through its level 1 (odd layer counts: the last layer leaves bitmap[0] marked for the next batch's layer 0)
+__global__ void __launch_bounds__(256)
+k_clear_two_level(uint32_t *__restrict__ bitmap, uint32_t *__restrict__ bitmap_l1, uint32_t n_words_l1) {
+  const unsigned lane = lane_id();
+  for (unsigned w1 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w1 < n_words_l1; w1 += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t bits1 = bitmap_l1[w1];
+    if (bits1 >> lane & 1u) bitmap[w1 * 32u + lane] = 0u;
+    __syncwarp();
+    if (lane == 0 && bits1) bitmap_l1[w1] = 0u;
+  }
 }
 
 // UP_DEGREE weights: sampled degrees (out = CSR row length, in = CSC column length), core/FullyRepGraph.hpp:189-207.
@@ -534,7 +609,7 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
                uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst, uint32_t *__restrict__ bitmap, LayerMeta *meta,
                const LayerMeta *prev, int fanout, const BatchParams *params, uint32_t layer, int merge, int bottom, int hash_slots,
                uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor, uint32_t *__restrict__ src_to_dst,
-               uint32_t cap_src, uint32_t cap_edges, uint32_t cap_dst) {
+               uint32_t cap_src, uint32_t cap_edges, uint32_t cap_dst, uint32_t *__restrict__ bitmap_l1) {
   extern __shared__ uint32_t s_dyn[];   // [cap_dst + 1] counts -> offsets, then the per-warp hash sets (fanout > 32)
   __shared__ unsigned s_warp[33];
   uint32_t *s_off = s_dyn;
@@ -592,20 +667,20 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
     uint32_t base, deg;
     if (dense) { base = dst_base[j]; deg = dst_deg[j]; }
     else { const uint32_t d = dst[j]; base = g_col_off[d]; deg = g_col_off[d + 1] - base; }
-    if (merge && gl == 0) { const uint32_t d = dst[j]; atomicOr(&bitmap[d >> 5], 1u << (d & 31)); }
+    if (merge && gl == 0) { const uint32_t d = dst[j]; mark_vertex(bitmap, bitmap_l1, d); }
     if (num == 0) continue;
     if (replay) {
       for (uint32_t t = gl; t < num; t += GROUP) {
         uint32_t v = sample_ans[off + t];
         edge_dst[off + t] = j;
-        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        mark_vertex(bitmap, bitmap_l1, v);
       }
     } else if (num == deg) {  // take all, stored order
       for (uint32_t t = gl; t < num; t += GROUP) {
         uint32_t v = g_row_idx[base + t];
         sample_ans[off + t] = v;
         edge_dst[off + t] = j;
-        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        mark_vertex(bitmap, bitmap_l1, v);
       }
     } else if (num <= GROUP) {
       const bool holder = gl < num;
@@ -632,7 +707,7 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
         uint32_t v = g_row_idx[base + pos];
         sample_ans[off + gl] = v;
         edge_dst[off + gl] = j;
-        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        mark_vertex(bitmap, bitmap_l1, v);
       }
     } else if (GROUP == 32) {  // fanout > 32: shared-memory set, 32 draws per round
       for (int t = lane; t < hash_slots; t += 32) my_hash[t] = 0xffffffffu;
@@ -660,7 +735,7 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
           uint32_t v = g_row_idx[base + pos];
           sample_ans[off + slot] = v;
           edge_dst[off + slot] = j;
-          atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+          mark_vertex(bitmap, bitmap_l1, v);
         }
         have += __popc(wins);
         __syncwarp();
@@ -941,6 +1016,9 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   if (s->n_words > max_items) max_items = s->n_words;
   s->max_tiles = (uint32_t)((max_items + SCAN_TILE - 1) / SCAN_TILE) + 1;
   size_t o_bitmap = take(s->n_words + 1), o_bitmap1 = take(s->n_words + 1), o_rank = take(s->n_words + 1);
+  const bool two_level = s->n_words > 32768;   // |V| > 1M: below that a flat pass over the words costs less than the extra atomics
+  s->n_words_l1 = two_level ? (s->n_words + 31) / 32 : 0;
+  size_t o_l1a = two_level ? take(s->n_words_l1 + 1) : 0, o_l1b = two_level ? take(s->n_words_l1 + 1) : 0;
   size_t o_state = take((size_t)s->max_tiles * 2 * 3 * n_layers);
   size_t o_meta = take((sizeof(LayerMeta) / 4) * (NB_MAX_LAYERS + 1));
   size_t o_params = take(sizeof(BatchParams) / 4 + 8);
@@ -970,6 +1048,7 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   }
   for (int i = 1; i < n_layers; i++) s->lay[i].destination = s->lay[i - 1].source;  // layer chaining (FullyRepGraph.hpp:309)
   s->bitmap[0] = base + o_bitmap; s->bitmap[1] = base + o_bitmap1; s->word_rank = base + o_rank;
+  s->bitmap_l1[0] = two_level ? base + o_l1a : nullptr; s->bitmap_l1[1] = two_level ? base + o_l1b : nullptr;
   s->tile_states = (unsigned long long *)(base + o_state);
   s->meta_dev = (LayerMeta *)(base + o_meta);
   s->params_dev = (BatchParams *)(base + o_params);
@@ -1028,11 +1107,17 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
              csr = s->flags & NB_SAMPLER_BUILD_CSR;
   const BatchParams *pp = s->params_dev;
   // with an odd number of layers the last layer leaves bitmap[0] marked, and layer 0 of the next batch uses it
-  if (s->L & 1) NB_CUDA(cudaMemsetAsync(s->bitmap[0], 0, (size_t)(s->n_words + 1) * 4, st));
+  if (s->L & 1) {
+    if (s->bitmap_l1[0]) {
+      k_clear_two_level<<<nb_grid(s->n_words_l1, 8, 8), 256, 0, st>>>(s->bitmap[0], s->bitmap_l1[0], s->n_words_l1);
+      NB_LAUNCH_CHECK(ctx);
+    } else NB_CUDA(cudaMemsetAsync(s->bitmap[0], 0, (size_t)(s->n_words + 1) * 4, st));
+  }
   for (int i = 0; i < s->L; i++) {
     LayerBuf &b = s->lay[i];
     LayerMeta *m = s->meta_dev + i;
     uint32_t *bm = s->bitmap[i & 1], *bm_other = (s->L > 1) ? s->bitmap[(i + 1) & 1] : nullptr;
+    uint32_t *bm_l1 = s->bitmap_l1[i & 1], *bm_other_l1 = (s->L > 1) ? s->bitmap_l1[(i + 1) & 1] : nullptr;
     ScanWs ws0 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 0) * s->max_tiles, s->max_tiles, pp),
            ws1 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 1) * s->max_tiles, s->max_tiles, pp),
            ws2 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 2) * s->max_tiles, s->max_tiles, pp);
@@ -1058,7 +1143,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
         if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_sample_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; } \
         k_sample_fused<G><<<grid, FS_THREADS, smem_sample, st>>>(g->col_off, g->row_idx, b.destination, b.dst_base, b.dst_deg, i > 0 ? 1 : 0,  \
             b.column_offset, b.sample_ans, b.edge_dst, bm, m, i ? m - 1 : nullptr, s->fanout[i], pp, (uint32_t)i, merge ? 1 : 0, bottom,   \
-            hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, b.cap_dst);                       \
+            hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, b.cap_dst, bm_l1);                \
       } while (0)
       if (group == 32) NB_FS(32); else if (group == 16) NB_FS(16); else NB_FS(8);
 #undef NB_FS
@@ -1068,7 +1153,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
       k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
       NB_LAUNCH_CHECK(ctx);
       launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
-                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src);
+                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1);
       NB_LAUNCH_CHECK(ctx);
     }
     // ---- dedup ranks + source emission + relabel (+ histogram, weights)
@@ -1086,13 +1171,18 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
           b.cap_src, g->col_off, next_base, next_deg);
       NB_LAUNCH_CHECK(ctx);
     } else {
-      BitmapOp bop{bm, s->word_rank, m, m + 1, s->n_words, b.cap_src};
-      k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+      if (bm_l1) {
+        Bitmap2Op bop{bm, bm_l1, s->word_rank, m, m + 1, s->n_words_l1, b.cap_src};
+        k_scan<Bitmap2Op><<<nb_grid(s->n_words_l1, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+      } else {
+        BitmapOp bop{bm, s->word_rank, m, m + 1, s->n_words, b.cap_src};
+        k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+      }
       NB_LAUNCH_CHECK(ctx);
       k_relabel<<<nb_grid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
           b.sample_ans, b.row_indices, bm, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
           merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp,
-          b.source, s->n_words, bm_other, g->col_off, next_base, next_deg);
+          b.source, s->n_words, bm_other, g->col_off, next_base, next_deg, bm_l1, bm_other_l1, s->n_words_l1);
       NB_LAUNCH_CHECK(ctx);
     }
     if (up) {

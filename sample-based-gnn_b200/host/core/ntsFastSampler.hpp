@@ -43,15 +43,21 @@ class FastSampler : public NtsReferenceFastSampler {
   nb_graph *nb_g = nullptr;
   int nb_device = -1;
   std::vector<nb_sampler *> nb_slot;   /* one arena per pipeline slot, created on first use (merge / up_degree are known by then) */
+  std::vector<uint32_t> nb_cap;        /* seeds the slot's arena was sized for */
   int nb_slots = 1;
   uint32_t nb_max_batch = 0;
   std::atomic<uint64_t> nb_counter{0};
   uint64_t nb_seed = 0x5EED0004ull;
 
-  nb_sampler *nb_get(int slot) {
+  nb_sampler *nb_get(int slot, uint32_t n_seeds) {
     std::lock_guard<std::mutex> lock(nb_mutex());
-    if ((int)nb_slot.size() < nb_slots) nb_slot.resize(nb_slots, nullptr);
-    if (nb_slot[slot]) return nb_slot[slot];
+    if ((int)nb_slot.size() < nb_slots) { nb_slot.resize(nb_slots, nullptr); nb_cap.resize(nb_slots, 0); }
+    if (nb_slot[slot] && n_seeds <= nb_cap[slot]) return nb_slot[slot];
+    if (nb_slot[slot]) {   /* GS_SAMPLE_CACHE samples whole super-batches through a sampler it constructed with BATCH_SIZE: the reference's
+                              fixed 20M-word arena absorbs that (core/FullyRepGraph.hpp:113-116); here the slot's arena is re-sized */
+      NTS_B200_CHECK(nb_sampler_destroy(nb_slot[slot]));
+      nb_slot[slot] = nullptr;
+    }
     nb_ctx *ctx = ssgs[slot]->cs->ctx;
     if (!nb_g) {   /* the global CSC goes to HBM once per (graph, device): train / eval / test samplers share it */
       nb_device = nb_ctx_device(ctx);
@@ -69,7 +75,8 @@ class FastSampler : public NtsReferenceFastSampler {
     const bool merge = ssgs[slot]->sampled_sgs.size() && ssgs[slot]->sampled_sgs[0]->is_merge_src_dst;
     const uint32_t flags = (merge ? NB_SAMPLER_MERGE_SRC_DST : 0u) | (graph->config->up_degree ? NB_SAMPLER_UP_DEGREE : 0u);
     if (const char *e = getenv("NB_SAMPLER_SEED")) nb_seed = strtoull(e, nullptr, 0);
-    NTS_B200_CHECK(nb_sampler_create(ctx, nb_g, layer, fanout.data(), nb_max_batch, flags, 0, &nb_slot[slot]));
+    nb_cap[slot] = std::max(nb_max_batch, n_seeds);
+    NTS_B200_CHECK(nb_sampler_create(ctx, nb_g, layer, fanout.data(), nb_cap[slot], flags, 0, &nb_slot[slot]));
     return nb_slot[slot];
   }
 
@@ -78,7 +85,7 @@ class FastSampler : public NtsReferenceFastSampler {
     ssg = sg;
     assert(work_offset < work_range[1]);
     const uint32_t actual = std::min((VertexId)batch_size_, work_range[1] - work_offset);
-    nb_sampler *s = nb_get(slot);
+    nb_sampler *s = nb_get(slot, actual);
     nb_layer_view views[8];
     const int w = weightType == WeightType::Sum ? NB_WEIGHT_SUM : weightType == WeightType::Mean ? NB_WEIGHT_MEAN_SAMPLED : NB_WEIGHT_NONE;
     NTS_B200_CHECK(nb_sampler_sample(s, &sample_nids[work_offset], actual, 0, nb_seed, nb_counter.fetch_add(1), w, CacheFlag, omit_value, views, 1));

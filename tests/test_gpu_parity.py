@@ -159,6 +159,34 @@ def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, b
                 assert got.size == f and np.unique(got).size == f and np.isin(got, nb).all()
 
 
+@pytest.mark.parametrize("fanout,merge", [([25, 10], False), ([5, 5, 5], True)])
+def test_two_level_dedup_bitmap_on_a_large_graph(nts, cs, fanout, merge):
+    """|V| > 1M switches the dedup to the two-level bitmap (O(|V|/1024 + S + E) per layer): every array must still equal the oracle's,
+    over several batches on the same sampler (the bitmaps are cleared through level 1, including the odd-layer-count case)."""
+    V, E = 1_500_000, 6_000_000
+    rng = np.random.default_rng(21)
+    pairs = np.stack([rng.integers(0, V, E), rng.integers(0, V, E)], 1).astype(np.uint32)
+    graph = nts.FullyRepGraph(cs, V, edge_pairs=pairs)
+    co, ri = oracle.build_csc(pairs, V)
+    ind, outd = oracle.degrees(pairs, V)
+    seeds_all = rng.permutation(V)[:3 * 1024].astype(np.uint32)
+    sampler = nts.FastSampler(graph, seeds_all, len(fanout), 1024, fanout, cuda_stream=cs, merge_src_dst=merge, build_csr=True)
+    for b in range(3):
+        seeds = seeds_all[b * 1024:(b + 1) * 1024]
+        sg = sampler.sample_gpu_fast(1024)
+        ans = [u32(l.dev_sample_ans) for l in sg.sampled_sgs]
+        ref = oracle.sample_batch(seeds, co, ri, fanout, V, ind, outd, merge_src_dst=merge, replay=ans)
+        for i, (l, r) in enumerate(zip(sg.sampled_sgs, ref)):
+            assert l.src_size == r["source"].size, (b, i)
+            assert np.array_equal(u32(l.dev_source), r["source"]), (b, i)
+            assert np.array_equal(u32(l.dev_column_offset), r["column_offset"]), (b, i)
+            assert np.array_equal(u32(l.dev_row_indices), r["row_indices"]), (b, i)
+            assert np.array_equal(u32(l.dev_row_offset), r["row_offset"]) and np.array_equal(u32(l.dev_column_indices), r["column_indices"]), (b, i)
+            assert np.array_equal(u32(l.dev_edge_weight_forward), bits(r["e_w_f"])), (b, i)
+            if merge:
+                assert np.array_equal(u32(l.dev_dst_local_id), r["dst_local_id"]), (b, i)
+
+
 def test_sampler_paths_agree_bit_for_bit(nts, cs):
     """the small-shape kernels and the general pipeline: same RNG counters -> same draws -> every array identical; hub rows in the CSR"""
     lib, check = nts._capi.lib(), nts._capi.check
