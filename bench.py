@@ -43,6 +43,10 @@ REF_GPU_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_driver")
 
 def reddit_shaped_graph(scale=1.0):
     """In-edge CSC with a power-law in-degree (mean ~492, min 1) and popularity-skewed sources."""
+    cache = os.environ.get("NB_BENCH_GRAPH_CACHE")    # sweeps: the (deterministic) graph is generated once and re-read by later runs
+    if cache and scale == 1.0 and os.path.exists(cache + ".npz"):
+        z = np.load(cache + ".npz")
+        return int(z["v"]), z["col_off"], z["src"]
     v = max(1000, int(V * scale))
     e = int(E_TARGET * scale * scale) if scale != 1.0 else E_TARGET
     rng = np.random.default_rng(SEED_GRAPH)
@@ -56,6 +60,8 @@ def reddit_shaped_graph(scale=1.0):
     for a in range(0, total, chunk):
         b = min(total, a + chunk)
         src[a:b] = np.minimum((rng.random(b - a) ** 1.6 * v).astype(np.int64), v - 1)
+    if cache and scale == 1.0 and int(os.environ.get("RANK", "0")) == 0 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        np.savez(cache, v=v, col_off=col_off.astype(np.uint32), src=src)
     return v, col_off.astype(np.uint32), src
 
 

@@ -107,6 +107,8 @@ int nb_device_count(int *count);
  *   "sampler_fused" / NB_SAMPLER_FUSED : 1 (default) = samplers created afterwards use the small-shape kernels (a layer's prefix
  *       sums recomputed per block in shared memory: 2 launches per layer instead of 4) wherever the layer fits; 0 = general path only.
  *       Both give identical results.
+ *   "sampler_two_level" : -1 (default) = samplers created afterwards pick the dedup bitmap layout by density (two levels when the graph
+ *       has several times more bitmap words than a batch can touch: O(|V|/1024 + S + E) per layer instead of O(|V|/32)); 0 / 1 force it
  *   "trace" / NB_TRACE : 1 = wall-clock time spent inside every entry point is accumulated (host side); 2 = the call's stream is
  *       synchronised before the clock stops (host + GPU time per call; serialises, diagnostic only). The table goes to stderr at
  *       exit or through nb_trace_dump(). Replaces the reference's get_time() accumulators (core/ntsFastSampler.hpp:30-37) and

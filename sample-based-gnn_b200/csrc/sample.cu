@@ -41,6 +41,8 @@ struct LayerBuf {
 #define NB_MAX_LAYERS 8
 static int g_sampler_fused = -1;   // "sampler_fused" / NB_SAMPLER_FUSED: 1 (default) = small-shape path where it fits, 0 = general path only
 void nb_sampler_set_fused(int on) { g_sampler_fused = on; }
+static int g_sampler_two_level = -1;   // "sampler_two_level": -1 (default) = by density, 0 = flat dedup bitmap, 1 = two-level (tests)
+void nb_sampler_set_two_level(int mode) { g_sampler_two_level = mode; }
 struct nb_sampler {
   nb_ctx *ctx;
   nb_graph *g;
@@ -138,14 +140,40 @@ struct Bitmap2Op {
   LayerMeta *meta, *next_meta;
   uint32_t n_words1, cap_src;
   __device__ unsigned n() const { return n_words1; }
+  // the 32 level-0 words under a level-1 word are one 128-byte line: fetched as eight independent 16-byte loads (a bit-by-bit walk
+  // would serialise up to 32 dependent-latency loads per item)
   __device__ unsigned load(unsigned w1) const {
-    uint32_t bits = bm1[w1], s = 0;
-    while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; s += __popc(bm0[w1 * 32u + b]); }
+    const uint32_t bits = bm1[w1];
+    if (!bits) return 0u;
+    const uint4 *line = reinterpret_cast<const uint4 *>(bm0 + (size_t)w1 * 32u);
+    uint4 q[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) q[k] = line[k];
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      s += (bits >> (4 * k) & 1u) ? __popc(q[k].x) : 0u;
+      s += (bits >> (4 * k + 1) & 1u) ? __popc(q[k].y) : 0u;
+      s += (bits >> (4 * k + 2) & 1u) ? __popc(q[k].z) : 0u;
+      s += (bits >> (4 * k + 3) & 1u) ? __popc(q[k].w) : 0u;
+    }
     return s;
   }
   __device__ void store(unsigned w1, unsigned excl, unsigned) const {
-    uint32_t bits = bm1[w1], run = excl;
-    while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; word_rank[w1 * 32u + b] = run; run += __popc(bm0[w1 * 32u + b]); }
+    const uint32_t bits = bm1[w1];
+    if (!bits) return;
+    const uint4 *line = reinterpret_cast<const uint4 *>(bm0 + (size_t)w1 * 32u);
+    uint4 q[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) q[k] = line[k];
+    unsigned run = excl;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (bits >> (4 * k + j) & 1u) { word_rank[(size_t)w1 * 32u + 4 * k + j] = run; run += __popc(w[j]); }
+    }
   }
   __device__ void total(unsigned t) const {
     meta->n_src = t;
@@ -1016,7 +1044,13 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
   if (s->n_words > max_items) max_items = s->n_words;
   s->max_tiles = (uint32_t)((max_items + SCAN_TILE - 1) / SCAN_TILE) + 1;
   size_t o_bitmap = take(s->n_words + 1), o_bitmap1 = take(s->n_words + 1), o_rank = take(s->n_words + 1);
-  const bool two_level = s->n_words > 32768;   // |V| > 1M: below that a flat pass over the words costs less than the extra atomics
+  // two levels pay off when the marks are sparse: a batch touches at most cap_src level-0 words, so a flat pass over all of them only
+  // wastes time when there are several times more words than that (papers100M: 3.47M words for <= 256K sources; products: 76K words,
+  // nearly all touched -- flat is faster there, measured 0.17 vs 0.30 ms per step)
+  uint64_t max_cap_src = 0;
+  for (int i = 0; i < n_layers; i++) max_cap_src = max_cap_src > s->lay[i].cap_src ? max_cap_src : s->lay[i].cap_src;
+  const bool two_level = g_sampler_two_level >= 0 ? (g_sampler_two_level == 1 && s->n_words > 64)
+                                                  : ((uint64_t)s->n_words > 4 * max_cap_src && s->n_words > 32768);
   s->n_words_l1 = two_level ? (s->n_words + 31) / 32 : 0;
   size_t o_l1a = two_level ? take(s->n_words_l1 + 1) : 0, o_l1b = two_level ? take(s->n_words_l1 + 1) : 0;
   size_t o_state = take((size_t)s->max_tiles * 2 * 3 * n_layers);
@@ -1158,7 +1192,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
     }
     // ---- dedup ranks + source emission + relabel (+ histogram, weights)
     const size_t smem_relabel = ((size_t)((s->n_words + 31) & ~31u) + s->n_words + 1) * 4;
-    if (s->fused && smem_relabel <= FS_SMEM_MAX) {
+    if (s->fused && !bm_l1 && smem_relabel <= FS_SMEM_MAX) {
       static bool attr = false;
       if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_relabel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
       const uint64_t work = (uint64_t)b.cap_edges + b.cap_dst + (uint64_t)s->n_words * 32;

@@ -161,7 +161,7 @@ def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, b
 
 @pytest.mark.parametrize("fanout,merge", [([25, 10], False), ([5, 5, 5], True)])
 def test_two_level_dedup_bitmap_on_a_large_graph(nts, cs, fanout, merge):
-    """|V| > 1M switches the dedup to the two-level bitmap (O(|V|/1024 + S + E) per layer): every array must still equal the oracle's,
+    """The two-level dedup bitmap (O(|V|/1024 + S + E) per layer, chosen by density for very large graphs): every array must still equal the oracle's,
     over several batches on the same sampler (the bitmaps are cleared through level 1, including the odd-layer-count case)."""
     V, E = 1_500_000, 6_000_000
     rng = np.random.default_rng(21)
@@ -170,7 +170,13 @@ def test_two_level_dedup_bitmap_on_a_large_graph(nts, cs, fanout, merge):
     co, ri = oracle.build_csc(pairs, V)
     ind, outd = oracle.degrees(pairs, V)
     seeds_all = rng.permutation(V)[:3 * 1024].astype(np.uint32)
-    sampler = nts.FastSampler(graph, seeds_all, len(fanout), 1024, fanout, cuda_stream=cs, merge_src_dst=merge, build_csr=True)
+    nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_two_level", 1))       # by density this size would still take the flat layout
+    nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_fused", 0))           # the small-shape relabel keeps its ranks in shared memory
+    try:
+        sampler = nts.FastSampler(graph, seeds_all, len(fanout), 1024, fanout, cuda_stream=cs, merge_src_dst=merge, build_csr=True)
+    finally:
+        nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_two_level", -1))
+        nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_fused", 1))
     for b in range(3):
         seeds = seeds_all[b * 1024:(b + 1) * 1024]
         sg = sampler.sample_gpu_fast(1024)
