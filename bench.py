@@ -953,6 +953,19 @@ def main_b200(args):
     except Exception:
         pass
     other = {}
+    if world > 1 and not args.no_other_configs and args.scaling == "weak":
+        # strong scaling of the headline step: fixed global batch 1024, local batch 1024 / N (toolkits/GAT_SAMPLE_ALL_MULTI.hpp:322)
+        import copy
+        a2 = copy.copy(args)
+        a2.scaling = "strong"
+        try:
+            so = run_hot_path(env, a2, wl, ["fused"], 3, sample_clocks=False)
+            other["strong scaling of the headline step"] = {
+                "global_batch": BATCH, "per_gpu_batch": so["B"], "value": so["sm"]["fused"]["value"], "unit": "edges/s",
+                "ms_per_step": so["sm"]["fused"]["ms_per_step"], "windows_ms_per_step": so["sm"]["fused"]["windows_ms_per_step"],
+                "steps_per_epoch": int(all_seeds.size // BATCH), "epoch_ms_est": so["sm"]["fused"]["ms_per_step"] * (all_seeds.size // BATCH)}
+        except Exception as ex:
+            other["strong scaling of the headline step"] = {"failed": f"{type(ex).__name__}: {ex}"[:300]}
     if not args.no_other_configs and args.scale == 1.0:
         for key, fn in (("configs[3] GAT, data parallel", lambda: run_gat_config(env, args, v, col_off, src, all_seeds, peak_all)),
                         ("configs[2] products-shaped", lambda: run_products_config(env, args, peak_all)),

@@ -178,6 +178,17 @@ int nb_graph_destroy(nb_graph *g);
 int nb_graph_info(nb_graph *g, uint32_t *n_vertices, uint64_t *n_edges, const uint32_t **column_offset_dev,
                   const uint32_t **row_indices_dev, const uint32_t **in_degree_dev, const uint32_t **out_degree_dev);
 
+/* ---- feature / label / mask files (host side) ------------------------------------------------------
+ * nb_read_feature_table <- GNNDatum::readFeature_Label_Mask's feature part (core/ntsDataloador.hpp:999-1063): the text file
+ *                          ("id v0 ... v{F-1}" per line, vertices in any order) parsed by all host threads with strtof (the conversion
+ *                          operator>> ends in: bit-identical values) into out[(id - id_begin) * F ...] for id in [id_begin, id_end).
+ *                          use_binary_cache: a raw copy (<path>.nb_f32: "NBF1", |V|, F, floats) is written after the first parse and
+ *                          read instead of the text on later calls while it is at least as new as the text file.
+ * nb_read_label_mask    <- the label ("id label") and mask ("id train|eval|val|test") parts of the same reader. */
+int nb_read_feature_table(const char *path, uint32_t n_vertices, uint32_t feature_size, uint32_t id_begin, uint32_t id_end, float *out,
+                          int use_binary_cache, int *from_cache_out);
+int nb_read_label_mask(const char *label_path, const char *mask_path, uint32_t id_begin, uint32_t id_end, int64_t *label_out, int32_t *mask_out);
+
 /* ---- sampler -----------------------------------------------------------------------------
  * nb_sampler_create <- SampledSubgraph(layers, batch, fanout, |V|, Cuda_Stream*) (FullyRepGraph.hpp:91-131).
  *   Arenas are sized from max_batch * prod(fanout) (bounded by |V| and |E|) and checked, never

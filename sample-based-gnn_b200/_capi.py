@@ -56,6 +56,8 @@ _SIGS = {
     "nb_memcpy_h2d": (I32, [P, P, P, SZ, I32]),
     "nb_memcpy_d2h": (I32, [P, P, P, SZ, I32]),
     "nb_memset_async": (I32, [P, P, I32, SZ]),
+    "nb_read_feature_table": (I32, [C.c_char_p, U32, U32, U32, U32, P, I32, C.POINTER(I32)]),
+    "nb_read_label_mask": (I32, [C.c_char_p, C.c_char_p, U32, U32, P, P]),
     "nb_graph_create": (I32, [P, U32, U64, P, P, P, P, C.POINTER(P)]),
     "nb_graph_create_from_pairs": (I32, [P, U32, U64, P, I32, C.POINTER(P)]),
     "nb_graph_create_from_device": (I32, [P, U32, U64, P, P, C.POINTER(P)]),

@@ -13,6 +13,10 @@ full() {  # name, kernel regex, skip, count, command...
   "$@" > $OUT/ncu_plain_$name.log 2>&1 || { echo "plain $name failed"; return; }
   ncu --set full --clock-control none --import-source on --kernel-name "regex:$re" --launch-skip $skip --launch-count $cnt -f -o $OUT/r2_full_$name "$@" > $OUT/ncu_$name.log 2>&1
   ncu -i $OUT/r2_full_$name.ncu-rep --page raw --csv --metrics $M > $OUT/r2_full_$name.csv 2>/dev/null
+  # the reports themselves are tens of MB each (gpurun_out/ travels back only below 64 MiB): keep the summaries, and for the dominant
+  # kernel the per-instruction source page
+  if [ "$name" = bench ]; then ncu -i $OUT/r2_full_$name.ncu-rep --page source --csv --kernel-name "regex:k_segment_reduce" 2>/dev/null | head -400 > $OUT/r2_source_segment_reduce.csv; fi
+  rm -f $OUT/r2_full_$name.ncu-rep
 }
 # the device-resident (fused) arm runs first: skip its warm-up launches, then take two steps' worth of every kernel
 full bench "k_segment_reduce|k_sample_fused|k_relabel_fused|k_csr|k_pack_gather" 27 18 $BENCH
