@@ -39,6 +39,8 @@ TRAIN_FRAC = 0.66
 SEED_GRAPH, SEED_SHUFFLE, SEED_SAMPLER = 0x5EED0001, 0x5EED0003, 0x5EED0004
 REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 REF_GPU_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_driver")
+CPP_E2E = os.path.join(ROOT, "sample-based-gnn_b200", "lib", "cpp_e2e_bench")
+CPP_E2E_ARGS = []          # [pitch, steps, warmup, windows], set by main_b200
 
 
 def reddit_shaped_graph(scale=1.0):
@@ -154,6 +156,14 @@ def run_reference_driver(v, col_off, src, seeds, batches, warmup, threads, gpu_b
                 gpu_box.append(json.loads([l for l in g.stdout.splitlines() if l.startswith("{")][-1]))
             except Exception as ex:  # a reported extra, never fatal
                 gpu_box.append({"failed": str(ex)[:300]})
+        if gpu_box is not None and os.path.exists(CPP_E2E) and CPP_E2E_ARGS:
+            # the same e2e loop driven from C++ through the adaptor header (tools/cpp_e2e_bench.cpp), same edge / seed files
+            try:
+                c = subprocess.run([CPP_E2E, ef, str(v), sf, str(BATCH), ",".join(map(str, FANOUT)), str(F0), str(F1)] + CPP_E2E_ARGS,
+                                   capture_output=True, text=True, timeout=600)
+                gpu_box.append({"cpp_e2e": json.loads([l for l in c.stdout.splitlines() if l.startswith("{")][-1])})
+            except Exception as ex:
+                gpu_box.append({"cpp_e2e": {"failed": (str(ex) + " " + (c.stderr[-200:] if "c" in dir() else ""))[:400]}})
     return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
 
 
@@ -1016,6 +1026,7 @@ def main_b200(args):
                 pass
         cpu = None
         ref_gpu_box = []
+        CPP_E2E_ARGS[:] = [str(PITCH), str(K), str(W), str(R)]
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r, kind, threads = cpu_baseline_run(v, col_off, src, all_seeds, args.cpu_batches, 2, ref_gpu_box)
@@ -1028,6 +1039,8 @@ def main_b200(args):
             except Exception as ex:  # the checker must never take the bench down
                 cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         ref_gpu = None
+        cpp_e2e = next((x["cpp_e2e"] for x in ref_gpu_box if "cpp_e2e" in x), None)
+        ref_gpu_box = [x for x in ref_gpu_box if "cpp_e2e" not in x]
         if ref_gpu_box:
             g = ref_gpu_box[0]
             ref_gpu = dict(g)
@@ -1067,6 +1080,7 @@ def main_b200(args):
                         "d2h_bytes_per_step": B * F1 * 4 + 3 * 32, "ms_per_step": a_["ms_per_step"],
                         "windows_ms_per_step": a_["windows_ms_per_step"], "host_issue_ms_per_step": a_["host_issue_ms_per_step"],
                         "host_blocked_in_sampler_wait_ms_per_step": round(res["api"]["host_wait_ms_per_step"], 5),
+                        "cpp_host": cpp_e2e,
                         "path": "FastSampler.sample_gpu_fast(slot i+1, async, high-priority stream) || wait(slot i) -> load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
                 "gpu_launches": int(round(launches_all)), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "other_configs": other,
                 "materialized_x0": {"value": m_["value"], "unit": "edges/s", "ms_per_step": m_["ms_per_step"],

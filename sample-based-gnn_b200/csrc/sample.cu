@@ -585,10 +585,7 @@ k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restr
 //   k_csr_fill_fused = row_offset scan (in smem, per block) + stable-fill step 1;  k_csr_rows handles long rows itself
 // i.e. 2 launches per layer (+2 for a layer whose CSR is built): 6 instead of 11 for the benchmark's two layers.
 // Results are bit-identical to the general path (same arithmetic, same ordering rules); tests run both.
-#ifndef NB_FS_THREADS
-#define NB_FS_THREADS 256   // a block fits the 256-thread slot per SM that the aggregation leaves free (aggregate.cu), so the next batch's
-#endif                      // sampling runs UNDER the current batch's aggregation instead of after it
-constexpr int FS_THREADS = NB_FS_THREADS;
+constexpr int FS_THREADS = 512;   // two such blocks fit an SM: they find room next to a training-stream kernel sooner than one 1024-thread block
 constexpr size_t FS_SMEM_MAX = 200 * 1024;
 
 // exclusive prefix of one value per thread over the block; *total = block sum. s_warp: 33 words of shared memory.
@@ -633,20 +630,6 @@ __device__ __forceinline__ unsigned block_scan_array(unsigned *s_v, unsigned n, 
 }
 
 // One sampling layer's count + scan + neighbour selection. Selection code and RNG counters are those of k_sample: same draws.
-// Block b owns the contiguous dst range [lo, hi). Every block reads all the counts once (n_dst words from L2) and keeps three things:
-// the sum below its range, the grand total, and its own range's counts in shared memory (scanned there) -- so the shared-memory
-// footprint is a few hundred bytes and a 256-thread block fits wherever an SM has a free slot.
-__device__ __forceinline__ unsigned block_sum(unsigned v, unsigned *s_warp) {
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  v = warp_sum_u32(v);
-  __syncthreads();
-  if (lane == 0) s_warp[warp] = v;
-  __syncthreads();
-  unsigned t = 0;
-  for (unsigned w = 0; w < nwarps; w++) t += s_warp[w];
-  return t;
-}
-
 template <int GROUP>
 __global__ void __launch_bounds__(FS_THREADS)
 k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_row_idx, const uint32_t *__restrict__ dst,
@@ -654,41 +637,38 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
                uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst, uint32_t *__restrict__ bitmap, LayerMeta *meta,
                const LayerMeta *prev, int fanout, const BatchParams *params, uint32_t layer, int merge, int bottom, int hash_slots,
                uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor, uint32_t *__restrict__ src_to_dst,
-               uint32_t cap_src, uint32_t cap_edges, uint32_t chunk, uint32_t *__restrict__ bitmap_l1) {
-  extern __shared__ uint32_t s_dyn[];   // [chunk + 1] counts -> offsets of this block's dst range, then the per-warp hash sets (fanout > 32)
+               uint32_t cap_src, uint32_t cap_edges, uint32_t cap_dst, uint32_t *__restrict__ bitmap_l1) {
+  extern __shared__ uint32_t s_dyn[];   // [cap_dst + 1] counts -> offsets, then the per-warp hash sets (fanout > 32)
   __shared__ unsigned s_warp[33];
   uint32_t *s_off = s_dyn;
-  uint32_t *s_hash = s_dyn + ((chunk + 1 + 31) & ~31u);
+  uint32_t *s_hash = s_dyn + ((cap_dst + 1 + 31) & ~31u);
   const unsigned n_dst = prev ? (prev->err ? 0u : meta->n_dst) : params->n_seeds;
   const uint32_t *omit = bottom ? params->omit : nullptr;
   const uint32_t omit_value = params->omit_value;
   const int replay = params->replay;
-  const unsigned lo = min(n_dst, blockIdx.x * chunk), hi = min(n_dst, lo + chunk);
-  // 1. counts, exactly CountOp::load; every block walks all of them
-  unsigned below = 0, all = 0;
+  // 1. counts (every block, redundantly: n_dst words from L2), exactly CountOp::load
   for (unsigned i = threadIdx.x; i < n_dst; i += FS_THREADS) {
     uint32_t deg;
     if (dense) deg = dst_deg[i];
-    else { const uint32_t d = dst[i]; deg = g_col_off[d + 1] - g_col_off[d]; }
+    else {
+      const uint32_t d = dst[i], b = g_col_off[d];
+      deg = g_col_off[d + 1] - b;
+      if (blockIdx.x == 0) { dst_base[i] = b; dst_deg[i] = deg; }
+    }
     uint32_t c = (fanout < 0 || deg < (uint32_t)fanout) ? deg : (uint32_t)fanout;
     if (omit) {
       const uint32_t f = omit[dst[i]];
       if (omit_value == 0xffffffffu ? (f != 0xffffffffu) : (f == omit_value)) c = 0;
     }
-    all += c;
-    if (i < lo) below += c;
-    else if (i < hi) s_off[i - lo] = c;
+    s_off[i] = c;
   }
-  const unsigned base_off = block_sum(below, s_warp);
-  const unsigned E = block_sum(all, s_warp);
   __syncthreads();
-  // 2. exclusive scan of this block's range -> column offsets
-  block_scan_array(s_off, hi - lo, s_warp);
-  for (unsigned i = threadIdx.x; i < hi - lo; i += FS_THREADS) col_off[lo + i] = base_off + s_off[i];
+  // 2. exclusive scan -> column offsets
+  const unsigned E = block_scan_array(s_off, n_dst, s_warp);
   const unsigned err = (prev && prev->err) ? prev->err : (E > cap_edges ? 1u : 0u);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    col_off[n_dst] = E;
-    meta->n_dst = n_dst; meta->n_edges = E; meta->n_src = 0; meta->long_rows = 0; meta->err = err;
+  if (blockIdx.x == 0) {
+    for (unsigned i = threadIdx.x; i <= n_dst; i += FS_THREADS) col_off[i] = s_off[i];
+    if (threadIdx.x == 0) { meta->n_dst = n_dst; meta->n_edges = E; meta->n_src = 0; meta->long_rows = 0; meta->err = err; }
   }
   if (err) return;
   if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
@@ -706,11 +686,12 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
   constexpr unsigned GPW = 32 / GROUP;
   const unsigned gl = lane % GROUP, gid = lane / GROUP;
   const unsigned gmask = GROUP == 32 ? FULL_MASK : (((1u << GROUP) - 1u) << (gid * GROUP));
+  const unsigned groups = gridDim.x * (FS_THREADS / 32) * GPW;
   uint32_t *my_hash = s_hash + (threadIdx.x >> 5) * hash_slots;
   const Philox rng(key);
-  for (unsigned j = lo + (threadIdx.x >> 5) * GPW + gid; j < hi; j += (FS_THREADS / 32) * GPW) {
-    const uint32_t off = base_off + s_off[j - lo];
-    const uint32_t num = s_off[j - lo + 1] - s_off[j - lo];
+  for (unsigned j = (blockIdx.x * (FS_THREADS / 32) + (threadIdx.x >> 5)) * GPW + gid; j < n_dst; j += groups) {
+    const uint32_t off = s_off[j];
+    const uint32_t num = s_off[j + 1] - off;
     uint32_t base, deg;
     if (dense) { base = dst_base[j]; deg = dst_deg[j]; }
     else { const uint32_t d = dst[j]; base = g_col_off[d]; deg = g_col_off[d + 1] - base; }
@@ -1182,23 +1163,21 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
     // ---- count + scan + neighbour selection
     uint32_t hs = 1; while (s->fanout[i] > 32 && hs < 2u * (uint32_t)s->fanout[i]) hs <<= 1;
     const int hash_slots = s->fanout[i] > 32 ? (int)hs : 0;
-    // block count: enough groups for one dst per group where the layer is large, at most four blocks per SM
-    const int group = (s->fanout[i] < 0 || s->fanout[i] > 16) ? 32 : (s->fanout[i] > 8 ? 16 : 8);
-    const unsigned per_block = (FS_THREADS / 32) * (32 / group);
-    unsigned fs_grid = (b.cap_dst + per_block - 1) / per_block;
-    if (fs_grid > (unsigned)ctx->sm_count * 4u) fs_grid = (unsigned)ctx->sm_count * 4u;
-    if (fs_grid < 1) fs_grid = 1;
-    const uint32_t fs_chunk = (b.cap_dst + fs_grid - 1) / fs_grid;
-    const size_t smem_sample = ((size_t)((fs_chunk + 1 + 31) & ~31u) + (size_t)hash_slots * (FS_THREADS / 32)) * 4;
-    if (s->fused && smem_sample <= FS_SMEM_MAX && b.cap_dst <= 262144) {   // every block reads all counts: keep that pass short
-      const unsigned grid = fs_grid;
+    const size_t smem_sample = ((size_t)((b.cap_dst + 1 + 31) & ~31u) + (size_t)hash_slots * (FS_THREADS / 32)) * 4;
+    if (s->fused && smem_sample <= FS_SMEM_MAX) {
+      const int group = (s->fanout[i] < 0 || s->fanout[i] > 16) ? 32 : (s->fanout[i] > 8 ? 16 : 8);
+      const unsigned per_block = (FS_THREADS / 32) * (32 / group);
+      unsigned grid = (b.cap_dst + per_block - 1) / per_block;
+      const unsigned max_grid = (unsigned)ctx->sm_count * (smem_sample <= 96 * 1024 ? 2u : 1u);
+      if (grid > max_grid) grid = max_grid;
+      if (grid < 1) grid = 1;
 #define NB_FS(G)                                                                                                                   \
       do {                                                                                                                         \
         static bool attr = false;                                                                                                  \
         if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_sample_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; } \
         k_sample_fused<G><<<grid, FS_THREADS, smem_sample, st>>>(g->col_off, g->row_idx, b.destination, b.dst_base, b.dst_deg, i > 0 ? 1 : 0,  \
             b.column_offset, b.sample_ans, b.edge_dst, bm, m, i ? m - 1 : nullptr, s->fanout[i], pp, (uint32_t)i, merge ? 1 : 0, bottom,   \
-            hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, fs_chunk, bm_l1);                 \
+            hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, b.cap_dst, bm_l1);                \
       } while (0)
       if (group == 32) NB_FS(32); else if (group == 16) NB_FS(16); else NB_FS(8);
 #undef NB_FS
@@ -1218,7 +1197,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
       if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_relabel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
       const uint64_t work = (uint64_t)b.cap_edges + b.cap_dst + (uint64_t)s->n_words * 32;
       unsigned grid = (unsigned)((work + FS_THREADS - 1) / FS_THREADS);
-      const unsigned max_grid = (unsigned)ctx->sm_count * (smem_relabel <= 48 * 1024 ? 4u : smem_relabel <= 96 * 1024 ? 2u : 1u);
+      const unsigned max_grid = (unsigned)ctx->sm_count * (smem_relabel <= 96 * 1024 ? 2u : 1u);
       if (grid > max_grid) grid = max_grid;
       k_relabel_fused<<<grid, FS_THREADS, smem_relabel, st>>>(
           b.sample_ans, b.row_indices, bm, b.row_count, b.destination, merge ? b.dst_local_id : nullptr, merge ? b.src_to_dst : nullptr,
@@ -1254,7 +1233,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
         static bool attr = false;
         if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_csr_fill_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
         unsigned grid = (b.cap_edges + FS_THREADS - 1) / FS_THREADS;
-        const unsigned max_grid = (unsigned)ctx->sm_count * (smem_csr <= 48 * 1024 ? 4u : smem_csr <= 96 * 1024 ? 2u : 1u);
+        const unsigned max_grid = (unsigned)ctx->sm_count * (smem_csr <= 96 * 1024 ? 2u : 1u);
         if (grid > max_grid) grid = max_grid;
         if (grid < 1) grid = 1;
         k_csr_fill_fused<<<grid, FS_THREADS, smem_csr, st>>>(b.row_indices, b.row_count, b.row_offset, b.row_cursor, b.csr_tmp, m);
