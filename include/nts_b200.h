@@ -109,6 +109,9 @@ int nb_device_count(int *count);
  *       Both give identical results.
  *   "sampler_two_level" : -1 (default) = samplers created afterwards pick the dedup bitmap layout by density (two levels when the graph
  *       has several times more bitmap words than a batch can touch: O(|V|/1024 + S + E) per layer instead of O(|V|/32)); 0 / 1 force it
+ *   "gather_keep_min_uses" : 2 (default) = a source row that the batch's bottom layer reads at least this many times gets the
+ *       "keep in L2" hint bit in nb_layer_view.gather_index (read with evict_last by nb_aggregate_gathered_fwd_dyn); other rows stream
+ *       through (evict_first). Changes cache behaviour only, never results.
  *   "trace" / NB_TRACE : 1 = wall-clock time spent inside every entry point is accumulated (host side); 2 = the call's stream is
  *       synchronised before the clock stops (host + GPU time per call; serialises, diagnostic only). The table goes to stderr at
  *       exit or through nb_trace_dump(). Replaces the reference's get_time() accumulators (core/ntsFastSampler.hpp:30-37) and

@@ -392,14 +392,16 @@ k_gat_bwd_att(const float *__restrict__ h, const float *__restrict__ rs, const f
     __syncthreads();
   }
 }
-// stage 2: datt[k] = sum over blocks, in block order (deterministic run to run)
+// stage 2: datt[k] = sum over the block partials. One warp per output column: lane l adds blocks l, l+32, ... in order, the 32 lane
+// sums are combined by a fixed shuffle tree -- a fixed summation order, so the result is deterministic run to run.
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_att_reduce(const float *__restrict__ partial, uint32_t n_blocks, uint32_t n2f, float *__restrict__ datt) {
-  const unsigned k = blockIdx.x * GAT_THREADS + threadIdx.x;
+  const unsigned lane = lane_id(), k = (blockIdx.x * GAT_THREADS + threadIdx.x) >> 5;
   if (k >= n2f) return;
   float acc = 0.f;
-  for (uint32_t b = 0; b < n_blocks; b++) acc += partial[(uint64_t)b * n2f + k];
-  datt[k] = acc;
+  for (uint32_t b = lane; b < n_blocks; b += 32) acc += partial[(uint64_t)b * n2f + k];
+  acc = warp_sum(acc);
+  if (lane == 0) datt[k] = acc;
 }
 
 template <int VEC>
@@ -542,7 +544,7 @@ int nb_gat_bwd(nb_ctx *ctx, const float *h, const float *att, float negative_slo
   if (rc) return rc;
   k_gat_bwd_att<<<att_blocks, GAT_THREADS, 0, ctx->stream>>>(h, rs, dd, n_src, F, partial);
   NB_LAUNCH_CHECK(ctx);
-  k_gat_att_reduce<<<(2 * F + GAT_THREADS - 1) / GAT_THREADS, GAT_THREADS, 0, ctx->stream>>>(partial, att_blocks, 2 * F, datt);
+  k_gat_att_reduce<<<(2 * F * 32 + GAT_THREADS - 1) / GAT_THREADS, GAT_THREADS, 0, ctx->stream>>>(partial, att_blocks, 2 * F, datt);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
 }

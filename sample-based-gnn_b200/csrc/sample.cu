@@ -41,6 +41,8 @@ struct LayerBuf {
 #define NB_MAX_LAYERS 8
 static int g_sampler_fused = -1;   // "sampler_fused" / NB_SAMPLER_FUSED: 1 (default) = small-shape path where it fits, 0 = general path only
 void nb_sampler_set_fused(int on) { g_sampler_fused = on; }
+static int g_gather_keep_min = 2;   // "gather_keep_min_uses": sources a batch reads at least this often get the evict_last hint bit
+void nb_sampler_set_keep_min(int n) { g_gather_keep_min = n < 1 ? 1 : n; }
 static int g_sampler_two_level = -1;   // "sampler_two_level": -1 (default) = by density, 0 = flat dedup bitmap, 1 = two-level (tests)
 void nb_sampler_set_two_level(int mode) { g_sampler_two_level = mode; }
 struct nb_sampler {
@@ -862,11 +864,11 @@ k_csr_fill_fused(const uint32_t *__restrict__ row_indices, const uint32_t *__res
 // with bit 31 set when this batch reads that source more than once (row_count = the finished per-source histogram).
 __global__ void __launch_bounds__(256)
 k_pack_gather_index(const uint32_t *__restrict__ sample_ans, const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ row_count,
-                    uint32_t *__restrict__ gather_idx, const LayerMeta *meta) {
+                    uint32_t *__restrict__ gather_idx, const LayerMeta *meta, uint32_t keep_min) {
   if (meta->err) return;
   const unsigned E = meta->n_edges;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
-    gather_idx[e] = sample_ans[e] | (row_count[row_indices[e]] > 1u ? 0x80000000u : 0u);
+    gather_idx[e] = sample_ans[e] | (row_count[row_indices[e]] >= keep_min ? 0x80000000u : 0u);
 }
 
 // degrees from the CSC when the caller has none (clamped >= 1, core/graph.hpp:4525-4530)
@@ -1224,7 +1226,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
       NB_LAUNCH_CHECK(ctx);
     }
     if (b.gather_idx) {
-      k_pack_gather_index<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.sample_ans, b.row_indices, b.row_count, b.gather_idx, m);
+      k_pack_gather_index<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.sample_ans, b.row_indices, b.row_count, b.gather_idx, m, (uint32_t)g_gather_keep_min);
       NB_LAUNCH_CHECK(ctx);
     }
     if (layer_csr) {
