@@ -328,9 +328,13 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
     st_comm = torch.cuda.Stream(dev, priority=-1)
     cs_comm = nts.Cuda_Stream(local, st_comm)
     exchange = args.exchange if world > 1 else "none"
+    inline_push = exchange == "split-inline"     # A/B: begin's push kernel in the training stream instead of the library's side stream
+    if inline_push:
+        exchange = "split"
     peer_ar = None
     if exchange in ("split", "one"):
         from sample_based_gnn_b200 import dist as nbdist
+        check(lib.nb_set_option(b"peer_push_side_stream", 0 if inline_push else 1))
         peer_ar = nbdist.PeerAllReduce(cs_train if exchange == "split" else cs_comm, n_grad)
     comm_box, pending_box, open_box = [None], [None], [False]
 
@@ -1061,7 +1065,9 @@ def main_b200(args):
                     "gather kernel (HBM table)": round(g["gather_hbm_table_ms"] / km["gather"], 2) if km["gather"] else None,
                     "aggregate fwd F=602 (vs cuSPARSE)": round(g["spmm_fwd_F0_ms"] / km["agg_fwd_602"], 2) if km["agg_fwd_602"] else None}
         f_, a_, m_ = sm["fused"], sm["api"], sm["materialized"]
-        ex_name = {"split": "own kernels over NVLink peer memory: nb_peer_allreduce_begin behind the backward / _end before the next top hop, in the training stream",
+        ex_name = {"split": ("own kernels over NVLink peer memory: nb_peer_allreduce_begin behind the backward (push, "
+                             + ("in the training stream" if args.exchange == "split-inline" else "forked onto the library's side stream")
+                             + ") / _end before the next top hop (join + rank-ordered reduce in the training stream)"),
                    "one": "one kernel over NVLink peer memory (nb_peer_allreduce_sum) on a communication stream", "nccl": "NCCL all_reduce on a communication stream",
                    "none": "none (single GPU)"}[exchange]
         line = {"metric": "sampled_edges_per_s", "value": f_["value"], "unit": "edges/s", "n_gpus": world, "steps": K,
@@ -1103,9 +1109,9 @@ if __name__ == "__main__":
     ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
     ap.add_argument("--sample-priority", type=int, default=-1, help="CUDA stream priority of the sampling stream (-1 = high: its small kernels get SM slots ahead of the queued aggregation blocks; 0.184 -> 0.158 ms per step, profiles/r2_sweep_pipeline.txt)")
-    ap.add_argument("--exchange", default="split", choices=["split", "one", "nccl"],
-                    help="dense-gradient sum at N>1: split = peer-memory push behind the backward + reduce before the next top hop, in the "
-                         "training stream (default); one = one peer-memory kernel on a communication stream; nccl = NCCL all_reduce")
+    ap.add_argument("--exchange", default="split", choices=["split", "split-inline", "one", "nccl"],
+                    help="dense-gradient sum at N>1: split = peer-memory push behind the backward (beside the next bottom aggregation) + reduce "
+                         "before the next top hop (default); split-inline = the same with the push in the training stream; one = one peer-memory kernel on a communication stream; nccl = NCCL all_reduce")
     ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of exactly --steps steps each; the median window is reported")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: fixed global batch 1024, local batch 1024/N")

@@ -375,12 +375,16 @@ int nb_vmm_free(void *dev_ptr);
  * allocated with nb_vmm_alloc and mapped by every other rank with nb_vmm_import) holds arrival flags and two slots of `world`
  * regions. blocks[r] = rank r's block as mapped on ctx's device (blocks[rank] = the local allocation).
  * nb_peer_allreduce_begin : PUSH -- this rank's buffer is written into its region of every rank's slot (remote stores over
- *                           NVLink), then a flag per chunk; waits for nobody.
+ *                           NVLink), then a flag per chunk; waits for nobody. The push kernel is ordered behind everything
+ *                           enqueued on ctx's stream so far but runs on a side stream of the communicator (option
+ *                           "peer_push_side_stream", default 1; 0 = in ctx's stream), beside what the caller enqueues next:
+ *                           `in` must stay unchanged until nb_peer_allreduce_end has been enqueued.
  * nb_peer_allreduce_end   : REDUCE -- waits (bounded, ~20 s, then nb_peer_comm_check reports it) for every rank's flags and
  *                           sums the regions of the LOCAL slot in rank order: bit-identical on every rank, deterministic.
  *                           Whatever the caller enqueues between begin and end (the next batch's gather + aggregation)
- *                           absorbs rank skew; both kernels run in ctx's stream, so they never wait for SM slots behind a
- *                           persistent kernel of another stream. One exchange in flight per communicator.
+ *                           absorbs rank skew; the reduce kernel (the only one that waits) runs in ctx's stream behind the
+ *                           local push, so it never waits for SM slots behind a persistent kernel of another stream.
+ *                           One exchange in flight per communicator.
  * nb_peer_allreduce_sum   : both phases in ONE launch.
  * Every rank issues the same sequence of calls with the same n.
  * nb_peer_comm_stats      : exchanges ended, and the time their reduce phases spent polling for the slowest peer (sum / max, ns)

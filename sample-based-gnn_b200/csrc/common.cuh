@@ -92,6 +92,7 @@ uint64_t nb_trace_now_ns();
 void nb_trace_add(const char *name, uint64_t ns);  // name must be a string literal (the table is keyed by its address)
 void nb_sampler_set_two_level(int mode);
 void nb_sampler_set_keep_min(int n);
+void nb_peer_set_push_side(int v);
 void nb_sampler_set_fused(int on);   // sample.cu: small-shape sampler path on/off for samplers created afterwards
 void nb_agg_set_option(int which, int value);  // 0: resident blocks per SM of the segment reduction (1..8), 1: persistent grid on/off, 2: block-per-row path for long segments on/off
 #define NB_GUARD(ctx)                                                                              \

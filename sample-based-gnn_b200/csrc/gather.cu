@@ -343,6 +343,7 @@ int nb_set_option(const char *name, int value) {
   if (!strcmp(name, "agg_pipe_wide")) { nb_agg_set_option(3, value); return NB_OK; }
   if (!strcmp(name, "sampler_fused")) { nb_sampler_set_fused(value); return NB_OK; }   // read when a sampler is created
   if (!strcmp(name, "sampler_two_level")) { nb_sampler_set_two_level(value); return NB_OK; }
+  if (!strcmp(name, "peer_push_side_stream")) { nb_peer_set_push_side(value); return NB_OK; }   // read by nb_peer_comm_create
   if (!strcmp(name, "gather_keep_min_uses")) { nb_sampler_set_keep_min(value); return NB_OK; }   // read when a sampler's graph is captured
   if (!strcmp(name, "trace")) { nb_trace_set_level(value); return NB_OK; }
   if (!strcmp(name, "mirror_host_tables")) { nb_mirror_host_enable(value, 0); return NB_OK; }

@@ -12,9 +12,11 @@
 //       never arrives raises an error flag after ~20 s instead of hanging the GPU) and sums the `world` regions of the LOCAL slot
 //       in rank order: the same order on every rank, so the result is bit-identical everywhere and run to run.
 // All reads of the reduce phase are local HBM reads; whatever time passes between begin and end (the next batch's gather and
-// bottom aggregation in the training loop, ~0.2 ms) absorbs rank skew, and because both kernels run in the caller's stream they
-// never compete for SM slots with a persistent kernel of another stream (round 1's one-kernel rendezvous on a side stream could not
-// start while the segment reduction owned every thread slot, and the other ranks spun for it: 0.52 scaling efficiency at N=8).
+// bottom aggregation in the training loop, ~0.2 ms) absorbs rank skew. The push kernel never waits, so it may run on a side stream
+// beside the caller's next kernels (default; 0.1805 -> 0.1743 ms per step at N=2, profiles/r2_exchange_ab_n2_side_push.txt); the reduce
+// kernel, the only one that polls, runs in the caller's stream behind the local push: it never competes for SM slots with a
+// persistent kernel of another stream (round 1's one-kernel rendezvous on a side stream could not start while the segment
+// reduction owned every thread slot, and the other ranks spun for it: 0.52 scaling efficiency at N=8).
 // nb_peer_allreduce_sum = both phases in one launch (k_peer_exchange<PUSH|REDUCE>).
 // Two slots: rank r pushes exchange s+2 into slot (s & 1) only after its own reduce of s+1, which saw every peer's flag s+1,
 // which every peer stores after its own reduce of s (stream order reduce(s) -> push(s+1)): nobody still reads slot (s & 1).
@@ -42,7 +44,14 @@ struct nb_peer_comm {
   uint32_t seq_done;   // exchanges ended
   uint64_t max_floats;
   PeerStats *stats_dev;
+  // push on a side stream ("peer_push_side_stream", default on): begin's kernel waits for nobody and only stores, so it can run
+  // beside whatever the caller enqueues next instead of in front of it; end joins it before the reduce kernel
+  cudaStream_t push_stream;
+  cudaEvent_t ev_ready, ev_pushed;
 };
+
+static int g_peer_push_side = 1;
+void nb_peer_set_push_side(int v) { g_peer_push_side = v ? 1 : 0; }
 
 __device__ __forceinline__ float4 ld_volatile4(const float *p) {
   float4 v;
@@ -129,6 +138,15 @@ k_peer_exchange(PeerParams c, const float *in, float *out, uint32_t n, uint32_t 
 static int peer_launch(nb_peer_comm *c, int phases, const float *in, float *out, uint64_t n) {
   nb_ctx *ctx = c->ctx;
   const uint32_t seq = (phases & PEER_PUSH) ? c->seq : c->seq_done;
+  if (c->push_stream && phases == PEER_PUSH) {          // fork: the push runs beside the caller's next kernels
+    NB_CUDA(cudaEventRecord(c->ev_ready, ctx->stream));
+    NB_CUDA(cudaStreamWaitEvent(c->push_stream, c->ev_ready, 0));
+    k_peer_exchange<PEER_PUSH><<<PEER_CTAS, PEER_THREADS, 0, c->push_stream>>>(c->p, in, out, (uint32_t)n, seq, c->stats_dev);
+    NB_LAUNCH_CHECK(ctx);
+    NB_CUDA(cudaEventRecord(c->ev_pushed, c->push_stream));
+    return NB_OK;
+  }
+  if (c->push_stream && phases == PEER_REDUCE) NB_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_pushed, 0));   // join
   if (phases == (PEER_PUSH | PEER_REDUCE)) k_peer_exchange<PEER_PUSH | PEER_REDUCE><<<PEER_CTAS, PEER_THREADS, 0, ctx->stream>>>(c->p, in, out, (uint32_t)n, seq, c->stats_dev);
   else if (phases == PEER_PUSH) k_peer_exchange<PEER_PUSH><<<PEER_CTAS, PEER_THREADS, 0, ctx->stream>>>(c->p, in, out, (uint32_t)n, seq, c->stats_dev);
   else k_peer_exchange<PEER_REDUCE><<<PEER_CTAS, PEER_THREADS, 0, ctx->stream>>>(c->p, in, out, (uint32_t)n, seq, c->stats_dev);
@@ -156,6 +174,14 @@ int nb_peer_comm_create(nb_ctx *ctx, uint32_t rank, uint32_t world, uint64_t max
   }
   c->p.rank = rank; c->p.world = world;
   c->p.slot_bytes = ((max_floats + 3) / 4 * 16 + 255) & ~255ull;
+  c->push_stream = nullptr; c->ev_ready = nullptr; c->ev_pushed = nullptr;
+  if (g_peer_push_side && world > 1) {
+    int lo = 0, hi = 0;
+    NB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    NB_CUDA(cudaStreamCreateWithPriority(&c->push_stream, cudaStreamNonBlocking, hi));
+    NB_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    NB_CUDA(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
+  }
   NB_CUDA(cudaMalloc(&c->stats_dev, sizeof(PeerStats)));
   NB_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(PeerStats), ctx->stream));
   // this rank's flags start at zero; the caller barriers (host side) before the first exchange
@@ -168,6 +194,7 @@ int nb_peer_comm_create(nb_ctx *ctx, uint32_t rank, uint32_t world, uint64_t max
 int nb_peer_comm_destroy(nb_peer_comm *c) {
   if (!c) return NB_OK;
   DeviceGuard guard(c->ctx->device);
+  if (c->push_stream) { cudaStreamSynchronize(c->push_stream); cudaStreamDestroy(c->push_stream); cudaEventDestroy(c->ev_ready); cudaEventDestroy(c->ev_pushed); }
   cudaFree(c->stats_dev);
   delete c;
   return NB_OK;
