@@ -264,22 +264,30 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
     P = max(1, args.pipeline)
     PITCH = wl.pitch                                  # row pitch of the F0-wide tensors, in floats
 
-    st_sample, st_train = torch.cuda.Stream(dev, priority=args.sample_priority), torch.cuda.Stream(dev)
-    cs_sample, cs_train = nts.Cuda_Stream(local, st_sample), nts.Cuda_Stream(local, st_train)
+    # --sample-streams NS: pipeline slot k samples on stream k % NS. One sampling stream serialises the batches' sampler graphs;
+    # with two, batch i+1's sampling overlaps batch i's (both under the aggregation of earlier batches)
+    NS = max(1, min(args.sample_streams, P))
+    st_samples = [torch.cuda.Stream(dev, priority=args.sample_priority) for _ in range(NS)]
+    cs_samples = [nts.Cuda_Stream(local, s_) for s_ in st_samples]
+    st_sample, cs_sample = st_samples[0], cs_samples[0]
+    st_train = torch.cuda.Stream(dev)
+    cs_train = nts.Cuda_Stream(local, st_train)
     # e2e path: the host waits for every batch's sampled sizes, so sampling is on its critical path and gets a high-priority
     # stream (its small kernels are scheduled ahead of the resident gather / aggregation blocks of the previous batch). In the
     # device-resident path nothing waits for the sampler, and a normal-priority stream leaves the aggregation undisturbed.
-    st_sample_api = torch.cuda.Stream(dev, priority=-1)
-    cs_sample_api = nts.Cuda_Stream(local, st_sample_api)
+    PA = max(2, args.api_pipeline)                    # e2e: FastSampler pipeline slots (the reference's PIPELINE_NUM); PA - 1 batches are sampled ahead
+    NSA = max(1, min(args.sample_streams, PA))
+    st_samples_api = [torch.cuda.Stream(dev, priority=-1) for _ in range(NSA)]
+    cs_samples_api = [nts.Cuda_Stream(local, s_) for s_ in st_samples_api]
     with torch.cuda.stream(st_train):
         graph = nts.FullyRepGraph(cs_sample, v, column_offset=col_off, row_indices=src)
         # one sampler (arena) per pipeline slot, all on the sampling stream (the reference's PIPELINE_NUM SampledSubgraphs)
         # bottom_csr=False: the bottom hop's backward never runs in the GCN toolkits (core/ntsContext.hpp:443), so its CSR is not built
-        sampler = nts.FastSampler(graph, my_seeds, 2, B, FANOUT, pipeline_num=P, cuda_stream=[cs_sample] * P, build_csr=True,
+        sampler = nts.FastSampler(graph, my_seeds, 2, B, FANOUT, pipeline_num=P, cuda_stream=[cs_samples[k_ % NS] for k_ in range(P)], build_csr=True,
                                   bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
-        fast = nts.FastSampler(graph, my_seeds, 2, B, FANOUT, pipeline_num=2, cuda_stream=[cs_sample_api] * 2, build_csr=True,
+        fast = nts.FastSampler(graph, my_seeds, 2, B, FANOUT, pipeline_num=PA, cuda_stream=[cs_samples_api[k_ % NSA] for k_ in range(PA)], build_csr=True,
                                bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
-        api_ev = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
+        api_ev = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(PA)]
         gen = torch.Generator(device=dev).manual_seed(0x5EED0002)
         table = torch.empty((v, PITCH), device=dev)                               # HBM-resident feature table
         for a_ in range(0, v, 1 << 22):                                           # filled in chunks: no second table-sized temporary
@@ -305,8 +313,8 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
 
     # fixed arena pointers and device-side size addresses of every pipeline slot
     slots = []
-    with torch.cuda.stream(st_sample):
-        for k in range(P):
+    for k in range(P):
+        with torch.cuda.stream(st_samples[k % NS]):
             views = (nts._capi.LayerView * 2)()
             check(lib.nb_sampler_sample(sampler._samplers[k], ptr(my_seeds[:B]), B, 0, SEED_SAMPLER + rank, 0,
                                         nts.WeightType.Sum, None, 0xFFFFFFFF, views, 1))
@@ -377,6 +385,8 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
             issue_allreduce()
         exchange_before_consumer()
 
+    tl_box = [None]   # --timeline: per-step events [sample start, sample end, train start, after bottom hop, after top fwd, after top bwd]
+
     def step_async(i, timed, fused=True):
         """value: inputs resident in HBM, no host synchronisation anywhere (sizes stay on the device). Batch i is sampled on
         the sampling stream into arena i % P while the training stream works on batch i-1. fused: the bottom hop aggregates
@@ -384,11 +394,23 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         never written. fused=False materialises X0 first (gather kernel + aggregation over X0), as the reference does."""
         sl = slots[i % P]
         top, bot, nd, ns, caps = sl["top"], sl["bot"], sl["nd"], sl["ns"], sl["caps"]
+        st_sample, cs_sample = st_samples[(i % P) % NS], cs_samples[(i % P) % NS]
         st_sample.wait_event(sl["consumed"])
+        tl = tl_box[0]
+        if tl is not None:
+            tl.append([ev() for _ in range(6)])
+            tl[-1][0].record(st_sample)
         check(lib.nb_sampler_sample(sampler._samplers[i % P], ptr(seeds_dev[i * B:(i + 1) * B]), B, 1,
                                     SEED_SAMPLER + rank, i, nts.WeightType.Sum, None, 0xFFFFFFFF, None, 0))
+        if tl is not None:
+            tl[-1][1].record(st_sample)
+        # the batch's sizes (LayerMeta of both layers, adjacent: one 64-byte copy) go to the host for the edge count of the metric;
+        # on the sampling stream, so the copy engine's latency stays off the training stream
+        check(lib.nb_memcpy_d2h(cs_sample._h, ptr(sizes_both[i]), nd[0].value, 64, 0))
         sl["sampled"].record(st_sample)
         st_train.wait_event(sl["sampled"])
+        if tl is not None:
+            tl[-1][2].record(st_train)
         if timed:
             a, b, c = ev(), ev(), ev()
             a.record(st_train)
@@ -418,12 +440,17 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
             if timed:
                 b.record(st_train)
                 kern_ev["agg_fwd_602_from_table"].append((a, b))
+        if tl is not None:
+            tl[-1][3].record(st_train)
         exchange_before_consumer()
         check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(h1), ptr(y0), top.edge_weight_forward, top.row_indices,
                                            top.column_offset, nd[0], caps[0][0], F1, F1, F1))
+        if tl is not None:
+            tl[-1][4].record(st_train)
         check(lib.nb_aggregate_csr_bwd_dyn(cs_train._h, ptr(dy0), ptr(dh1), top.edge_weight_backward, top.row_offset,
                                            top.column_indices, ns[0], caps[0][2], F1, F1, F1))
-        check(lib.nb_memcpy_d2h(cs_train._h, ptr(sizes_both[i]), nd[0].value, 64, 0))   # LayerMeta of both layers (adjacent), one copy
+        if tl is not None:
+            tl[-1][5].record(st_train)
         sl["consumed"].record(st_train)
         exchange_after_backward()
 
@@ -433,7 +460,8 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
 
     def api_issue(i):
         """sample batch i asynchronously on the sampling stream into slot i % 2 (FastSampler pipeline slot, as PIPELINE_NUM=2)"""
-        k = i % 2
+        k = i % PA
+        st_sample_api = st_samples_api[k % NSA]
         st_sample_api.wait_event(api_ev[k]["consumed"])
         fast.work_offset = i * B
         with torch.cuda.stream(st_sample_api):
@@ -443,16 +471,16 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
 
     def step_api(i, timed):
         """e2e: the reference-shaped API a user calls -- host seeds in, sizes and the batch's top-layer output back on the
-        host every step. Batch i+1 is sampled (pipeline slot (i+1) % 2) while batch i is gathered / aggregated."""
-        if api_state["issued"] < i:
-            api_issue(i)
-        k = i % 2
+        host every step. Batches i+1 .. i+PA-1 are sampled (their own pipeline slots) while batch i is aggregated."""
+        while api_state["issued"] < min(i + PA - 2, n_steps - 1):   # (re)fill the pipeline: slots of batches i .. i+PA-2
+            api_issue(api_state["issued"] + 1 if api_state["issued"] >= i else i)
+        k = i % PA
         tw = time.perf_counter()
         sg = fast.wait(k)                                           # host waits for the sizes of batch i only
         api_state["wait_s"] += time.perf_counter() - tw
-        if i + 1 < n_steps:
-            api_issue(i + 1)                                        # the next batch samples (other pipeline slot, high-priority stream)
-                                                                    # while this one is gathered / aggregated and the host issues its ops
+        if i + PA - 1 < n_steps:
+            api_issue(i + PA - 1)                                   # batch i-1's slot is free again: sample ahead (high-priority streams)
+                                                                    # while this batch is aggregated and the host issues its ops
         st_train.wait_event(api_ev[k]["sampled"])
         t, bt = sg.sampled_sgs
         if args.materialize_x0:
@@ -510,7 +538,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                 peer_ar.stats(reset=True)
             for w in range(R):
                 align_ranks()
-                launches0 = cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count()
+                launches0 = sum(c_.launch_count() for c_ in cs_samples + cs_samples_api) + cs_train.launch_count() + cs_comm.launch_count()
                 t0, t1 = ev(), ev()
                 if clocks:
                     clocks.mark(True)
@@ -528,7 +556,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                 torch.cuda.synchronize()
                 if clocks:
                     clocks.mark(False)
-                launches += cs_sample.launch_count() + cs_train.launch_count() + cs_sample_api.launch_count() + cs_comm.launch_count() - launches0
+                launches += sum(c_.launch_count() for c_ in cs_samples + cs_samples_api) + cs_train.launch_count() + cs_comm.launch_count() - launches0
                 if world > 1:
                     dist.barrier()
                 torch.cuda.synchronize()
@@ -548,6 +576,45 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
     clk = clocks.summary() if clocks else None
     res["api"] = run("api") if "api" in modes else res["fused"]                     # --modes: tuning sweeps skip the other arms
     res["materialized"] = run("materialized") if "materialized" in modes else res["fused"]
+
+    # the sampler by itself: one batch after the other on one stream, nothing else on the GPU (its serial latency per batch)
+    sampler_alone_us = None
+    if sample_clocks:
+        torch.cuda.synchronize()
+        a_, b_ = ev(), ev()
+        n_alone = min(60, n_steps)
+        for rep in range(2):                     # first pass warms up
+            a_.record(st_samples[0])
+            for i in range(n_alone):
+                check(lib.nb_sampler_sample(sampler._samplers[0], ptr(seeds_dev[i * B:(i + 1) * B]), B, 1,
+                                            SEED_SAMPLER + rank, i, nts.WeightType.Sum, None, 0xFFFFFFFF, None, 0))
+            b_.record(st_samples[0])
+            torch.cuda.synchronize()
+        sampler_alone_us = a_.elapsed_time(b_) / n_alone * 1e3
+    timeline = None
+    if args.timeline and sample_clocks:     # diagnostic: where a step's time goes on the device (events between the kernels cost ~1 us each: not a bench value)
+        tl_box[0] = []
+        with torch.cuda.stream(st_train):
+            comm_box[0], pending_box[0], open_box[0] = None, None, False
+            for i in range(W, W + args.timeline):
+                step_async(i, False, True)
+            exchange_flush()
+        torch.cuda.synchronize()
+        tl, tl_box[0] = tl_box[0][8:], None
+        ref = tl[0][2]
+        T = np.array([[ref.elapsed_time(e) for e in row] for row in tl]) * 1e3      # us
+        timeline = {"steps": len(tl), "unit": "us, mean over steps",
+                    "step_period": float(np.diff(T[:, 5]).mean()),
+                    "sampler_graph": float((T[:, 1] - T[:, 0]).mean()),
+                    "sample_end_to_train_start": float((T[:, 2] - T[:, 1]).mean()),
+                    "prev_bwd_end_to_train_start": float((T[1:, 2] - T[:-1, 5]).mean()),
+                    "bottom_hop": float((T[:, 3] - T[:, 2]).mean()),
+                    "top_fwd(+exchange end)": float((T[:, 4] - T[:, 3]).mean()),
+                    "top_bwd": float((T[:, 5] - T[:, 4]).mean()),
+                    "sample_start_after_prev_prev_bwd_end": float((T[2:, 0] - T[:-2, 5]).mean()),
+                    "sample_end_before_prev_bwd_end": float((T[:-1, 5] - T[1:, 1]).mean())}
+        if rank == 0:
+            print("timeline " + json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in timeline.items()}), file=sys.stderr, flush=True)
 
     # ---- exchange correctness, on the exact path the timed region used: bit-identical to the rank-ordered fp32 sum ------------
     exchange_check = None
@@ -608,7 +675,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         wait_all = {"mean_us_max_over_ranks": round(reduce([w_[1]], MAX)[0], 2), "max_us_over_ranks": round(reduce([w_[2]], MAX)[0], 2),
                     "exchanges_per_rank": w_[0]}
 
-    out = dict(res=res, sm=sm, launches_all=launches_all, wait_all=wait_all, exchange_check=exchange_check, clk=clk, exchange=exchange,
+    out = dict(timeline=timeline, sampler_alone_us=sampler_alone_us, res=res, sm=sm, launches_all=launches_all, wait_all=wait_all, exchange_check=exchange_check, clk=clk, exchange=exchange,
                B=B, P=P, PITCH=PITCH, K=K, W=W, R=R, e_total=e_total, n_train=int(all_seeds.size))
     if peer_ar is not None:
         assert not peer_ar.timed_out(), "peer all-reduce: a rank never arrived"
@@ -673,12 +740,14 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
     n_steps = W + R * K
     mine = shard_seeds(all_seeds, rank, world)
     mine = np.tile(mine, -(-n_steps * B // mine.size))[: n_steps * B]
-    st_s, st_t = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev)
-    cs_s, cs_t = nts.Cuda_Stream(local, st_s), nts.Cuda_Stream(local, st_t)
+    PO = 3                                            # FastSampler pipeline slots: two batches are sampled ahead, on two streams
+    st_ss, st_t = [torch.cuda.Stream(dev, priority=-1) for _ in range(2)], torch.cuda.Stream(dev)
+    cs_ss, cs_t = [nts.Cuda_Stream(local, s_) for s_ in st_ss], nts.Cuda_Stream(local, st_t)
+    st_s, cs_s = st_ss[0], cs_ss[0]
     H, NC = F1, NCLS
     with torch.cuda.stream(st_t):
         graph = nts.FullyRepGraph(cs_s, v, column_offset=col_off, row_indices=src)
-        smp = nts.FastSampler(graph, mine, 2, B, FANOUT, pipeline_num=2, cuda_stream=[cs_s] * 2, merge_src_dst=True, build_csr=True,
+        smp = nts.FastSampler(graph, mine, 2, B, FANOUT, pipeline_num=PO, cuda_stream=[cs_ss[k_ % 2] for k_ in range(PO)], merge_src_dst=True, build_csr=True,
                               rng_seed=SEED_SAMPLER + 100 + rank)
         gen = torch.Generator(device=dev).manual_seed(5)
         table = torch.rand((v, F0), generator=gen, device=dev)
@@ -693,12 +762,13 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
     if world > 1:
         from sample_based_gnn_b200 import dist as nbdist
         peer = nbdist.PeerAllReduce(cs_t, grads.numel())
-    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
+    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(PO)]
     state = {"issued": -1, "open": False}
     gat_ev, work = [], []
 
     def issue(i):
-        k = i % 2
+        k = i % PO
+        st_s = st_ss[k % 2]
         st_s.wait_event(ev_s[k]["consumed"])
         smp.work_offset = i * B
         with torch.cuda.stream(st_s):
@@ -707,9 +777,9 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
         state["issued"] = i
 
     def step(i, timed):
-        if state["issued"] < i:
-            issue(i)
-        k = i % 2
+        while state["issued"] < min(i + PO - 2, n_steps - 1):
+            issue(state["issued"] + 1 if state["issued"] >= i else i)
+        k = i % PO
         sg = smp.wait(k)
         st_t.wait_event(ev_s[k]["sampled"])
         top, bot = sg.sampled_sgs
@@ -732,8 +802,8 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
         if peer is not None:
             peer.begin(grads)
             state["open"] = True
-        if i + 1 < n_steps:
-            issue(i + 1)
+        if i + PO - 1 < n_steps:
+            issue(i + PO - 1)
         work.append(top.e_size + bot.e_size)
         del o1, o0
 
@@ -794,8 +864,10 @@ def run_papers_config(env, args, peak):
     if free < need:
         return {"skipped": f"needs ~{need / 1e9:.0f} GB of free HBM per GPU at N={world}, {free / 1e9:.0f} GB free"}
     B, K, W, R = BATCH, args.steps, max(3, args.warmup), 3
-    st_s, st_t = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev)
-    cs_s, cs_t = nts.Cuda_Stream(local, st_s), nts.Cuda_Stream(local, st_t)
+    PO = 3                                            # FastSampler pipeline slots: two batches are sampled ahead, on two streams
+    st_ss, st_t = [torch.cuda.Stream(dev, priority=-1) for _ in range(2)], torch.cuda.Stream(dev)
+    cs_ss, cs_t = [nts.Cuda_Stream(local, s_) for s_ in st_ss], nts.Cuda_Stream(local, st_t)
+    st_s, cs_s = st_ss[0], cs_ss[0]
     from sample_based_gnn_b200 import dist as nbdist
     with torch.cuda.stream(st_t):
         co, src = power_law_graph_gpu(torch, V, E, 0xFACE)
@@ -808,7 +880,7 @@ def run_papers_config(env, args, peak):
         mine = shard_seeds(train, rank, world)
         n_steps = W + R * K
         mine = np.tile(mine, -(-n_steps * B // mine.size))[: n_steps * B]
-        smp = nts.FastSampler(graph, mine, 2, B, FANOUT, pipeline_num=2, cuda_stream=[cs_s] * 2, build_csr=True, bottom_csr=False,
+        smp = nts.FastSampler(graph, mine, 2, B, FANOUT, pipeline_num=PO, cuda_stream=[cs_ss[k_ % 2] for k_ in range(PO)], build_csr=True, bottom_csr=False,
                               rng_seed=SEED_SAMPLER + 200 + rank)
         gen = torch.Generator(device=dev).manual_seed(11 + rank)
         n_local = (V - rank + world - 1) // world
@@ -830,12 +902,13 @@ def run_papers_config(env, args, peak):
         grads = torch.rand(F * H + H * 172, device=dev)
     torch.cuda.synchronize()
     peer = nbdist.PeerAllReduce(cs_t, grads.numel()) if world > 1 else None
-    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
+    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(PO)]
     state = {"issued": -1, "open": False}
     g_ev, s_ev, work, rows_n = [], [], [], []
 
     def issue(i):
-        k = i % 2
+        k = i % PO
+        st_s = st_ss[k % 2]
         st_s.wait_event(ev_s[k]["consumed"])
         smp.work_offset = i * B
         with torch.cuda.stream(st_s):
@@ -848,9 +921,9 @@ def run_papers_config(env, args, peak):
         state["issued"] = i
 
     def step(i, timed):
-        if state["issued"] < i:
-            issue(i)
-        k = i % 2
+        while state["issued"] < min(i + PO - 2, n_steps - 1):
+            issue(state["issued"] + 1 if state["issued"] >= i else i)
+        k = i % PO
         sg = smp.wait(k)
         st_t.wait_event(ev_s[k]["sampled"])
         top, bot = sg.sampled_sgs
@@ -871,8 +944,8 @@ def run_papers_config(env, args, peak):
         ev_s[k]["consumed"].record(st_t)
         if peer is not None:
             peer.begin(grads); state["open"] = True
-        if i + 1 < n_steps:
-            issue(i + 1)
+        if i + PO - 1 < n_steps:
+            issue(i + PO - 1)
         work.append(top.e_size + bot.e_size)
         del y1
 
@@ -1030,7 +1103,7 @@ def main_b200(args):
                 pass
         cpu = None
         ref_gpu_box = []
-        CPP_E2E_ARGS[:] = [str(PITCH), str(K), str(W), str(R)]
+        CPP_E2E_ARGS[:] = [str(PITCH), str(K), str(W), str(R), str(max(2, args.api_pipeline)), str(args.sample_streams)]
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r, kind, threads = cpu_baseline_run(v, col_off, src, all_seeds, args.cpu_batches, 2, ref_gpu_box)
@@ -1074,7 +1147,7 @@ def main_b200(args):
                 "warmup": W, "ms_per_step": f_["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(v, e_total),
-                "run": {"per_gpu_batch": B, "global_batch": B * world, "pipeline_num": P, "row_pitch_floats": PITCH,
+                "run": {"per_gpu_batch": B, "global_batch": B * world, "pipeline_num": P, "sampling_streams": args.sample_streams, "row_pitch_floats": PITCH,
                         "parallelism": f"dp{world}: seeds sharded contiguously; dense-gradient sum per step = {ex_name}" if world > 1 else "single GPU",
                         "windows": R, "window_rule": "each window times exactly `steps` steps between device-aligned events; the median window is reported",
                         "windows_ms_per_step": f_["windows_ms_per_step"], "host_issue_ms_per_step": f_["host_issue_ms_per_step"],
@@ -1087,11 +1160,15 @@ def main_b200(args):
                         "windows_ms_per_step": a_["windows_ms_per_step"], "host_issue_ms_per_step": a_["host_issue_ms_per_step"],
                         "host_blocked_in_sampler_wait_ms_per_step": round(res["api"]["host_wait_ms_per_step"], 5),
                         "cpp_host": cpp_e2e,
-                        "path": "FastSampler.sample_gpu_fast(slot i+1, async, high-priority stream) || wait(slot i) -> load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
+                        "pipeline_num": max(2, args.api_pipeline),
+                        "path": "FastSampler.sample_gpu_fast(slots i+1 .. i+PIPELINE_NUM-1, async, high-priority streams) || wait(slot i) -> load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
                 "gpu_launches": int(round(launches_all)), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "other_configs": other,
                 "materialized_x0": {"value": m_["value"], "unit": "edges/s", "ms_per_step": m_["ms_per_step"],
                                     "windows_ms_per_step": m_["windows_ms_per_step"],
                                     "note": "same step with X0 materialised first (gather kernel, then aggregation over X0), as the reference's load_feature_gpu does"}}
+        if o.get("timeline"):
+            line["timeline_diagnostic"] = o["timeline"]
+        line["sampler_alone_us_per_batch"] = round(o["sampler_alone_us"], 2) if o.get("sampler_alone_us") else None
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -1105,7 +1182,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only; the metric is quoted at 1.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2, help="PIPELINE_NUM: sampler arenas in flight (sampling overlaps training)")
+    ap.add_argument("--pipeline", type=int, default=4, help="PIPELINE_NUM: sampler arenas in flight (sampling overlaps training)")
     ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
     ap.add_argument("--sample-priority", type=int, default=-1, help="CUDA stream priority of the sampling stream (-1 = high: its small kernels get SM slots ahead of the queued aggregation blocks; 0.184 -> 0.158 ms per step, profiles/r2_sweep_pipeline.txt)")
@@ -1113,6 +1190,10 @@ if __name__ == "__main__":
                     help="dense-gradient sum at N>1: split = peer-memory push behind the backward (beside the next bottom aggregation) + reduce "
                          "before the next top hop (default); split-inline = the same with the push in the training stream; one = one peer-memory kernel on a communication stream; nccl = NCCL all_reduce")
     ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
+    ap.add_argument("--api-pipeline", type=int, default=4, help="e2e arm: FastSampler pipeline slots (PIPELINE_NUM); PIPELINE_NUM - 1 batches are sampled ahead")
+    ap.add_argument("--sample-streams", type=int, default=2, help="sampling streams; pipeline slot k samples on stream k %% NS (one stream serialises the batches' sampler graphs "
+                         "and puts them on the step's critical path: 0.168 -> 0.155 ms per step with two, profiles/r2_sweep_sample_streams.txt)")
+    ap.add_argument("--timeline", type=int, default=0, help="diagnostic: after the timed arms, N more steps with events between the kernels; prints where a step's time goes")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of exactly --steps steps each; the median window is reported")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: fixed global batch 1024, local batch 1024/N")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the products / GAT / papers100M records (tuning runs)")

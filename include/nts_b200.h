@@ -89,7 +89,7 @@ typedef struct nb_layer_view {
   const uint32_t *src_to_dst;     /* [n_src] index of the dst equal to this src, or 0xffffffff (new) */
   const uint32_t *source_use_count; /* [n_src] number of this layer's edges that read each source (new; the CSR row lengths) */
   const uint32_t *gather_index;   /* [n_edges], bottom layer only (NULL elsewhere, and when |V| >= 2^31): sample_ans[e] with bit 31
-                                     set when the batch reads that source more than once -- the index + L2 hint that
+                                     set when the batch reads that source at least "gather_keep_min_uses" (3) times -- the index + L2 hint that
                                      nb_aggregate_gathered_fwd_dyn consumes (new) */
 } nb_layer_view;
 
@@ -104,12 +104,17 @@ int nb_device_count(int *count);
  *       (the buffer must not change after that); 0 (default) = gather over PCIe like the reference
  *   "mirror_host_adjacency" / NB_MIRROR_HOST_ADJACENCY : 1 (default) = the same for the adjacency array that the stage-shaped
  *       sampling calls receive as a mapped host pointer (core/ntsFastSampler.hpp:159-166); the topology never changes after load
- *   "sampler_fused" / NB_SAMPLER_FUSED : 1 (default) = samplers created afterwards use the small-shape kernels (a layer's prefix
- *       sums recomputed per block in shared memory: 2 launches per layer instead of 4) wherever the layer fits; 0 = general path only.
- *       Both give identical results.
+ *   "sampler_fused" / NB_SAMPLER_FUSED : 0 (default) = samplers created afterwards use the general kernels (single-pass look-back scans
+ *       in global memory, 256-thread blocks of <= 40 registers: they fit beside the running aggregation's blocks); 1 = the small-shape
+ *       kernels (a layer's prefix sums in shared memory, fewer launches) wherever a layer fits. Identical results; measured on the
+ *       Reddit shape the general kernels are faster alone (80 vs 110-135 us per batch) and beside the aggregation
+ *       (profiles/r2_sweep_sampler_residency*.txt). "sampler_tail" (1) and "sampler_block_threads" (256 | 512) shape the small-shape path.
+ *   "sampler_blocks_per_sm" : 2 (default) = no kernel of a sampler's batch graph launches more than this many blocks per SM, so that a
+ *       batch sampled beside the previous batch's aggregation lives in the slot that kernel leaves free instead of displacing its
+ *       blocks (0.146 -> 0.139 ms per step); 0 = every kernel sized for its own work (lowest latency on an idle GPU: 80 vs 86 us)
  *   "sampler_two_level" : -1 (default) = samplers created afterwards pick the dedup bitmap layout by density (two levels when the graph
  *       has several times more bitmap words than a batch can touch: O(|V|/1024 + S + E) per layer instead of O(|V|/32)); 0 / 1 force it
- *   "gather_keep_min_uses" : 2 (default) = a source row that the batch's bottom layer reads at least this many times gets the
+ *   "gather_keep_min_uses" : 3 (default) = a source row that the batch's bottom layer reads at least this many times gets the
  *       "keep in L2" hint bit in nb_layer_view.gather_index (read with evict_last by nb_aggregate_gathered_fwd_dyn); other rows stream
  *       through (evict_first). Changes cache behaviour only, never results.
  *   "trace" / NB_TRACE : 1 = wall-clock time spent inside every entry point is accumulated (host side); 2 = the call's stream is

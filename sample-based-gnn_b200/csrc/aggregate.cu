@@ -21,11 +21,13 @@
 constexpr int AGG_THREADS = 256;
 // 7 resident blocks per SM, not 8: the free 256-thread slot lets the next batch's sampling kernels and the gradient exchange start
 // under a running aggregation instead of waiting for its tail (same-call sweep, profiles/r2_sweep_occupancy.txt: 0.1554 -> 0.1522 ms per step)
-static int g_agg_blocks_per_sm = 7, g_agg_persistent = 1, g_agg_long_rows = 0, g_agg_pipe_wide = 1;  // pipe: 0 never, 1 rows of <= 64 vectors, 2 always
+static int g_agg_blocks_per_sm = 7, g_agg_persistent = 1, g_agg_long_rows = 0, g_agg_pipe_wide = 1, g_agg_short_rows = 1, g_agg_deep_small = 1;  // pipe: 0 never, 1 rows of <= 64 vectors, 2 always
 void nb_agg_set_option(int which, int value) {
   if (which == 0) g_agg_blocks_per_sm = value < 1 ? 1 : value > 8 ? 8 : value;
   else if (which == 1) g_agg_persistent = value;
   else if (which == 2) g_agg_long_rows = value;
+  else if (which == 4) g_agg_short_rows = value;
+  else if (which == 5) g_agg_deep_small = value;
   else g_agg_pipe_wide = value;
 }
 
@@ -221,6 +223,90 @@ __device__ __noinline__ void segment_block_reduce(uint32_t r, const float *__res
   }
 }
 
+// Short rows -- the CSR of a sampled layer (backward: ~1-2 entries per source row) with rows of <= 32 vectors: one warp per row
+// chains three dependent loads (offsets -> index/weight -> data) for a single 512-byte row, and the launch is bound by that
+// latency times the number of waves. Here a warp owns ROWS consecutive rows: one load fetches their ROWS+1 offsets, one
+// coalesced load the indices / weights of all their entries (they are contiguous), and the rows' data loads are in flight
+// together. Per row the entries are still accumulated in stored order (mul, then add): same bits as k_segment_reduce.
+template <int VEC, int ROWS>
+__global__ void __launch_bounds__(AGG_THREADS)
+k_segment_reduce_short(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
+                       const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
+                       const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch) {
+  constexpr uint32_t JOINT = 4;   // entries per row handled in the joint phase; longer rows finish one at a time, 4 loads in flight
+  const unsigned lane = lane_id();
+  const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * AGG_THREADS) >> 5;
+  if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
+  const bool active = lane < nvec;
+  const uint64_t col = (uint64_t)lane * VEC;
+  for (unsigned r0 = warp * ROWS; r0 < n_rows; r0 += warps * ROWS) {
+    const unsigned nr = min((unsigned)ROWS, n_rows - r0);
+    const uint32_t off = lane <= nr ? offsets[r0 + lane] : 0u;
+    uint32_t beg[ROWS], len[ROWS];
+    uint32_t maxlen = 0;
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) {
+      const uint32_t b = __shfl_sync(FULL_MASK, off, i), e = __shfl_sync(FULL_MASK, off, i + 1);
+      beg[i] = b;
+      len[i] = (unsigned)i < nr ? e - b : 0u;
+      maxlen = max(maxlen, len[i]);
+    }
+    const uint32_t e0 = beg[0], total = __shfl_sync(FULL_MASK, off, nr) - e0;
+    uint32_t my_idx = 0;
+    float my_w = 1.0f;
+    if (lane < total) {   // the first 32 entries of the group in one coalesced load
+      my_idx = idx[e0 + lane];
+      if (weight) my_w = weight[e0 + lane];
+    }
+    Vec<VEC> acc[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) acc[i].zero();
+    const uint32_t joint = min(maxlen, JOINT);
+    for (uint32_t j = 0; j < joint; j++) {
+      Vec<VEC> x[ROWS];
+      float w[ROWS];
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) {
+        if (j < len[i]) {   // warp-uniform
+          const uint32_t e = beg[i] + j - e0;
+          uint32_t s;
+          if (e < 32) { s = __shfl_sync(FULL_MASK, my_idx, e); w[i] = __shfl_sync(FULL_MASK, my_w, e); }
+          else { s = idx[e0 + e]; w[i] = weight ? weight[e0 + e] : 1.0f; }
+          if (active) x[i].load(in + (uint64_t)s * pitch + col);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < ROWS; i++)
+        if (j < len[i] && active) acc[i].axpy(x[i], w[i]);
+    }
+    if (maxlen > JOINT) {
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) {
+        for (uint32_t j = JOINT; j < len[i]; j += 4) {
+          Vec<VEC> x[4];
+          float w[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (j + u < len[i]) {
+              const uint32_t e = beg[i] + j + u;
+              const uint32_t s = idx[e];
+              w[u] = weight ? weight[e] : 1.0f;
+              if (active) x[u].load(in + (uint64_t)s * pitch + col);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (j + u < len[i] && active) acc[i].axpy(x[u], w[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ROWS; i++)
+      if ((unsigned)i < nr && active) acc[i].store(out + (uint64_t)(r0 + i) * out_pitch + col);
+  }
+}
+
 template <int VEC, int CHUNK, int UNR, bool PIPE>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_segment_reduce_lb(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
@@ -407,8 +493,15 @@ k_push(const float *__restrict__ in, float *__restrict__ out, const float *__res
 template <int VEC>
 static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                           const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
-                          uint64_t out_pitch, SegEpilogue epi, bool packed_index) {
+                          uint64_t out_pitch, SegEpilogue epi, bool packed_index, int shape = 0) {
   const uint32_t nvec = F / VEC;
+  if (shape == NB_SEG_SHORT_ROWS && g_agg_short_rows && !push && !packed_index && !epi.c2c && !epi.e1 && nvec <= 32) {
+    constexpr int ROWS = 4;
+    const unsigned grid = nb_grid(n_rows, (AGG_THREADS / 32) * ROWS, 8);
+    k_segment_reduce_short<VEC, ROWS><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch);
+    NB_LAUNCH_CHECK(ctx);
+    return NB_OK;
+  }
   // block path for long segments: staging batch sized to SEG_STAGE_BYTES of dynamic shared memory
   uint32_t long_batch = 0;
   size_t smem = 0;
@@ -431,7 +524,12 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
     else if (packed_index) k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), true><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
     else k_segment_reduce<VEC, C, (C <= 2 ? 4 : C <= 4 ? 3 : 2), false><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi); \
   } while (0)
-  if (per_lane <= 1) NB_SEG(1);
+  // a launch whose rows all fit on the GPU at once (a top hop: 1024 columns) is pure latency: the row's entries x load latency
+  // / loads in flight. Registers are free there, so 16 (8) entries are in flight instead of 4.
+  const bool small = g_agg_deep_small && !push && !packed_index && !long_batch && n_rows <= (unsigned)ctx->sm_count * 16u;
+  if (small && per_lane <= 1) k_segment_reduce<VEC, 1, 16, false><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi);
+  else if (small && per_lane <= 2) k_segment_reduce<VEC, 2, 8, false><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi);
+  else if (per_lane <= 1) NB_SEG(1);
   else if (per_lane <= 2) NB_SEG(2);
   else if (per_lane <= 4) NB_SEG(4);
   else if (per_lane <= 5) NB_SEG(5);
@@ -460,7 +558,7 @@ int nb_run_segment_gat(nb_ctx *ctx, const float *dout, float *dh, const uint32_t
 
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                    const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
-                   uint64_t out_pitch, const float *e1, const float *e2, const float *va, const float *vb, bool packed_index) {
+                   uint64_t out_pitch, const float *e1, const float *e2, const float *va, const float *vb, bool packed_index, int shape) {
   SegEpilogue epi{e1, e2, va, vb};
   if (n_rows == 0) return NB_OK;
   if (!in_pitch) in_pitch = F;
@@ -468,15 +566,15 @@ int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const fl
   uint32_t fe = F;
   int vec = (push || e1) ? nb_pick_vec(F, in, in_pitch, out, out_pitch) : nb_pick_vec(F, in, in_pitch, out, out_pitch, &fe);
   if (e1 && vec > 1 && (((uintptr_t)va | (uintptr_t)vb) % (4 * vec))) vec = 1;  // epilogue vectors must allow the same vector loads
-  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index);
-  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index);
-  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index);
+  if (vec == 4) return launch_segment<4>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index, shape);
+  if (vec == 2) return launch_segment<2>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index, shape);
+  return launch_segment<1>(ctx, push, in, out, w, idx, offsets, n_rows, fe, n_rows_dev, in_pitch, out_pitch, epi, packed_index, shape);
 }
 
 static int run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,
                        const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev = nullptr,
-                       uint64_t in_pitch = 0, uint64_t out_pitch = 0) {
-  return nb_run_segment(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch, nullptr, nullptr, nullptr, nullptr);
+                       uint64_t in_pitch = 0, uint64_t out_pitch = 0, int shape = 0) {
+  return nb_run_segment(ctx, push, in, out, w, idx, offsets, n_rows, F, n_rows_dev, in_pitch, out_pitch, nullptr, nullptr, nullptr, nullptr, false, shape);
 }
 
 extern "C" {
@@ -498,7 +596,7 @@ int nb_aggregate_csr_bwd(nb_ctx *ctx, const float *input, float *output, const f
   NB_REQUIRE(feature_size > 0, NB_ERR_ARG, "feature_size must be > 0");
   (void)n_dst;
   NB_GUARD(ctx);
-  return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, n_src, feature_size);
+  return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, n_src, feature_size, nullptr, 0, 0, NB_SEG_SHORT_ROWS);
 }
 
 // Extents from device memory (nb_sampler_sizes_dev): no host round trip between sampling and aggregation.
@@ -517,7 +615,8 @@ int nb_aggregate_csr_bwd_dyn(nb_ctx *ctx, const float *input, float *output, con
   NB_REQUIRE(ctx && (max_src == 0 || (output && row_offset)), NB_ERR_ARG, "nb_aggregate_csr_bwd_dyn: NULL argument");
   NB_REQUIRE(feature_size > 0 && input_pitch >= feature_size && output_pitch >= feature_size, NB_ERR_ARG, "bad feature_size / pitch");
   NB_GUARD(ctx);
-  return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, max_src, feature_size, n_src_dev, input_pitch, output_pitch);
+  return run_segment(ctx, false, input, output, weight_backward, column_indices, row_offset, max_src, feature_size, n_src_dev, input_pitch, output_pitch,
+                     NB_SEG_SHORT_ROWS);
 }
 
 // The bottom hop fused with the feature gather (FastSampler::load_feature_gpu + SingleGPU[All]SampleGraphOp::forward in one kernel)

@@ -49,7 +49,8 @@ int nb_ctx_scratch(nb_ctx *ctx, size_t bytes, void **out);
 // segment reduction out[r,:] = sum_j w[j] in[idx[j],:] (+ e1[r] va + e2[r] vb); aggregate.cu
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *offsets,
                    uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch, uint64_t out_pitch, const float *e1,
-                   const float *e2, const float *va, const float *vb, bool packed_index = false);
+                   const float *e2, const float *va, const float *vb, bool packed_index = false, int shape = 0);
+constexpr int NB_SEG_SHORT_ROWS = 1;   // shape hint: rows are the CSR rows of a sampled layer (~1-2 entries each)
 int nb_run_segment_gat(nb_ctx *ctx, const float *dout, float *dh, const uint32_t *column_indices, const uint32_t *row_offset, uint32_t n_src,
                        uint32_t F, const uint32_t *c2c, const float *alpha, const float *ds, const float *dsum, const uint32_t *src_to_dst,
                        const float *va, const float *vb, float *rs_out, float *dd_out);
@@ -92,6 +93,10 @@ uint64_t nb_trace_now_ns();
 void nb_trace_add(const char *name, uint64_t ns);  // name must be a string literal (the table is keyed by its address)
 void nb_sampler_set_two_level(int mode);
 void nb_sampler_set_keep_min(int n);
+void nb_sampler_set_tail(int v);
+void nb_sampler_set_block(int v);
+void nb_sampler_set_bps(int v);
+void nb_sampler_set_capture_prio(int v);
 void nb_peer_set_push_side(int v);
 void nb_sampler_set_fused(int on);   // sample.cu: small-shape sampler path on/off for samplers created afterwards
 void nb_agg_set_option(int which, int value);  // 0: resident blocks per SM of the segment reduction (1..8), 1: persistent grid on/off, 2: block-per-row path for long segments on/off

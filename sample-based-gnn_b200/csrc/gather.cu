@@ -341,9 +341,15 @@ int nb_set_option(const char *name, int value) {
   if (!strcmp(name, "agg_persistent")) { nb_agg_set_option(1, value); return NB_OK; }
   if (!strcmp(name, "agg_long_rows")) { nb_agg_set_option(2, value); return NB_OK; }
   if (!strcmp(name, "agg_pipe_wide")) { nb_agg_set_option(3, value); return NB_OK; }
+  if (!strcmp(name, "agg_short_rows")) { nb_agg_set_option(4, value); return NB_OK; }   // CSR backward: 4 rows per warp in flight (default 1)
+  if (!strcmp(name, "agg_deep_small")) { nb_agg_set_option(5, value); return NB_OK; }   // small launches: 16 / 8 entries in flight (default 1)
   if (!strcmp(name, "sampler_fused")) { nb_sampler_set_fused(value); return NB_OK; }   // read when a sampler is created
   if (!strcmp(name, "sampler_two_level")) { nb_sampler_set_two_level(value); return NB_OK; }
   if (!strcmp(name, "peer_push_side_stream")) { nb_peer_set_push_side(value); return NB_OK; }   // read by nb_peer_comm_create
+  if (!strcmp(name, "sampler_block_threads")) { nb_sampler_set_block(value); return NB_OK; }   // read when a sampler's graph is captured
+  if (!strcmp(name, "sampler_blocks_per_sm")) { nb_sampler_set_bps(value); return NB_OK; }   // read when a sampler's graph is captured
+  if (!strcmp(name, "sampler_capture_priority")) { nb_sampler_set_capture_prio(value); return NB_OK; }
+  if (!strcmp(name, "sampler_tail")) { nb_sampler_set_tail(value); return NB_OK; }   // read when a sampler's graph is captured
   if (!strcmp(name, "gather_keep_min_uses")) { nb_sampler_set_keep_min(value); return NB_OK; }   // read when a sampler's graph is captured
   if (!strcmp(name, "trace")) { nb_trace_set_level(value); return NB_OK; }
   if (!strcmp(name, "mirror_host_tables")) { nb_mirror_host_enable(value, 0); return NB_OK; }

@@ -32,17 +32,19 @@ struct LayerBuf {
   uint32_t *destination, *column_offset, *sample_ans, *row_indices, *edge_dst, *source;
   uint32_t *row_offset, *row_count, *row_cursor, *column_indices, *csr_tmp, *csr_to_csc, *long_rows;
   uint32_t *dst_local_id, *src_to_dst;
-  uint32_t *gather_idx;           // [cap_edges], bottom layer only: global src id | (the batch reads that source more than once) << 31
+  uint32_t *gather_idx;           // [cap_edges], bottom layer only: global src id | (the batch reads that source >= gather_keep_min_uses times) << 31
   uint32_t *dst_base, *dst_deg;   // [cap_dst] g_col_off[d] and the in-degree of every dst, written by whoever produced `destination`
                                   // (the previous layer's source emission; layer 0: the sampling kernel itself)
   float *ewf, *ewb;
 };
 
 #define NB_MAX_LAYERS 8
-static int g_sampler_fused = -1;   // "sampler_fused" / NB_SAMPLER_FUSED: 1 (default) = small-shape path where it fits, 0 = general path only
+static int g_sampler_fused = -1;   // "sampler_fused" / NB_SAMPLER_FUSED: 0 (default) = general kernels (look-back scans), 1 = small-shape kernels where a layer fits
 void nb_sampler_set_fused(int on) { g_sampler_fused = on; }
-static int g_gather_keep_min = 2;   // "gather_keep_min_uses": sources a batch reads at least this often get the evict_last hint bit
+static int g_gather_keep_min = 3;   // "gather_keep_min_uses": sources a batch reads at least this often get the evict_last hint bit
 void nb_sampler_set_keep_min(int n) { g_gather_keep_min = n < 1 ? 1 : n; }
+static int g_sampler_tail = 1;    // "sampler_tail": 1 (default) = prefix sums by the relabel kernel's last block + CSR branch in the captured graph
+void nb_sampler_set_tail(int v) { g_sampler_tail = v ? 1 : 0; }
 static int g_sampler_two_level = -1;   // "sampler_two_level": -1 (default) = by density, 0 = flat dedup bitmap, 1 = two-level (tests)
 void nb_sampler_set_two_level(int mode) { g_sampler_two_level = mode; }
 struct nb_sampler {
@@ -53,6 +55,7 @@ struct nb_sampler {
   uint32_t flags, max_batch;
   LayerBuf lay[NB_MAX_LAYERS];
   LayerMeta *meta_dev;   // [L+1]
+  cudaEvent_t ev_fork[NB_MAX_LAYERS], ev_join[NB_MAX_LAYERS];   // CSR branch of the captured graph
   LayerMeta *meta_host;  // the sizes of the batch that nb_sampler_wait / a synchronous sample last completed (points into meta_ring)
   LayerMeta *meta_ring;  // pinned [RING][NB_MAX_LAYERS+1]: every batch in flight copies its sizes into its own slot, so a second
                          // asynchronous nb_sampler_sample before nb_sampler_wait cannot tear the sizes the host reads
@@ -245,7 +248,8 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
          const uint32_t *__restrict__ col_off, uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst,
          uint32_t *__restrict__ bitmap, const LayerMeta *meta, int fanout, const BatchParams *params, uint32_t layer,
          int merge, int hash_slots, uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor,
-         uint32_t *__restrict__ src_to_dst, uint32_t cap_src, uint32_t *__restrict__ bitmap_l1 = nullptr) {
+         uint32_t *__restrict__ src_to_dst, uint32_t cap_src, uint32_t *__restrict__ bitmap_l1 = nullptr,
+         const uint32_t *__restrict__ dst_base = nullptr, const uint32_t *__restrict__ dst_deg = nullptr) {
   extern __shared__ uint32_t s_hash[];
   if (meta->err) return;
   if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
@@ -268,12 +272,12 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
   uint32_t *my_hash = s_hash + (threadIdx.x >> 5) * hash_slots;
   const Philox rng(key);
   for (unsigned j = (blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5)) * GPW + gid; j < n_dst; j += groups) {
-    const uint32_t d = dst[j];
-    const uint32_t base = g_col_off[d];
-    const uint32_t deg = g_col_off[d + 1] - base;
+    uint32_t base, deg;
+    if (dst_base) { base = dst_base[j]; deg = dst_deg[j]; }   // left by the relabel kernel that emitted this dst list: no dependent hop
+    else { const uint32_t d = dst[j]; base = g_col_off[d]; deg = g_col_off[d + 1] - base; }
     const uint32_t off = col_off[j];
     const uint32_t num = col_off[j + 1] - off;
-    if (merge && gl == 0) mark_vertex(bitmap, bitmap_l1, d);
+    if (merge && gl == 0) mark_vertex(bitmap, bitmap_l1, dst[j]);
     if (num == 0) continue;
     if (replay) {
       for (uint32_t t = gl; t < num; t += GROUP) {
@@ -353,17 +357,18 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
 static void launch_sample(cudaStream_t st, unsigned cap_dst, int fanout, const uint32_t *g_col_off, const uint32_t *g_row_idx,
                           const uint32_t *dst, const uint32_t *col_off, uint32_t *sample_ans, uint32_t *edge_dst, uint32_t *bitmap,
                           const LayerMeta *meta, const BatchParams *params, uint32_t layer, int merge, uint32_t *row_count = nullptr,
-                          uint32_t *row_cursor = nullptr, uint32_t *src_to_dst = nullptr, uint32_t cap_src = 0, uint32_t *bitmap_l1 = nullptr) {
+                          uint32_t *row_cursor = nullptr, uint32_t *src_to_dst = nullptr, uint32_t cap_src = 0, uint32_t *bitmap_l1 = nullptr,
+                          const uint32_t *dst_base = nullptr, const uint32_t *dst_deg = nullptr, unsigned bps = 8) {
   uint32_t hs = 1; while (fanout > 32 && hs < 2u * (uint32_t)fanout) hs <<= 1;
   const int hash_slots = fanout > 32 ? (int)hs : 0;
   const int group = (fanout < 0 || fanout > 16) ? 32 : (fanout > 8 ? 16 : 8);
   const unsigned per_block = SAMPLE_WARPS * (32 / group);
-  unsigned grid = nb_grid(cap_dst, per_block, 8);
+  unsigned grid = nb_grid(cap_dst, per_block, bps);
   if (row_count && grid < NB_SM_COUNT) grid = NB_SM_COUNT;  // enough threads for the scratch clear
   const size_t smem = (size_t)hash_slots * SAMPLE_WARPS * 4;
-  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1);
-  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1);
-  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1);
+  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg);
+  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg);
+  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg);
 }
 
 // global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
@@ -587,8 +592,22 @@ k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restr
 //   k_csr_fill_fused = row_offset scan (in smem, per block) + stable-fill step 1;  k_csr_rows handles long rows itself
 // i.e. 2 launches per layer (+2 for a layer whose CSR is built): 6 instead of 11 for the benchmark's two layers.
 // Results are bit-identical to the general path (same arithmetic, same ordering rules); tests run both.
-constexpr int FS_THREADS = 512;   // two such blocks fit an SM: they find room next to a training-stream kernel sooner than one 1024-thread block
+constexpr int FS_THREADS = 512;   // upper bound of the small-shape kernels' block size; the launch uses g_sampler_block threads
+// "sampler_block_threads": 256 (default) or 512. The sampler runs beside the previous batch's aggregation, whose two resident
+// blocks per SM leave ~11K registers: a 256-thread block of <= 40 registers fits there, a 512-thread block waits for a retiring one.
+static int g_sampler_block = 256;
+// "sampler_blocks_per_sm": 0 = every kernel sized for its own work (up to 8 blocks per SM); n > 0 = at most n blocks per SM for every
+// kernel of the batch graph: with 1, the sampler lives entirely in the slot the aggregation leaves free and never displaces its blocks
+static int g_sampler_bps = 2;
+void nb_sampler_set_bps(int v) { g_sampler_bps = v < 0 ? 0 : v; }
+static int g_sampler_capture_prio = 1;   // "sampler_capture_priority": capture streams carry the launch stream's priority
+void nb_sampler_set_capture_prio(int v) { g_sampler_capture_prio = v; }
+static inline unsigned sgrid(uint64_t work, unsigned items, unsigned bps) {
+  return nb_grid(work, items, g_sampler_bps > 0 && (unsigned)g_sampler_bps < bps ? (unsigned)g_sampler_bps : bps);
+}
+void nb_sampler_set_block(int v) { g_sampler_block = v >= 512 ? 512 : 256; }
 constexpr size_t FS_SMEM_MAX = 200 * 1024;
+constexpr uint32_t FS_TAIL_MAX = 49152;   // per-source arrays up to this long are scanned by the relabel kernel's last block
 
 // exclusive prefix of one value per thread over the block; *total = block sum. s_warp: 33 words of shared memory.
 __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *s_warp, unsigned *total) {
@@ -649,7 +668,7 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
   const uint32_t omit_value = params->omit_value;
   const int replay = params->replay;
   // 1. counts (every block, redundantly: n_dst words from L2), exactly CountOp::load
-  for (unsigned i = threadIdx.x; i < n_dst; i += FS_THREADS) {
+  for (unsigned i = threadIdx.x; i < n_dst; i += blockDim.x) {
     uint32_t deg;
     if (dense) deg = dst_deg[i];
     else {
@@ -669,13 +688,13 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
   const unsigned E = block_scan_array(s_off, n_dst, s_warp);
   const unsigned err = (prev && prev->err) ? prev->err : (E > cap_edges ? 1u : 0u);
   if (blockIdx.x == 0) {
-    for (unsigned i = threadIdx.x; i <= n_dst; i += FS_THREADS) col_off[i] = s_off[i];
+    for (unsigned i = threadIdx.x; i <= n_dst; i += blockDim.x) col_off[i] = s_off[i];
     if (threadIdx.x == 0) { meta->n_dst = n_dst; meta->n_edges = E; meta->n_src = 0; meta->long_rows = 0; meta->err = err; }
   }
   if (err) return;
   if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
     const unsigned bound = min(cap_src, E + (merge ? n_dst : 0u));
-    for (unsigned k = blockIdx.x * FS_THREADS + threadIdx.x; k < bound; k += gridDim.x * FS_THREADS) {
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < bound; k += gridDim.x * blockDim.x) {
       row_count[k] = 0;
       row_cursor[k] = 0;
       if (src_to_dst) src_to_dst[k] = 0xffffffffu;
@@ -688,10 +707,10 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
   constexpr unsigned GPW = 32 / GROUP;
   const unsigned gl = lane % GROUP, gid = lane / GROUP;
   const unsigned gmask = GROUP == 32 ? FULL_MASK : (((1u << GROUP) - 1u) << (gid * GROUP));
-  const unsigned groups = gridDim.x * (FS_THREADS / 32) * GPW;
+  const unsigned groups = gridDim.x * (blockDim.x / 32) * GPW;
   uint32_t *my_hash = s_hash + (threadIdx.x >> 5) * hash_slots;
   const Philox rng(key);
-  for (unsigned j = (blockIdx.x * (FS_THREADS / 32) + (threadIdx.x >> 5)) * GPW + gid; j < n_dst; j += groups) {
+  for (unsigned j = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * GPW + gid; j < n_dst; j += groups) {
     const uint32_t off = s_off[j];
     const uint32_t num = s_off[j + 1] - off;
     uint32_t base, deg;
@@ -774,39 +793,52 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
   }
 }
 
+struct RelabelTail {          // what the last block of k_relabel_fused leaves behind (all optional)
+  int enabled;
+  uint32_t *next_col_off;     // [n_src + 1] column offsets of the NEXT layer (its dst list is this layer's source), or NULL
+  uint32_t next_cap_edges;
+  int next_fanout, next_bottom;
+  uint32_t *row_offset;       // [n_src + 1] CSR row offsets of THIS layer, or NULL
+};
+
 // dedup + relabel of one layer: bitmap ranks in shared memory, `source` ascending, local ids, CSR histogram, weights, and the next
 // layer's per-dst adjacency base / degree (its dst list IS this `source`). Same results as k_scan<BitmapOp> + k_relabel.
-__global__ void __launch_bounds__(FS_THREADS)
+__global__ void __launch_bounds__(FS_THREADS, 3)
 k_relabel_fused(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ bitmap,
                 uint32_t *__restrict__ row_count, const uint32_t *__restrict__ dst, uint32_t *__restrict__ dst_local_id,
                 uint32_t *__restrict__ src_to_dst, LayerMeta *meta, LayerMeta *next_meta, int histogram, int fuse_weights,
                 float *__restrict__ ewf, const uint32_t *__restrict__ edge_dst, const uint32_t *__restrict__ col_off,
                 const uint32_t *__restrict__ in_deg, const uint32_t *__restrict__ out_deg, const BatchParams *params,
                 uint32_t *__restrict__ source, uint32_t n_words, uint32_t *__restrict__ other_bitmap, uint32_t cap_src,
-                const uint32_t *__restrict__ g_col_off, uint32_t *__restrict__ next_base, uint32_t *__restrict__ next_deg) {
-  extern __shared__ uint32_t s_dyn[];   // [n_words] bits, [n_words + 1] ranks
+                const uint32_t *__restrict__ g_col_off, uint32_t *__restrict__ next_base, uint32_t *__restrict__ next_deg,
+                RelabelTail tail) {
+  extern __shared__ uint32_t s_dyn[];   // [n_words] bits, [n_words + 1] ranks; the tail reuses it for [n_src + 1] counts
   __shared__ unsigned s_warp[33];
+  __shared__ unsigned s_last;
   uint32_t *s_bits = s_dyn, *s_rank = s_dyn + ((n_words + 31) & ~31u);
-  const unsigned stride = gridDim.x * FS_THREADS, tid = blockIdx.x * FS_THREADS + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (other_bitmap)
     for (unsigned w = tid; w <= n_words; w += stride) other_bitmap[w] = 0u;
-  if (meta->err) return;
-  for (unsigned w = threadIdx.x; w < n_words; w += FS_THREADS) {
-    const uint32_t b = bitmap[w];
-    s_bits[w] = b;
-    s_rank[w] = __popc(b);
+  const unsigned err_in = meta->err;      // left by this layer's sampling kernel; the same for every block
+  unsigned S = 0;
+  if (!err_in) {
+    for (unsigned w = threadIdx.x; w < n_words; w += blockDim.x) {
+      const uint32_t b = bitmap[w];
+      s_bits[w] = b;
+      s_rank[w] = __popc(b);
+    }
+    __syncthreads();
+    S = block_scan_array(s_rank, n_words, s_warp);
+    if (tid == 0) {
+      meta->n_src = S;
+      if (S > cap_src) meta->err = 2;
+      next_meta->n_dst = S;
+    }
   }
-  __syncthreads();
-  const unsigned S = block_scan_array(s_rank, n_words, s_warp);
-  if (tid == 0) {
-    meta->n_src = S;
-    if (S > cap_src) meta->err = 2;
-    next_meta->n_dst = S;
-  }
-  if (S > cap_src) return;
+  const bool ok = !err_in && S <= cap_src;
   const unsigned E = meta->n_edges, nd = meta->n_dst;
   const int weight_type = params->weight_type;
-  {
+  if (ok) {
     const unsigned lane = lane_id();
     for (unsigned w = tid >> 5; w < n_words; w += stride >> 5) {
       const uint32_t bits = s_bits[w];
@@ -821,23 +853,88 @@ k_relabel_fused(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ 
       }
     }
   }
-  for (unsigned e = tid; e < E; e += stride) {
-    const uint32_t v = sample_ans[e];
-    const uint32_t local = s_rank[v >> 5] + __popc(s_bits[v >> 5] & ((1u << (v & 31)) - 1u));
-    row_indices[e] = local;
-    if (histogram) atomicAdd(&row_count[local], 1u);
-    if (fuse_weights && weight_type != NB_WEIGHT_NONE) {
-      const uint32_t j = edge_dst[e];
-      ewf[e] = edge_weight_fn(out_deg[v], in_deg[dst[j]], col_off[j + 1] - col_off[j], weight_type);
+  if (ok) {
+    const bool weights = fuse_weights && weight_type != NB_WEIGHT_NONE;
+    constexpr int U = 4;   // edges per thread in flight: the chain sample_ans -> out_deg / edge_dst -> dst -> in_deg is all latency
+    for (unsigned e0 = tid; e0 < E; e0 += U * stride) {
+      uint32_t v[U], j[U], od[U], cb[U], ce[U], d[U], id[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned e = e0 + u * stride;
+        v[u] = e < E ? sample_ans[e] : 0u;
+        j[u] = (weights && e < E) ? edge_dst[e] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (weights && e0 + u * stride < E) { od[u] = out_deg[v[u]]; d[u] = dst[j[u]]; cb[u] = col_off[j[u]]; ce[u] = col_off[j[u] + 1]; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (weights && e0 + u * stride < E) id[u] = in_deg[d[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned e = e0 + u * stride;
+        if (e < E) {
+          const uint32_t local = s_rank[v[u] >> 5] + __popc(s_bits[v[u] >> 5] & ((1u << (v[u] & 31)) - 1u));
+          row_indices[e] = local;
+          if (histogram) atomicAdd(&row_count[local], 1u);
+          if (weights) ewf[e] = edge_weight_fn(od[u], id[u], ce[u] - cb[u], weight_type);
+        }
+      }
     }
   }
-  if (dst_local_id)
+  if (ok && dst_local_id)
     for (unsigned j = tid; j < nd; j += stride) {
       const uint32_t v = dst[j];
       const uint32_t local = s_rank[v >> 5] + __popc(s_bits[v >> 5] & ((1u << (v & 31)) - 1u));
       dst_local_id[j] = local;
       src_to_dst[local] = j;
     }
+  if (!tail.enabled) return;
+  // ---- tail: the block that finishes last turns the finished per-source arrays into prefix sums, so that neither the next layer's
+  // sampling kernel nor this layer's CSR fill needs a scan of its own (every one of their blocks used to redo it in shared memory)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&meta->pad0, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) meta->pad0 = 0u;   // re-armed for the next batch (graph replay)
+  if (tail.next_col_off) {   // the next layer's CountOp: its dst list is this `source`, the degrees are in next_deg
+    unsigned total = 0;
+    if (ok) {
+      const uint32_t *omit = tail.next_bottom ? params->omit : nullptr;
+      const uint32_t omit_value = params->omit_value;
+      for (unsigned k = threadIdx.x; k < S; k += blockDim.x) {
+        const uint32_t deg = __ldcg(next_deg + k);
+        uint32_t c = (tail.next_fanout < 0 || deg < (uint32_t)tail.next_fanout) ? deg : (uint32_t)tail.next_fanout;
+        if (omit) {
+          const uint32_t f = omit[__ldcg(source + k)];
+          if (omit_value == 0xffffffffu ? (f != 0xffffffffu) : (f == omit_value)) c = 0;
+        }
+        s_dyn[k] = c;
+      }
+      __syncthreads();
+      total = block_scan_array(s_dyn, S, s_warp);
+      for (unsigned k = threadIdx.x; k <= S; k += blockDim.x) tail.next_col_off[k] = s_dyn[k];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {   // exactly CountOp::total
+      next_meta->n_dst = ok ? S : 0u;
+      next_meta->n_edges = total;
+      next_meta->n_src = 0;
+      next_meta->long_rows = 0;
+      next_meta->err = !ok ? (err_in ? err_in : 2u) : (total > tail.next_cap_edges ? 1u : 0u);
+      if (!ok) tail.next_col_off[0] = 0u;
+    }
+  }
+  if (tail.row_offset && ok) {   // this layer's CSR row offsets from the finished use counts (RowOp)
+    for (unsigned k = threadIdx.x; k < S; k += blockDim.x) s_dyn[k] = __ldcg(row_count + k);
+    __syncthreads();
+    block_scan_array(s_dyn, S, s_warp);
+    for (unsigned k = threadIdx.x; k <= S; k += blockDim.x) tail.row_offset[k] = s_dyn[k];
+  }
 }
 
 // CSR build step 1 with the row-offset scan done per block in shared memory (same results as k_scan<RowOp> + k_csr_fill)
@@ -847,21 +944,21 @@ k_csr_fill_fused(const uint32_t *__restrict__ row_indices, const uint32_t *__res
   extern __shared__ uint32_t s_dyn[];   // [n_src + 1]
   __shared__ unsigned s_warp[33];
   const unsigned S = meta->err ? 0u : meta->n_src;
-  for (unsigned i = threadIdx.x; i < S; i += FS_THREADS) s_dyn[i] = row_count[i];
+  for (unsigned i = threadIdx.x; i < S; i += blockDim.x) s_dyn[i] = row_count[i];
   __syncthreads();
   block_scan_array(s_dyn, S, s_warp);
   if (blockIdx.x == 0)
-    for (unsigned i = threadIdx.x; i <= S; i += FS_THREADS) row_offset[i] = s_dyn[i];
+    for (unsigned i = threadIdx.x; i <= S; i += blockDim.x) row_offset[i] = s_dyn[i];
   if (meta->err) return;
   const unsigned E = meta->n_edges;
-  for (unsigned e = blockIdx.x * FS_THREADS + threadIdx.x; e < E; e += gridDim.x * FS_THREADS) {
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
     const uint32_t s = row_indices[e];
     csr_tmp[s_dyn[s] + atomicAdd(&row_cursor[s], 1u)] = e;
   }
 }
 
 // Bottom layer: the packed index the gather-fused aggregation consumes (aggregate.cu, GATHERED): global source id of every edge
-// with bit 31 set when this batch reads that source more than once (row_count = the finished per-source histogram).
+// with bit 31 set when this batch reads that source at least keep_min times (row_count = the finished per-source histogram).
 __global__ void __launch_bounds__(256)
 k_pack_gather_index(const uint32_t *__restrict__ sample_ans, const uint32_t *__restrict__ row_indices, const uint32_t *__restrict__ row_count,
                     uint32_t *__restrict__ gather_idx, const LayerMeta *meta, uint32_t keep_min) {
@@ -1097,9 +1194,13 @@ int nb_sampler_create(nb_ctx *ctx, nb_graph *g, int n_layers, const int *fanout,
     NB_CUDA(cudaEventCreateWithFlags(&s->stage_done[r], cudaEventDisableTiming));
     NB_CUDA(cudaEventCreateWithFlags(&s->meta_ready[r], cudaEventDisableTiming));
   }
+  for (int i = 0; i < NB_MAX_LAYERS; i++) {
+    NB_CUDA(cudaEventCreateWithFlags(&s->ev_fork[i], cudaEventDisableTiming));
+    NB_CUDA(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming));
+  }
   const char *ng = getenv("NB_NO_GRAPH");
   s->use_graph = !(ng && ng[0] == '1');
-  if (g_sampler_fused < 0) { const char *e = getenv("NB_SAMPLER_FUSED"); g_sampler_fused = e ? atoi(e) : 1; }
+  if (g_sampler_fused < 0) { const char *e = getenv("NB_SAMPLER_FUSED"); g_sampler_fused = e ? atoi(e) : 0; }
   s->fused = g_sampler_fused;
   NB_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = s;
@@ -1112,6 +1213,7 @@ int nb_sampler_destroy(nb_sampler *s) {
   cudaStreamSynchronize(s->ctx->stream);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   for (int r = 0; r < nb_sampler::RING; r++) { cudaFreeHost(s->stage[r]); cudaEventDestroy(s->stage_done[r]); cudaEventDestroy(s->meta_ready[r]); }
+  for (int i = 0; i < NB_MAX_LAYERS; i++) { cudaEventDestroy(s->ev_fork[i]); cudaEventDestroy(s->ev_join[i]); }
   cudaFree(s->arena);
   cudaFreeHost(s->meta_ring);
   delete s;
@@ -1136,7 +1238,9 @@ static void fill_view(nb_sampler *s, int i, nb_layer_view *v) {
 
 // Every kernel of one mini-batch. All arguments are constants of the sampler (per-batch values come from
 // params_dev), so the sequence is captured once into a CUDA graph and replayed.
-static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
+// side != NULL (graph capture): a layer's CSR kernels depend only on that layer's relabel, so they are forked onto `side` and run
+// beside the next layers' sampling; joined at the end. side == NULL: everything in order on st.
+static int enqueue_kernels(nb_sampler *s, cudaStream_t st, cudaStream_t side = nullptr) {
   nb_ctx *ctx = s->ctx;
   nb_graph *g = s->g;
   const bool merge = s->flags & NB_SAMPLER_MERGE_SRC_DST, up = s->flags & NB_SAMPLER_UP_DEGREE,
@@ -1145,13 +1249,17 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
   // with an odd number of layers the last layer leaves bitmap[0] marked, and layer 0 of the next batch uses it
   if (s->L & 1) {
     if (s->bitmap_l1[0]) {
-      k_clear_two_level<<<nb_grid(s->n_words_l1, 8, 8), 256, 0, st>>>(s->bitmap[0], s->bitmap_l1[0], s->n_words_l1);
+      k_clear_two_level<<<sgrid(s->n_words_l1, 8, 8), 256, 0, st>>>(s->bitmap[0], s->bitmap_l1[0], s->n_words_l1);
       NB_LAUNCH_CHECK(ctx);
     } else NB_CUDA(cudaMemsetAsync(s->bitmap[0], 0, (size_t)(s->n_words + 1) * 4, st));
   }
+  const unsigned fs_threads = (unsigned)g_sampler_block;
+  bool have_col_off = false;   // this layer's column offsets + meta were left by the previous layer's relabel (RelabelTail)
+  bool forked = false;
   for (int i = 0; i < s->L; i++) {
     LayerBuf &b = s->lay[i];
     LayerMeta *m = s->meta_dev + i;
+    bool have_row_off = false;
     uint32_t *bm = s->bitmap[i & 1], *bm_other = (s->L > 1) ? s->bitmap[(i + 1) & 1] : nullptr;
     uint32_t *bm_l1 = s->bitmap_l1[i & 1], *bm_other_l1 = (s->L > 1) ? s->bitmap_l1[(i + 1) & 1] : nullptr;
     ScanWs ws0 = nb_scan_ws(s->tile_states + (size_t)(3 * i + 0) * s->max_tiles, s->max_tiles, pp),
@@ -1165,19 +1273,23 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
     // ---- count + scan + neighbour selection
     uint32_t hs = 1; while (s->fanout[i] > 32 && hs < 2u * (uint32_t)s->fanout[i]) hs <<= 1;
     const int hash_slots = s->fanout[i] > 32 ? (int)hs : 0;
-    const size_t smem_sample = ((size_t)((b.cap_dst + 1 + 31) & ~31u) + (size_t)hash_slots * (FS_THREADS / 32)) * 4;
-    if (s->fused && smem_sample <= FS_SMEM_MAX) {
+    const size_t smem_sample = ((size_t)((b.cap_dst + 1 + 31) & ~31u) + (size_t)hash_slots * (fs_threads / 32)) * 4;
+    if (s->fused && have_col_off) {
+      launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
+                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, b.dst_base, b.dst_deg, g_sampler_bps > 0 ? (unsigned)g_sampler_bps : 8u);
+      NB_LAUNCH_CHECK(ctx);
+    } else if (s->fused && smem_sample <= FS_SMEM_MAX) {
       const int group = (s->fanout[i] < 0 || s->fanout[i] > 16) ? 32 : (s->fanout[i] > 8 ? 16 : 8);
-      const unsigned per_block = (FS_THREADS / 32) * (32 / group);
+      const unsigned per_block = (fs_threads / 32) * (32 / group);
       unsigned grid = (b.cap_dst + per_block - 1) / per_block;
-      const unsigned max_grid = (unsigned)ctx->sm_count * (smem_sample <= 96 * 1024 ? 2u : 1u);
+      const unsigned max_grid = (unsigned)ctx->sm_count * (g_sampler_bps > 0 ? 1u : smem_sample <= 96 * 1024 ? 2u : 1u);
       if (grid > max_grid) grid = max_grid;
       if (grid < 1) grid = 1;
 #define NB_FS(G)                                                                                                                   \
       do {                                                                                                                         \
         static bool attr = false;                                                                                                  \
         if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_sample_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; } \
-        k_sample_fused<G><<<grid, FS_THREADS, smem_sample, st>>>(g->col_off, g->row_idx, b.destination, b.dst_base, b.dst_deg, i > 0 ? 1 : 0,  \
+        k_sample_fused<G><<<grid, fs_threads, smem_sample, st>>>(g->col_off, g->row_idx, b.destination, b.dst_base, b.dst_deg, i > 0 ? 1 : 0,  \
             b.column_offset, b.sample_ans, b.edge_dst, bm, m, i ? m - 1 : nullptr, s->fanout[i], pp, (uint32_t)i, merge ? 1 : 0, bottom,   \
             hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, b.cap_dst, bm_l1);                \
       } while (0)
@@ -1186,75 +1298,110 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st) {
       NB_LAUNCH_CHECK(ctx);
     } else {
       CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, i ? m - 1 : nullptr, b.cap_edges, s->fanout[i], bottom};
-      k_scan<CountOp><<<nb_grid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
+      k_scan<CountOp><<<sgrid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
       NB_LAUNCH_CHECK(ctx);
       launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
-                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1);
+                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, nullptr, nullptr, g_sampler_bps > 0 ? (unsigned)g_sampler_bps : 8u);
       NB_LAUNCH_CHECK(ctx);
     }
     // ---- dedup ranks + source emission + relabel (+ histogram, weights)
-    const size_t smem_relabel = ((size_t)((s->n_words + 31) & ~31u) + s->n_words + 1) * 4;
+    have_col_off = false;
+    size_t smem_relabel = ((size_t)((s->n_words + 31) & ~31u) + s->n_words + 1) * 4;
     if (s->fused && !bm_l1 && smem_relabel <= FS_SMEM_MAX) {
       static bool attr = false;
       if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_relabel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
-      const uint64_t work = (uint64_t)b.cap_edges + b.cap_dst + (uint64_t)s->n_words * 32;
-      unsigned grid = (unsigned)((work + FS_THREADS - 1) / FS_THREADS);
-      const unsigned max_grid = (unsigned)ctx->sm_count * (smem_relabel <= 96 * 1024 ? 2u : 1u);
+      RelabelTail tail{};
+      const size_t smem_tail = ((size_t)b.cap_src + 1) * 4;
+      if (g_sampler_tail && b.cap_src <= FS_TAIL_MAX && smem_tail <= FS_SMEM_MAX) {
+        if (i + 1 < s->L) {
+          tail.next_col_off = s->lay[i + 1].column_offset;
+          tail.next_cap_edges = s->lay[i + 1].cap_edges;
+          tail.next_fanout = s->fanout[i + 1];
+          tail.next_bottom = i + 1 == s->L - 1 ? 1 : 0;
+        }
+        if (layer_csr) tail.row_offset = b.row_offset;
+        tail.enabled = (tail.next_col_off || tail.row_offset) ? 1 : 0;
+        if (tail.enabled && smem_tail > smem_relabel) smem_relabel = smem_tail;
+      }
+      const uint64_t work = (uint64_t)b.cap_edges / 4 + b.cap_dst + (uint64_t)s->n_words * 32;
+      unsigned grid = (unsigned)((work + fs_threads - 1) / fs_threads);
+      const unsigned per_sm = (unsigned)(FS_SMEM_MAX / smem_relabel);
+      const unsigned bps_cap = g_sampler_bps > 0 ? (unsigned)g_sampler_bps : 4u;
+      const unsigned max_grid = (unsigned)ctx->sm_count * (per_sm > bps_cap ? bps_cap : per_sm < 1u ? 1u : per_sm);
       if (grid > max_grid) grid = max_grid;
-      k_relabel_fused<<<grid, FS_THREADS, smem_relabel, st>>>(
+      k_relabel_fused<<<grid, fs_threads, smem_relabel, st>>>(
           b.sample_ans, b.row_indices, bm, b.row_count, b.destination, merge ? b.dst_local_id : nullptr, merge ? b.src_to_dst : nullptr,
           m, m + 1, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp, b.source, s->n_words, bm_other,
-          b.cap_src, g->col_off, next_base, next_deg);
+          b.cap_src, g->col_off, next_base, next_deg, tail);
       NB_LAUNCH_CHECK(ctx);
+      have_col_off = tail.next_col_off != nullptr;
+      have_row_off = tail.row_offset != nullptr;
     } else {
       if (bm_l1) {
         Bitmap2Op bop{bm, bm_l1, s->word_rank, m, m + 1, s->n_words_l1, b.cap_src};
-        k_scan<Bitmap2Op><<<nb_grid(s->n_words_l1, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+        k_scan<Bitmap2Op><<<sgrid(s->n_words_l1, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
       } else {
         BitmapOp bop{bm, s->word_rank, m, m + 1, s->n_words, b.cap_src};
-        k_scan<BitmapOp><<<nb_grid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+        k_scan<BitmapOp><<<sgrid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
       }
       NB_LAUNCH_CHECK(ctx);
-      k_relabel<<<nb_grid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
+      k_relabel<<<sgrid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
           b.sample_ans, b.row_indices, bm, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
           merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp,
           b.source, s->n_words, bm_other, g->col_off, next_base, next_deg, bm_l1, bm_other_l1, s->n_words_l1);
       NB_LAUNCH_CHECK(ctx);
     }
     if (up) {
-      k_weights_sampled<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
+      k_weights_sampled<<<sgrid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
       NB_LAUNCH_CHECK(ctx);
     }
     if (b.gather_idx) {
-      k_pack_gather_index<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.sample_ans, b.row_indices, b.row_count, b.gather_idx, m, (uint32_t)g_gather_keep_min);
+      k_pack_gather_index<<<sgrid(b.cap_edges, 256, 8), 256, 0, st>>>(b.sample_ans, b.row_indices, b.row_count, b.gather_idx, m, (uint32_t)g_gather_keep_min);
       NB_LAUNCH_CHECK(ctx);
     }
     if (layer_csr) {
+      cudaStream_t cst = st;
+      if (side && i + 1 < s->L) {   // fork: the rest of this layer's work is off the chain the next layer waits for
+        NB_CUDA(cudaEventRecord(s->ev_fork[i], st));
+        NB_CUDA(cudaStreamWaitEvent(side, s->ev_fork[i], 0));
+        cst = side;
+        forked = true;
+      }
       const size_t smem_csr = ((size_t)b.cap_src + 1) * 4;
-      if (s->fused && smem_csr <= FS_SMEM_MAX) {
+      if (have_row_off) {
+        k_csr_fill<<<sgrid(b.cap_edges, 256, 8), 256, 0, cst>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
+        NB_LAUNCH_CHECK(ctx);
+        k_csr_rows<<<sgrid(b.cap_src, 256, 8), 256, 0, cst>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
+                                                                  b.ewb, b.ewf, b.long_rows, m, pp, 1);
+        NB_LAUNCH_CHECK(ctx);
+      } else if (s->fused && smem_csr <= FS_SMEM_MAX) {
         static bool attr = false;
         if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_csr_fill_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
-        unsigned grid = (b.cap_edges + FS_THREADS - 1) / FS_THREADS;
-        const unsigned max_grid = (unsigned)ctx->sm_count * (smem_csr <= 96 * 1024 ? 2u : 1u);
+        unsigned grid = (b.cap_edges + fs_threads - 1) / fs_threads;
+        const unsigned max_grid = (unsigned)ctx->sm_count * (g_sampler_bps > 0 ? 1u : smem_csr <= 96 * 1024 ? 2u : 1u);
         if (grid > max_grid) grid = max_grid;
         if (grid < 1) grid = 1;
-        k_csr_fill_fused<<<grid, FS_THREADS, smem_csr, st>>>(b.row_indices, b.row_count, b.row_offset, b.row_cursor, b.csr_tmp, m);
+        k_csr_fill_fused<<<grid, fs_threads, smem_csr, cst>>>(b.row_indices, b.row_count, b.row_offset, b.row_cursor, b.csr_tmp, m);
         NB_LAUNCH_CHECK(ctx);
-        k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
+        k_csr_rows<<<sgrid(b.cap_src, 256, 8), 256, 0, cst>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
                                                                  b.ewb, b.ewf, b.long_rows, m, pp, 1);
         NB_LAUNCH_CHECK(ctx);
       } else {
         RowOp rop{b.row_count, b.row_offset, m};
-        k_scan<RowOp><<<nb_grid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(rop, ws2);
+        k_scan<RowOp><<<sgrid(b.cap_src, SCAN_TILE, 4), SCAN_THREADS, 0, cst>>>(rop, ws2);
         NB_LAUNCH_CHECK(ctx);
-        k_csr_fill<<<nb_grid(b.cap_edges, 256, 8), 256, 0, st>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
+        k_csr_fill<<<sgrid(b.cap_edges, 256, 8), 256, 0, cst>>>(b.row_indices, b.row_offset, b.row_cursor, b.csr_tmp, m);
         NB_LAUNCH_CHECK(ctx);
-        k_csr_rows<<<nb_grid(b.cap_src, 256, 8), 256, 0, st>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
+        k_csr_rows<<<sgrid(b.cap_src, 256, 8), 256, 0, cst>>>(b.row_offset, b.csr_tmp, b.column_indices, b.csr_to_csc, b.edge_dst,
                                                                  b.ewb, b.ewf, b.long_rows, m, pp, 1);
         NB_LAUNCH_CHECK(ctx);
       }
+      if (cst != st) NB_CUDA(cudaEventRecord(s->ev_join[i], side));
     }
   }
+  if (forked)
+    for (int i = 0; i + 1 < s->L; i++)
+      if (csr) NB_CUDA(cudaStreamWaitEvent(st, s->ev_join[i], 0));   // join: the batch is complete when st is
   return NB_OK;
 }
 
@@ -1287,14 +1434,20 @@ static int run_batch(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int
   NB_CUDA(cudaStreamIsCapturing(st, &cap));
   if (s->use_graph && cap == cudaStreamCaptureStatusNone) {
     if (!s->graph_exec) {
-      cudaStream_t cst;
-      NB_CUDA(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
+      // the capture streams carry the priority of the stream the graph will be launched on: kernel nodes keep the priority of the
+      // stream they were captured from
+      cudaStream_t cst, side = nullptr;
+      int prio = 0;
+      if (g_sampler_capture_prio) NB_CUDA(cudaStreamGetPriority(st, &prio));
+      NB_CUDA(cudaStreamCreateWithPriority(&cst, cudaStreamNonBlocking, prio));
+      if (g_sampler_tail) NB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio));
       cudaGraph_t graph = nullptr;
       NB_CUDA(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
       const uint64_t launches0 = ctx->launches;
-      int rc = enqueue_kernels(s, cst);
+      int rc = enqueue_kernels(s, cst, side);
       cudaError_t ce = cudaStreamEndCapture(cst, &graph);
       cudaStreamDestroy(cst);
+      if (side) cudaStreamDestroy(side);
       s->graph_kernels = ctx->launches - launches0;  // kernels per replay (what NB_LAUNCH_CHECK counted during capture)
       s->ctx->launches = launches0;
       if (rc != NB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }

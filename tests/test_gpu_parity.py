@@ -30,12 +30,29 @@ def cs(nts):
     return nts.Cuda_Stream.on_torch_stream(0)  # same stream as torch's ops, like the toolkits
 
 
-@pytest.fixture(params=["fused", "general"])
+SAMPLER_PATHS = {   # (sampler_fused, sampler_tail, sampler_block_threads)
+    "fused": (1, 1, 256),            # small-shape kernels, prefix sums left by the relabel kernel's last block
+    "fused-512": (1, 1, 512),
+    "fused-notail": (1, 0, 512),     # every block rescans in shared memory (the earlier kernel order)
+    "general": (0, 1, 256),          # the default: look-back scans in global memory, any size; CSR kernels on a branch of the graph
+    "general-inline": (0, 0, 256),   # the same without the branch
+}
+
+
+def set_sampler_path(nts, name):
+    lib, check = nts._capi.lib(), nts._capi.check
+    fused, tail, block = SAMPLER_PATHS[name]
+    check(lib.nb_set_option(b"sampler_fused", fused))
+    check(lib.nb_set_option(b"sampler_tail", tail))
+    check(lib.nb_set_option(b"sampler_block_threads", block))
+
+
+@pytest.fixture(params=list(SAMPLER_PATHS))
 def sampler_path(nts, request):
-    """both sampler pipelines: the small-shape kernels (default where a layer fits in shared memory) and the general one"""
-    nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_fused", 1 if request.param == "fused" else 0))
+    """every sampler pipeline: the small-shape kernels in their variants and the general one"""
+    set_sampler_path(nts, request.param)
     yield request.param
-    nts._capi.check(nts._capi.lib().nb_set_option(b"sampler_fused", 1))
+    set_sampler_path(nts, "general")
 
 
 def make_graph(nts, cs, V, avg_deg, seed, unique=True, max_deg=None):
@@ -138,7 +155,7 @@ def test_gpu_sampler_pipeline_matches_oracle_on_its_own_draws(nts, cs, fanout, b
         assert np.array_equal(u32(l.dev_source_use_count), use), i            # per-source use counts (the CSR row lengths)
         if i == len(fanout) - 1:                                               # bottom layer: packed gather index = id | hint bit
             gi = u32(l.dev_gather_index)
-            assert np.array_equal(gi & 0x7FFFFFFF, ans[i]) and np.array_equal(gi >> 31, (use[r["row_indices"]] > 1).astype(np.uint32)), i
+            assert np.array_equal(gi & 0x7FFFFFFF, ans[i]) and np.array_equal(gi >> 31, (use[r["row_indices"]] >= 3).astype(np.uint32)), i   # gather_keep_min_uses = 3
         else:
             assert l.dev_gather_index is None
         if merge:
@@ -202,11 +219,13 @@ def test_sampler_paths_agree_bit_for_bit(nts, cs):
     graph = nts.FullyRepGraph(cs, V, edge_pairs=np.concatenate([pairs, hub]))        # vertex 17 is a source of 6000 columns
     seeds = np.random.default_rng(2).permutation(V)[:1024].astype(np.uint32)
     out = {}
-    for fused in (1, 0):
-        check(lib.nb_set_option(b"sampler_fused", fused))
-        for fanout, merge, up in (([25, 10], False, False), ([40, 4, 3], True, False), ([6, 6], False, True)):
+    for fused in SAMPLER_PATHS:
+        set_sampler_path(nts, fused)
+        for fanout, merge, up in (([25, 10], False, False), ([40, 4, 3], True, False), ([6, 6], False, True), ([3, 2, 2], False, False)):
             sm = nts.FastSampler(graph, seeds, len(fanout), 1024, fanout, cuda_stream=cs, merge_src_dst=merge, up_degree=up, build_csr=True)
-            sg = sm.sample_gpu_fast(1024)
+            for _ in range(3):           # the third replay of the captured graph: counters and bitmaps must have re-armed themselves
+                sm.work_offset = 0
+                sg = sm.sample_gpu_fast(1024)
             arrs = []
             for l in sg.sampled_sgs:
                 arrs += [u32(l.dev_column_offset), u32(l.dev_sample_ans), u32(l.dev_source), u32(l.dev_row_indices), u32(l.dev_row_offset),
@@ -214,13 +233,13 @@ def test_sampler_paths_agree_bit_for_bit(nts, cs):
                 if merge:
                     arrs += [u32(l.dev_dst_local_id), u32(l.dev_src_to_dst)]
             out[(fused, tuple(fanout))] = arrs
-    check(lib.nb_set_option(b"sampler_fused", 1))
+    set_sampler_path(nts, "general")
     for (fused, fan), arrs in out.items():
-        if fused:
-            other = out[(0, fan)]
+        if fused != "general":
+            other = out[("general", fan)]
             assert len(arrs) == len(other)
             for k, (a, b) in enumerate(zip(arrs, other)):
-                assert np.array_equal(a, b), (fan, k)
+                assert np.array_equal(a, b), (fused, fan, k)
 
 
 def test_gpu_sampler_is_reproducible_and_counter_based(nts, cs):
@@ -418,6 +437,43 @@ def test_long_segments_take_the_block_path_with_identical_bits(nts, cs, F, pitch
         dx = torch.empty((R, pitch), device="cuda")
         cs.aggregate_bwd_pitched(xp, dx, d_w, d_off, d_idx, R, F, pitch, pitch)
         assert np.array_equal(bits(f32(dx)[:, :F]), bits(oracle.aggregate_bwd_csr(X, off, idx, w)))
+
+
+@pytest.mark.parametrize("F", [16, 100, 128, 256])
+@pytest.mark.parametrize("R", [3, 1000, 6001])
+def test_short_row_and_small_launch_kernels_keep_the_bits(nts, cs, F, R):
+    """The CSR backward of rows <= 32 vectors wide runs 4 rows per warp (agg_short_rows), launches whose rows all fit on the
+    GPU at once keep 16 / 8 entries in flight (agg_deep_small): both are scheduling only -- same bits as the oracle and as
+    the plain warp-per-row kernel, for empty rows, 1-entry rows, rows around the joint-phase length and hub rows."""
+    lib, check = nts._capi.lib(), nts._capi.check
+    rng = np.random.default_rng(F * 7 + R)
+    lens = rng.choice(np.array([0, 1, 1, 1, 2, 3, 4, 5, 9, 33, 70], np.uint32), R)
+    lens[R // 2] = 300
+    off = np.zeros(R + 1, np.uint32)
+    off[1:] = np.cumsum(lens)
+    E, S = int(off[-1]), 700
+    idx = rng.integers(0, S, E).astype(np.uint32)
+    w = rng.standard_normal(E).astype(np.float32)
+    X = rng.standard_normal((S, F)).astype(np.float32)
+    x = torch.from_numpy(X).cuda()
+    d_off, d_idx, d_w = (torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda() for a in (off, idx, w))
+    want = oracle.aggregate_fwd(X, off, idx, w)
+    try:
+        for short, deep in ((1, 1), (0, 0), (1, 0), (0, 1)):
+            check(lib.nb_set_option(b"agg_short_rows", short))
+            check(lib.nb_set_option(b"agg_deep_small", deep))
+            y = torch.full((R, F), 3.0, device="cuda")
+            cs.aggregate_fwd_pitched(x, y, d_w, d_idx, d_off, R, F, F, F)
+            assert np.array_equal(bits(f32(y)), bits(want)), (short, deep, "fwd")
+            dx = torch.full((R, F), 5.0, device="cuda")
+            cs.aggregate_bwd_pitched(x, dx, d_w, d_off, d_idx, R, F, F, F)
+            assert np.array_equal(bits(f32(dx)), bits(want)), (short, deep, "bwd")
+            dx = torch.full((R, F), 5.0, device="cuda")
+            cs.aggregate_bwd_pitched(x, dx, None, d_off, d_idx, R, F, F, F)
+            assert np.array_equal(bits(f32(dx)), bits(oracle.aggregate_fwd(X, off, idx, np.ones(E, np.float32)))), (short, deep, "bwd, no weights")
+    finally:
+        check(lib.nb_set_option(b"agg_short_rows", 1))
+        check(lib.nb_set_option(b"agg_deep_small", 1))
 
 
 @pytest.mark.parametrize("V,E,seed", [(1, 5, 0), (7, 0, 1), (2708, 13566, 2), (300, 70000, 3), (70000, 300000, 4), (20_000_000, 3_000_000, 5),
