@@ -108,7 +108,11 @@ int nb_device_count(int *count);
  *       in global memory, 256-thread blocks of <= 40 registers: they fit beside the running aggregation's blocks); 1 = the small-shape
  *       kernels (a layer's prefix sums in shared memory, fewer launches) wherever a layer fits. Identical results; measured on the
  *       Reddit shape the general kernels are faster alone (80 vs 110-135 us per batch) and beside the aggregation
- *       (profiles/r2_sweep_sampler_residency*.txt). "sampler_tail" (1) and "sampler_block_threads" (256 | 512) shape the small-shape path.
+ *       (profiles/r2_sweep_sampler_residency*.txt). "sampler_block_threads" (256 | 512) shapes the small-shape path.
+ *   "sampler_csr_branch" : 1 (default) = in the captured batch graph a layer's CSR kernels run on a parallel branch beside the next layer's
+ *       sampling (90 vs 103 us per batch alone); "sampler_tail" : bit 0 / bit 1 = the popcount scan of the dedup bitmap / the next layer's
+ *       count scan are left to the last block of the sampling / relabel kernel instead of a scan kernel (default 0: a single block's scan of
+ *       25K items loses to the look-back scan kernel, profiles/r2_sampler_tail_ab.txt). Identical results either way.
  *   "sampler_blocks_per_sm" : 2 (default) = no kernel of a sampler's batch graph launches more than this many blocks per SM, so that a
  *       batch sampled beside the previous batch's aggregation lives in the slot that kernel leaves free instead of displacing its
  *       blocks (0.146 -> 0.139 ms per step); 0 = every kernel sized for its own work (lowest latency on an idle GPU: 80 vs 86 us)

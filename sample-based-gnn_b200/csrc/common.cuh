@@ -94,6 +94,7 @@ void nb_trace_add(const char *name, uint64_t ns);  // name must be a string lite
 void nb_sampler_set_two_level(int mode);
 void nb_sampler_set_keep_min(int n);
 void nb_sampler_set_tail(int v);
+void nb_sampler_set_csr_branch(int v);
 void nb_sampler_set_block(int v);
 void nb_sampler_set_bps(int v);
 void nb_sampler_set_capture_prio(int v);

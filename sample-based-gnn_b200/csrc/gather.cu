@@ -349,6 +349,7 @@ int nb_set_option(const char *name, int value) {
   if (!strcmp(name, "sampler_block_threads")) { nb_sampler_set_block(value); return NB_OK; }   // read when a sampler's graph is captured
   if (!strcmp(name, "sampler_blocks_per_sm")) { nb_sampler_set_bps(value); return NB_OK; }   // read when a sampler's graph is captured
   if (!strcmp(name, "sampler_capture_priority")) { nb_sampler_set_capture_prio(value); return NB_OK; }
+  if (!strcmp(name, "sampler_csr_branch")) { nb_sampler_set_csr_branch(value); return NB_OK; }
   if (!strcmp(name, "sampler_tail")) { nb_sampler_set_tail(value); return NB_OK; }   // read when a sampler's graph is captured
   if (!strcmp(name, "gather_keep_min_uses")) { nb_sampler_set_keep_min(value); return NB_OK; }   // read when a sampler's graph is captured
   if (!strcmp(name, "trace")) { nb_trace_set_level(value); return NB_OK; }

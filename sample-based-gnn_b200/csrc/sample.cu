@@ -43,8 +43,13 @@ static int g_sampler_fused = -1;   // "sampler_fused" / NB_SAMPLER_FUSED: 0 (def
 void nb_sampler_set_fused(int on) { g_sampler_fused = on; }
 static int g_gather_keep_min = 3;   // "gather_keep_min_uses": sources a batch reads at least this often get the evict_last hint bit
 void nb_sampler_set_keep_min(int n) { g_gather_keep_min = n < 1 ? 1 : n; }
-static int g_sampler_tail = 1;    // "sampler_tail": 1 (default) = prefix sums by the relabel kernel's last block + CSR branch in the captured graph
-void nb_sampler_set_tail(int v) { g_sampler_tail = v ? 1 : 0; }
+// "sampler_tail": bit 0 = the sampling kernel's last block does the bitmap's popcount scan, bit 1 = the relabel kernel's last block does
+// the next layer's count scan (and, on the small-shape path, the CSR row offsets). Default 0: measured, a single block's scan of 7-25K
+// items (10-25 us) loses to the multi-block look-back scan kernel it replaces (profiles/r2_sampler_tail_ab.txt); kept for small layers.
+static int g_sampler_tail = 0;
+static int g_sampler_csr_branch = 1;   // "sampler_csr_branch": a layer's CSR kernels on a parallel branch of the captured graph
+void nb_sampler_set_csr_branch(int v) { g_sampler_csr_branch = v ? 1 : 0; }
+void nb_sampler_set_tail(int v) { g_sampler_tail = v & 3; }
 static int g_sampler_two_level = -1;   // "sampler_two_level": -1 (default) = by density, 0 = flat dedup bitmap, 1 = two-level (tests)
 void nb_sampler_set_two_level(int mode) { g_sampler_two_level = mode; }
 struct nb_sampler {
@@ -229,6 +234,102 @@ struct RowOp {
 //   open-addressing set in shared memory.
 // Philox4x32-10 counter = (dst slot, lane + 32*draw block, layer, rng_offset), key = rng_seed.
 // mode 1 (replay): sample_ans was supplied; only edge_dst and the bitmap marks are produced.
+// exclusive prefix of one value per thread over the block; *total = block sum. s_warp: 33 words of shared memory.
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *s_warp, unsigned *total) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();   // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < nwarps ? s_warp[lane] : 0u, wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(FULL_MASK, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[warp] + incl - v;
+}
+
+// in place: s_v[0..n) values -> exclusive prefix sums, s_v[n] = total (returned). Every thread of the block calls it.
+__device__ __forceinline__ unsigned block_scan_array(unsigned *s_v, unsigned n, unsigned *s_warp) {
+  const unsigned ipt = (n + blockDim.x - 1) / blockDim.x;
+  const unsigned a = min(n, threadIdx.x * ipt), b = min(n, a + ipt);
+  unsigned sum = 0;
+  for (unsigned i = a; i < b; i++) sum += s_v[i];
+  unsigned total;
+  unsigned run = block_excl_scan(sum, s_warp, &total);
+  for (unsigned i = a; i < b; i++) { const unsigned c = s_v[i]; s_v[i] = run; run += c; }
+  if (threadIdx.x == 0) s_v[n] = total;
+  __syncthreads();
+  return total;
+}
+
+
+// Executed by ONE whole block: store(i, exclusive prefix of load(0..i)) for i < n, streaming tiles of blockDim.x * 8 items with a
+// running carry; returns the total to every thread. The "last block" tails of the sampling / relabel kernels use it to leave the
+// prefix sums the NEXT kernel needs, instead of a scan kernel of its own between the two.
+template <class Load, class Store>
+__device__ __forceinline__ unsigned block_scan_stream(unsigned n, Load load, Store store, unsigned *s_warp) {
+  constexpr unsigned IPT = 8;
+  unsigned carry = 0;
+  for (unsigned base = 0; base < n; base += blockDim.x * IPT) {
+    const unsigned i0 = base + threadIdx.x * IPT;
+    unsigned v[IPT], sum = 0;
+#pragma unroll
+    for (unsigned k = 0; k < IPT; k++) { v[k] = i0 + k < n ? load(i0 + k) : 0u; sum += v[k]; }
+    unsigned total;
+    unsigned run = carry + block_excl_scan(sum, s_warp, &total);
+#pragma unroll
+    for (unsigned k = 0; k < IPT; k++) {
+      if (i0 + k < n) store(i0 + k, run);
+      run += v[k];
+    }
+    carry += total;
+  }
+  return carry;
+}
+
+// true in exactly one block of the grid: the one whose threads all arrive here last. counter must be 0 before the launch and is 0 again
+// afterwards (graph replay). Everything the other blocks wrote before the call is visible to the block that gets `true`.
+__device__ __forceinline__ bool last_block_arrives(uint32_t *counter) {
+  __shared__ unsigned s_is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (last) *counter = 0u;
+    s_is_last = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_is_last) __threadfence();
+  return s_is_last != 0u;
+}
+
+// tail of a sampling kernel (flat bitmap): BitmapOp's popcount scan by the last block -- word_rank, n_src, capacity check
+__device__ __noinline__ void bitmap_rank_tail(const uint32_t *bitmap, uint32_t *word_rank, uint32_t n_words, LayerMeta *meta,
+                                                 LayerMeta *next_meta, uint32_t cap_src, bool ok, unsigned *s_warp) {
+  if (!last_block_arrives(&meta->pad1)) return;
+  if (!ok) { if (threadIdx.x == 0) next_meta->n_dst = 0u; return; }
+  const unsigned t = block_scan_stream(n_words, [&](unsigned w) { return (unsigned)__popc(__ldcg(bitmap + w)); },
+                                       [&](unsigned w, unsigned excl) { word_rank[w] = excl; }, s_warp);
+  if (threadIdx.x == 0) {   // BitmapOp::total
+    meta->n_src = t;
+    if (t > cap_src) meta->err = 2;
+    next_meta->n_dst = t;
+  }
+}
+
 constexpr int SAMPLE_WARPS = 8;
 
 // Dedup bitmap, two levels when the graph is large: level 0 has one bit per vertex, level 1 one bit per level-0 word, set by the
@@ -246,13 +347,16 @@ template <int GROUP>
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32)
 k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_row_idx, const uint32_t *__restrict__ dst,
          const uint32_t *__restrict__ col_off, uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst,
-         uint32_t *__restrict__ bitmap, const LayerMeta *meta, int fanout, const BatchParams *params, uint32_t layer,
+         uint32_t *__restrict__ bitmap, LayerMeta *meta, int fanout, const BatchParams *params, uint32_t layer,
          int merge, int hash_slots, uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor,
          uint32_t *__restrict__ src_to_dst, uint32_t cap_src, uint32_t *__restrict__ bitmap_l1 = nullptr,
-         const uint32_t *__restrict__ dst_base = nullptr, const uint32_t *__restrict__ dst_deg = nullptr) {
+         const uint32_t *__restrict__ dst_base = nullptr, const uint32_t *__restrict__ dst_deg = nullptr,
+         uint32_t *__restrict__ tail_word_rank = nullptr, uint32_t tail_words = 0) {
   extern __shared__ uint32_t s_hash[];
-  if (meta->err) return;
-  if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
+  __shared__ unsigned s_warp[33];
+  const bool ok = meta->err == 0;   // left by the kernel that produced this layer's column offsets: the same for every block
+  if (!ok && !tail_word_rank) return;
+  if (ok && row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
     const unsigned bound = min(cap_src, meta->n_edges + (merge ? meta->n_dst : 0u));
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < bound; k += gridDim.x * blockDim.x) {
       row_count[k] = 0;
@@ -263,7 +367,7 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
   const uint64_t key = params->rng_seed ^ (params->rng_offset >> 32 << 32);
   const uint32_t rng_offset = (uint32_t)params->rng_offset;
   const int replay = params->replay;
-  const unsigned n_dst = meta->n_dst;
+  const unsigned n_dst = ok ? meta->n_dst : 0u;
   const unsigned lane = lane_id();
   constexpr unsigned GPW = 32 / GROUP;                       // groups per warp
   const unsigned gl = lane % GROUP, gid = lane / GROUP;      // lane in group, group in warp
@@ -352,13 +456,15 @@ k_sample(const uint32_t *__restrict__ g_col_off, const uint32_t *__restrict__ g_
       }
     }
   }
+  if (tail_word_rank) bitmap_rank_tail(bitmap, tail_word_rank, tail_words, meta, meta + 1, cap_src, ok, s_warp);
 }
 
 static void launch_sample(cudaStream_t st, unsigned cap_dst, int fanout, const uint32_t *g_col_off, const uint32_t *g_row_idx,
                           const uint32_t *dst, const uint32_t *col_off, uint32_t *sample_ans, uint32_t *edge_dst, uint32_t *bitmap,
-                          const LayerMeta *meta, const BatchParams *params, uint32_t layer, int merge, uint32_t *row_count = nullptr,
+                          LayerMeta *meta, const BatchParams *params, uint32_t layer, int merge, uint32_t *row_count = nullptr,
                           uint32_t *row_cursor = nullptr, uint32_t *src_to_dst = nullptr, uint32_t cap_src = 0, uint32_t *bitmap_l1 = nullptr,
-                          const uint32_t *dst_base = nullptr, const uint32_t *dst_deg = nullptr, unsigned bps = 8) {
+                          const uint32_t *dst_base = nullptr, const uint32_t *dst_deg = nullptr, unsigned bps = 8,
+                          uint32_t *tail_word_rank = nullptr, uint32_t tail_words = 0) {
   uint32_t hs = 1; while (fanout > 32 && hs < 2u * (uint32_t)fanout) hs <<= 1;
   const int hash_slots = fanout > 32 ? (int)hs : 0;
   const int group = (fanout < 0 || fanout > 16) ? 32 : (fanout > 8 ? 16 : 8);
@@ -366,14 +472,22 @@ static void launch_sample(cudaStream_t st, unsigned cap_dst, int fanout, const u
   unsigned grid = nb_grid(cap_dst, per_block, bps);
   if (row_count && grid < NB_SM_COUNT) grid = NB_SM_COUNT;  // enough threads for the scratch clear
   const size_t smem = (size_t)hash_slots * SAMPLE_WARPS * 4;
-  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg);
-  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg);
-  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg);
+  if (group == 32) k_sample<32><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg, tail_word_rank, tail_words);
+  else if (group == 16) k_sample<16><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg, tail_word_rank, tail_words);
+  else k_sample<8><<<grid, SAMPLE_WARPS * 32, smem, st>>>(g_col_off, g_row_idx, dst, col_off, sample_ans, edge_dst, bitmap, meta, fanout, params, layer, merge, hash_slots, row_count, row_cursor, src_to_dst, cap_src, bitmap_l1, dst_base, dst_deg, tail_word_rank, tail_words);
 }
 
 // global -> local ids: rank(v) = word_rank[v/32] + popc(bitmap[v/32] below bit v%32); CSR histogram.
 // Reference: sample_processing_update_ri_gpu_kernel cuda/ntsCUDATransferKernel.cuh:1136-1150,
 // sample_set_dst_local :1189-1196; CPU :1085-1099.
+struct NextCount {            // k_relabel's tail: the next layer's CountOp (all optional)
+  uint32_t *col_off = nullptr;  // [n_src + 1] column offsets of the next layer
+  LayerMeta *next_meta = nullptr;
+  uint32_t cap_edges = 0;
+  int fanout = 0, bottom = 0;
+};
+__device__ __forceinline__ LayerMeta *meta_mut(const LayerMeta *m) { return const_cast<LayerMeta *>(m); }
+
 __device__ __forceinline__ float edge_weight_fn(uint32_t od, uint32_t id, uint32_t col_len, int weight_type) {
   float w = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn((float)od), __fsqrt_rn((float)id)));
   if (weight_type == NB_WEIGHT_MEAN) w = __fdiv_rn(w, (float)id);
@@ -394,7 +508,8 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
           uint32_t *__restrict__ source, uint32_t n_words, uint32_t *__restrict__ other_bitmap,
           const uint32_t *__restrict__ g_col_off = nullptr, uint32_t *__restrict__ next_base = nullptr,
           uint32_t *__restrict__ next_deg = nullptr, const uint32_t *__restrict__ bitmap_l1 = nullptr,
-          uint32_t *__restrict__ other_bitmap_l1 = nullptr, uint32_t n_words_l1 = 0) {
+          uint32_t *__restrict__ other_bitmap_l1 = nullptr, uint32_t n_words_l1 = 0, NextCount tail = NextCount{}) {
+  __shared__ unsigned s_warp[33];
   const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
   // the next layer marks the other bitmap: clear it here, off the critical path (no memset node per layer)
   if (other_bitmap) {
@@ -410,10 +525,12 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
       for (unsigned w = tid; w <= n_words; w += stride) other_bitmap[w] = 0u;
     }
   }
-  if (meta->err) return;
-  const unsigned E = meta->n_edges, nd = meta->n_dst;
+  const unsigned err_in = meta->err;   // left by the kernels before this one: the same for every block
+  if (err_in && !tail.col_off) return;
+  const unsigned E = err_in ? 0u : meta->n_edges, nd = err_in ? 0u : meta->n_dst;
   const int weight_type = params->weight_type;
-  if (bitmap_l1) {   // `source` ascending: warp per level-1 word, lane per touched level-0 word, a short serial walk over its bits
+  if (err_in) {
+  } else if (bitmap_l1) {   // `source` ascending: warp per level-1 word, lane per touched level-0 word, a short serial walk over its bits
     const unsigned lane = lane_id();
     for (unsigned w1 = tid >> 5; w1 < n_words_l1; w1 += stride >> 5) {
       if (bitmap_l1[w1] >> lane & 1u) {
@@ -462,6 +579,32 @@ k_relabel(const uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ row_in
       dst_local_id[j] = local;
       src_to_dst[local] = j;
     }
+  // tail: the block that finishes last leaves the NEXT layer's column offsets and meta (CountOp's scan; that layer's dst list is this
+  // `source`, its degrees are in next_deg), so the next sampling kernel starts without a scan kernel in between
+  if (tail.col_off && last_block_arrives(&meta_mut(meta)->pad0)) {
+    LayerMeta *nm = tail.next_meta;
+    if (err_in) {
+      if (threadIdx.x == 0) { nm->n_dst = 0; nm->n_edges = 0; nm->n_src = 0; nm->long_rows = 0; nm->err = err_in; tail.col_off[0] = 0u; }
+      return;
+    }
+    const unsigned S = meta->n_src;
+    const uint32_t *omit = tail.bottom ? params->omit : nullptr;
+    const uint32_t omit_value = params->omit_value;
+    const int fanout = tail.fanout;
+    const unsigned t = block_scan_stream(S, [&](unsigned k) {
+      const uint32_t deg = __ldcg(next_deg + k);
+      uint32_t c = (fanout < 0 || deg < (uint32_t)fanout) ? deg : (uint32_t)fanout;
+      if (omit) {
+        const uint32_t f = omit[__ldcg(source + k)];
+        if (omit_value == 0xffffffffu ? (f != 0xffffffffu) : (f == omit_value)) c = 0;
+      }
+      return c; }, [&](unsigned k, unsigned excl) { tail.col_off[k] = excl; }, s_warp);
+    if (threadIdx.x == 0) {   // CountOp::total
+      tail.col_off[S] = t;
+      nm->n_dst = S; nm->n_edges = t; nm->n_src = 0; nm->long_rows = 0;
+      nm->err = t > tail.cap_edges ? 1u : 0u;
+    }
+  }
 }
 
 // clears a two-level bitmap through its level 1 (odd layer counts: the last layer leaves bitmap[0] marked for the next batch's layer 0)
@@ -607,48 +750,8 @@ static inline unsigned sgrid(uint64_t work, unsigned items, unsigned bps) {
 }
 void nb_sampler_set_block(int v) { g_sampler_block = v >= 512 ? 512 : 256; }
 constexpr size_t FS_SMEM_MAX = 200 * 1024;
-constexpr uint32_t FS_TAIL_MAX = 49152;   // per-source arrays up to this long are scanned by the relabel kernel's last block
-
-// exclusive prefix of one value per thread over the block; *total = block sum. s_warp: 33 words of shared memory.
-__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *s_warp, unsigned *total) {
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  unsigned incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned t = __shfl_up_sync(FULL_MASK, incl, o);
-    if (lane >= o) incl += t;
-  }
-  __syncthreads();   // s_warp may still be read from a previous call
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    unsigned w = lane < nwarps ? s_warp[lane] : 0u, wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(FULL_MASK, wi, o);
-      if (lane >= o) wi += t;
-    }
-    s_warp[lane] = wi - w;
-    if (lane == 31) s_warp[32] = wi;
-  }
-  __syncthreads();
-  *total = s_warp[32];
-  return s_warp[warp] + incl - v;
-}
-
-// in place: s_v[0..n) values -> exclusive prefix sums, s_v[n] = total (returned). Every thread of the block calls it.
-__device__ __forceinline__ unsigned block_scan_array(unsigned *s_v, unsigned n, unsigned *s_warp) {
-  const unsigned ipt = (n + blockDim.x - 1) / blockDim.x;
-  const unsigned a = min(n, threadIdx.x * ipt), b = min(n, a + ipt);
-  unsigned sum = 0;
-  for (unsigned i = a; i < b; i++) sum += s_v[i];
-  unsigned total;
-  unsigned run = block_excl_scan(sum, s_warp, &total);
-  for (unsigned i = a; i < b; i++) { const unsigned c = s_v[i]; s_v[i] = run; run += c; }
-  if (threadIdx.x == 0) s_v[n] = total;
-  __syncthreads();
-  return total;
-}
+constexpr uint32_t FS_TAIL_MAX = 49152;
+constexpr uint32_t FS_RANK_TAIL_MAX = 16384, FS_COUNT_TAIL_MAX = 32768;   // longest scans left to a kernel's last block (general path tails)   // per-source arrays up to this long are scanned by the relabel kernel's last block
 
 // One sampling layer's count + scan + neighbour selection. Selection code and RNG counters are those of k_sample: same draws.
 template <int GROUP>
@@ -658,7 +761,8 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
                uint32_t *__restrict__ sample_ans, uint32_t *__restrict__ edge_dst, uint32_t *__restrict__ bitmap, LayerMeta *meta,
                const LayerMeta *prev, int fanout, const BatchParams *params, uint32_t layer, int merge, int bottom, int hash_slots,
                uint32_t *__restrict__ row_count, uint32_t *__restrict__ row_cursor, uint32_t *__restrict__ src_to_dst,
-               uint32_t cap_src, uint32_t cap_edges, uint32_t cap_dst, uint32_t *__restrict__ bitmap_l1) {
+               uint32_t cap_src, uint32_t cap_edges, uint32_t cap_dst, uint32_t *__restrict__ bitmap_l1,
+               uint32_t *__restrict__ tail_word_rank = nullptr, uint32_t tail_words = 0) {
   extern __shared__ uint32_t s_dyn[];   // [cap_dst + 1] counts -> offsets, then the per-warp hash sets (fanout > 32)
   __shared__ unsigned s_warp[33];
   uint32_t *s_off = s_dyn;
@@ -691,8 +795,8 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
     for (unsigned i = threadIdx.x; i <= n_dst; i += blockDim.x) col_off[i] = s_off[i];
     if (threadIdx.x == 0) { meta->n_dst = n_dst; meta->n_edges = E; meta->n_src = 0; meta->long_rows = 0; meta->err = err; }
   }
-  if (err) return;
-  if (row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
+  if (err && !tail_word_rank) return;
+  if (!err && row_count) {  // per-src scratch of this layer: S <= E (+V when dst are merged into src)
     const unsigned bound = min(cap_src, E + (merge ? n_dst : 0u));
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < bound; k += gridDim.x * blockDim.x) {
       row_count[k] = 0;
@@ -710,7 +814,7 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
   const unsigned groups = gridDim.x * (blockDim.x / 32) * GPW;
   uint32_t *my_hash = s_hash + (threadIdx.x >> 5) * hash_slots;
   const Philox rng(key);
-  for (unsigned j = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * GPW + gid; j < n_dst; j += groups) {
+  for (unsigned j = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * GPW + gid; j < (err ? 0u : n_dst); j += groups) {
     const uint32_t off = s_off[j];
     const uint32_t num = s_off[j + 1] - off;
     uint32_t base, deg;
@@ -791,6 +895,7 @@ k_sample_fused(const uint32_t *__restrict__ g_col_off, const uint32_t *__restric
       }
     }
   }
+  if (tail_word_rank) bitmap_rank_tail(bitmap, tail_word_rank, tail_words, meta, meta + 1, cap_src, err == 0, s_warp);
 }
 
 struct RelabelTail {          // what the last block of k_relabel_fused leaves behind (all optional)
@@ -1274,15 +1379,23 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st, cudaStream_t side = n
     uint32_t hs = 1; while (s->fanout[i] > 32 && hs < 2u * (uint32_t)s->fanout[i]) hs <<= 1;
     const int hash_slots = s->fanout[i] > 32 ? (int)hs : 0;
     const size_t smem_sample = ((size_t)((b.cap_dst + 1 + 31) & ~31u) + (size_t)hash_slots * (fs_threads / 32)) * 4;
-    if (s->fused && have_col_off) {
+    // general path with tails ("sampler_tail"): the sampling kernel's last block does the bitmap's popcount scan, the relabel
+    // kernel's last block the next layer's count scan -- a layer is 2 kernels instead of 4, with the same look-back-free results
+    const bool tails = g_sampler_tail && !s->fused;
+    const bool rank_tail = tails && (g_sampler_tail & 1) && !bm_l1 && s->n_words <= FS_RANK_TAIL_MAX;
+    uint32_t *tail_rank = rank_tail ? s->word_rank : nullptr;
+    const unsigned sample_bps = g_sampler_bps > 0 ? (unsigned)g_sampler_bps : 8u;
+    if (have_col_off) {
       launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
-                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, b.dst_base, b.dst_deg, g_sampler_bps > 0 ? (unsigned)g_sampler_bps : 8u);
+                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, b.dst_base, b.dst_deg,
+                    sample_bps, tail_rank, s->n_words);
       NB_LAUNCH_CHECK(ctx);
-    } else if (s->fused && smem_sample <= FS_SMEM_MAX) {
+    } else if ((s->fused && smem_sample <= FS_SMEM_MAX) || (tails && b.cap_dst <= 4096 && smem_sample <= 40 * 1024)) {
+      // small-shape sampling kernel: every block scans the layer's counts in shared memory (layer 0 of the general path: 1024 seeds)
       const int group = (s->fanout[i] < 0 || s->fanout[i] > 16) ? 32 : (s->fanout[i] > 8 ? 16 : 8);
       const unsigned per_block = (fs_threads / 32) * (32 / group);
       unsigned grid = (b.cap_dst + per_block - 1) / per_block;
-      const unsigned max_grid = (unsigned)ctx->sm_count * (g_sampler_bps > 0 ? 1u : smem_sample <= 96 * 1024 ? 2u : 1u);
+      const unsigned max_grid = (unsigned)ctx->sm_count * (g_sampler_bps > 0 ? (s->fused ? 1u : (unsigned)g_sampler_bps) : smem_sample <= 96 * 1024 ? 2u : 1u);
       if (grid > max_grid) grid = max_grid;
       if (grid < 1) grid = 1;
 #define NB_FS(G)                                                                                                                   \
@@ -1291,7 +1404,8 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st, cudaStream_t side = n
         if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_sample_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; } \
         k_sample_fused<G><<<grid, fs_threads, smem_sample, st>>>(g->col_off, g->row_idx, b.destination, b.dst_base, b.dst_deg, i > 0 ? 1 : 0,  \
             b.column_offset, b.sample_ans, b.edge_dst, bm, m, i ? m - 1 : nullptr, s->fanout[i], pp, (uint32_t)i, merge ? 1 : 0, bottom,   \
-            hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, b.cap_dst, bm_l1);                \
+            hash_slots, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, b.cap_edges, b.cap_dst, bm_l1,                 \
+            s->fused ? nullptr : tail_rank, s->n_words);                                                                            \
       } while (0)
       if (group == 32) NB_FS(32); else if (group == 16) NB_FS(16); else NB_FS(8);
 #undef NB_FS
@@ -1301,7 +1415,8 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st, cudaStream_t side = n
       k_scan<CountOp><<<sgrid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
       NB_LAUNCH_CHECK(ctx);
       launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
-                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, nullptr, nullptr, g_sampler_bps > 0 ? (unsigned)g_sampler_bps : 8u);
+                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, nullptr, nullptr,
+                    sample_bps, tail_rank, s->n_words);
       NB_LAUNCH_CHECK(ctx);
     }
     // ---- dedup ranks + source emission + relabel (+ histogram, weights)
@@ -1312,7 +1427,7 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st, cudaStream_t side = n
       if (!attr) { NB_CUDA(cudaFuncSetAttribute(k_relabel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX)); attr = true; }
       RelabelTail tail{};
       const size_t smem_tail = ((size_t)b.cap_src + 1) * 4;
-      if (g_sampler_tail && b.cap_src <= FS_TAIL_MAX && smem_tail <= FS_SMEM_MAX) {
+      if ((g_sampler_tail & 2) && b.cap_src <= FS_TAIL_MAX && smem_tail <= FS_SMEM_MAX) {
         if (i + 1 < s->L) {
           tail.next_col_off = s->lay[i + 1].column_offset;
           tail.next_cap_edges = s->lay[i + 1].cap_edges;
@@ -1340,16 +1455,23 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st, cudaStream_t side = n
       if (bm_l1) {
         Bitmap2Op bop{bm, bm_l1, s->word_rank, m, m + 1, s->n_words_l1, b.cap_src};
         k_scan<Bitmap2Op><<<sgrid(s->n_words_l1, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
-      } else {
+        NB_LAUNCH_CHECK(ctx);
+      } else if (!rank_tail) {
         BitmapOp bop{bm, s->word_rank, m, m + 1, s->n_words, b.cap_src};
         k_scan<BitmapOp><<<sgrid(s->n_words, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(bop, ws1);
+        NB_LAUNCH_CHECK(ctx);
       }
-      NB_LAUNCH_CHECK(ctx);
+      NextCount nc{};
+      if (tails && (g_sampler_tail & 2) && i + 1 < s->L && b.cap_src <= FS_COUNT_TAIL_MAX) {
+        nc.col_off = s->lay[i + 1].column_offset; nc.next_meta = m + 1; nc.cap_edges = s->lay[i + 1].cap_edges;
+        nc.fanout = s->fanout[i + 1]; nc.bottom = i + 1 == s->L - 1 ? 1 : 0;
+      }
       k_relabel<<<sgrid((uint64_t)b.cap_edges + b.cap_dst, 256, 8), 256, 0, st>>>(
           b.sample_ans, b.row_indices, bm, s->word_rank, b.row_count, b.destination, merge ? b.dst_local_id : nullptr,
           merge ? b.src_to_dst : nullptr, m, histogram, up ? 0 : 1, b.ewf, b.edge_dst, b.column_offset, g->in_deg, g->out_deg, pp,
-          b.source, s->n_words, bm_other, g->col_off, next_base, next_deg, bm_l1, bm_other_l1, s->n_words_l1);
+          b.source, s->n_words, bm_other, g->col_off, next_base, next_deg, bm_l1, bm_other_l1, s->n_words_l1, nc);
       NB_LAUNCH_CHECK(ctx);
+      have_col_off = nc.col_off != nullptr;
     }
     if (up) {
       k_weights_sampled<<<sgrid(b.cap_edges, 256, 8), 256, 0, st>>>(b.ewf, b.row_indices, b.edge_dst, b.column_offset, b.row_count, m, pp);
@@ -1440,7 +1562,7 @@ static int run_batch(nb_sampler *s, const uint32_t *seeds, uint32_t n_seeds, int
       int prio = 0;
       if (g_sampler_capture_prio) NB_CUDA(cudaStreamGetPriority(st, &prio));
       NB_CUDA(cudaStreamCreateWithPriority(&cst, cudaStreamNonBlocking, prio));
-      if (g_sampler_tail) NB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio));
+      if (g_sampler_csr_branch) NB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio));
       cudaGraph_t graph = nullptr;
       NB_CUDA(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
       const uint64_t launches0 = ctx->launches;

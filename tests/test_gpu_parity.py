@@ -30,21 +30,23 @@ def cs(nts):
     return nts.Cuda_Stream.on_torch_stream(0)  # same stream as torch's ops, like the toolkits
 
 
-SAMPLER_PATHS = {   # (sampler_fused, sampler_tail, sampler_block_threads)
-    "fused": (1, 1, 256),            # small-shape kernels, prefix sums left by the relabel kernel's last block
-    "fused-512": (1, 1, 512),
-    "fused-notail": (1, 0, 512),     # every block rescans in shared memory (the earlier kernel order)
-    "general": (0, 1, 256),          # the default: look-back scans in global memory, any size; CSR kernels on a branch of the graph
-    "general-inline": (0, 0, 256),   # the same without the branch
+SAMPLER_PATHS = {   # (sampler_fused, sampler_tail bits, sampler_block_threads, sampler_csr_branch)
+    "general": (0, 0, 256, 1),        # the default: look-back scans in global memory, any size; CSR kernels on a branch of the graph
+    "general-inline": (0, 0, 256, 0),  # the same without the branch
+    "general-tails": (0, 3, 256, 1),   # popcount / count scans left to the last block of the sampling / relabel kernels
+    "fused": (1, 3, 256, 1),           # small-shape kernels (prefix sums per block in shared memory) + relabel tail
+    "fused-512": (1, 2, 512, 0),
+    "fused-notail": (1, 0, 512, 1),
 }
 
 
 def set_sampler_path(nts, name):
     lib, check = nts._capi.lib(), nts._capi.check
-    fused, tail, block = SAMPLER_PATHS[name]
+    fused, tail, block, branch = SAMPLER_PATHS[name]
     check(lib.nb_set_option(b"sampler_fused", fused))
     check(lib.nb_set_option(b"sampler_tail", tail))
     check(lib.nb_set_option(b"sampler_block_threads", block))
+    check(lib.nb_set_option(b"sampler_csr_branch", branch))
 
 
 @pytest.fixture(params=list(SAMPLER_PATHS))
