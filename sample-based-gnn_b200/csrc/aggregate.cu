@@ -21,7 +21,7 @@
 constexpr int AGG_THREADS = 256;
 // 7 resident blocks per SM, not 8: the free 256-thread slot lets the next batch's sampling kernels and the gradient exchange start
 // under a running aggregation instead of waiting for its tail (same-call sweep, profiles/r2_sweep_occupancy.txt: 0.1554 -> 0.1522 ms per step)
-static int g_agg_blocks_per_sm = 7, g_agg_persistent = 1, g_agg_long_rows = 0, g_agg_pipe_wide = 1, g_agg_short_rows = 1, g_agg_deep_small = 1;  // pipe: 0 never, 1 rows of <= 64 vectors, 2 always
+static int g_agg_blocks_per_sm = 7, g_agg_persistent = 1, g_agg_long_rows = 0, g_agg_pipe_wide = 1, g_agg_short_rows = 0, g_agg_deep_small = 1;  // pipe: 0 never, 1 rows of <= 64 vectors, 2 always
 void nb_agg_set_option(int which, int value) {
   if (which == 0) g_agg_blocks_per_sm = value < 1 ? 1 : value > 8 ? 8 : value;
   else if (which == 1) g_agg_persistent = value;
@@ -223,16 +223,18 @@ __device__ __noinline__ void segment_block_reduce(uint32_t r, const float *__res
   }
 }
 
+// ("agg_short_rows", off by default: measured, it does not beat the warp-per-row kernel -- 13.0 vs 12.5 us on the top hop's 24K rows,
+// 162 vs 133 us inside the GAT backward's 150K rows, where its 88-100 registers halve the occupancy; profiles/r2_gat_short_rows_ab.txt)
 // Short rows -- the CSR of a sampled layer (backward: ~1-2 entries per source row) with rows of <= 32 vectors: one warp per row
 // chains three dependent loads (offsets -> index/weight -> data) for a single 512-byte row, and the launch is bound by that
 // latency times the number of waves. Here a warp owns ROWS consecutive rows: one load fetches their ROWS+1 offsets, one
 // coalesced load the indices / weights of all their entries (they are contiguous), and the rows' data loads are in flight
 // together. Per row the entries are still accumulated in stored order (mul, then add): same bits as k_segment_reduce.
-template <int VEC, int ROWS>
+template <int VEC, int ROWS, bool GAT>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_segment_reduce_short(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ weight,
                        const uint32_t *__restrict__ idx, const uint32_t *__restrict__ offsets, uint32_t n_rows,
-                       const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch) {
+                       const uint32_t *__restrict__ n_rows_dev, uint32_t nvec, uint64_t pitch, uint64_t out_pitch, SegEpilogue epi) {
   constexpr uint32_t JOINT = 4;   // entries per row handled in the joint phase; longer rows finish one at a time, 4 loads in flight
   const unsigned lane = lane_id();
   const unsigned warp = (blockIdx.x * AGG_THREADS + threadIdx.x) >> 5;
@@ -240,6 +242,8 @@ k_segment_reduce_short(const float *__restrict__ in, float *__restrict__ out, co
   if (n_rows_dev) n_rows = min(n_rows, *n_rows_dev);
   const bool active = lane < nvec;
   const uint64_t col = (uint64_t)lane * VEC;
+  Vec<VEC> va, vb;   // GAT: the two epilogue vectors, the same for every row
+  if (GAT) { va.zero(); vb.zero(); if (active) { va.load_cached(epi.va + col); vb.load_cached(epi.vb + col); } }
   for (unsigned r0 = warp * ROWS; r0 < n_rows; r0 += warps * ROWS) {
     const unsigned nr = min((unsigned)ROWS, n_rows - r0);
     const uint32_t off = lane <= nr ? offsets[r0 + lane] : 0u;
@@ -254,14 +258,16 @@ k_segment_reduce_short(const float *__restrict__ in, float *__restrict__ out, co
     }
     const uint32_t e0 = beg[0], total = __shfl_sync(FULL_MASK, off, nr) - e0;
     uint32_t my_idx = 0;
-    float my_w = 1.0f;
+    float my_w = 1.0f, my_ds = 0.f;
     if (lane < total) {   // the first 32 entries of the group in one coalesced load
       my_idx = idx[e0 + lane];
-      if (weight) my_w = weight[e0 + lane];
+      if (GAT) { const uint32_t e = epi.c2c[e0 + lane]; my_w = epi.alpha[e]; my_ds = epi.ds[e]; }
+      else if (weight) my_w = weight[e0 + lane];
     }
     Vec<VEC> acc[ROWS];
+    float s1[ROWS];
 #pragma unroll
-    for (int i = 0; i < ROWS; i++) acc[i].zero();
+    for (int i = 0; i < ROWS; i++) { acc[i].zero(); s1[i] = 0.f; }
     const uint32_t joint = min(maxlen, JOINT);
     for (uint32_t j = 0; j < joint; j++) {
       Vec<VEC> x[ROWS];
@@ -271,8 +277,14 @@ k_segment_reduce_short(const float *__restrict__ in, float *__restrict__ out, co
         if (j < len[i]) {   // warp-uniform
           const uint32_t e = beg[i] + j - e0;
           uint32_t s;
-          if (e < 32) { s = __shfl_sync(FULL_MASK, my_idx, e); w[i] = __shfl_sync(FULL_MASK, my_w, e); }
-          else { s = idx[e0 + e]; w[i] = weight ? weight[e0 + e] : 1.0f; }
+          if (e < 32) {
+            s = __shfl_sync(FULL_MASK, my_idx, e); w[i] = __shfl_sync(FULL_MASK, my_w, e);
+            if (GAT) s1[i] += __shfl_sync(FULL_MASK, my_ds, e);
+          } else {
+            s = idx[e0 + e];
+            if (GAT) { const uint32_t ce = epi.c2c[e0 + e]; w[i] = epi.alpha[ce]; s1[i] += epi.ds[ce]; }
+            else w[i] = weight ? weight[e0 + e] : 1.0f;
+          }
           if (active) x[i].load(in + (uint64_t)s * pitch + col);
         }
       }
@@ -291,13 +303,27 @@ k_segment_reduce_short(const float *__restrict__ in, float *__restrict__ out, co
             if (j + u < len[i]) {
               const uint32_t e = beg[i] + j + u;
               const uint32_t s = idx[e];
-              w[u] = weight ? weight[e] : 1.0f;
+              if (GAT) { const uint32_t ce = epi.c2c[e]; w[u] = epi.alpha[ce]; s1[i] += epi.ds[ce]; }
+              else w[u] = weight ? weight[e] : 1.0f;
               if (active) x[u].load(in + (uint64_t)s * pitch + col);
             }
           }
 #pragma unroll
           for (int u = 0; u < 4; u++)
             if (j + u < len[i] && active) acc[i].axpy(x[u], w[u]);
+        }
+      }
+    }
+    if (GAT) {   // out[r,:] += s1 va + s2 vb, s1 = sum of the row's ds, s2 = dsum of the dst this source also is (gat.cu)
+      uint32_t d = 0xffffffffu;
+      if (lane < nr) d = epi.src_to_dst[r0 + lane];
+      float s2l = d != 0xffffffffu ? epi.dsum[d] : 0.f;
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) {
+        const float s2 = __shfl_sync(FULL_MASK, s2l, i);
+        if ((unsigned)i < nr) {
+          if (lane == 0) { epi.rs_out[r0 + i] = s1[i]; epi.dd_out[r0 + i] = s2; }
+          if (active) { acc[i].axpy(va, s1[i]); acc[i].axpy(vb, s2); }
         }
       }
     }
@@ -495,10 +521,11 @@ static int launch_segment(nb_ctx *ctx, bool push, const float *in, float *out, c
                           const uint32_t *offsets, uint32_t n_rows, uint32_t F, const uint32_t *n_rows_dev, uint64_t in_pitch,
                           uint64_t out_pitch, SegEpilogue epi, bool packed_index, int shape = 0) {
   const uint32_t nvec = F / VEC;
-  if (shape == NB_SEG_SHORT_ROWS && g_agg_short_rows && !push && !packed_index && !epi.c2c && !epi.e1 && nvec <= 32) {
+  if (shape == NB_SEG_SHORT_ROWS && g_agg_short_rows && !push && !packed_index && !epi.e1 && nvec <= 32) {
     constexpr int ROWS = 4;
     const unsigned grid = nb_grid(n_rows, (AGG_THREADS / 32) * ROWS, 8);
-    k_segment_reduce_short<VEC, ROWS><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch);
+    if (epi.c2c) k_segment_reduce_short<VEC, ROWS, true><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi);
+    else k_segment_reduce_short<VEC, ROWS, false><<<grid, AGG_THREADS, 0, ctx->stream>>>(in, out, w, idx, offsets, n_rows, n_rows_dev, nvec, in_pitch, out_pitch, epi);
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;
   }
@@ -551,9 +578,9 @@ int nb_run_segment_gat(nb_ctx *ctx, const float *dout, float *dh, const uint32_t
   epi.c2c = c2c; epi.alpha = alpha; epi.ds = ds; epi.dsum = dsum; epi.src_to_dst = src_to_dst; epi.rs_out = rs_out; epi.dd_out = dd_out;
   int vec = nb_pick_vec(F, dout, F, dh, F);
   if (vec > 1 && (((uintptr_t)va | (uintptr_t)vb) % (4 * vec))) vec = 1;
-  if (vec == 4) return launch_segment<4>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false);
-  if (vec == 2) return launch_segment<2>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false);
-  return launch_segment<1>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false);
+  if (vec == 4) return launch_segment<4>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false, NB_SEG_SHORT_ROWS);
+  if (vec == 2) return launch_segment<2>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false, NB_SEG_SHORT_ROWS);
+  return launch_segment<1>(ctx, false, dout, dh, nullptr, column_indices, row_offset, n_src, F, nullptr, F, F, epi, false, NB_SEG_SHORT_ROWS);
 }
 
 int nb_run_segment(nb_ctx *ctx, bool push, const float *in, float *out, const float *w, const uint32_t *idx,

@@ -341,7 +341,7 @@ int nb_set_option(const char *name, int value) {
   if (!strcmp(name, "agg_persistent")) { nb_agg_set_option(1, value); return NB_OK; }
   if (!strcmp(name, "agg_long_rows")) { nb_agg_set_option(2, value); return NB_OK; }
   if (!strcmp(name, "agg_pipe_wide")) { nb_agg_set_option(3, value); return NB_OK; }
-  if (!strcmp(name, "agg_short_rows")) { nb_agg_set_option(4, value); return NB_OK; }   // CSR backward: 4 rows per warp in flight (default 1)
+  if (!strcmp(name, "agg_short_rows")) { nb_agg_set_option(4, value); return NB_OK; }   // CSR backward: 4 rows per warp in flight (default 0: no gain measured)
   if (!strcmp(name, "agg_deep_small")) { nb_agg_set_option(5, value); return NB_OK; }   // small launches: 16 / 8 entries in flight (default 1)
   if (!strcmp(name, "sampler_fused")) { nb_sampler_set_fused(value); return NB_OK; }   // read when a sampler is created
   if (!strcmp(name, "sampler_two_level")) { nb_sampler_set_two_level(value); return NB_OK; }

@@ -97,17 +97,19 @@ struct CountOp {
   const LayerMeta *prev; // previous layer's (NULL for layer 0): an arena overflow there empties every later layer
   uint32_t cap_edges;
   int fanout, bottom;    // omit applies to the bottom layer only (ntsFastSampler.hpp:747-763)
+  const uint32_t *dst_deg = nullptr;   // [n] degrees of the dst list when the previous layer's relabel left them (layers >= 1): no random hop
   __device__ unsigned n() const {
     if (prev) return prev->err ? 0u : meta->n_dst;
     return params->n_seeds;
   }
   __device__ unsigned load(unsigned i) const {
-    uint32_t d = dst[i];
-    uint32_t deg = g_col_off[d + 1] - g_col_off[d];
+    uint32_t deg;
+    if (dst_deg) deg = dst_deg[i];
+    else { const uint32_t d = dst[i]; deg = g_col_off[d + 1] - g_col_off[d]; }
     uint32_t c = (fanout < 0 || deg < (uint32_t)fanout) ? deg : (uint32_t)fanout;
     const uint32_t *omit = bottom ? params->omit : nullptr;
     if (omit) {
-      uint32_t f = omit[d];
+      uint32_t f = omit[dst[i]];
       const uint32_t omit_value = params->omit_value;
       if (omit_value == 0xffffffffu ? (f != 0xffffffffu) : (f == omit_value)) c = 0;
     }
@@ -1411,11 +1413,14 @@ static int enqueue_kernels(nb_sampler *s, cudaStream_t st, cudaStream_t side = n
 #undef NB_FS
       NB_LAUNCH_CHECK(ctx);
     } else {
-      CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, i ? m - 1 : nullptr, b.cap_edges, s->fanout[i], bottom};
+      // layers >= 1: the previous layer's relabel left every dst's adjacency base / degree next to the dst list (coalesced reads here
+      // instead of two dependent random ones per dst)
+      const uint32_t *dbase = i > 0 ? b.dst_base : nullptr, *ddeg = i > 0 ? b.dst_deg : nullptr;
+      CountOp cop{g->col_off, b.destination, pp, b.column_offset, m, i ? m - 1 : nullptr, b.cap_edges, s->fanout[i], bottom, ddeg};
       k_scan<CountOp><<<sgrid(b.cap_dst, SCAN_TILE, 4), SCAN_THREADS, 0, st>>>(cop, ws0);
       NB_LAUNCH_CHECK(ctx);
       launch_sample(st, b.cap_dst, s->fanout[i], g->col_off, g->row_idx, b.destination, b.column_offset, b.sample_ans, b.edge_dst, bm, m,
-                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, nullptr, nullptr,
+                    pp, (uint32_t)i, merge ? 1 : 0, rc_ptr, b.row_cursor, merge ? b.src_to_dst : nullptr, b.cap_src, bm_l1, dbase, ddeg,
                     sample_bps, tail_rank, s->n_words);
       NB_LAUNCH_CHECK(ctx);
     }

@@ -474,7 +474,7 @@ def test_short_row_and_small_launch_kernels_keep_the_bits(nts, cs, F, R):
             cs.aggregate_bwd_pitched(x, dx, None, d_off, d_idx, R, F, F, F)
             assert np.array_equal(bits(f32(dx)), bits(oracle.aggregate_fwd(X, off, idx, np.ones(E, np.float32)))), (short, deep, "bwd, no weights")
     finally:
-        check(lib.nb_set_option(b"agg_short_rows", 1))
+        check(lib.nb_set_option(b"agg_short_rows", 0))      # the defaults
         check(lib.nb_set_option(b"agg_deep_small", 1))
 
 
@@ -649,8 +649,16 @@ def _gat_goldens():
     return sorted(os.path.basename(f)[4:-4] for f in glob.glob(os.path.join(d, "gat_*.npz")))
 
 
+@pytest.fixture(params=[0, 1])
+def gat_short_rows(nts, request):
+    """the fused GAT backward's CSR reduction through the warp-per-row kernel (default) and the 4-rows-per-warp one"""
+    nts._capi.check(nts._capi.lib().nb_set_option(b"agg_short_rows", request.param))
+    yield request.param
+    nts._capi.check(nts._capi.lib().nb_set_option(b"agg_short_rows", 0))
+
+
 @pytest.mark.parametrize("name", _gat_goldens())
-def test_gat_against_reference_kernel_records(nts, cs, name):
+def test_gat_against_reference_kernel_records(nts, cs, name, gat_short_rows):
     """a14 pinned: tests/golden/gat_*.npz hold the outputs of the reference's OWN CUDA kernels (cuda/ntsCUDADistKernel.cuh, run on a
     B200 by oracle/_ref/ref_gpu_driver <- oracle/make_gat_golden.py) for the op chain of toolkits/GAT_SAMPLE_ALL_MULTI.hpp:383-464.
     Legacy-shaped ops and the fused layer, forward and backward, against those records. Tolerance: 1e-5 relative (north star) plus an

@@ -11,6 +11,10 @@ import __graft_entry__ as ge  # noqa: E402
 import bench as B  # noqa: E402
 
 nts = ge.load_package()
+for kv in sys.argv[1:]:       # name=value pairs for nb_set_option (A/B of tuning knobs)
+    name, value = kv.split("=")
+    nts._capi.check(nts._capi.lib().nb_set_option(name.encode(), int(value)))
+    print("option", name, value)
 v, col_off, src = B.reddit_shaped_graph(1.0)
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
