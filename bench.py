@@ -1186,9 +1186,11 @@ if __name__ == "__main__":
     ap.add_argument("--pitch", type=int, default=608, help="row pitch in floats of the 602-wide tensors (0 = dense 602)")
     ap.add_argument("--cpu-batches", type=int, default=20)
     ap.add_argument("--sample-priority", type=int, default=-1, help="CUDA stream priority of the sampling stream (-1 = high: its small kernels get SM slots ahead of the queued aggregation blocks; 0.184 -> 0.158 ms per step, profiles/r2_sweep_pipeline.txt)")
-    ap.add_argument("--exchange", default="split", choices=["split", "split-inline", "one", "nccl"],
-                    help="dense-gradient sum at N>1: split = peer-memory push behind the backward (beside the next bottom aggregation) + reduce "
-                         "before the next top hop (default); split-inline = the same with the push in the training stream; one = one peer-memory kernel on a communication stream; nccl = NCCL all_reduce")
+    ap.add_argument("--exchange", default="one", choices=["split", "split-inline", "one", "nccl"],
+                    help="dense-gradient sum at N>1: one (default) = one peer-memory kernel (push + rank-ordered reduce) on a communication stream beside the "
+                         "next bottom aggregation; split = push behind the backward + reduce in the training stream before the next top hop "
+                         "(the in-line kernel costs ~9 us of the step: 0.156 vs 0.146 ms at N=8, profiles/r2b_scale_matrix.txt); split-inline = "
+                         "the same with the push in the training stream too; nccl = NCCL all_reduce")
     ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
     ap.add_argument("--api-pipeline", type=int, default=4, help="e2e arm: FastSampler pipeline slots (PIPELINE_NUM); PIPELINE_NUM - 1 batches are sampled ahead")
     ap.add_argument("--sample-streams", type=int, default=2, help="sampling streams; pipeline slot k samples on stream k %% NS (one stream serialises the batches' sampler graphs "

@@ -53,11 +53,6 @@ struct nb_peer_comm {
 static int g_peer_push_side = 1;
 void nb_peer_set_push_side(int v) { g_peer_push_side = v ? 1 : 0; }
 
-__device__ __forceinline__ float4 ld_volatile4(const float *p) {
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -121,9 +116,17 @@ k_peer_exchange(PeerParams c, const float *in, float *out, uint32_t n, uint32_t 
     const uint64_t region = c.slot_bytes / 4;
     for (uint32_t i = lo + threadIdx.x; i < hi; i += PEER_THREADS) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (uint32_t p = 0; p < c.world; p++) {
-        const float4 v = ld_volatile4(slot + p * region + 4 * (uint64_t)i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      // the regions were written by the peers before the flags this block has just observed (volatile poll, system fence, barrier):
+      // L1-bypassing loads see them, and unlike volatile ones eight of them are in flight at once (volatile loads issue one after
+      // the other: 8 ranks x 3 iterations of L2 latency made the reduce phase 13 us of the step at N=8)
+      for (uint32_t p0 = 0; p0 < c.world; p0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (p0 + k < c.world) v[k] = __ldcg(reinterpret_cast<const float4 *>(slot + (p0 + k) * region) + i);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (p0 + k < c.world) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }   // rank order
       }
       if (4 * i + 3 < n) *reinterpret_cast<float4 *>(out + 4 * (uint64_t)i) = acc;
       else {

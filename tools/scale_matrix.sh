@@ -1,17 +1,15 @@
 #!/bin/bash
-# One call on an 8-GPU box: where to put the dense-gradient exchange, measured at N=4 and N=8 side by side, then the default line.
+# One call on an 8-GPU box: weak scaling of the headline step and where to put the dense-gradient exchange, same box, same call.
 # usage: bash tools/scale_matrix.sh > gpurun_out/scale_matrix.txt
 export NB_BENCH_GRAPH_CACHE=/dev/shm/nb_reddit_graph
 python -c "import bench; bench.reddit_shaped_graph(1.0)" 2>/dev/null
 run() { N=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
-        bench.py --gpus $N --steps 20 --warmup 5 "$@" 2>/dev/null | tail -1; }
-fmt='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print("value_ms", round(d["ms_per_step"],4), d["run"]["windows_ms_per_step"], "e2e_ms", round(d["e2e"]["ms_per_step"],4), "check", (d.get("exchange_check") or "")[:14], "wait_us", d.get("exchange_wait_us"))'
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-configs --modes fused,api 2>/dev/null | tail -1 | python -c "$fmt" | sed 's/^/N=1 : /'
-for cfg in "4 split" "8 split" "8 one" "8 nccl"; do
-  set -- $cfg; N=$1; EX=$2; shift 2
-  echo -n "N=$N exchange=$EX $* : "
-  run $N --no-cpu-baseline --no-other-configs --modes fused,api --exchange $EX "$@" | python -c "$fmt"
+        bench.py --gpus $N --steps 20 --warmup 5 "$@" 2>/tmp/err_$N.txt | tail -1; grep timeline /tmp/err_$N.txt | cut -c1-400 | sed 's/^/      /' >&2; }
+fmt='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print("value_ms", round(d["ms_per_step"],4), d["run"]["windows_ms_per_step"], "check", (d.get("exchange_check") or "")[:14], "wait_us", d.get("exchange_wait_us"), "clocks", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])'
+COMMON="--no-cpu-baseline --no-other-configs --modes fused --timeline 60"
+python bench.py --steps 20 --warmup 5 $COMMON 2>/tmp/err_1.txt | tail -1 | python -c "$fmt" | sed 's/^/N=1 : /'; grep timeline /tmp/err_1.txt | cut -c1-400 | sed 's/^/      /'
+for cfg in "8 split" "8 one" "8 nccl" "4 split" "8 split"; do
+  set -- $cfg; N=$1; EX=$2
+  echo -n "N=$N exchange=$EX : "
+  run $N $COMMON --exchange $EX 2>/tmp/tl.txt | python -c "$fmt"; cat /tmp/tl.txt
 done
-# the default line (what the driver runs), with the other configs: GAT strong scaling, products, full-size papers100M sharded over the 8 GPUs
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29911 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2_bench_n8_default.json 2> gpurun_out/r2_bench_n8_default.err
-tail -c 600 gpurun_out/r2_bench_n8_default.err
