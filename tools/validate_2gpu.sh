@@ -1,4 +1,5 @@
 #!/bin/bash
+# one 2-GPU call: multi-GPU tests, the default bench line at N=2 (all configs), the reference arm under torchrun
 export NB_BENCH_GRAPH_CACHE=/dev/shm/nb_reddit_graph
 python -c "import bench; bench.reddit_shaped_graph(1.0)" 2>/dev/null
 timeout 600 python -m pytest -m gpu -q -x tests/test_gpu_multi.py 2>&1 | tail -3 > gpurun_out/r2x_mgpu_tests.log
