@@ -270,7 +270,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
     st_samples = [torch.cuda.Stream(dev, priority=args.sample_priority) for _ in range(NS)]
     cs_samples = [nts.Cuda_Stream(local, s_) for s_ in st_samples]
     st_sample, cs_sample = st_samples[0], cs_samples[0]
-    st_train = torch.cuda.Stream(dev)
+    st_train = torch.cuda.Stream(dev, priority=args.train_priority)
     cs_train = nts.Cuda_Stream(local, st_train)
     # e2e path: the host waits for every batch's sampled sizes, so sampling is on its critical path and gets a high-priority
     # stream (its small kernels are scheduled ahead of the resident gather / aggregation blocks of the previous batch). In the
@@ -1192,6 +1192,7 @@ if __name__ == "__main__":
                          "(the in-line kernel costs ~9 us of the step: 0.156 vs 0.146 ms at N=8, profiles/r2b_scale_matrix.txt); split-inline = "
                          "the same with the push in the training stream too; nccl = NCCL all_reduce")
     ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
+    ap.add_argument("--train-priority", type=int, default=0, help="CUDA stream priority of the training stream (0 = normal, negative = higher)")
     ap.add_argument("--api-pipeline", type=int, default=4, help="e2e arm: FastSampler pipeline slots (PIPELINE_NUM); PIPELINE_NUM - 1 batches are sampled ahead")
     ap.add_argument("--sample-streams", type=int, default=2, help="sampling streams; pipeline slot k samples on stream k %% NS (one stream serialises the batches' sampler graphs "
                          "and puts them on the step's critical path: 0.168 -> 0.155 ms per step with two, profiles/r2_sweep_sample_streams.txt)")

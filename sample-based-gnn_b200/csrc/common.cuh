@@ -93,6 +93,9 @@ uint64_t nb_trace_now_ns();
 void nb_trace_add(const char *name, uint64_t ns);  // name must be a string literal (the table is keyed by its address)
 void nb_sampler_set_two_level(int mode);
 void nb_sampler_set_keep_min(int n);
+// TMA tensor-map gather (tile::gather4), gather4.cu; NB_ERR_UNSUPPORTED = shape not eligible, caller falls back
+int nb_gather4_launch(nb_ctx *ctx, float *out, uint64_t out_pitch, const float *table, uint64_t table_pitch, const uint32_t *ids_dev,
+                      uint32_t n_rows, uint32_t F);
 void nb_sampler_set_tail(int v);
 void nb_sampler_set_csr_branch(int v);
 void nb_sampler_set_block(int v);

@@ -366,8 +366,12 @@ int nb_gather_rows(nb_ctx *ctx, float *out, const float *table, const uint32_t *
   NB_GUARD(ctx);
   if (n_rows == 0) return NB_OK;
   table = (const float *)nb_mirror_host(ctx, table);
+  if (gather_variant() == 2) {   // tile::gather4 through tensor maps (gather4.cu): A/B variant, falls through when the shape is not eligible
+    const int rc = nb_gather4_launch(ctx, out, out_pitch, table, table_pitch, ids_dev, n_rows, feature_size);
+    if (rc != NB_ERR_UNSUPPORTED) return rc;
+  }
   // rows of <= 128 floats: the register path with 4 rows per warp beats bulk copies of 400-512 byte rows (tools/gather_bench.py)
-  const uint32_t tb = gather_variant() == 1 && feature_size > 128 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
+  const uint32_t tb = gather_variant() >= 1 && feature_size > 128 ? tma_row_bytes(feature_size, table, table_pitch, out, out_pitch) : 0;
   if (tb) return launch_gather_tma<0>(ctx, out, table, table_pitch, nullptr, 0, nullptr, nullptr, 0, ids_dev, n_rows, nullptr, tb, out_pitch);
   uint32_t fe = feature_size;
   int vec = nb_pick_vec(feature_size, table, table_pitch, out, out_pitch, &fe);

@@ -931,6 +931,29 @@ def test_padded_rows_and_tma_gather_match_dense(nts, cs):
         assert top.forward(torch.ones((sg.sampled_sgs[0].src_size, 4), device="cuda")).shape[0] == sg.sampled_sgs[0].v_size
 
 
+@pytest.mark.parametrize("F,pitch", [(128, 128), (100, 100), (64, 64), (256, 256), (602, 608), (608, 608), (512, 520), (1000, 1000)])
+@pytest.mark.parametrize("n", [1, 3, 4, 1001, 20000])
+def test_tensor_map_gather4_variant_copies_the_same_rows(nts, cs, F, pitch, n):
+    """nb_set_option("gather_variant", 2): rows move through TMA tensor maps, four per instruction (tile::gather4), and leave through
+    tiled tensor stores. Every eligible shape gives the bits of a plain index; groups that are not a multiple of four rows are clipped
+    at the output map's edge (the rows behind them are not touched); shapes it cannot take fall back."""
+    lib, check, ptr = nts._capi.lib(), nts._capi.check, nts._capi.ptr
+    V = 50000
+    g = torch.Generator(device="cuda").manual_seed(F * 131 + n)
+    table = torch.zeros((V, pitch), device="cuda")
+    table[:, :F] = torch.randn((V, F), device="cuda", generator=g)
+    ids = torch.randint(0, V, (n,), device="cuda", dtype=torch.int32, generator=g)
+    out = torch.full((n + 5, pitch), 9.0, device="cuda")
+    try:
+        check(lib.nb_set_option(b"gather_variant", 2))
+        check(lib.nb_gather_rows(cs._h, ptr(out), ptr(table), ptr(ids), n, F, pitch, pitch))
+        cs.CUDA_DEVICE_SYNCHRONIZE()
+    finally:
+        check(lib.nb_set_option(b"gather_variant", 1))
+    assert torch.equal(out[:n, :F], table[ids.long()][:, :F])
+    assert bool((out[n:] == 9.0).all())
+
+
 def test_async_sampling_pipeline_slots_and_no_bottom_csr(nts, cs):
     """sample_gpu_fast(sync=False) + wait(): two pipeline slots in flight give the same subgraphs as the synchronous call;
     bottom_csr=False drops only the bottom layer's CSR."""

@@ -22,7 +22,7 @@ with torch.cuda.stream(stream):
         torch.cuda.synchronize()
         ms = np.median([ev[i].elapsed_time(ev[i+1]) for i in range(9)])
         ok = torch.equal(out[:, :F], table[ids[11].long()][:, :F])
-        print(f"{name:40s} {ms*1e3:8.1f} us  {N*(4+8*F)/ms/1e6:8.1f} GB/s (alg)  ok={ok}")
+        print(f"{name:62s} {ms*1e3:8.1f} us  {N*(4+8*F)/ms/1e6:8.1f} GB/s (alg)  ok={ok}")
     dense = torch.rand((V, 602), device='cuda')
     out_dense = torch.empty((N, 602), device='cuda')
     padded = torch.zeros((V, 608), device='cuda'); padded[:, :602] = dense
@@ -33,16 +33,20 @@ with torch.cuda.stream(stream):
     bench("LSU pitch 608->608 F=608 (float4)", padded, out_pad, 608, 608, 0, 608)
     bench("TMA pitch 608->608 F=602", padded, out_pad, 608, 608, 1)
     bench("TMA pitch 608->608 F=608", padded, out_pad, 608, 608, 1, 608)
+    bench("TMA tensor map, tile::gather4 608->608 F=602 (4 boxes of 152)", padded, out_pad, 608, 608, 2)
+    bench("TMA tensor map, tile::gather4 608->608 F=608", padded, out_pad, 608, 608, 2, 608)
     t128 = torch.rand((V, 128), device='cuda'); o128 = torch.empty((N, 128), device='cuda')
     F=128
     bench("LSU F=128", t128, o128, 128, 128, 0, 128)
     bench("TMA F=128", t128, o128, 128, 128, 1, 128)
+    bench("tile::gather4 F=128", t128, o128, 128, 128, 2, 128)
     # narrow rows (products F=100, papers F=128) on a table larger than L2: TMA bulk rows vs one row per warp vs 4 rows per warp
     V = 2449029
     for Fn in (100, 128, 64, 256):
         F = Fn
         tn = torch.rand((V, Fn), device='cuda'); on = torch.empty((N, Fn), device='cuda')
         bench(f"TMA F={Fn} (V=2.4M)", tn, on, Fn, Fn, 1, Fn)
+        bench(f"tile::gather4 F={Fn} (4 rows per instruction)", tn, on, Fn, Fn, 2, Fn)
         check(lib.nb_set_option(b"gather_narrow_rows", 1))
         bench(f"LSU F={Fn} 1 row/warp", tn, on, Fn, Fn, 0, Fn)
         check(lib.nb_set_option(b"gather_narrow_rows", 4))
