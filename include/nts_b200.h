@@ -102,6 +102,8 @@ int nb_device_count(int *count);
  *       2 = nb_gather_rows through TMA tensor maps, four rows per instruction (cp.async.bulk.tensor.2d tile::gather4 + tiled tensor stores),
  *       falling back where a shape is not eligible. Measured (profiles/r2b_gather4_ab.txt): F=602 117.6 us vs 120.7 (variant 1); F=100 / 128
  *       28.7 / 27.9 us vs 22.5 / 24.5 for the register path with 4 rows per warp -- not the default for any shape
+ *   "table_gather_tma" : 0 (default) = nb_table_gather reads shard rows through the register path; 1 = as TMA bulk copies. Measured
+ *       identical over NVLink (profiles/r2b_shard_gather_tma_ab_n2.txt)
  *   "mirror_host_tables" / NB_MIRROR_HOST_TABLES : 1 = a feature table found in mapped pinned HOST memory (the reference's zero-copy
  *       table, core/ntsDataloador.hpp:187) is copied to HBM once, on the first gather that sees it, and read from HBM afterwards
  *       (the buffer must not change after that); 0 (default) = gather over PCIe like the reference

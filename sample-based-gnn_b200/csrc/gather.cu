@@ -219,6 +219,7 @@ static uint32_t tma_row_bytes(uint32_t F, const void *a, uint64_t pitch_a, const
   return bytes;
 }
 
+static int g_table_gather_tma = 0;   // "table_gather_tma": sharded-table gather through TMA bulk copies (A/B; tools/shard_bench.py)
 static int g_gather_variant = -1;  // NB_GATHER_VARIANT: 0 = registers (LDG/STG), 1 = TMA bulk when eligible (default)
 static int gather_variant() {
   if (g_gather_variant < 0) {
@@ -336,6 +337,7 @@ extern "C" {
 int nb_set_option(const char *name, int value) {
   NB_REQUIRE(name, NB_ERR_ARG, "nb_set_option: NULL name");
   if (!strcmp(name, "gather_variant")) { g_gather_variant = value; return NB_OK; }
+  if (!strcmp(name, "table_gather_tma")) { g_table_gather_tma = value; return NB_OK; }
   if (!strcmp(name, "gather_narrow_rows")) { g_gather_narrow_rows = value; return NB_OK; }
   if (!strcmp(name, "agg_blocks_per_sm")) { nb_agg_set_option(0, value); return NB_OK; }
   if (!strcmp(name, "agg_persistent")) { nb_agg_set_option(1, value); return NB_OK; }
@@ -492,6 +494,10 @@ int nb_table_gather(nb_ctx *ctx, nb_table *t, float *out, const uint32_t *ids_de
   NB_REQUIRE(out_pitch >= t->feature_size, NB_ERR_ARG, "nb_table_gather: bad pitch");
   NB_GUARD(ctx);
   // shard bases come from cudaMalloc / IPC mappings: 256-byte aligned
+  if (g_table_gather_tma && t->n_shards > 1) {   // "table_gather_tma": rows of peer shards as TMA bulk copies (thousands in flight per SM)
+    const uint32_t tb = tma_row_bytes(t->feature_size, nullptr, t->pitch, out, out_pitch);
+    if (tb) return launch_gather_tma<2>(ctx, out, nullptr, t->pitch, nullptr, 0, nullptr, t->shards_dev, t->n_shards, ids_dev, n_rows, nullptr, tb, out_pitch);
+  }
   int vec = nb_pick_vec(t->feature_size, nullptr, t->pitch, out, out_pitch);
   return launch_gather<2>(ctx, out, nullptr, t->pitch, nullptr, 0, nullptr, t->shards_dev, t->n_shards, ids_dev, n_rows,
                           t->feature_size, out_pitch, nullptr, vec);

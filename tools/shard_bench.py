@@ -17,11 +17,22 @@ def main():
     os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nts = ge.load_package()
+    for kv in sys.argv[1:]:       # name=value pairs for nb_set_option (A/B of tuning knobs)
+        name, value = kv.split("=")
+        nts._capi.check(nts._capi.lib().nb_set_option(name.encode(), int(value)))
+        if rank == 0:
+            print("option", name, value)
     from sample_based_gnn_b200 import dist as nd
     cs = nts.Cuda_Stream.on_torch_stream(local)
-    V, F, N = int(os.environ.get("SHARD_V", 111_059_956 // 4)), 128, 400_000          # quarter of papers100M's vertices: 14.2 GB of rows in total
+    V, F, N = int(os.environ.get("SHARD_V", 111_059_956 // 4)), 128, int(os.environ.get("SHARD_ROWS", 400_000))          # quarter of papers100M's vertices: 14.2 GB of rows in total
     n_local = (V - rank + world - 1) // world
-    mine = torch.rand((n_local, F), device="cuda")
+    # row v holds ((v * 131 + column) mod 8191): every gathered row can be checked without seeing the peer's shard
+    mine = torch.empty((n_local, F), device="cuda")
+    cols = torch.arange(F, device="cuda", dtype=torch.int64)[None, :]
+    for a in range(0, n_local, 1 << 21):
+        b = min(n_local, a + (1 << 21))
+        gid = torch.arange(a, b, device="cuda", dtype=torch.int64)[:, None] * world + rank
+        mine[a:b] = ((gid * 131 + cols) % 8191).float()
     st = nd.ShardedTable(cs, mine, V, F)
     g = torch.Generator(device="cuda").manual_seed(rank)
     ids = [torch.randint(0, V, (N,), device="cuda", dtype=torch.int32, generator=g) for _ in range(8)]
@@ -54,9 +65,12 @@ def main():
     if rank == 0:
         for r, x in enumerate(allms):
             print(f"SHARD_RANK {r}: all-peers {x[0]} ms; per-peer GB/s {x[1]}")
-    # correctness of one remote row
-    v = int(ids[(reps - 1) % 8][0])
-    owner, row = v % world, v // world
+    # correctness of every row of one gather (local and remote)
+    st.gather(out, ids[0], N)
+    torch.cuda.synchronize()
+    want = ((ids[0].to(torch.int64)[:, None] * 131 + cols) % 8191).float()
+    assert torch.equal(out, want), "sharded gather returned wrong rows"
+    del want
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
