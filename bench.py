@@ -271,7 +271,12 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
     cs_samples = [nts.Cuda_Stream(local, s_) for s_ in st_samples]
     st_sample, cs_sample = st_samples[0], cs_samples[0]
     st_train = torch.cuda.Stream(dev, priority=args.train_priority)
+    # --agg-stream 1 (default): the bottom hop runs on a stream of its own. Y1 = A X0 involves no weights (GCN / GraphSAGE aggregate first, then
+    # apply W), so like sampling and the gather it belongs to the data stage of the pipeline: batch i+1's bottom hop runs beside batch i's
+    # weight-dependent chain (top hop forward / backward, and in a trainer the dense layers and the optimizer). Y1 has one buffer per slot.
+    st_agg = torch.cuda.Stream(dev) if args.agg_stream else st_train
     cs_train = nts.Cuda_Stream(local, st_train)
+    cs_agg = nts.Cuda_Stream(local, st_agg) if args.agg_stream else cs_train
     # e2e path: the host waits for every batch's sampled sizes, so sampling is on its critical path and gets a high-priority
     # stream (its small kernels are scheduled ahead of the resident gather / aggregation blocks of the previous batch). In the
     # device-resident path nothing waits for the sampler, and a normal-priority stream leaves the aggregation undisturbed.
@@ -287,7 +292,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                                   bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
         fast = nts.FastSampler(graph, my_seeds, 2, B, FANOUT, pipeline_num=PA, cuda_stream=[cs_samples_api[k_ % NSA] for k_ in range(PA)], build_csr=True,
                                bottom_csr=False, rng_seed=SEED_SAMPLER + rank)
-        api_ev = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(PA)]
+        api_ev = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event(), aggregated=torch.cuda.Event()) for _ in range(PA)]
         gen = torch.Generator(device=dev).manual_seed(0x5EED0002)
         table = torch.empty((v, PITCH), device=dev)                               # HBM-resident feature table
         for a_ in range(0, v, 1 << 22):                                           # filled in chunks: no second table-sized temporary
@@ -297,7 +302,8 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
             table[a_:b_, :F0] = torch.rand((b_ - a_, F0), generator=gen, device=dev) * 2 - 1
         cap_s1, cap_s0 = min(B * FANOUT[0] * FANOUT[1], v), min(B * FANOUT[0], v)
         x0 = torch.zeros((cap_s1, PITCH), device=dev)
-        y1 = torch.zeros((cap_s0, PITCH), device=dev)
+        y1s = [torch.zeros((cap_s0, PITCH), device=dev) for _ in range(P if args.agg_stream else 1)]
+        y1 = y1s[0]
         h1 = torch.rand((cap_s0, F1), generator=gen, device=dev)                 # stands in for relu(Y1 W1)
         y0 = torch.empty((B, F1), device=dev)
         dy0 = torch.rand((B, F1), generator=gen, device=dev)
@@ -323,7 +329,8 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                 check(lib.nb_sampler_sizes_dev(sampler._samplers[k], l, C.byref(nd[l]), None, C.byref(ns[l]), C.byref(caps[l][0]),
                                                C.byref(caps[l][1]), C.byref(caps[l][2])))
             assert caps[1][2].value <= cap_s1 and caps[0][2].value <= cap_s0
-            slots.append(dict(top=views[0], bot=views[1], nd=nd, ns=ns, caps=caps, sampled=torch.cuda.Event(), consumed=torch.cuda.Event()))
+            slots.append(dict(top=views[0], bot=views[1], nd=nd, ns=ns, caps=caps, sampled=torch.cuda.Event(), consumed=torch.cuda.Event(),
+                              aggregated=torch.cuda.Event()))
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -398,7 +405,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         st_sample.wait_event(sl["consumed"])
         tl = tl_box[0]
         if tl is not None:
-            tl.append([ev() for _ in range(6)])
+            tl.append([ev() for _ in range(7)])
             tl[-1][0].record(st_sample)
         check(lib.nb_sampler_sample(sampler._samplers[i % P], ptr(seeds_dev[i * B:(i + 1) * B]), B, 1,
                                     SEED_SAMPLER + rank, i, nts.WeightType.Sum, None, 0xFFFFFFFF, None, 0))
@@ -408,22 +415,23 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         # on the sampling stream, so the copy engine's latency stays off the training stream
         check(lib.nb_memcpy_d2h(cs_sample._h, ptr(sizes_both[i]), nd[0].value, 64, 0))
         sl["sampled"].record(st_sample)
-        st_train.wait_event(sl["sampled"])
+        st_agg.wait_event(sl["sampled"])        # (implies consumed(i - P): this slot's Y1 buffer is free again)
+        y1 = y1s[(i % P) % len(y1s)]
         if tl is not None:
-            tl[-1][2].record(st_train)
+            tl[-1][2].record(st_agg)
         if timed:
             a, b, c = ev(), ev(), ev()
-            a.record(st_train)
+            a.record(st_agg)
         if not fused:
-            check(lib.nb_gather_rows_dyn(cs_train._h, ptr(x0), ptr(table), bot.source, ns[1], caps[1][2], F0, PITCH, PITCH))
+            check(lib.nb_gather_rows_dyn(cs_agg._h, ptr(x0), ptr(table), bot.source, ns[1], caps[1][2], F0, PITCH, PITCH))
             if timed:
-                b.record(st_train)
+                b.record(st_agg)
             if exchange in ("one", "nccl"):
                 issue_allreduce()
-            check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(x0), ptr(y1), bot.edge_weight_forward, bot.row_indices,
+            check(lib.nb_aggregate_csc_fwd_dyn(cs_agg._h, ptr(x0), ptr(y1), bot.edge_weight_forward, bot.row_indices,
                                                bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
             if timed:
-                c.record(st_train)
+                c.record(st_agg)
                 kern_ev["gather"].append((a, b))
                 kern_ev["agg_fwd_602"].append((b, c))
         else:
@@ -432,16 +440,21 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
             # load_feature_gpu + the bottom hop's forward as one kernel: rows come straight from the table through the layer's
             # packed gather index; its hint bit steers L2 (rows the batch reads again are kept, single-use rows are not)
             if args.no_l2_hints:   # A/B: the same rows through the plain global ids, no eviction hints
-                check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
+                check(lib.nb_aggregate_csc_fwd_dyn(cs_agg._h, ptr(table), ptr(y1), bot.edge_weight_forward, bot.sample_ans,
                                                    bot.column_offset, nd[1], caps[1][0], F0, PITCH, PITCH))
             else:
-                check(lib.nb_aggregate_gathered_fwd_dyn(cs_train._h, ptr(table), PITCH, bot.gather_index, ptr(y1), bot.edge_weight_forward,
+                check(lib.nb_aggregate_gathered_fwd_dyn(cs_agg._h, ptr(table), PITCH, bot.gather_index, ptr(y1), bot.edge_weight_forward,
                                                         bot.column_offset, nd[1], caps[1][0], F0, PITCH))
             if timed:
-                b.record(st_train)
+                b.record(st_agg)
                 kern_ev["agg_fwd_602_from_table"].append((a, b))
         if tl is not None:
-            tl[-1][3].record(st_train)
+            tl[-1][3].record(st_agg)
+        if st_agg is not st_train:
+            sl["aggregated"].record(st_agg)
+            st_train.wait_event(sl["aggregated"])   # Y1 of this batch is ready: the weight-dependent chain may start
+        if tl is not None:
+            tl[-1][6].record(st_train)
         exchange_before_consumer()
         check(lib.nb_aggregate_csc_fwd_dyn(cs_train._h, ptr(h1), ptr(y0), top.edge_weight_forward, top.row_indices,
                                            top.column_offset, nd[0], caps[0][0], F1, F1, F1))
@@ -456,6 +469,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
 
     api_state = {"issued": -1, "checksum": 0.0, "wait_s": 0.0}
     y0_ring = [torch.empty((B, F1)).pin_memory() for _ in range(2)]
+    y0_np = [t_.numpy() for t_ in y0_ring]             # the host reads the results through numpy views (no tensor indexing per step)
     y0_done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def api_issue(i):
@@ -464,8 +478,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         st_sample_api = st_samples_api[k % NSA]
         st_sample_api.wait_event(api_ev[k]["consumed"])
         fast.work_offset = i * B
-        with torch.cuda.stream(st_sample_api):
-            fast.sample_gpu_fast(B, ssg_id=k, sync=False)          # stages + uploads the seeds from host memory
+        fast.sample_gpu_fast(B, ssg_id=k, sync=False)              # stages + uploads the seeds from host memory; runs on the slot's stream
         api_ev[k]["sampled"].record(st_sample_api)
         api_state["issued"] = i
 
@@ -481,15 +494,20 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         if i + PA - 1 < n_steps:
             api_issue(i + PA - 1)                                   # batch i-1's slot is free again: sample ahead (high-priority streams)
                                                                     # while this batch is aggregated and the host issues its ops
-        st_train.wait_event(api_ev[k]["sampled"])
+        st_agg.wait_event(api_ev[k]["sampled"])
         t, bt = sg.sampled_sgs
-        if args.materialize_x0:
-            xx = fast.load_feature_gpu(cs_train, sg, x0[:bt.src_size, :F0], table[:, :F0])
-        else:
-            xx = fast.load_feature_gpu(cs_train, sg, x0[:, :F0], table[:, :F0], lazy=True)   # a promise: nothing is copied
-        if exchange in ("one", "nccl"):
-            issue_allreduce()
-        yy1 = nts.SingleGPUAllSampleGraphOp(sg, 1, cs_train).forward(xx)   # lazy: aggregates straight from the table
+        with torch.cuda.stream(st_agg):     # the weight-free bottom hop: the data stage's stream (Y1 is allocated on it too)
+            if args.materialize_x0:
+                xx = fast.load_feature_gpu(cs_agg, sg, x0[:bt.src_size, :F0], table[:, :F0])
+            else:
+                xx = fast.load_feature_gpu(cs_agg, sg, x0[:, :F0], table[:, :F0], lazy=True)   # a promise: nothing is copied
+            if exchange in ("one", "nccl"):
+                issue_allreduce()
+            yy1 = nts.SingleGPUAllSampleGraphOp(sg, 1, cs_agg).forward(xx)   # lazy: aggregates straight from the table
+            if st_agg is not st_train:
+                api_ev[k]["aggregated"].record(st_agg)
+        if st_agg is not st_train:
+            st_train.wait_event(api_ev[k]["aggregated"])
         op_top = nts.SingleGPUAllSampleGraphOp(sg, 0, cs_train)
         exchange_before_consumer()                                  # updated weights before the top hop
         yy0 = op_top.forward(h1[:t.src_size])
@@ -501,7 +519,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         y0_done[i % 2].record(st_train)
         if i > 0:
             y0_done[(i - 1) % 2].synchronize()
-            api_state["checksum"] += float(y0_ring[(i - 1) % 2][0, 0])
+            api_state["checksum"] += float(y0_np[(i - 1) % 2][0, 0])
         sizes_np[i, 8:11] = (bt.v_size, bt.e_size, bt.src_size)    # host bookkeeping of the work done (numpy view of the pinned buffer)
         sizes_np[i, 1] = t.e_size
         del yy1
@@ -538,7 +556,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                 peer_ar.stats(reset=True)
             for w in range(R):
                 align_ranks()
-                launches0 = sum(c_.launch_count() for c_ in cs_samples + cs_samples_api) + cs_train.launch_count() + cs_comm.launch_count()
+                launches0 = sum(c_.launch_count() for c_ in cs_samples + cs_samples_api + ([cs_agg] if cs_agg is not cs_train else [])) + cs_train.launch_count() + cs_comm.launch_count()
                 t0, t1 = ev(), ev()
                 if clocks:
                     clocks.mark(True)
@@ -550,13 +568,13 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                 if mode == "api":                  # the host consumes the last step's output inside the window
                     last = W + (w + 1) * K - 1
                     y0_done[last % 2].synchronize()
-                    api_state["checksum"] += float(y0_ring[last % 2][0, 0])
+                    api_state["checksum"] += float(y0_np[last % 2][0, 0])
                 t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes all streams
                 h1_ = time.perf_counter()
                 torch.cuda.synchronize()
                 if clocks:
                     clocks.mark(False)
-                launches += sum(c_.launch_count() for c_ in cs_samples + cs_samples_api) + cs_train.launch_count() + cs_comm.launch_count() - launches0
+                launches += sum(c_.launch_count() for c_ in cs_samples + cs_samples_api + ([cs_agg] if cs_agg is not cs_train else [])) + cs_train.launch_count() + cs_comm.launch_count() - launches0
                 if world > 1:
                     dist.barrier()
                 torch.cuda.synchronize()
@@ -602,17 +620,17 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         torch.cuda.synchronize()
         tl, tl_box[0] = tl_box[0][8:], None
         ref = tl[0][2]
-        T = np.array([[ref.elapsed_time(e) for e in row] for row in tl]) * 1e3      # us
-        timeline = {"steps": len(tl), "unit": "us, mean over steps",
+        T = np.array([[ref.elapsed_time(e) for e in row] for row in tl]) * 1e3      # us; columns: sample start, sample end, bottom start,
+        timeline = {"steps": len(tl), "unit": "us, mean over steps",                # bottom end, top fwd end, top bwd end, top chain start
                     "step_period": float(np.diff(T[:, 5]).mean()),
                     "sampler_graph": float((T[:, 1] - T[:, 0]).mean()),
-                    "sample_end_to_train_start": float((T[:, 2] - T[:, 1]).mean()),
-                    "prev_bwd_end_to_train_start": float((T[1:, 2] - T[:-1, 5]).mean()),
                     "bottom_hop": float((T[:, 3] - T[:, 2]).mean()),
-                    "top_fwd(+exchange end)": float((T[:, 4] - T[:, 3]).mean()),
+                    "bottom_hop_period": float(np.diff(T[:, 3]).mean()),
+                    "bottom_end_to_top_start": float((T[:, 6] - T[:, 3]).mean()),
+                    "top_fwd(+exchange end)": float((T[:, 4] - T[:, 6]).mean()),
                     "top_bwd": float((T[:, 5] - T[:, 4]).mean()),
-                    "sample_start_after_prev_prev_bwd_end": float((T[2:, 0] - T[:-2, 5]).mean()),
-                    "sample_end_before_prev_bwd_end": float((T[:-1, 5] - T[1:, 1]).mean())}
+                    "prev_bwd_end_to_top_start": float((T[1:, 6] - T[:-1, 5]).mean()),
+                    "sample_end_to_bottom_start": float((T[:, 2] - T[:, 1]).mean())}
         if rank == 0:
             print("timeline " + json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in timeline.items()}), file=sys.stderr, flush=True)
 
@@ -681,7 +699,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         assert not peer_ar.timed_out(), "peer all-reduce: a rank never arrived"
         peer_ar.close()
     assert exchange_check is None or ("MISMATCH" not in exchange_check and "DISAGREE" not in exchange_check), exchange_check
-    del sampler, fast, graph, table, x0, y1, h1, slots
+    del sampler, fast, graph, table, x0, y1, y1s, h1, slots
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     return out
@@ -1103,7 +1121,7 @@ def main_b200(args):
                 pass
         cpu = None
         ref_gpu_box = []
-        CPP_E2E_ARGS[:] = [str(PITCH), str(K), str(W), str(R), str(max(2, args.api_pipeline)), str(args.sample_streams)]
+        CPP_E2E_ARGS[:] = [str(PITCH), str(K), str(W), str(R), str(max(2, args.api_pipeline)), str(args.sample_streams), str(args.agg_stream)]
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r, kind, threads = cpu_baseline_run(v, col_off, src, all_seeds, args.cpu_batches, 2, ref_gpu_box)
@@ -1147,7 +1165,7 @@ def main_b200(args):
                 "warmup": W, "ms_per_step": f_["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(v, e_total),
-                "run": {"per_gpu_batch": B, "global_batch": B * world, "pipeline_num": P, "sampling_streams": args.sample_streams, "row_pitch_floats": PITCH,
+                "run": {"per_gpu_batch": B, "global_batch": B * world, "pipeline_num": P, "sampling_streams": args.sample_streams, "bottom_hop_on_its_own_stream": bool(args.agg_stream), "row_pitch_floats": PITCH,
                         "parallelism": f"dp{world}: seeds sharded contiguously; dense-gradient sum per step = {ex_name}" if world > 1 else "single GPU",
                         "windows": R, "window_rule": "each window times exactly `steps` steps between device-aligned events; the median window is reported",
                         "windows_ms_per_step": f_["windows_ms_per_step"], "host_issue_ms_per_step": f_["host_issue_ms_per_step"],
@@ -1161,7 +1179,7 @@ def main_b200(args):
                         "host_blocked_in_sampler_wait_ms_per_step": round(res["api"]["host_wait_ms_per_step"], 5),
                         "cpp_host": cpp_e2e,
                         "pipeline_num": max(2, args.api_pipeline),
-                        "path": "FastSampler.sample_gpu_fast(slots i+1 .. i+PIPELINE_NUM-1, async, high-priority streams) || wait(slot i) -> load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
+                        "path": "FastSampler.sample_gpu_fast(slots i+1 .. i+PIPELINE_NUM-1, async, high-priority streams) || wait(slot i) -> [aggregation stream] load_feature_gpu(lazy) -> SingleGPUAllSampleGraphOp fwd/fwd/bwd -> D2H of the output into a 2-deep pinned ring; the host reads step i-1's output while step i runs"},
                 "gpu_launches": int(round(launches_all)), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "other_configs": other,
                 "materialized_x0": {"value": m_["value"], "unit": "edges/s", "ms_per_step": m_["ms_per_step"],
                                     "windows_ms_per_step": m_["windows_ms_per_step"],
@@ -1192,6 +1210,7 @@ if __name__ == "__main__":
                          "(the in-line kernel costs ~9 us of the step: 0.156 vs 0.146 ms at N=8, profiles/r2b_scale_matrix.txt); split-inline = "
                          "the same with the push in the training stream too; nccl = NCCL all_reduce")
     ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
+    ap.add_argument("--agg-stream", type=int, default=1, help="1 = the (weight-free) bottom hop runs on its own stream, one Y1 buffer per slot: batch i+1's bottom hop beside batch i's top hop; 0 = everything in the training stream")
     ap.add_argument("--train-priority", type=int, default=0, help="CUDA stream priority of the training stream (0 = normal, negative = higher)")
     ap.add_argument("--api-pipeline", type=int, default=4, help="e2e arm: FastSampler pipeline slots (PIPELINE_NUM); PIPELINE_NUM - 1 batches are sampled ahead")
     ap.add_argument("--sample-streams", type=int, default=2, help="sampling streams; pipeline slot k samples on stream k %% NS (one stream serialises the batches' sampler graphs "
