@@ -1211,7 +1211,9 @@ if __name__ == "__main__":
                          "the same with the push in the training stream too; nccl = NCCL all_reduce")
     ap.add_argument("--modes", default="fused,api,materialized", help="tuning sweeps: run only some arms (a skipped arm repeats the headline's numbers)")
     ap.add_argument("--agg-stream", type=int, default=1, help="1 = the (weight-free) bottom hop runs on its own stream, one Y1 buffer per slot: batch i+1's bottom hop beside batch i's top hop; 0 = everything in the training stream")
-    ap.add_argument("--train-priority", type=int, default=0, help="CUDA stream priority of the training stream (0 = normal, negative = higher)")
+    ap.add_argument("--train-priority", type=int, default=-1, help="CUDA stream priority of the training stream (0 = normal, negative = higher). With the bottom hop on its own stream "
+                         "the weight-dependent chain (exchange end, top hop forward / backward) is the critical path at N > 1: its few blocks go ahead of the bottom hop's "
+                         "(N=2: 0.150 -> 0.133 ms per step; N=1: 0.1265 vs 0.128, profiles/r2c_sweep_n2_train_priority.txt)")
     ap.add_argument("--api-pipeline", type=int, default=4, help="e2e arm: FastSampler pipeline slots (PIPELINE_NUM); PIPELINE_NUM - 1 batches are sampled ahead")
     ap.add_argument("--sample-streams", type=int, default=2, help="sampling streams; pipeline slot k samples on stream k %% NS (one stream serialises the batches' sampler graphs "
                          "and puts them on the step's critical path: 0.168 -> 0.155 ms per step with two, profiles/r2_sweep_sample_streams.txt)")
