@@ -80,8 +80,9 @@ def shard_seeds(ids, rank, world):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled from the first warm-up step to the end of the last timed window of the headline mode
-    (NVML in-process, ~0.5 ms period); samples that fall inside a timed window are counted separately."""
+    """SM clock and throttle reasons sampled from the first warm-up step of `value` to the end of the last timed window of `e2e`
+    (NVML in-process: a background thread at ~0.5 ms period plus one sample by the main thread per timed window, taken while the GPU is
+    still executing that window); samples that fall inside a timed window are counted separately."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -111,8 +112,27 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.0005)
 
+    def ensure_started(self):
+        if not getattr(self, "_started_once", False):
+            self._started_once = True
+            self.start()
+
     def mark(self, inside):
         self.in_window = inside
+
+    def sample_now(self):
+        """one sample from the calling thread. The timed windows are a few milliseconds long and the host runs ahead of the GPU, so the
+        background thread may see none of a window (GIL, NVML latency): the main thread takes one itself right after it has issued a
+        window's last step, while the GPU is still executing that window."""
+        if self.nv is None:
+            return
+        try:
+            mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            self.sm.append(mhz)
+            self.sm_timed.append(mhz)
+            self.mask |= self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            pass
 
     def summary(self):
         self.stop_flag = True
@@ -547,7 +567,7 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
         launches = 0
         with torch.cuda.stream(st_train):
             if clocks:
-                clocks.start()
+                clocks.ensure_started()
             for i in range(W):
                 step(i, False)
             exchange_flush()
@@ -571,6 +591,8 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                     api_state["checksum"] += float(y0_np[last % 2][0, 0])
                 t1.record(st_train)   # every batch's sampling is consumed on the training stream, so this closes all streams
                 h1_ = time.perf_counter()
+                if clocks:
+                    clocks.sample_now()           # the GPU is still inside this window (the host ran ahead)
                 torch.cuda.synchronize()
                 if clocks:
                     clocks.mark(False)
@@ -590,9 +612,9 @@ def run_hot_path(env, args, wl, modes, R, sample_clocks=True):
                     host_wait_ms_per_step=api_state["wait_s"] * 1e3 / (W + R * K))
 
     clocks = ClockSampler(local) if sample_clocks else None
-    res = {"fused": run("fused", clocks)}
+    res = {"fused": run("fused", clocks)}                                           # clocks: sampled through the timed windows of `value` and `e2e`
+    res["api"] = run("api", clocks) if "api" in modes else res["fused"]             # --modes: tuning sweeps skip the other arms
     clk = clocks.summary() if clocks else None
-    res["api"] = run("api") if "api" in modes else res["fused"]                     # --modes: tuning sweeps skip the other arms
     res["materialized"] = run("materialized") if "materialized" in modes else res["fused"]
 
     # the sampler by itself: one batch after the other on one stream, nothing else on the GPU (its serial latency per batch)
