@@ -784,6 +784,8 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
     st_ss, st_t = [torch.cuda.Stream(dev, priority=-1) for _ in range(2)], torch.cuda.Stream(dev)
     cs_ss, cs_t = [nts.Cuda_Stream(local, s_) for s_ in st_ss], nts.Cuda_Stream(local, st_t)
     st_s, cs_s = st_ss[0], cs_ss[0]
+    st_d = torch.cuda.Stream(dev)                     # data stream: the feature gather of the next batch (no weights involved)
+    cs_d = nts.Cuda_Stream(local, st_d)
     H, NC = F1, NCLS
     with torch.cuda.stream(st_t):
         graph = nts.FullyRepGraph(cs_s, v, column_offset=col_off, row_indices=src)
@@ -792,7 +794,7 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
         gen = torch.Generator(device=dev).manual_seed(5)
         table = torch.rand((v, F0), generator=gen, device=dev)
         cap1, cap0 = min(B * 26 * 11, v), min(B * 26, v)
-        x0 = torch.empty((cap1, F0), device=dev)
+        x0s = [torch.empty((cap1, F0), device=dev) for _ in range(PO)]   # one X0 per slot: the gather is weight-free, it runs on a data stream
         h1, h0 = torch.randn((cap1, H), generator=gen, device=dev), torch.randn((cap0, NC), generator=gen, device=dev)
         att1, att0 = torch.randn(2 * H, generator=gen, device=dev) * 0.3, torch.randn(2 * NC, generator=gen, device=dev) * 0.3
         d1, d0 = torch.randn((cap0, H), generator=gen, device=dev), torch.randn((B, NC), generator=gen, device=dev)
@@ -802,7 +804,7 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
     if world > 1:
         from sample_based_gnn_b200 import dist as nbdist
         peer = nbdist.PeerAllReduce(cs_t, grads.numel())
-    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(PO)]
+    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event(), gathered=torch.cuda.Event()) for _ in range(PO)]
     state = {"issued": -1, "open": False}
     gat_ev, work = [], []
 
@@ -821,9 +823,11 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
             issue(state["issued"] + 1 if state["issued"] >= i else i)
         k = i % PO
         sg = smp.wait(k)
-        st_t.wait_event(ev_s[k]["sampled"])
+        st_d.wait_event(ev_s[k]["sampled"])
         top, bot = sg.sampled_sgs
-        smp.load_feature_gpu(cs_t, sg, x0[:bot.src_size], table)       # X0 feeds the dense W0, so it is materialised
+        smp.load_feature_gpu(cs_d, sg, x0s[k][:bot.src_size], table)   # X0 feeds the dense W0, so it is materialised -- on the data stream,
+        ev_s[k]["gathered"].record(st_d)                               # beside the previous batch's (weight-dependent, latency-bound) GAT hops
+        st_t.wait_event(ev_s[k]["gathered"])
         op1, op0 = nts.GATFusedOp(sg, 1, cs_t), nts.GATFusedOp(sg, 0, cs_t)
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -881,7 +885,7 @@ def run_gat_config(env, args, v, col_off, src, all_seeds, peak):
     gbs = gat_bytes / (ms * 1e-3) / 1e9
     if peer is not None:
         peer.close()
-    del smp, graph, table, x0
+    del smp, graph, table, x0s
     torch.cuda.synchronize(); torch.cuda.empty_cache()
     return {"workload": f"GAT_SAMPLE_ALL_MULTI shape on the Reddit-shaped graph: global batch {B * world} (local {B}), fanout 25-10, merge-src-dst sampling, "
                         f"gather F=602 + fused GAT layer fwd+bwd on both hops (128 / 41) + gradient exchange, operator API with host sizes",
@@ -908,6 +912,8 @@ def run_papers_config(env, args, peak):
     st_ss, st_t = [torch.cuda.Stream(dev, priority=-1) for _ in range(2)], torch.cuda.Stream(dev)
     cs_ss, cs_t = [nts.Cuda_Stream(local, s_) for s_ in st_ss], nts.Cuda_Stream(local, st_t)
     st_s, cs_s = st_ss[0], cs_ss[0]
+    st_d = torch.cuda.Stream(dev)                     # data stream: the feature gather of the next batch (no weights involved)
+    cs_d = nts.Cuda_Stream(local, st_d)
     from sample_based_gnn_b200 import dist as nbdist
     with torch.cuda.stream(st_t):
         co, src = power_law_graph_gpu(torch, V, E, 0xFACE)
@@ -929,20 +935,20 @@ def run_papers_config(env, args, peak):
             b = min(n_local, a + (1 << 22))
             rows[a:b] = torch.rand((b - a, F), generator=gen, device=dev)
         if world > 1:
-            shard = nbdist.ShardedTable(cs_t, rows, V, F)
+            shard = nbdist.ShardedTable(cs_d, rows, V, F)
             del rows
             torch.cuda.empty_cache()
             gather = lambda x, ids, n: shard.gather(x, ids, n)
         else:
             shard = None
-            gather = lambda x, ids, n: cs_t.zero_copy_feature_move_gpu(x, rows, ids, F, n, F, F)
+            gather = lambda x, ids, n: cs_d.zero_copy_feature_move_gpu(x, rows, ids, F, n, F, F)
         cap1, cap0 = B * 25 * 10, B * 25
-        x0 = torch.empty((cap1, F), device=dev)
+        x0s = [torch.empty((cap1, F), device=dev) for _ in range(PO)]    # one X0 per slot: the gather (weight-free) runs on a data stream
         h1, dy0 = torch.rand((cap0, H), device=dev), torch.rand((B, H), device=dev)
         grads = torch.rand(F * H + H * 172, device=dev)
     torch.cuda.synchronize()
     peer = nbdist.PeerAllReduce(cs_t, grads.numel()) if world > 1 else None
-    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(PO)]
+    ev_s = [dict(sampled=torch.cuda.Event(), consumed=torch.cuda.Event(), gathered=torch.cuda.Event()) for _ in range(PO)]
     state = {"issued": -1, "open": False}
     g_ev, s_ev, work, rows_n = [], [], [], []
 
@@ -965,16 +971,19 @@ def run_papers_config(env, args, peak):
             issue(state["issued"] + 1 if state["issued"] >= i else i)
         k = i % PO
         sg = smp.wait(k)
-        st_t.wait_event(ev_s[k]["sampled"])
+        st_d.wait_event(ev_s[k]["sampled"])
         top, bot = sg.sampled_sgs
+        x0 = x0s[k]
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(st_t)
-        gather(x0[:bot.src_size], bot.dev_source, bot.src_size)
+            a.record(st_d)
+        gather(x0[:bot.src_size], bot.dev_source, bot.src_size)          # data stream: beside the previous batch's aggregation
         if timed:
-            b.record(st_t)
+            b.record(st_d)
             g_ev.append((a, b))
             rows_n.append(bot.src_size)
+        ev_s[k]["gathered"].record(st_d)
+        st_t.wait_event(ev_s[k]["gathered"])
         y1 = nts.SingleGPUAllSampleGraphOp(sg, 1, cs_t).forward(x0[:bot.src_size])
         if state["open"]:
             peer.end(grads); state["open"] = False
@@ -1027,7 +1036,7 @@ def run_papers_config(env, args, peak):
         peer.close()
     if shard is not None:
         shard.close()
-    del smp, graph, x0
+    del smp, graph, x0s
     torch.cuda.synchronize(); torch.cuda.empty_cache()
     rec = {"workload": f"papers100M-shaped synthetic graph at full size ({V} vertices, {e_total} edges), F=128, fanout 25-10, batch {B} per GPU; "
                        f"topology replicated, 56.8 GB feature table row-sharded over {world} GPU(s) in HBM ({n_local * F * 4 / 1e9:.1f} GB per GPU), "
