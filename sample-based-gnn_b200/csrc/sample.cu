@@ -727,16 +727,17 @@ k_csr_long_rows(const uint32_t *__restrict__ row_offset, const uint32_t *__restr
 }
 
 // =============================================================================================
-// Small-shape path. A 1024-seed mini-batch is latency bound, not bandwidth bound: a layer has 1K-25K dst and 25K-250K
-// edges, and the general pipeline above spends most of its time in launch gaps and in chains of dependent loads
-// (11 launches, ~8 us each). When the per-layer arrays fit in shared memory every block recomputes the layer's prefix
-// sums for itself (a few tens of KB from L2) instead of waiting for a separate scan kernel:
+// Small-shape path ("sampler_fused" = 1; NOT the default). When the per-layer arrays fit in shared memory every block recomputes the
+// layer's prefix sums for itself (a few tens of KB from L2) instead of waiting for a separate scan kernel:
 //   k_sample_fused   = count + exclusive scan (in smem, per block) + neighbour selection + bitmap marks
 //   k_relabel_fused  = popcount scan of the dedup bitmap (in smem, per block) + `source` emission + relabel + histogram +
 //                      weights (+ the next layer's per-dst adjacency base / degree, so its sampler skips one dependent load)
 //   k_csr_fill_fused = row_offset scan (in smem, per block) + stable-fill step 1;  k_csr_rows handles long rows itself
-// i.e. 2 launches per layer (+2 for a layer whose CSR is built): 6 instead of 11 for the benchmark's two layers.
-// Results are bit-identical to the general path (same arithmetic, same ordering rules); tests run both.
+// i.e. 7 launches instead of 12 for the benchmark's two layers. Results are bit-identical to the general path (same arithmetic, same
+// ordering rules); the tests run every variant. It was the default for half a round. Measured again once batches were sampled on two
+// streams beside the aggregation of earlier batches, it lost on both counts: alone (110-135 us per batch vs 80-90: every block redoes a
+// 25K-entry scan) and as a neighbour (blocks with 100 KB of shared memory / 512 threads do not fit the slot the aggregation leaves free,
+// so they displace its blocks: 0.151-0.167 vs 0.139 ms per step) -- profiles/r2_sweep_sampler_residency.txt.
 constexpr int FS_THREADS = 512;   // upper bound of the small-shape kernels' block size; the launch uses g_sampler_block threads
 // "sampler_block_threads": 256 (default) or 512. The sampler runs beside the previous batch's aggregation, whose two resident
 // blocks per SM leave ~11K registers: a 256-thread block of <= 40 registers fits there, a 512-thread block waits for a retiring one.
