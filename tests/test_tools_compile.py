@@ -2,6 +2,7 @@
 import ast
 import glob
 import os
+import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -19,3 +20,12 @@ def test_bench_cli_contract():
     for flag in ('"--gpus"', '"--steps"', '"--warmup"', '"--impl"'):
         assert flag in src
     assert 'ap.add_argument("--gpus", type=int, default=1)' in src
+
+
+def test_tool_scripts_parse():
+    """the sweep / validation shell scripts under tools/ (they run on a GPU box) are at least syntactically valid"""
+    scripts = sorted(glob.glob(os.path.join(ROOT, "tools", "*.sh")))
+    assert len(scripts) >= 6
+    for f in scripts:
+        r = subprocess.run(["bash", "-n", f], capture_output=True, text=True)
+        assert r.returncode == 0, (f, r.stderr)
